@@ -1,0 +1,441 @@
+// api.cu — C-ABI entry points: model lifetime, encode / forward drivers, host-buffer pipeline.
+//
+// The reference has no native layer: its "operator API" for this path is the Python module tree
+// built by RQVAE.__init__ (reference RQ-VAE/models/rqvae.py:45-58) and the calls made by the encode
+// driver (reference RQ-VAE/infer.py:88-177).  Each entry point below names the call it replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <new>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rqb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiling: event pairs recorded around selected launches, resolved at read time
+struct ProfState {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[PROF_NSLOTS];
+    std::vector<cudaEvent_t> pool;
+    double ms[PROF_NSLOTS] = {0};
+    long long count[PROF_NSLOTS] = {0};
+    cudaEvent_t open_ev[PROF_NSLOTS] = {nullptr};
+};
+static ProfState g_prof;
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_get_event() {
+    if (!g_prof.pool.empty()) { cudaEvent_t e = g_prof.pool.back(); g_prof.pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int slot, cudaStream_t s) {
+    if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_get_event();
+    cudaEventRecord(e, s);
+    g_prof.open_ev[slot] = e;
+}
+void prof_end(int slot, cudaStream_t s) {
+    if (!g_prof.enabled) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof.open_ev[slot]) return;
+    cudaEvent_t e = prof_get_event();
+    cudaEventRecord(e, s);
+    g_prof.pending[slot].push_back({g_prof.open_ev[slot], e});
+    g_prof.open_ev[slot] = nullptr;
+}
+static void prof_resolve() {
+    for (int k = 0; k < PROF_NSLOTS; ++k) {
+        for (auto &pr : g_prof.pending[k]) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+                g_prof.ms[k] += ms;
+                g_prof.count[k] += 1;
+            }
+            g_prof.pool.push_back(pr.first);
+            g_prof.pool.push_back(pr.second);
+        }
+        g_prof.pending[k].clear();
+    }
+    (void)cudaGetLastError();
+}
+
+int ws_reserve(Workspace &w, size_t bytes) {
+    if (w.bytes >= bytes) return 0;
+    if (w.ptr) {
+        RQB_CUDA(cudaDeviceSynchronize());   // the old block may still be in use by queued kernels
+        RQB_CUDA(cudaFree(w.ptr));
+        w.ptr = nullptr;
+        w.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&w.ptr, want);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();   // clear the sticky-free allocation error
+        set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return RQB200_ENOMEM;
+    }
+    w.bytes = want;
+    return 0;
+}
+
+// K-blocking of the reference's CPU sgemm (verified by oracle/make_golden.py):
+// one chain for K <= 384, two halves for 384 < K <= 768, else blocks of 384 with the remainder last.
+static int default_kblocks(int K, int *out) {
+    if (K <= 384) { out[0] = K; return 1; }
+    if (K <= 768) { out[0] = K - K / 2; out[1] = K / 2; return 2; }
+    int n = 0;
+    while (K > 0 && n < 16) { out[n] = K < 384 ? K : 384; K -= out[n]; ++n; }
+    return K > 0 ? -1 : n;
+}
+
+static void free_linear(Linear &l) {
+    if (l.W) cudaFree(l.W);
+    if (l.b) cudaFree(l.b);
+    if (l.W_tc) cudaFree(l.W_tc);
+    if (l.absW_rowmax) cudaFree(l.absW_rowmax);
+    l = Linear();
+}
+
+}  // namespace rqb
+
+using namespace rqb;
+
+extern "C" int rqb200_abi_version(void) { return RQB200_ABI_VERSION; }
+extern "C" const char *rqb200_last_error(void) { return rqb::g_err; }
+
+extern "C" long long rqb200_launch_count(void) { return rqb::g_launches.load(); }
+
+extern "C" int rqb200_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(rqb::g_prof_mu);
+    rqb::prof_resolve();
+    rqb::g_prof.enabled = on != 0;
+    if (on) for (int k = 0; k < rqb::PROF_NSLOTS; ++k) { rqb::g_prof.ms[k] = 0; rqb::g_prof.count[k] = 0; }
+    return 0;
+}
+
+extern "C" int rqb200_profile_read(double *ms_out, long long *count_out, int nslots) {
+    std::lock_guard<std::mutex> lk(rqb::g_prof_mu);
+    rqb::prof_resolve();
+    for (int k = 0; k < nslots && k < rqb::PROF_NSLOTS; ++k) { ms_out[k] = rqb::g_prof.ms[k]; count_out[k] = rqb::g_prof.count[k]; }
+    return 0;
+}
+
+extern "C" int rqb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int rqb200_model_create(rqb200_model **out, int device, int n_layers, const int *dims,
+                                   int n_levels, const int *K) {
+    RQB_CHECK(out != nullptr && dims != nullptr && K != nullptr, "NULL argument");
+    RQB_CHECK(n_layers >= 1 && n_layers <= RQB200_MAX_LAYERS, "n_layers=%d out of range", n_layers);
+    RQB_CHECK(n_levels >= 1 && n_levels <= RQB200_MAX_LEVELS, "n_levels=%d out of range", n_levels);
+    for (int i = 0; i <= n_layers; ++i) RQB_CHECK(dims[i] >= 1, "dims[%d]=%d", i, dims[i]);
+    for (int l = 0; l < n_levels; ++l) RQB_CHECK(K[l] >= 1, "K[%d]=%d", l, K[l]);
+    int ndev = rqb200_device_count();
+    RQB_CHECK(ndev > 0, "no CUDA device: this library has no CPU fallback");
+    RQB_CHECK(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
+    RQB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RQB_CUDA(cudaGetDeviceProperties(&prop, device));
+    RQB_CHECK(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+              prop.major, prop.minor);
+    rqb200_model *m = new (std::nothrow) rqb200_model();
+    if (!m) { set_error("out of host memory"); return RQB200_ENOMEM; }
+    m->device = device;
+    m->n_layers = n_layers;
+    for (int i = 0; i <= n_layers; ++i) m->dims[i] = dims[i];
+    m->L = n_levels;
+    m->e = dims[n_layers];
+    for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
+        m->K[l] = l < n_levels ? K[l] : 0;
+        m->cb[l] = nullptr; m->cc[l] = nullptr; m->cb_set[l] = false;
+    }
+    for (int l = 0; l < n_levels; ++l) {
+        if (cudaMalloc(&m->cb[l], sizeof(float) * (size_t)K[l] * m->e) != cudaSuccess ||
+            cudaMalloc(&m->cc[l], sizeof(float) * (size_t)K[l]) != cudaSuccess) {
+            set_error("cudaMalloc codebook failed");
+            rqb200_model_destroy(m);
+            return RQB200_ENOMEM;
+        }
+    }
+    if (cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        rqb200_model_destroy(m);
+        return RQB200_ECUDA;
+    }
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreateWithFlags(&m->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            rqb200_model_destroy(m);
+            return RQB200_ECUDA;
+        }
+    *out = m;
+    return 0;
+}
+
+extern "C" void rqb200_model_destroy(rqb200_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < RQB200_MAX_LAYERS; ++i) { free_linear(m->enc[i]); free_linear(m->dec[i]); }
+    for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
+        if (m->cb[l]) cudaFree(m->cb[l]);
+        if (m->cc[l]) cudaFree(m->cc[l]);
+    }
+    Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1]};
+    for (Workspace *w : ws)
+        if (w->ptr) cudaFree(w->ptr);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    for (int i = 0; i < 4; ++i)
+        if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+    (void)cudaGetLastError();
+    delete m;
+}
+
+extern "C" int rqb200_model_set_linear(rqb200_model *m, int which, int layer, const float *W,
+                                       const float *b, const int *kblocks, int nblk) {
+    RQB_CHECK(m != nullptr && W != nullptr, "NULL argument");
+    RQB_CHECK(which == 0 || which == 1, "which must be 0 (encoder) or 1 (decoder)");
+    RQB_CHECK(layer >= 0 && layer < m->n_layers, "layer %d out of range", layer);
+    RQB_CUDA(cudaSetDevice(m->device));
+    Linear &l = which == 0 ? m->enc[layer] : m->dec[layer];
+    const int in = which == 0 ? m->dims[layer] : m->dims[m->n_layers - layer];
+    const int out = which == 0 ? m->dims[layer + 1] : m->dims[m->n_layers - layer - 1];
+    if (!l.W) {
+        RQB_CUDA(cudaMalloc(&l.W, sizeof(float) * (size_t)in * out));
+        RQB_CUDA(cudaMalloc(&l.b, sizeof(float) * (size_t)out));
+    }
+    l.in = in; l.out = out;
+    RQB_CUDA(cudaMemcpy(l.W, W, sizeof(float) * (size_t)in * out, cudaMemcpyDefault));
+    if (b) RQB_CUDA(cudaMemcpy(l.b, b, sizeof(float) * (size_t)out, cudaMemcpyDefault));
+    else RQB_CUDA(cudaMemset(l.b, 0, sizeof(float) * (size_t)out));
+    if (kblocks) {
+        RQB_CHECK(nblk >= 1 && nblk <= 8, "nblk=%d out of range (1..8)", nblk);
+        int tot = 0;
+        for (int i = 0; i < nblk; ++i) { RQB_CHECK(kblocks[i] > 0, "kblocks[%d]=%d", i, kblocks[i]); tot += kblocks[i]; l.kblocks[i] = kblocks[i]; }
+        RQB_CHECK(tot == in, "kblocks sum to %d, expected %d", tot, in);
+        l.nblk = nblk;
+    } else {
+        l.nblk = default_kblocks(in, l.kblocks);
+        RQB_CHECK(l.nblk >= 1 && l.nblk <= 8, "in_features=%d needs more than 8 K-blocks", in);
+    }
+    if (l.W_tc) { cudaFree(l.W_tc); l.W_tc = nullptr; l.W_tc_bytes = 0; }   // stale tensor-core image
+    l.set = true;
+    return 0;
+}
+
+extern "C" int rqb200_model_set_codebook(rqb200_model *m, int level, const float *E) {
+    RQB_CHECK(m != nullptr && E != nullptr, "NULL argument");
+    RQB_CHECK(level >= 0 && level < m->L, "level %d out of range", level);
+    RQB_CUDA(cudaSetDevice(m->device));
+    RQB_CUDA(cudaMemcpy(m->cb[level], E, sizeof(float) * (size_t)m->K[level] * m->e, cudaMemcpyDefault));
+    RQB_TRY(codebook_norms(m->cb[level], m->K[level], m->e, m->cc[level], 0));
+    RQB_CUDA(cudaStreamSynchronize(0));
+    m->cb_set[level] = true;
+    return 0;
+}
+
+extern "C" int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out) {
+    RQB_CHECK(m != nullptr && E_out != nullptr, "NULL argument");
+    RQB_CHECK(level >= 0 && level < m->L, "level %d out of range", level);
+    RQB_CUDA(cudaSetDevice(m->device));
+    RQB_CUDA(cudaMemcpy(E_out, m->cb[level], sizeof(float) * (size_t)m->K[level] * m->e, cudaMemcpyDefault));
+    return 0;
+}
+
+static int check_encoder(const rqb200_model *m) {
+    for (int i = 0; i < m->n_layers; ++i)
+        if (!m->enc[i].set) { set_error("encoder layer %d not loaded", i); return RQB200_ESTATE; }
+    return 0;
+}
+static int check_decoder(const rqb200_model *m) {
+    for (int i = 0; i < m->n_layers; ++i)
+        if (!m->dec[i].set) { set_error("decoder layer %d not loaded", i); return RQB200_ESTATE; }
+    return 0;
+}
+static int check_codebooks(const rqb200_model *m) {
+    for (int l = 0; l < m->L; ++l)
+        if (!m->cb_set[l]) { set_error("codebook %d not loaded", l); return RQB200_ESTATE; }
+    return 0;
+}
+
+// runs the MLP layer by layer through the two ping-pong activation buffers; the last layer
+// writes to y.  Activations of at most `max_dim` floats per row.
+static int run_mlp(rqb200_model *m, int which, const float *x, const int64_t *rows, int64_t n, float *y,
+                   cudaStream_t s) {
+    const Linear *ls = which == 0 ? m->enc : m->dec;
+    int maxdim = 0;
+    for (int i = 0; i + 1 < m->n_layers; ++i) maxdim = ls[i].out > maxdim ? ls[i].out : maxdim;
+    if (m->n_layers > 1) {
+        RQB_TRY(ws_reserve(m->act[0], sizeof(float) * (size_t)n * maxdim));
+        if (m->n_layers > 2) RQB_TRY(ws_reserve(m->act[1], sizeof(float) * (size_t)n * maxdim));
+    }
+    const float *cur = x;
+    for (int i = 0; i < m->n_layers; ++i) {
+        const bool last = i == m->n_layers - 1;
+        float *dst = last ? y : (float *)m->act[i & 1].ptr;
+        {
+            ProfScope ps(i == 0 ? PROF_LINEAR0 : PROF_LINEAR_REST, s);
+            RQB_TRY(linear_exact(ls[i], cur, i == 0 ? rows : nullptr, n, dst, !last, s));
+        }
+        cur = dst;
+    }
+    return 0;
+}
+
+extern "C" int rqb200_mlp_exact(rqb200_model *m, int which, const float *x_dev, const int64_t *rows_dev,
+                                int64_t n, float *y_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(which == 0 || which == 1, "which must be 0 or 1");
+    RQB_CHECK(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && y_dev != nullptr, "NULL buffer");
+    RQB_TRY(which == 0 ? check_encoder(m) : check_decoder(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    return run_mlp(m, which, x_dev, rows_dev, n, y_dev, (cudaStream_t)stream);
+}
+
+extern "C" int rqb200_quantize(rqb200_model *m, const float *z_dev, int64_t n, int64_t *codes_dev,
+                               const int64_t *rows_out_dev, float *xq_dev, double *sumsq_dev,
+                               float *last_residual_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    RQB_CHECK(z_dev != nullptr && codes_dev != nullptr, "NULL buffer");
+    RQB_TRY(check_codebooks(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    return quantize_exact(m, z_dev, n, codes_dev, rows_out_dev, xq_dev, sumsq_dev, last_residual_dev,
+                          nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rqb200_distances(rqb200_model *m, int level, const float *r_dev, int64_t n, float *d_dev,
+                                void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    if (n == 0) return 0;
+    RQB_CHECK(r_dev != nullptr && d_dev != nullptr, "NULL buffer");
+    RQB_TRY(check_codebooks(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    return distances_exact(m, level, r_dev, n, d_dev, (cudaStream_t)stream);
+}
+
+namespace rqb {
+int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes, float *z_out,
+                     int64_t *stats_host, cudaStream_t s);   // encode_tc.cu
+}
+
+extern "C" int rqb200_get_indices(rqb200_model *m, int mode, const float *x_dev, int64_t n,
+                                  int64_t *codes_dev, float *z_out_dev, int64_t *stats_host, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(n >= 0, "n < 0");
+    if (stats_host) stats_host[0] = 0;
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && codes_dev != nullptr, "NULL buffer");
+    RQB_TRY(check_encoder(m));
+    RQB_TRY(check_codebooks(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    if (mode == RQB200_ENCODE_FAST) return get_indices_fast(m, x_dev, n, codes_dev, z_out_dev, stats_host, s);
+    RQB_CHECK(mode == RQB200_ENCODE_EXACT, "unknown mode %d", mode);
+    float *z = z_out_dev;
+    if (!z) {
+        RQB_TRY(ws_reserve(m->misc, sizeof(float) * (size_t)n * m->e));
+        z = (float *)m->misc.ptr;
+    }
+    RQB_TRY(run_mlp(m, 0, x_dev, nullptr, n, z, s));
+    return quantize_exact(m, z, n, codes_dev, nullptr, nullptr, nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int rqb200_forward(rqb200_model *m, const float *x_dev, int64_t n, float *out_dev,
+                              int64_t *codes_dev, double *sumsq_dev, double *recon_sum_dev, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(n >= 0, "n < 0");
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && codes_dev != nullptr, "NULL buffer");
+    RQB_TRY(check_encoder(m));
+    RQB_TRY(check_decoder(m));
+    RQB_TRY(check_codebooks(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    // misc: z[n,e] | xq[n,e] | (out[n,in] if the caller does not want it)
+    const size_t ze = sizeof(float) * (size_t)n * m->e;
+    const size_t oe = out_dev ? 0 : sizeof(float) * (size_t)n * m->dims[0];
+    RQB_TRY(ws_reserve(m->misc, 2 * ze + oe));
+    float *z = (float *)m->misc.ptr;
+    float *xq = z + (size_t)n * m->e;
+    float *out = out_dev ? out_dev : xq + (size_t)n * m->e;
+    RQB_TRY(run_mlp(m, 0, x_dev, nullptr, n, z, s));
+    RQB_TRY(quantize_exact(m, z, n, codes_dev, nullptr, xq, sumsq_dev, nullptr, nullptr, s));
+    RQB_TRY(run_mlp(m, 1, xq, nullptr, n, out, s));
+    if (recon_sum_dev) RQB_TRY(recon_error(out, x_dev, n * (int64_t)m->dims[0], recon_sum_dev, s));
+    return 0;
+}
+
+// infer.py:88-103 (pass 1) + infer.py:139-177 (suffix) for a catalogue that lives in host memory:
+// chunked H2D on a copy stream, double-buffered against the encode kernels.
+extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float *x_host, int64_t n,
+                                          int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(n >= 0, "n < 0");
+    if (stats_host) { stats_host[0] = 0; stats_host[1] = 0; stats_host[2] = 0; }
+    if (n == 0) return 0;
+    RQB_CHECK(x_host != nullptr && codes_host != nullptr, "NULL buffer");
+    RQB_TRY(check_encoder(m));
+    RQB_TRY(check_codebooks(m));
+    RQB_CUDA(cudaSetDevice(m->device));
+    if (chunk_rows <= 0) chunk_rows = 131072;
+    if (chunk_rows > n) chunk_rows = n;
+    const int in = m->dims[0], L = m->L;
+    const size_t chunk_bytes = sizeof(float) * (size_t)chunk_rows * in;
+    RQB_TRY(ws_reserve(m->hostpipe[0], chunk_bytes + sizeof(int64_t) * (size_t)n * (2 * L + 1)));
+    RQB_TRY(ws_reserve(m->hostpipe[1], chunk_bytes));
+    float *xbuf[2] = {(float *)m->hostpipe[0].ptr, (float *)m->hostpipe[1].ptr};
+    int64_t *codes = (int64_t *)((char *)m->hostpipe[0].ptr + chunk_bytes);
+    int64_t *out = codes + (size_t)n * L;
+    cudaStream_t cs = m->copy_stream;
+    cudaStream_t ks = 0;
+    // ev[0], ev[1]: chunk in buffer b copied;  ev[2], ev[3]: buffer b consumed
+    int64_t rescued = 0;
+    int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t r0 = c * chunk_rows;
+        const int64_t rows = (n - r0) < chunk_rows ? (n - r0) : chunk_rows;
+        if (c >= 2) RQB_CUDA(cudaStreamWaitEvent(cs, m->ev[2 + b], 0));
+        RQB_CUDA(cudaMemcpyAsync(xbuf[b], x_host + (size_t)r0 * in, sizeof(float) * (size_t)rows * in,
+                                 cudaMemcpyHostToDevice, cs));
+        RQB_CUDA(cudaEventRecord(m->ev[b], cs));
+        RQB_CUDA(cudaStreamWaitEvent(ks, m->ev[b], 0));
+        int64_t st = 0;
+        RQB_TRY(rqb200_get_indices(m, mode, xbuf[b], rows, codes + (size_t)r0 * L, nullptr, &st, ks));
+        rescued += st;
+        RQB_CUDA(cudaEventRecord(m->ev[2 + b], ks));
+    }
+    int64_t distinct = 0, maxgroup = 0;
+    RQB_TRY(rqb200_suffix_dedup(m, codes, n, L, m->K, out, stats_host ? &distinct : nullptr,
+                                stats_host ? &maxgroup : nullptr, ks));
+    RQB_CUDA(cudaMemcpyAsync(codes_host, out, sizeof(int64_t) * (size_t)n * (L + 1), cudaMemcpyDeviceToHost, ks));
+    RQB_CUDA(cudaStreamSynchronize(ks));
+    if (stats_host) { stats_host[0] = rescued; stats_host[1] = distinct; stats_host[2] = maxgroup; }
+    return 0;
+}

@@ -1,0 +1,109 @@
+// common.cuh — shared declarations of the rqvae_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rqvae_b200.h"
+
+namespace rqb {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void set_error(const char *fmt, ...);
+void count_launch();          // bumps the process-wide kernel-launch counter (rqb200_launch_count)
+
+// per-kernel device timing (cudaEvent pairs on the launching stream), enabled by rqb200_profile_enable
+enum ProfSlot { PROF_LINEAR0 = 0, PROF_LINEAR_REST = 1, PROF_QUANTIZE = 2, PROF_DEDUP = 3, PROF_TC_ENCODER = 4,
+                PROF_SINKHORN = 5, PROF_NSLOTS = 8 };
+void prof_begin(int slot, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+struct ProfScope {
+    int slot; cudaStream_t s;
+    ProfScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_) { prof_begin(slot, s); }
+    ~ProfScope() { prof_end(slot, s); }
+};
+
+#define RQB_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            rqb::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return RQB200_ECUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define RQB_CHECK(cond, ...)                                                                \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            rqb::set_error(__VA_ARGS__);                                                    \
+            return RQB200_EINVAL;                                                           \
+        }                                                                                   \
+    } while (0)
+
+#define RQB_TRY(expr)                                                                       \
+    do {                                                                                    \
+        int _rc = (expr);                                                                   \
+        if (_rc != 0) return _rc;                                                           \
+    } while (0)
+
+#define RQB_LAUNCH_CHECK() RQB_CUDA(cudaGetLastError())
+
+struct Linear {
+    int in = 0, out = 0;
+    float *W = nullptr;      // [out, in] row-major (device)
+    float *b = nullptr;      // [out]
+    int kblocks[16];
+    int nblk = 0;
+    bool set = false;
+    // tensor-core path: split-bf16 images of W, packed per K-slab in UMMA SW128 layout
+    void *W_tc = nullptr;
+    size_t W_tc_bytes = 0;
+    float *absW_rowmax = nullptr;
+};
+
+struct Workspace {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace rqb
+
+struct rqb200_model {
+    int device = 0;
+    int n_layers = 0;
+    int dims[RQB200_MAX_LAYERS + 1];
+    rqb::Linear enc[RQB200_MAX_LAYERS];
+    rqb::Linear dec[RQB200_MAX_LAYERS];
+    int L = 0;
+    int e = 0;
+    int K[RQB200_MAX_LEVELS];
+    float *cb[RQB200_MAX_LEVELS];   // [K, e]
+    float *cc[RQB200_MAX_LEVELS];   // [K]  sum of squares in the reference's order
+    bool cb_set[RQB200_MAX_LEVELS];
+    rqb::Workspace act[2];          // ping-pong activations for the MLP
+    rqb::Workspace sortws;          // radix sort scratch
+    rqb::Workspace misc;            // rescue lists, counters
+    rqb::Workspace hostpipe[2];     // device chunks of the host-buffer pipeline
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace rqb {
+
+int ws_reserve(Workspace &w, size_t bytes);
+
+// linear_exact.cu
+int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
+                 bool relu, cudaStream_t s);
+// quantize.cu
+int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
+int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
+                   const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
+                   float *margin_out, cudaStream_t s);
+int distances_exact(const rqb200_model *m, int level, const float *r, int64_t n, float *d,
+                    cudaStream_t s);
+int recon_error(const float *out, const float *x, int64_t count, double *recon_sum, cudaStream_t s);
+
+}  // namespace rqb

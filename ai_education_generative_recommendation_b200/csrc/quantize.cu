@@ -1,0 +1,345 @@
+// quantize.cu — the residual quantizer with use_sk=False, fused over all levels.
+//
+// Replaces ResidualVectorQuantizer.forward / VectorQuantizer.forward (reference
+// RQ-VAE/models/rq.py:39-56, vq.py:63-99): per level distance (vq.py:71-73), first-index argmin
+// (vq.py:75), gather (vq.py:87), mse numerators (vq.py:90-92), straight-through output
+// (vq.py:95) and residual / accumulate updates (rq.py:47-48) — one kernel, the residual never
+// leaves registers between levels, the [n,K] distance matrix is never materialised.
+//
+// Arithmetic is the reference's, operation by operation:
+//   xx   = torch.sum(r**2, dim=1)      → ATen vectorized_inner_sum: 8 lanes x 4 accumulators
+//   dot  = one sequential FMA chain over k
+//   d    = (xx + cc_j) - (2*dot)       → separate roundings, no contraction
+//   idx  = first minimum, NaN wins
+//   xres = r + (q - r);  r = r - xres;  x_q = x_q + xres
+//
+// Mapping: one row per thread (E values in registers), codebook chunk + its norms staged in shared
+// memory and read as warp-wide broadcasts (conflict free), four independent chains in flight per
+// thread.  Bound: fp32 FMA pipe (L*K*E FMA per row); HBM traffic is 4E+8L bytes per row.
+#include "common.cuh"
+
+namespace rqb {
+
+namespace {
+
+constexpr int QT = 128;            // threads (= rows) per CTA
+constexpr int CHUNK_FLOATS = 16384;   // 64 KB codebook chunk
+
+// torch.sum(v*v) over E contiguous fp32 values, ATen order (see oracle/rqvae_oracle.c).
+template <int E>
+__device__ __forceinline__ float sumsq_aten(const float (&v)[E]) {
+    static_assert(E < 512, "cascade levels of multi_row_sum are not needed below 512");
+    constexpr int VEC = E / 8;          // 8-lane vectors
+    constexpr int SIZE_ILP = VEC / 4;   // groups of 4 vectors
+    float part[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[k][l] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < SIZE_ILP; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                float x = v[i * 32 + k * 8 + l];
+                part[k][l] = __fadd_rn(part[k][l], __fmul_rn(x, x));
+            }
+#pragma unroll
+    for (int i = SIZE_ILP * 4; i < VEC; ++i)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            float x = v[i * 8 + l];
+            part[0][l] = __fadd_rn(part[0][l], __fmul_rn(x, x));
+        }
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[0][l] = __fadd_rn(part[0][l], part[k][l]);
+    float fin = 0.0f;
+#pragma unroll
+    for (int k = VEC * 8; k < E; ++k) fin = __fadd_rn(fin, __fmul_rn(v[k], v[k]));
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, part[0][l]);
+    return fin;
+}
+
+template <int E>
+__global__ void __launch_bounds__(256) sumsq_rows_kernel(const float *__restrict__ v, int n,
+                                                         float *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) r[k] = v[(int64_t)i * E + k];
+    out[i] = sumsq_aten<E>(r);
+}
+
+struct QuantArgs {
+    const float *cb[RQB200_MAX_LEVELS];
+    const float *cc[RQB200_MAX_LEVELS];
+    int K[RQB200_MAX_LEVELS];
+    int L;
+};
+
+__device__ __forceinline__ bool better(float d, float best) {
+    // torch.argmin: NaN is the minimum; first index wins ties
+    return !(best != best) && ((d != d) || d < best);
+}
+
+// MODE 0: codes (+ optional xq / sumsq / last residual / margin).  MODE 1: distances of one level.
+template <int E, int MODE>
+__global__ void __launch_bounds__(QT)
+quantize_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
+                const int64_t *__restrict__ rows_out, float *__restrict__ xq_out,
+                double *__restrict__ sumsq_out, float *__restrict__ last_residual,
+                float *__restrict__ margin_out, float *__restrict__ dist_out, int dist_level) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int CH = CHUNK_FLOATS / E;    // codes per chunk
+    float *s_cb = smem;                     // [CH][E]
+    float *s_cc = smem + CH * E;            // [CH]
+    __shared__ double s_loss[RQB200_MAX_LEVELS];
+
+    const int tid = threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * QT + tid;
+    const bool live = row < n;
+
+    if (tid < RQB200_MAX_LEVELS) s_loss[tid] = 0.0;
+
+    float r[E], xq[E];
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {
+        float4 v = live ? *reinterpret_cast<const float4 *>(z + row * E + k) : make_float4(0, 0, 0, 0);
+        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+    }
+    float min_margin = __int_as_float(0x7f800000);
+
+    const int L = (MODE == 1) ? 1 : qa.L;
+    for (int l0 = 0; l0 < L; ++l0) {
+        const int l = (MODE == 1) ? dist_level : l0;
+        const int K = qa.K[l];
+        const float *cb = qa.cb[l];
+        const float *cc = qa.cc[l];
+        if (MODE == 0 && last_residual && l == qa.L - 1 && live) {
+#pragma unroll
+            for (int k = 0; k < E; k += 4)
+                *reinterpret_cast<float4 *>(last_residual + row * E + k) =
+                    make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]);
+        }
+        const float xx = sumsq_aten<E>(r);
+        int best = 0;
+        float bestd = 0.0f, second = __int_as_float(0x7f800000);
+        for (int c0 = 0; c0 < K; c0 += CH) {
+            const int cn = min(CH, K - c0);
+            __syncthreads();
+            for (int i = tid; i < cn * E / 4; i += QT)
+                reinterpret_cast<float4 *>(s_cb)[i] =
+                    reinterpret_cast<const float4 *>(cb + (int64_t)c0 * E)[i];
+            for (int i = tid; i < cn; i += QT) s_cc[i] = cc[c0 + i];
+            __syncthreads();
+            int j = 0;
+            for (; j + 4 <= cn; j += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                const float4 *c4 = reinterpret_cast<const float4 *>(s_cb + j * E);
+#pragma unroll
+                for (int k = 0; k < E / 4; ++k) {
+                    float4 v0 = c4[k], v1 = c4[k + E / 4], v2 = c4[k + 2 * (E / 4)], v3 = c4[k + 3 * (E / 4)];
+                    a0 = __fmaf_rn(r[4 * k], v0.x, a0); a1 = __fmaf_rn(r[4 * k], v1.x, a1);
+                    a2 = __fmaf_rn(r[4 * k], v2.x, a2); a3 = __fmaf_rn(r[4 * k], v3.x, a3);
+                    a0 = __fmaf_rn(r[4 * k + 1], v0.y, a0); a1 = __fmaf_rn(r[4 * k + 1], v1.y, a1);
+                    a2 = __fmaf_rn(r[4 * k + 1], v2.y, a2); a3 = __fmaf_rn(r[4 * k + 1], v3.y, a3);
+                    a0 = __fmaf_rn(r[4 * k + 2], v0.z, a0); a1 = __fmaf_rn(r[4 * k + 2], v1.z, a1);
+                    a2 = __fmaf_rn(r[4 * k + 2], v2.z, a2); a3 = __fmaf_rn(r[4 * k + 2], v3.z, a3);
+                    a0 = __fmaf_rn(r[4 * k + 3], v0.w, a0); a1 = __fmaf_rn(r[4 * k + 3], v1.w, a1);
+                    a2 = __fmaf_rn(r[4 * k + 3], v2.w, a2); a3 = __fmaf_rn(r[4 * k + 3], v3.w, a3);
+                }
+                float dd[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float d = __fsub_rn(__fadd_rn(xx, s_cc[j + t]), __fmul_rn(2.0f, dd[t]));
+                    if (MODE == 1) {
+                        if (live) dist_out[row * K + c0 + j + t] = d;
+                    } else if (c0 + j + t == 0) {
+                        bestd = d;
+                    } else if (better(d, bestd)) {
+                        second = bestd; bestd = d; best = c0 + j + t;
+                    } else if (d < second) {
+                        second = d;
+                    }
+                }
+            }
+            for (; j < cn; ++j) {
+                float a0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < E; ++k) a0 = __fmaf_rn(r[k], s_cb[j * E + k], a0);
+                float d = __fsub_rn(__fadd_rn(xx, s_cc[j]), __fmul_rn(2.0f, a0));
+                if (MODE == 1) {
+                    if (live) dist_out[row * K + c0 + j] = d;
+                } else if (c0 + j == 0) {
+                    bestd = d;
+                } else if (better(d, bestd)) {
+                    second = bestd; bestd = d; best = c0 + j;
+                } else if (d < second) {
+                    second = d;
+                }
+            }
+        }
+        if (MODE == 1) return;
+        if (live) {
+            int64_t orow = rows_out ? rows_out[row] : row;
+            codes[orow * qa.L + l] = best;
+        }
+        min_margin = fminf(min_margin, __fsub_rn(second, bestd));
+        // gather q, losses, straight-through residual update
+        double lsum = 0.0;
+        const float4 *q4 = reinterpret_cast<const float4 *>(cb + (int64_t)best * E);
+#pragma unroll
+        for (int k = 0; k < E; k += 4) {
+            float4 q = q4[k / 4];
+            float qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float diff = __fsub_rn(qv[t], r[k + t]);
+                lsum += (double)diff * (double)diff;
+                float xres = __fadd_rn(r[k + t], diff);
+                r[k + t] = __fsub_rn(r[k + t], xres);
+                xq[k + t] = (l == 0) ? __fadd_rn(0.0f, xres) : __fadd_rn(xq[k + t], xres);
+            }
+        }
+        if (sumsq_out) {
+            if (!live) lsum = 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            if ((tid & 31) == 0) atomicAdd(&s_loss[l], lsum);
+        }
+    }
+    if (MODE == 0) {
+        if (xq_out && live) {
+#pragma unroll
+            for (int k = 0; k < E; k += 4)
+                *reinterpret_cast<float4 *>(xq_out + row * E + k) =
+                    make_float4(xq[k], xq[k + 1], xq[k + 2], xq[k + 3]);
+        }
+        if (margin_out && live) margin_out[row] = min_margin;
+        if (sumsq_out) {
+            __syncthreads();
+            if (tid < qa.L) atomicAdd(&sumsq_out[tid], s_loss[tid]);
+        }
+    }
+}
+
+QuantArgs make_args(const rqb200_model *m) {
+    QuantArgs qa;
+    qa.L = m->L;
+    for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
+        qa.cb[l] = l < m->L ? m->cb[l] : nullptr;
+        qa.cc[l] = l < m->L ? m->cc[l] : nullptr;
+        qa.K[l] = l < m->L ? m->K[l] : 0;
+    }
+    return qa;
+}
+
+template <int E, int MODE>
+int launch_quant(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
+                 const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
+                 float *margin, float *dist, int dist_level, cudaStream_t s) {
+    auto kern = quantize_kernel<E, MODE>;
+    constexpr int CH = CHUNK_FLOATS / E;
+    size_t smem = sizeof(float) * (CH * E + CH);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    unsigned grid = (unsigned)((n + QT - 1) / QT);
+    rqb::count_launch();
+    kern<<<grid, QT, smem, s>>>(z, n, make_args(m), codes, rows_out, xq, sumsq, last_residual, margin,
+                               dist, dist_level);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+#define RQB_DISPATCH_E(e, CALL)                                                     \
+    switch (e) {                                                                    \
+        case 8:   { constexpr int E = 8;   CALL; } break;                            \
+        case 16:  { constexpr int E = 16;  CALL; } break;                            \
+        case 32:  { constexpr int E = 32;  CALL; } break;                            \
+        case 48:  { constexpr int E = 48;  CALL; } break;                            \
+        case 64:  { constexpr int E = 64;  CALL; } break;                            \
+        case 96:  { constexpr int E = 96;  CALL; } break;                            \
+        case 128: { constexpr int E = 128; CALL; } break;                            \
+        default:                                                                    \
+            set_error("e_dim %d not supported (8,16,32,48,64,96,128)", e);          \
+            return RQB200_EINVAL;                                                   \
+    }
+
+__global__ void recon_error_kernel(const float *__restrict__ out, const float *__restrict__ x,
+                                   int64_t count, double *__restrict__ acc) {
+    double s2 = 0.0, s1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double d = (double)out[i] - (double)x[i];
+        s2 += d * d;
+        s1 += fabs(d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    __shared__ double w2[32], w1[32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { w2[wid] = s2; w1[wid] = s1; }
+    __syncthreads();
+    if (wid == 0) {
+        int nw = blockDim.x >> 5;
+        s2 = lane < nw ? w2[lane] : 0.0;
+        s1 = lane < nw ? w1[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane == 0) { atomicAdd(&acc[0], s2); atomicAdd(&acc[1], s1); }
+    }
+}
+
+}  // namespace
+
+int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s) {
+    count_launch();
+    RQB_DISPATCH_E(e, (sumsq_rows_kernel<E><<<(K + 255) / 256, 256, 0, s>>>(cb, K, cc)));
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
+                   const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
+                   float *margin_out, cudaStream_t s) {
+    if (n == 0) return 0;
+    ProfScope ps(PROF_QUANTIZE, s);
+    RQB_DISPATCH_E(m->e, return (launch_quant<E, 0>(m, z, n, codes, rows_out, xq, sumsq, last_residual,
+                                                   margin_out, nullptr, 0, s)));
+    return 0;
+}
+
+int distances_exact(const rqb200_model *m, int level, const float *r, int64_t n, float *d,
+                    cudaStream_t s) {
+    if (n == 0) return 0;
+    RQB_CHECK(level >= 0 && level < m->L, "level %d out of range", level);
+    RQB_DISPATCH_E(m->e, return (launch_quant<E, 1>(m, r, n, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                   nullptr, d, level, s)));
+    return 0;
+}
+
+int recon_error(const float *out, const float *x, int64_t count, double *recon_sum, cudaStream_t s) {
+    if (count == 0) return 0;
+    int64_t blocks = (count + 256 * 8 - 1) / (256 * 8);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    rqb::count_launch();
+    recon_error_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, x, count, recon_sum);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rqb

@@ -1,0 +1,291 @@
+// sinkhorn.cu — the use_sk branch of VectorQuantizer.forward and the collision re-encode step.
+//
+// Replaces (reference RQ-VAE/models/vq.py:51-61,74-83 and RQ-VAE/models/layers.py:85-108):
+//     d  = center_distance_for_constraint(d)          fp32: (d - mid) / (max - mid + 1e-5)
+//     Q  = sinkhorn_algorithm(d.double(), eps, iters)  fp64: exp(-d/eps), normalise total, then
+//          iters x { Q /= rowsum; Q /= B; Q /= colsum; Q /= K };  Q *= B
+//     idx = argmax(Q, -1)
+// and its only caller on the encode path, the per-group re-encode loop of reference
+// RQ-VAE/infer.py:109-130 (Sinkhorn on the LAST level only, one call per collision group).
+//
+// The reference launches ~200 tiny kernels per group; here one CTA owns one group: the [B,K] fp64
+// matrix lives in shared memory, distances are recomputed in the reference's fp32 order from the
+// residual entering the last level, and every division of the reference is kept as a separate
+// fp64 division so the iteration follows the same trajectory.  Latency/fp64-ALU bound by nature;
+// reported as time, not against a roofline.
+#include "common.cuh"
+
+namespace rqb {
+
+namespace {
+
+constexpr int SK_THREADS = 256;
+
+// torch.sum(v*v) for a runtime length e < 512 (ATen order; see oracle/rqvae_oracle.c)
+__device__ float sumsq_aten_rt(const float *v, int e) {
+    const int vec = e / 8, size_ilp = vec / 4;
+    float part[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[k][l] = 0.0f;
+    for (int i = 0; i < size_ilp; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                float x = v[i * 32 + k * 8 + l];
+                part[k][l] = __fadd_rn(part[k][l], __fmul_rn(x, x));
+            }
+    for (int i = size_ilp * 4; i < vec; ++i)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            float x = v[i * 8 + l];
+            part[0][l] = __fadd_rn(part[0][l], __fmul_rn(x, x));
+        }
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[0][l] = __fadd_rn(part[0][l], part[k][l]);
+    float fin = 0.0f;
+    for (int k = vec * 8; k < e; ++k) fin = __fadd_rn(fin, __fmul_rn(v[k], v[k]));
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, part[0][l]);
+    return fin;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ double block_sum(double v, double *s_red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < SK_THREADS / 32; ++w) t += s_red[w];
+    return t;
+}
+
+// Sinkhorn iterations on a [B,K] fp64 matrix owned by this CTA (shared or global memory).
+__device__ void sinkhorn_cta(double *Q, int B, int K, int iters, double *s_red) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = SK_THREADS / 32;
+    // sum_Q = Q.sum(-1).sum(-2);  Q /= sum_Q
+    double part = 0.0;
+    for (int i = wid; i < B; i += NW) {
+        double rs = 0.0;
+        for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
+        rs = warp_sum(rs);
+        if (lane == 0) part += rs;
+    }
+    double total = block_sum(part, s_red);
+    for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = Q[i] / total;
+    __syncthreads();
+    const double dB = (double)B, dK = (double)K;
+    for (int it = 0; it < iters; ++it) {
+        // Q /= Q.sum(dim=1, keepdim=True);  Q /= B
+        for (int i = wid; i < B; i += NW) {
+            double rs = 0.0;
+            for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
+            rs = warp_sum(rs);
+            for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / rs) / dB;
+        }
+        __syncthreads();
+        // Q /= Q.sum(dim=0, keepdim=True);  Q /= K
+        for (int j = tid; j < K; j += SK_THREADS) {
+            double cs = 0.0;
+            for (int i = 0; i < B; ++i) cs += Q[(size_t)i * K + j];
+            for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / cs) / dK;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = Q[i] * dB;
+    __syncthreads();
+}
+
+// argmax over K for each row (first maximum wins; NaN counts as maximum like torch.argmax)
+__device__ void argmax_rows(const double *Q, int B, int K, const int64_t *items, int64_t *codes, int L,
+                            int64_t *idx_out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = wid; i < B; i += SK_THREADS / 32) {
+        double best = 0.0;
+        int bj = -1;
+        for (int j = lane; j < K; j += 32) {
+            double v = Q[(size_t)i * K + j];
+            bool take = bj < 0 || (!(best != best) && ((v != v) || v > best));
+            if (take) { best = v; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (oj >= 0) {
+                bool onan = ov != ov, bnan = best != best;
+                bool take = bj < 0 || (onan && (!bnan || oj < bj)) ||
+                            (!onan && !bnan && (ov > best || (ov == best && oj < bj)));
+                if (take) { best = ov; bj = oj; }
+            }
+        }
+        if (lane == 0) {
+            if (codes) codes[items[i] * L + (L - 1)] = bj;
+            else idx_out[i] = bj;
+        }
+    }
+}
+
+// centre (fp32) + exp (fp64) in place: Q holds fp32 distances widened to double on entry
+__device__ void center_and_exp(double *Q, int count, double epsilon, float *s_mm) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mx = -__int_as_float(0x7f800000), mn = __int_as_float(0x7f800000);
+    for (int i = tid; i < count; i += SK_THREADS) {
+        float d = (float)Q[i];
+        mx = fmaxf(mx, d);
+        mn = fminf(mn, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    __syncthreads();
+    if (lane == 0) { s_mm[wid] = mx; s_mm[32 + wid] = mn; }
+    __syncthreads();
+    for (int w = 0; w < SK_THREADS / 32; ++w) { mx = fmaxf(mx, s_mm[w]); mn = fminf(mn, s_mm[32 + w]); }
+    const float middle = __fdiv_rn(__fadd_rn(mx, mn), 2.0f);
+    const float amplitude = __fadd_rn(__fsub_rn(mx, middle), 1e-5f);
+    for (int i = tid; i < count; i += SK_THREADS) {
+        float c = __fdiv_rn(__fsub_rn((float)Q[i], middle), amplitude);
+        Q[i] = exp(-((double)c) / epsilon);
+    }
+    __syncthreads();
+}
+
+// one CTA per collision group (infer.py:120-129 for one `collision_items` list)
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_regroup_kernel(const float *__restrict__ residual, const int64_t *__restrict__ items,
+                        const int64_t *__restrict__ offsets, int e, const float *__restrict__ cb,
+                        const float *__restrict__ cc, int K, int L, int cap_rows, double epsilon, int iters,
+                        int64_t *__restrict__ codes) {
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    __shared__ double s_red[SK_THREADS / 32];
+    __shared__ float s_mm[64];
+    const int64_t g0 = offsets[blockIdx.x], g1 = offsets[blockIdx.x + 1];
+    const int B = (int)(g1 - g0);
+    if (B < 2 || B > cap_rows) return;     // oversized groups are re-encoded by the host-driven path
+    double *Q = reinterpret_cast<double *>(sk_smem);                    // [B][K]
+    float *s_r = reinterpret_cast<float *>(Q + (size_t)cap_rows * K);   // [B][e]
+    float *s_xx = s_r + (size_t)cap_rows * e;                           // [B]
+    const int64_t *gi = items + g0;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < B * e; i += SK_THREADS) s_r[i] = residual[gi[i / e] * e + (i % e)];
+    __syncthreads();
+    for (int i = tid; i < B; i += SK_THREADS) s_xx[i] = sumsq_aten_rt(s_r + (size_t)i * e, e);
+    __syncthreads();
+    // d[i][j] = (xx_i + cc_j) - 2 * <r_i, c_j>   (vq.py:71-73)
+    for (int p = tid; p < B * K; p += SK_THREADS) {
+        const int i = p / K, j = p % K;
+        const float *r = s_r + (size_t)i * e;
+        const float *c = cb + (size_t)j * e;
+        float acc = 0.0f;
+        for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
+        Q[p] = (double)__fsub_rn(__fadd_rn(s_xx[i], cc[j]), __fmul_rn(2.0f, acc));
+    }
+    __syncthreads();
+    center_and_exp(Q, B * K, epsilon, s_mm);
+    sinkhorn_cta(Q, B, K, iters, s_red);
+    argmax_rows(Q, B, K, gi, codes, L, nullptr);
+}
+
+// ---- general [B,K] matrices in global memory (training-size batches) ----------------------------
+// One CTA walks the whole matrix: simple and exact in structure; B*K is at most a few million here.
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_global_kernel(double *__restrict__ Q, int B, int K, double epsilon, int iters) {
+    __shared__ double s_red[SK_THREADS / 32];
+    for (int i = threadIdx.x; i < B * K; i += SK_THREADS) Q[i] = exp(-Q[i] / epsilon);   // layers.py:87
+    __syncthreads();
+    sinkhorn_cta(Q, B, K, iters, s_red);
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_assign_kernel(const float *__restrict__ d, double *__restrict__ Q, int B, int K, double epsilon,
+                       int iters, int64_t *__restrict__ idx) {
+    __shared__ double s_red[SK_THREADS / 32];
+    __shared__ float s_mm[64];
+    for (int i = threadIdx.x; i < B * K; i += SK_THREADS) Q[i] = (double)d[i];
+    __syncthreads();
+    center_and_exp(Q, B * K, epsilon, s_mm);
+    sinkhorn_cta(Q, B, K, iters, s_red);
+    argmax_rows(Q, B, K, nullptr, nullptr, 0, idx);
+}
+
+}  // namespace
+}  // namespace rqb
+
+using namespace rqb;
+
+extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
+                                       const int64_t *offsets_dev, int64_t n_groups, int max_group,
+                                       double epsilon, int iters, int64_t *codes_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    if (n_groups == 0) return 0;
+    RQB_CHECK(residual_dev && items_dev && offsets_dev && codes_dev, "NULL buffer");
+    RQB_CHECK(epsilon > 0.0, "epsilon must be > 0 (the argmin branch needs no re-encode)");
+    RQB_CHECK(m->e < 512, "e_dim >= 512 not supported");
+    RQB_CUDA(cudaSetDevice(m->device));
+    const int L = m->L, K = m->K[L - 1], e = m->e;
+    RQB_CHECK(m->cb_set[L - 1], "codebook %d not loaded", L - 1);
+    // rows that fit in shared memory next to the fp64 matrix
+    const size_t budget = 200 * 1024;
+    const size_t per_row = sizeof(double) * K + sizeof(float) * (e + 1);
+    int cap = (int)(budget / per_row);
+    RQB_CHECK(cap >= 2, "K=%d too large for the shared-memory Sinkhorn kernel", K);
+    if (max_group > 0 && max_group < cap) cap = max_group < 2 ? 2 : max_group;
+    size_t smem = per_row * cap + 16;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        RQB_CUDA(cudaFuncSetAttribute(sinkhorn_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(budget + 1024)));
+        smem_set = budget + 1024;
+    }
+    rqb::count_launch();
+    ProfScope ps(PROF_SINKHORN, (cudaStream_t)stream);
+    sinkhorn_regroup_kernel<<<(unsigned)n_groups, SK_THREADS, smem, (cudaStream_t)stream>>>(
+        residual_dev, items_dev, offsets_dev, e, m->cb[L - 1], m->cc[L - 1], K, L, cap, epsilon, iters, codes_dev);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rqb200_sinkhorn_group_cap(rqb200_model *m) {
+    if (!m) return 0;
+    const int L = m->L, K = m->K[L - 1], e = m->e;
+    return (int)((200 * 1024) / (sizeof(double) * K + sizeof(float) * (e + 1)));
+}
+
+extern "C" int rqb200_sinkhorn(double *Q_dev, int64_t B, int K, double epsilon, int iters, void *stream) {
+    if (B == 0) return 0;
+    RQB_CHECK(Q_dev != nullptr, "NULL buffer");
+    RQB_CHECK(epsilon != 0.0, "epsilon must be non-zero");
+    RQB_CHECK(B * (int64_t)K < ((int64_t)1 << 31), "matrix too large");
+    rqb::count_launch();
+    sinkhorn_global_kernel<<<1, SK_THREADS, 0, (cudaStream_t)stream>>>(Q_dev, (int)B, K, epsilon, iters);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, double epsilon, int iters,
+                                      double *scratch_dev, int64_t *idx_dev, void *stream) {
+    if (B == 0) return 0;
+    RQB_CHECK(d_dev && idx_dev && scratch_dev, "NULL buffer");
+    RQB_CHECK(epsilon > 0.0, "epsilon must be > 0");
+    RQB_CHECK(B * (int64_t)K < ((int64_t)1 << 31), "matrix too large");
+    rqb::count_launch();
+    sinkhorn_assign_kernel<<<1, SK_THREADS, 0, (cudaStream_t)stream>>>(d_dev, scratch_dev, (int)B, K, epsilon,
+                                                                      iters, idx_dev);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,206 @@
+"""The encode driver — drop-in for reference RQ-VAE/infer.py:44-184 (≡ RQ-VAE/generate_code.py:44-178).
+
+Same three passes, all on the device:
+  pass 1  every item → codes with use_sk=False                      (infer.py:93-103)
+  pass 2  ≤30 rounds: items sharing a full code are re-encoded group by group with Sinkhorn on the
+          LAST level only (infer.py:109-130).  Levels < L-1 are a pure function of the item, so only
+          the last-level code of colliding items is recomputed — from the residual the quantizer
+          kernel saved.
+  pass 3  suffix column: out[i, L] = #{j < i : codes[j] == codes[i]} (infer.py:152-163), np.save of the
+          [N, L+1] int64 array (infer.py:174-177) and the `_mapping.json` side file (infer.py:180-184).
+The reference's per-item string building / dict grouping is replaced by integer sort kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, ptr, stream_ptr
+from .rqvae import RQVAE
+
+MAX_LEVELS_OF_REFERENCE_DRIVER = 5     # prefix list ["<a_{}>",…,"<e_{}>"] has 5 entries (infer.py:90)
+
+
+def _as_rows(data):
+    if isinstance(data, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+    return data
+
+
+@torch.no_grad()
+def encode_latents(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Tensor:
+    """Encoder MLP over the whole catalogue → z[N, e] on the model's device.  `data` may be a CUDA tensor,
+    a CPU tensor or a numpy array (host data is streamed chunk by chunk through pinned staging)."""
+    data = _as_rows(data)
+    dev = model._device()
+    n = data.shape[0]
+    z = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
+    model._sync()
+    L = _cabi.lib()
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        chunk = data[r0:r1]
+        if not chunk.is_cuda:
+            chunk = chunk.contiguous().to(dev, non_blocking=True)
+        chunk = chunk.contiguous()
+        check(L.rqb200_mlp_exact(model._handle, 0, ptr(chunk), 0, r1 - r0, ptr(z[r0:r1]), stream_ptr(dev)))
+    return z
+
+
+@torch.no_grad()
+def collision_groups(model: RQVAE, codes: torch.Tensor):
+    """get_collision_item (infer.py:29-42) on device → (items[n_items], offsets[n_groups+1], max_group)."""
+    n, Lv = codes.shape
+    items = torch.empty((max(n, 1),), dtype=torch.int64, device=codes.device)
+    offsets = torch.empty((n + 1,), dtype=torch.int64, device=codes.device)
+    ng, ni, mg = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    check(_cabi.lib().rqb200_collision_groups(model._handle, ptr(codes), n, Lv, _cabi.int_array(model.num_emb_list),
+                                              ptr(items), ptr(offsets), ctypes.byref(ng), ctypes.byref(ni),
+                                              ctypes.byref(mg), stream_ptr(codes.device)))
+    return items[:ni.value], offsets[:ng.value + 1], int(mg.value)
+
+
+@torch.no_grad()
+def suffix_dedup(model: Optional[RQVAE], codes: torch.Tensor, num_emb_list=None) -> Tuple[torch.Tensor, dict]:
+    """Suffix column (infer.py:152-163) → ([N, L+1] int64, stats)."""
+    if not codes.is_cuda:
+        raise RuntimeError("suffix_dedup: CUDA tensor required (no CPU fallback)")
+    codes = codes.contiguous()
+    n, Lv = codes.shape
+    out = torch.empty((n, Lv + 1), dtype=torch.int64, device=codes.device)
+    nd, mg = ctypes.c_int64(0), ctypes.c_int64(0)
+    Ks = num_emb_list if num_emb_list is not None else (model.num_emb_list if model is not None else None)
+    handle = model._handle if model is not None else _scratch_handle(codes.device)
+    check(_cabi.lib().rqb200_suffix_dedup(handle, ptr(codes), n, Lv, _cabi.int_array(Ks) if Ks else None, ptr(out),
+                                          ctypes.byref(nd), ctypes.byref(mg), stream_ptr(codes.device)))
+    return out, {"distinct": int(nd.value), "max_conflicts": int(mg.value),
+                 "collision_rate": (n - int(nd.value)) / n if n else 0.0}
+
+
+_SCRATCH = {}
+
+
+def _scratch_handle(device):
+    """A minimal model handle that only owns sort workspace (for suffix_dedup without an RQVAE)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SCRATCH:
+        h = ctypes.c_void_p(None)
+        check(_cabi.lib().rqb200_model_create(ctypes.byref(h), idx, 1, _cabi.int_array([8, 8]), 1, _cabi.int_array([2])))
+        _SCRATCH[idx] = h
+    return _SCRATCH[idx]
+
+
+@torch.no_grad()
+def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 262144, verbose: bool = False
+                   ) -> Tuple[torch.Tensor, dict]:
+    """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats)."""
+    Lv = len(model.num_emb_list)
+    if Lv > MAX_LEVELS_OF_REFERENCE_DRIVER:
+        raise IndexError("list index out of range")        # what prefix[i] raises in the reference
+    was_training = model.training
+    model.eval()
+    try:
+        dev = model._device()
+        lib = _cabi.lib()
+        z = encode_latents(model, data, chunk_rows)
+        n = z.shape[0]
+        codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
+        residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
+        model._sync()
+        check(lib.rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
+        del z
+        # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
+        for vq in model.rq.vq_layers[:-1]:
+            vq.sk_epsilon = 0.0
+        last = model.rq.vq_layers[-1]
+        rounds = 0
+        if last.sk_epsilon is not None and last.sk_epsilon > 0:
+            cap = lib.rqb200_sinkhorn_group_cap(model._handle)
+            while rounds < max_rounds:
+                items, offsets, max_group = collision_groups(model, codes)
+                n_groups = offsets.numel() - 1
+                if n_groups <= 0:
+                    break
+                if verbose:
+                    print(f"Iteration {rounds}: Found {n_groups} collision groups")
+                new_codes = codes.clone()      # a round reads the codes of the previous round only
+                check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
+                                                  min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters),
+                                                  ptr(new_codes), stream_ptr(dev)))
+                if max_group > cap:
+                    _regroup_oversized(model, residual, items, offsets, cap, new_codes)
+                codes = new_codes
+                rounds += 1
+        out, stats = suffix_dedup(model, codes)
+        stats["rounds"] = rounds
+        return out, stats
+    finally:
+        if was_training:
+            model.train()
+
+
+def _regroup_oversized(model, residual, items, offsets, cap, codes):
+    """Groups too large for the shared-memory kernel: per group, distance matrix + global-memory Sinkhorn."""
+    off = offsets.cpu().tolist()
+    last = model.rq.vq_layers[-1]
+    Lv = len(model.num_emb_list)
+    for g in range(len(off) - 1):
+        if off[g + 1] - off[g] <= cap:
+            continue
+        idx = items[off[g]:off[g + 1]]
+        r = residual[idx].contiguous()
+        d = model._distances(Lv - 1, r)
+        codes[idx, Lv - 1] = model._sinkhorn_assign(d, last.sk_epsilon, last.sk_iters)
+
+
+def infer(params):
+    """Same contract as reference infer.py:44-184: params dict keys of main.py:6-36, writes
+    `semantic_id_file` (np.save [N, L+1] int64) and `<…>_mapping.json`."""
+    from .dataset import EmbDataset
+    h5_path = params["data_path"]
+    ckpt_path = os.path.join(params["ckpt_dir"], "best_collision_model.pth")
+    output_file = params["semantic_id_file"]
+    device = params["device"]
+    data = EmbDataset(h5_path)
+    model = RQVAE(in_dim=data.dim, num_emb_list=params["num_emb_list"], e_dim=params["e_dim"],
+                  layers=params["layers"], dropout_prob=params["dropout"], bn=params["batch_normalize"],
+                  loss_type=params["loss_type"], quant_loss_weight=params["quant_loss_weight"],
+                  kmeans_init=params["kmeans_init"], kmeans_iters=params["kmeans_iters"],
+                  sk_epsilons=params["sk_epsilons"], sk_iters=params["sk_iters"])
+    if os.path.exists(ckpt_path):
+        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+        if "state_dict" in ckpt:
+            model.load_state_dict(ckpt["state_dict"])
+            print(f"Loaded checkpoint from {ckpt_path}")
+        else:
+            model.load_state_dict(ckpt)
+            print(f"Loaded state dict from {ckpt_path}")
+    else:
+        print(f"Warning: No checkpoint found at {ckpt_path}, using randomly initialized model")
+    model = model.to(device)
+    model.eval()
+    print("Generating codes...")
+    codes, stats = generate_codes(model, data.embeddings, verbose=True)
+    codes_array = codes.cpu().numpy()
+    print("All indices number: ", len(codes_array))
+    print("Max number of conflicts: ", stats["max_conflicts"])
+    print("Collision Rate", stats["collision_rate"])
+    if len(np.unique(codes_array, axis=0)) != len(codes_array):     # infer.py:165-171 re-check
+        print("There still have duplicates")
+    else:
+        print("There are no duplicates in the codes after resolution.")
+    os.makedirs(os.path.dirname(output_file) or ".", exist_ok=True)
+    print(f"Saving codes to {output_file}")
+    print(f"the first 5 codes: {codes_array[:5]}")
+    np.save(output_file, codes_array)
+    mapping_file = output_file.replace(".npy", "_mapping.json")
+    with open(mapping_file, "w") as f:
+        json.dump({i: code.tolist() for i, code in enumerate(codes_array)}, f, indent=2)
+    print(f"Saved index-to-code mapping to {mapping_file}")
+    return codes_array

@@ -1,0 +1,143 @@
+"""GPU k-means for codebook initialisation — replaces reference RQ-VAE/models/layers.py:69-82.
+
+Seeding is k-means++ (D² sampling, single trial) driven by a torch Generator; Lloyd iterations run in
+the C-ABI kernels (rqb200_kmeans_assign / _accumulate / _update).  With a process group the samples are
+one shard per rank: the per-cluster sums[K,e], counts[K] and inertia are all-reduced (NCCL over
+NVLink on the GPU box, gloo in the CPU tests of the host logic) so every rank applies the same update.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import check, ptr, stream_ptr
+
+
+class CudaKMeansOps:
+    """Local (per-rank) pieces of one Lloyd iteration, on the CUDA kernels."""
+
+    def assign(self, x, centers):
+        n, e = x.shape
+        K = centers.shape[0]
+        cn = torch.empty((K,), dtype=torch.float32, device=x.device)
+        a = torch.empty((n,), dtype=torch.int64, device=x.device)
+        check(_cabi.lib().rqb200_kmeans_assign(ptr(x), n, e, ptr(centers), K, ptr(cn), ptr(a), stream_ptr(x.device)))
+        return a
+
+    def accumulate(self, x, assign, centers):
+        n, e = x.shape
+        K = centers.shape[0]
+        sums = torch.zeros((K, e), dtype=torch.float64, device=x.device)
+        counts = torch.zeros((K,), dtype=torch.int64, device=x.device)
+        inertia = torch.zeros((1,), dtype=torch.float64, device=x.device)
+        check(_cabi.lib().rqb200_kmeans_accumulate(ptr(x), n, e, ptr(assign), ptr(centers), K, ptr(sums),
+                                                   ptr(counts), ptr(inertia), stream_ptr(x.device)))
+        return sums, counts, inertia
+
+    def update(self, centers, sums, counts):
+        K, e = centers.shape
+        shift = torch.zeros((1,), dtype=torch.float64, device=centers.device)
+        check(_cabi.lib().rqb200_kmeans_update(ptr(centers), K, e, ptr(sums), ptr(counts), ptr(shift),
+                                               stream_ptr(centers.device)))
+        return shift
+
+    def min_sqdist(self, x, center, cur):
+        """cur = min(cur, ||x - center||²) — elementwise plumbing for the seeding only."""
+        d = ((x - center[None, :]) ** 2).sum(1)
+        return d if cur is None else torch.minimum(cur, d)
+
+
+def _all_reduce(t, group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def kmeans_pp_seed(x: torch.Tensor, K: int, gen: torch.Generator, ops, group=None) -> torch.Tensor:
+    """k-means++ seeding.  Sharded mode: every rank draws the same uniform numbers; the rank that owns the
+    selected global position broadcasts the chosen row through an all-reduce of a one-hot contribution."""
+    n, e = x.shape
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        sizes = torch.zeros(world, dtype=torch.float64, device=x.device)
+        sizes[rank] = n
+        _all_reduce(sizes, group)
+    else:
+        rank, world = 0, 1
+        sizes = torch.tensor([float(n)], dtype=torch.float64, device=x.device)
+    centers = torch.empty((K, e), dtype=torch.float32, device=x.device)
+    mind = None
+    for k in range(K):
+        u = torch.rand((), generator=gen, dtype=torch.float64).item()
+        if mind is None:
+            w_local = torch.ones((n,), dtype=torch.float64, device=x.device)
+        else:
+            w_local = mind.to(torch.float64)
+        tot = torch.zeros(world, dtype=torch.float64, device=x.device)
+        tot[rank] = w_local.sum()
+        _all_reduce(tot, group)
+        total = float(tot.sum().item())
+        if not (total > 0.0):                 # all remaining points coincide with a centre
+            w_local = torch.ones((n,), dtype=torch.float64, device=x.device)
+            tot = sizes.clone()
+            total = float(tot.sum().item())
+        target = u * total
+        before = float(tot[:rank].sum().item())
+        row = torch.zeros((e,), dtype=torch.float32, device=x.device)
+        mine = float(tot[rank].item())
+        last_nonempty = max((r for r in range(world) if float(tot[r].item()) > 0.0), default=0)
+        if n > 0 and mine > 0.0 and (before <= target < before + mine or
+                                     (rank == last_nonempty and target >= before + mine)):
+            cs = torch.cumsum(w_local, 0)
+            j = int(torch.searchsorted(cs, torch.tensor(target - before, dtype=torch.float64, device=x.device)).item())
+            j = min(max(j, 0), n - 1)
+            row = x[j].clone()
+        _all_reduce(row, group)
+        centers[k] = row
+        mind = ops.min_sqdist(x, row, mind)
+    return centers
+
+
+def kmeans_fit(samples: torch.Tensor, num_clusters: int, num_iters: int = 10, seed: Optional[int] = None,
+               init: Optional[torch.Tensor] = None, group=None, tol: float = 1e-4, ops=None,
+               return_info: bool = False):
+    ops = ops or CudaKMeansOps()
+    x = samples.detach().reshape(-1, samples.shape[-1]).to(torch.float32).contiguous()
+    n, e = x.shape
+    n_total = torch.tensor([float(n)], dtype=torch.float64, device=x.device)
+    _all_reduce(n_total, group)
+    if int(n_total.item()) < num_clusters:
+        # same failure as scikit-learn's KMeans inside the reference (layers.py:77)
+        raise ValueError(f"n_samples={int(n_total.item())} should be >= n_clusters={num_clusters}.")
+    if isinstance(ops, CudaKMeansOps) and not x.is_cuda:
+        raise RuntimeError("kmeans: CUDA tensor required (no CPU fallback)")
+    if init is not None:
+        centers = init.detach().to(torch.float32).to(x.device).contiguous().clone()
+    else:
+        gen = torch.Generator()
+        gen.manual_seed(2024 if seed is None else int(seed))
+        centers = kmeans_pp_seed(x, num_clusters, gen, ops, group)
+    # tolerance like scikit-learn: tol * mean feature variance
+    s1 = torch.cat([x.to(torch.float64).sum(0), (x.to(torch.float64) ** 2).sum(0)])
+    _all_reduce(s1, group)
+    nt = float(n_total.item())
+    var = (s1[e:] / nt - (s1[:e] / nt) ** 2).clamp_min(0).mean().item()
+    info = {"iters": 0, "inertia": None}
+    for it in range(int(num_iters)):
+        a = ops.assign(x, centers)
+        sums, counts, inertia = ops.accumulate(x, a, centers)
+        packed = torch.cat([sums.reshape(-1), counts.to(torch.float64), inertia])
+        _all_reduce(packed, group)
+        K = centers.shape[0]
+        sums = packed[:K * e].reshape(K, e).contiguous()
+        counts = packed[K * e:K * e + K].round().to(torch.int64).contiguous()
+        info["inertia"] = float(packed[-1].item())
+        shift = ops.update(centers, sums, counts)
+        info["iters"] = it + 1
+        if float(shift.item()) <= tol * var:
+            break
+    return (centers, info) if return_info else centers

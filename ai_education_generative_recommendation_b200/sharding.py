@@ -1,0 +1,120 @@
+"""Multi-GPU host logic: one process per GPU, item catalogue sharded by contiguous ranges.
+
+The reference is single-process; this is new design for BASELINE configs 3-5:
+  * encode shards independently (weights / codebooks replicated, no data-path collective);
+  * global collision handling needs ONE exchange step: every item's packed code is routed to the rank
+    that owns the key (all-to-all), the owner ranks equal keys in ascending GLOBAL item order, and the
+    ranks travel back (all-to-all).  The result is bit-identical to the single-GPU suffix column;
+  * the Sinkhorn re-encode rounds (reference infer.py:109-130) co-locate each collision group on the
+    key's owner together with the residual rows it needs.
+Collectives go through torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests); the
+per-rank work is behind a small `ops` object — `CudaShardOps` (C-ABI kernels) in production, an
+oracle-backed numpy twin only inside tests/.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from ._cabi import check, ptr, stream_ptr
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous item range [lo, hi) of `rank` ([r·N/G, (r+1)·N/G))."""
+    return (rank * n_total) // world, ((rank + 1) * n_total) // world
+
+
+def key_bits(num_emb_list) -> List[int]:
+    return [max(1, (int(k) - 1).bit_length()) for k in num_emb_list]
+
+
+class CudaShardOps:
+    """Per-rank pieces on the C-ABI kernels."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def pack_keys(self, codes: torch.Tensor, num_emb_list) -> torch.Tensor:
+        n, Lv = codes.shape
+        keys = torch.empty((n,), dtype=torch.int64, device=codes.device)
+        check(_cabi.lib().rqb200_pack_keys(ptr(codes.contiguous()), n, Lv, _cabi.int_array(num_emb_list), ptr(keys),
+                                           stream_ptr(codes.device)))
+        return keys
+
+    def rank_among_equal(self, keys: torch.Tensor, bits: int) -> torch.Tensor:
+        """out[i] = #{j < i : keys[j] == keys[i]} — stable radix sort + segmented rank."""
+        n = keys.numel()
+        out = torch.empty((n,), dtype=torch.int64, device=keys.device)
+        if n == 0:
+            return out
+        self.model._ensure_handle()
+        sk = keys.clone()
+        pos = torch.arange(n, dtype=torch.int64, device=keys.device)
+        lib = _cabi.lib()
+        s = stream_ptr(keys.device)
+        check(lib.rqb200_sort_pairs(self.model._handle, ptr(sk), ptr(pos), n, int(bits), s))
+        rk = torch.empty((n,), dtype=torch.int64, device=keys.device)
+        check(lib.rqb200_segment_rank(self.model._handle, ptr(sk), n, ptr(rk), s))
+        out[pos] = rk
+        return out
+
+
+def owner_of(keys: torch.Tensor, world: int) -> torch.Tensor:
+    """Rank that owns a key: a multiplicative hash so clustered codes spread evenly."""
+    h = keys * -7046029254386353131          # 0x9E3779B97F4A7C15 as int64 (wraps)
+    h = (h >> 33) & 0x3FFFFFFF
+    return h % world
+
+
+def _all_to_all(send: torch.Tensor, send_counts: torch.Tensor, group) -> Tuple[torch.Tensor, List[int]]:
+    world = dist.get_world_size(group)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc = send_counts.cpu().tolist()
+    rc = recv_counts.cpu().tolist()
+    tail = send.shape[1:]
+    recv = torch.empty((sum(rc),) + tuple(tail), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
+    assert len(rc) == world
+    return recv, rc
+
+
+def global_suffix(codes: torch.Tensor, num_emb_list, ops, group=None) -> torch.Tensor:
+    """[n_local, L] codes of this rank's contiguous shard → [n_local, L+1] with the GLOBAL suffix column
+    (identical to running the single-GPU dedup on the concatenated catalogue)."""
+    bits = sum(key_bits(num_emb_list))
+    if bits > 63:
+        raise ValueError("packed code needs more than 63 bits")
+    keys = ops.pack_keys(codes, num_emb_list)
+    if group is None or dist.get_world_size(group) == 1:
+        suffix = ops.rank_among_equal(keys, bits)
+        return torch.cat([codes, suffix[:, None]], dim=1)
+    world = dist.get_world_size(group)
+    owner = owner_of(keys, world)
+    order = torch.sort(owner, stable=True).indices            # bucket by destination, ascending item index inside
+    send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
+    recv_keys, rc = _all_to_all(keys[order], send_counts, group)
+    # arrivals are ordered (source rank, local index) == ascending global item index
+    rk = ops.rank_among_equal(recv_keys, bits)
+    back, _ = _all_to_all(rk, torch.tensor(rc, dtype=torch.int64, device=codes.device), group)
+    suffix = torch.empty_like(back)
+    suffix[order] = back
+    return torch.cat([codes, suffix[:, None]], dim=1)
+
+
+def global_stats(codes_with_suffix: torch.Tensor, group=None) -> dict:
+    """Collision statistics of infer.py:132-137 from the suffix column: an item is 'distinct' iff its
+    suffix is 0; the largest group is max suffix + 1."""
+    suf = codes_with_suffix[:, -1]
+    t = torch.stack([(suf == 0).sum(), torch.tensor(suf.numel(), device=suf.device)]).to(torch.int64)
+    mx = suf.max().reshape(1) + 1 if suf.numel() else torch.zeros(1, dtype=torch.int64, device=suf.device)
+    if group is not None and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    n = int(t[1].item())
+    distinct = int(t[0].item())
+    return {"distinct": distinct, "max_conflicts": int(mx.item()), "collision_rate": (n - distinct) / n if n else 0.0}

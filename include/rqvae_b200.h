@@ -1,0 +1,196 @@
+/*
+ * rqvae_b200.h — C ABI of the B200-native RQ-VAE semantic-ID encode path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.  The
+ * reference (CatchMan1/AI-education-generative-recommendation) is pure Python, so the
+ * binding a maintainer adds is a ctypes stub (INTEGRATION.md shows it); the Python
+ * package in this repo mirrors the reference's RQVAE / get_indices / infer() surface on
+ * top of exactly these entry points.  Reference citations are paths relative to the
+ * reference root, file:line.
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative RQB200_E* code on failure;
+ *     rqb200_last_error() returns a thread-local message for the last failure.
+ *   - "dev" pointers are CUDA device pointers on the model's device; `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).  Nothing synchronises
+ *     the device unless stated.  Inputs are borrowed, never copied silently.
+ *   - Row-major contiguous arrays; fp32 = IEEE binary32; codes are int64 like the
+ *     reference's LongTensor (vq.py:75, rq.py:54).
+ *   - There is no CPU fallback: every compute entry point needs a CUDA device.
+ */
+#ifndef RQVAE_B200_H
+#define RQVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define RQB200_ABI_VERSION 1
+
+#define RQB200_OK            0
+#define RQB200_EINVAL       -1   /* bad argument / unsupported shape            */
+#define RQB200_ECUDA        -2   /* CUDA runtime error (message has the detail) */
+#define RQB200_ENOMEM       -3
+#define RQB200_ESTATE       -4   /* model not fully loaded                       */
+
+#define RQB200_MAX_LAYERS    8
+#define RQB200_MAX_LEVELS    8
+
+typedef struct rqb200_model rqb200_model;   /* opaque: device-resident weights + workspaces */
+
+int         rqb200_abi_version(void);
+const char *rqb200_last_error(void);
+/* Number of CUDA devices visible (0 ⇒ every compute call will fail with RQB200_ECUDA). */
+int         rqb200_device_count(void);
+
+/* ---- instrumentation (bench.py) ----------------------------------------------------
+ * rqb200_launch_count: kernels this library has launched in this process so far.
+ * rqb200_profile_enable(1) makes the library record cudaEvent pairs around its main kernels on the
+ * launching stream; rqb200_profile_read waits for them and returns accumulated milliseconds and
+ * launch counts per slot: 0 first Linear (exact), 1 other Linears (exact), 2 quantizer, 3 dedup
+ * (sort + segmented rank), 4 tensor-core encoder, 5 Sinkhorn regroup.                        */
+long long rqb200_launch_count(void);
+int rqb200_profile_enable(int on);
+int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
+
+/* ---- model lifetime ---------------------------------------------------------------
+ * Replaces the module tree RQVAE.__init__ builds (rqvae.py:45-58): an encoder MLP
+ * `dims[0] → … → dims[n_layers]` (layers.py:18-32; ReLU after all but the last Linear),
+ * L codebooks of K[l] × e_dim (vq.py:21) and the mirrored decoder.                    */
+int rqb200_model_create(rqb200_model **out, int device, int n_layers, const int *dims,
+                        int n_levels, const int *K);
+void rqb200_model_destroy(rqb200_model *m);
+
+/* Upload one Linear of the encoder (which=0) or decoder (which=1).  W is [out,in] row-major
+ * as in nn.Linear.weight (layers.py:23); W / b may be host or device pointers (UVA).
+ * kblocks (host, nblk entries summing to `in`) is the K-blocking of the reference's CPU
+ * GEMM for this shape (see DESIGN.md "summation order"); NULL ⇒ the default rule.       */
+int rqb200_model_set_linear(rqb200_model *m, int which, int layer, const float *W, const float *b,
+                            const int *kblocks, int nblk);
+/* Upload codebook `level` ([K[level], e_dim], nn.Embedding.weight, vq.py:21). */
+int rqb200_model_set_codebook(rqb200_model *m, int level, const float *E);
+/* Copy the current codebook of `level` back (host or device destination). */
+int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out);
+
+/* ---- encoder MLP / decoder MLP (layers.py:42-43) ------------------------------------
+ * y[n, dims_out] = MLP(x[n, dims_in]) with the reference's exact fp32 summation order.
+ * rows (device int64, may be NULL) gathers input rows x[rows[i]] for i < n.            */
+int rqb200_mlp_exact(rqb200_model *m, int which, const float *x_dev, const int64_t *rows_dev,
+                     int64_t n, float *y_dev, void *stream);
+
+/* ---- residual quantizer, use_sk=False (rq.py:39-56, vq.py:63-99) --------------------
+ * z[n,e] → codes[n,L] int64; optional x_q[n,e] (Σ of straight-through outputs, rq.py:48),
+ * optional sumsq[L] (fp64, Σ(q-r)² per level — numerator of the mse at vq.py:90-91; added
+ * to whatever is already there), optional residual_out[n,e] (the residual entering the
+ * last level, used by the collision re-encode loop, infer.py:112-130).
+ * rows_out (may be NULL): codes row i is written to codes[rows_out[i]].                */
+int rqb200_quantize(rqb200_model *m, const float *z_dev, int64_t n, int64_t *codes_dev,
+                    const int64_t *rows_out_dev, float *xq_dev, double *sumsq_dev,
+                    float *last_residual_dev, void *stream);
+
+/* ---- RQVAE.get_indices(xs, use_sk=False) (rqvae.py:67-71) ---------------------------
+ * mode: RQB200_ENCODE_EXACT — SIMT fp32 in the reference's summation order;
+ *       RQB200_ENCODE_FAST  — tcgen05 split-bf16 tensor-core encoder + margin gate, rows
+ *                             inside the gate re-run by the exact kernels (same codes).
+ * z_out (may be NULL) receives the latent.  stats (host, may be NULL): [0]=rows rescued. */
+#define RQB200_ENCODE_EXACT 0
+#define RQB200_ENCODE_FAST  1
+int rqb200_get_indices(rqb200_model *m, int mode, const float *x_dev, int64_t n,
+                       int64_t *codes_dev, float *z_out_dev, int64_t *stats_host, void *stream);
+
+/* ---- RQVAE.forward(x, use_sk=False) + compute_loss pieces (rqvae.py:60-65,73-84) ----
+ * out[n,in] (may be NULL), codes[n,L], sumsq[L] as above, recon_sum[2] (fp64):
+ * [0] += Σ (out-x)², [1] += Σ |out-x|  (mse / l1 numerators, rqvae.py:75-78).          */
+int rqb200_forward(rqb200_model *m, const float *x_dev, int64_t n, float *out_dev,
+                   int64_t *codes_dev, double *sumsq_dev, double *recon_sum_dev, void *stream);
+
+/* ---- Sinkhorn branch (vq.py:74-83, layers.py:85-108) --------------------------------
+ * Last-level re-encode of collision groups (infer.py:109-130): groups are given CSR-style,
+ * items[offsets[g] .. offsets[g+1]) are row numbers into residual[n,e] (the residual
+ * entering the last level) and into codes[n,L]; for each group the [|g|,K] distance
+ * matrix is centred over the whole group (vq.py:51-61), run through fp64 Sinkhorn and the
+ * arg-max overwrites codes[item, L-1].  One CTA per group.                              */
+int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
+                            const int64_t *offsets_dev, int64_t n_groups, int max_group,
+                            double epsilon, int iters, int64_t *codes_dev, void *stream);
+/* Largest group (rows) rqb200_sinkhorn_regroup handles in shared memory for this model; larger
+ * groups are skipped by it and must go through rqb200_distances + rqb200_sinkhorn_assign.   */
+int rqb200_sinkhorn_group_cap(rqb200_model *m);
+/* sinkhorn_algorithm(distances, epsilon, iters) (layers.py:85-108): D[B,K] fp64 distances are
+ * replaced in place by Q.                                                               */
+int rqb200_sinkhorn(double *D_dev, int64_t B, int K, double epsilon, int iters, void *stream);
+/* Full use_sk branch for one batch at one level (vq.py:77-83): d (fp32 [B,K]) → indices[B] int64.
+ * scratch_dev: B*K doubles.                                                             */
+int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, double epsilon, int iters,
+                           double *scratch_dev, int64_t *idx_dev, void *stream);
+/* The fp32 distance matrix of vq.py:71-73 for one level: d[n,K[level]].                 */
+int rqb200_distances(rqb200_model *m, int level, const float *r_dev, int64_t n, float *d_dev,
+                     void *stream);
+
+/* ---- collisions and the suffix column (infer.py:18-42,139-177) ----------------------
+ * Workspace is owned by the model and grown on demand.
+ * rqb200_suffix_dedup: codes[n,L] → out[n,L+1] with out[i,L] = #{j<i : codes[j]==codes[i]}
+ *   (infer.py:152-163), bit-exact.  n_distinct_host / max_group_host (may be NULL) give the
+ *   statistics printed at infer.py:132-137; reading them synchronises the stream.
+ * K_host (may be NULL): codes[:,l] < K_host[l]; NULL ⇒ the column ranges are scanned on the
+ *   device first (one extra stream synchronisation).                                     */
+int rqb200_suffix_dedup(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L,
+                        const int *K_host, int64_t *out_dev, int64_t *n_distinct_host,
+                        int64_t *max_group_host, void *stream);
+/* get_collision_item (infer.py:29-42) on device: writes the item lists of all groups with
+ * >1 member, concatenated (ascending item index inside a group, groups ordered by key),
+ * items_dev[n] and offsets_dev[n+1] capacity.  Returns counts through host pointers
+ * (synchronises the stream).                                                            */
+int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L,
+                            const int *K_host, int64_t *items_dev, int64_t *offsets_dev,
+                            int64_t *n_groups_host,
+                            int64_t *n_items_host, int64_t *max_group_host, void *stream);
+/* Generic building blocks used by the multi-GPU dedup exchange: pack codes to u64 keys and
+ * stable-sort (key, value) pairs by key; segmented rank = position inside the equal-key run. */
+int rqb200_pack_keys(const int64_t *codes_dev, int64_t n, int L, const int *K_host,
+                     uint64_t *keys_dev, void *stream);
+int rqb200_sort_pairs(rqb200_model *m, uint64_t *keys_dev, int64_t *vals_dev, int64_t n,
+                      int key_bits, void *stream);
+int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_dev, int64_t n,
+                        int64_t *rank_dev, void *stream);
+
+/* ---- k-means codebook init (layers.py:69-82 via vq.py:40-49) ------------------------
+ * Lloyd steps on device.  kmeans_assign gives each sample its nearest centre (the quantizer's
+ * distance / first-index argmin); kmeans_accumulate adds per-cluster sums[K,e] (fp64),
+ * counts[K] (int64) and the inertia — the statistics that are all-reduced over NCCL when the
+ * samples are sharded; kmeans_update turns them into centres (empty clusters keep their
+ * previous centre) and adds the squared centre shift to *shift_dev.                       */
+int rqb200_kmeans_assign(const float *x_dev, int64_t n, int e, const float *centers_dev, int K,
+                         float *cnorm_scratch_dev /*[K]*/, int64_t *assign_dev, void *stream);
+int rqb200_kmeans_accumulate(const float *x_dev, int64_t n, int e, const int64_t *assign_dev,
+                             const float *centers_dev, int K, double *sums_dev, int64_t *counts_dev,
+                             double *inertia_dev, void *stream);
+int rqb200_kmeans_update(float *centers_dev, int K, int e, const double *sums_dev,
+                         const int64_t *counts_dev, double *shift_dev, void *stream);
+
+/* ---- synthetic catalogue (bench / tests) --------------------------------------------
+ * Integer-hash generator of clustered BERT-like item embeddings; the same function exists in
+ * numpy (package `synth.py`) so CPU and GPU produce identical bytes for any row range.    */
+int rqb200_synth_items(uint64_t seed, int64_t first_row, int64_t n, int dim, int64_t n_total,
+                       float *x_dev, void *stream);
+
+/* ---- host-buffer end-to-end call (what infer.py:88-177 does, use_sk=False pass + suffix)
+ * x_host[n,in] pinned or pageable host memory → codes_host[n,L+1] int64; chunks of
+ * `chunk_rows` are copied H2D on a side stream while the previous chunk is encoded.
+ * Synchronises before returning.  stats_host (may be NULL): [0] rows rescued by the exact
+ * kernels, [1] distinct codes, [2] largest collision group (infer.py:132-137).           */
+int rqb200_generate_codes_host(rqb200_model *m, int mode, const float *x_host, int64_t n,
+                               int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RQVAE_B200_H */

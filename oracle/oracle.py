@@ -1,0 +1,303 @@
+"""CPU oracle for the RQ-VAE semantic-ID encode path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference``
+legs may import this module, and only as the checker.  The product package never
+imports it.
+
+Parity status: PINNED — checked bit-for-bit against the reference's PyTorch CPU modules
+(oracle/make_golden.py, run in the build container where /root/reference exists) and
+against the committed golden vectors in tests/golden/.
+
+Each function cites the reference lines it restates (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librqvae_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/rqvae_oracle.c with gcc (building the checker is not using it)."""
+    src = os.path.join(_HERE, "rqvae_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librqvae_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        c_f = ctypes.POINTER(ctypes.c_float)
+        c_i = ctypes.POINTER(ctypes.c_int)
+        c_l = ctypes.POINTER(ctypes.c_int64)
+        c_d = ctypes.POINTER(ctypes.c_double)
+        L.rq_oracle_linear.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, c_f, c_f, ctypes.c_int,
+                                       ctypes.c_int, c_i, ctypes.c_int, c_f, ctypes.c_int]
+        L.rq_oracle_linear.restype = ctypes.c_int
+        L.rq_oracle_sumsq.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, c_f]
+        L.rq_oracle_sumsq.restype = None
+        L.rq_oracle_quantize.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, c_f, c_i, ctypes.c_int,
+                                         c_l, c_f, c_d, c_f, ctypes.c_int, ctypes.c_int]
+        L.rq_oracle_quantize.restype = ctypes.c_int
+        L.rq_oracle_suffix.argtypes = [c_l, ctypes.c_int64, ctypes.c_int, c_l]
+        L.rq_oracle_suffix.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _threads(threads: Optional[int]) -> int:
+    return int(threads) if threads else (os.cpu_count() or 1)
+
+
+# --------------------------------------------------------------------------- Linear / MLP
+
+def mkl_kblocks(in_dim: int, out_dim: int = 0) -> List[int]:
+    """K-blocking of the reference's CPU GEMM for ``nn.Linear`` (layers.py:23) as observed on
+    the reference run: one chain if K ≤ 384, two equal halves for
+    384 < K ≤ 768, otherwise blocks of 384 with the remainder last."""
+    K = int(in_dim)
+    if K <= 384:
+        return [K]
+    if K <= 768:
+        return [K - K // 2, K // 2] if K % 2 else [K // 2, K // 2]
+    out = []
+    while K > 0:
+        out.append(min(384, K))
+        K -= out[-1]
+    return out
+
+
+def linear(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool,
+           kblocks: Optional[Sequence[int]] = None, threads: Optional[int] = None) -> np.ndarray:
+    """``nn.Linear`` (+ReLU) exactly as the reference computes it on CPU (layers.py:23,28-30)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    n, k = x.shape
+    o = W.shape[0]
+    assert W.shape[1] == k
+    kb = np.asarray(kblocks if kblocks is not None else mkl_kblocks(k, o), dtype=np.int32)
+    y = np.empty((n, o), dtype=np.float32)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+    rc = lib().rq_oracle_linear(_fp(x), n, k, _fp(W), _fp(bb) if bb is not None else None, o,
+                                int(bool(relu)), kb.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                len(kb), _fp(y), _threads(threads))
+    if rc != 0:
+        raise ValueError(f"rq_oracle_linear failed rc={rc}")
+    return y
+
+
+def mlp(x: np.ndarray, weights: Sequence[np.ndarray], biases: Sequence[np.ndarray],
+        kblocks: Optional[Dict[int, Sequence[int]]] = None, threads: Optional[int] = None) -> np.ndarray:
+    """``MLPLayers.forward`` in eval mode (layers.py:18-32,42-43): Dropout is the identity, ReLU
+    after every Linear but the last, no BatchNorm (fold it into W/b first if present)."""
+    h = x
+    for i, (W, b) in enumerate(zip(weights, biases)):
+        kb = None if kblocks is None else kblocks.get(i)
+        h = linear(h, W, b, relu=(i != len(weights) - 1), kblocks=kb, threads=threads)
+    return h
+
+
+# --------------------------------------------------------------------------- quantizer
+
+def sumsq(v: np.ndarray) -> np.ndarray:
+    """``torch.sum(v**2, dim=1)`` (vq.py:71-72) with ATen's fp32 summation order."""
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    out = np.empty(v.shape[0], dtype=np.float32)
+    lib().rq_oracle_sumsq(_fp(v), v.shape[0], v.shape[1], _fp(out))
+    return out
+
+
+def quantize(z: np.ndarray, codebooks: Sequence[np.ndarray], want_xq: bool = True,
+             dist_level: int = -1, threads: Optional[int] = None
+             ) -> Tuple[np.ndarray, Optional[np.ndarray], np.ndarray, Optional[np.ndarray]]:
+    """``ResidualVectorQuantizer.forward`` with ``use_sk=False`` (rq.py:39-56, vq.py:63-99).
+
+    Returns (indices[n,L] int64, x_q[n,e] f32 | None, sum_sq[L] f64, distances | None) where
+    sum_sq[l] = Σ (q - r)² over the batch at level l (the mse numerator of vq.py:90-91)."""
+    z = np.ascontiguousarray(z, dtype=np.float32)
+    n, e = z.shape
+    L = len(codebooks)
+    K = np.asarray([c.shape[0] for c in codebooks], dtype=np.int32)
+    cat = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32) for c in codebooks], 0))
+    idx = np.empty((n, L), dtype=np.int64)
+    xq = np.empty((n, e), dtype=np.float32) if want_xq else None
+    loss = np.zeros(L, dtype=np.float64)
+    dist = np.empty((n, int(K[dist_level])), dtype=np.float32) if dist_level >= 0 else None
+    rc = lib().rq_oracle_quantize(
+        _fp(z), n, e, _fp(cat), K.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), L,
+        idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+        _fp(xq) if xq is not None else None,
+        loss.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+        _fp(dist) if dist is not None else None, dist_level, _threads(threads))
+    if rc != 0:
+        raise ValueError(f"rq_oracle_quantize failed rc={rc}")
+    return idx, xq, loss, dist
+
+
+def rq_loss(sum_sq: np.ndarray, n: int, e: int, beta: float) -> float:
+    """mean over levels of ``codebook_loss + beta*commitment_loss`` (vq.py:90-92, rq.py:53)."""
+    mse = sum_sq / float(n * e)
+    return float(np.mean(mse + beta * mse))
+
+
+def get_indices(x: np.ndarray, enc_w, enc_b, codebooks, threads: Optional[int] = None) -> np.ndarray:
+    """``RQVAE.get_indices(xs, use_sk=False)`` (rqvae.py:67-71)."""
+    z = mlp(x, enc_w, enc_b, threads=threads)
+    return quantize(z, codebooks, want_xq=False, threads=threads)[0]
+
+
+def forward(x, enc_w, enc_b, codebooks, dec_w, dec_b, beta=0.25, threads=None):
+    """``RQVAE.forward(x, use_sk=False)`` + ``compute_loss`` pieces (rqvae.py:60-65,73-84).
+    Returns (out, rq_loss, indices, recon_mse)."""
+    z = mlp(x, enc_w, enc_b, threads=threads)
+    idx, xq, ssq, _ = quantize(z, codebooks, threads=threads)
+    out = mlp(xq, dec_w, dec_b, threads=threads)
+    recon = float(np.mean((out.astype(np.float64) - np.asarray(x, dtype=np.float64)) ** 2))
+    return out, rq_loss(ssq, x.shape[0], z.shape[1], beta), idx, recon
+
+
+# --------------------------------------------------------------------------- Sinkhorn
+
+def center_distance(d: np.ndarray) -> np.ndarray:
+    """``VectorQuantizer.center_distance_for_constraint`` (vq.py:51-61) in fp32."""
+    d = np.asarray(d, dtype=np.float32)
+    mx, mn = d.max(), d.min()
+    middle = np.float32(mx + mn) / np.float32(2)
+    amplitude = np.float32(np.float32(mx - middle) + np.float32(1e-5))
+    assert amplitude > 0
+    return ((d - middle) / amplitude).astype(np.float32)
+
+
+def sinkhorn(d64: np.ndarray, epsilon: float, iters: int) -> np.ndarray:
+    """``sinkhorn_algorithm`` (layers.py:85-108) in fp64."""
+    Q = np.exp(-np.asarray(d64, dtype=np.float64) / epsilon)
+    B, K = Q.shape
+    Q /= Q.sum(-1, keepdims=True).sum(-2, keepdims=True)
+    for _ in range(iters):
+        Q /= Q.sum(axis=1, keepdims=True)
+        Q /= B
+        Q /= Q.sum(axis=0, keepdims=True)
+        Q /= K
+    Q *= B
+    return Q
+
+
+def sinkhorn_assign(d: np.ndarray, epsilon: float, iters: int) -> np.ndarray:
+    """The ``use_sk`` branch of ``VectorQuantizer.forward`` (vq.py:74-83): centre, fp64 Sinkhorn, argmax."""
+    Q = sinkhorn(center_distance(d).astype(np.float64), epsilon, iters)
+    return np.argmax(Q, axis=-1).astype(np.int64)
+
+
+def quantize_sk(z: np.ndarray, codebooks, sk_epsilons, sk_iters: int) -> np.ndarray:
+    """``ResidualVectorQuantizer.forward(use_sk=True)`` indices for one batch (rq.py:39-56, vq.py:63-99):
+    levels with ε>0 take the Sinkhorn argmax, the rest the plain argmin."""
+    r = np.ascontiguousarray(z, dtype=np.float32).copy()
+    out = []
+    for cb, eps in zip(codebooks, sk_epsilons):
+        cb = np.ascontiguousarray(cb, dtype=np.float32)
+        idx, _, _, dist = quantize(r, [cb], want_xq=False, dist_level=0, threads=1)
+        ind = idx[:, 0]
+        if eps > 0:
+            ind = sinkhorn_assign(dist, eps, sk_iters)
+        q = cb[ind]
+        xres = r + (q - r)
+        r = r - xres
+        out.append(ind)
+    return np.stack(out, axis=-1).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- collisions / suffix
+
+def suffix_dedup(codes: np.ndarray) -> np.ndarray:
+    """Suffix column of infer.py:152-163: ``suffix[i] = #{j < i : codes[j] == codes[i]}``; returns
+    ``[N, L+1]`` int64 like the array the reference saves (infer.py:177)."""
+    codes = np.ascontiguousarray(codes, dtype=np.int64)
+    n, L = codes.shape
+    out = np.empty((n, L + 1), dtype=np.int64)
+    rc = lib().rq_oracle_suffix(codes.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), n, L,
+                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    if rc != 0:
+        raise MemoryError("rq_oracle_suffix")
+    return out
+
+
+def collision_groups(codes: np.ndarray) -> List[np.ndarray]:
+    """``get_collision_item`` (infer.py:29-42): item-index groups sharing a full code, each in
+    ascending item order, groups in order of first occurrence."""
+    codes = np.ascontiguousarray(codes, dtype=np.int64)
+    _, inv, counts = np.unique(codes, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    order = np.argsort(inv, kind="stable")
+    bounds = np.concatenate([[0], np.cumsum(counts)])
+    groups = [order[bounds[g]:bounds[g + 1]] for g in range(len(counts)) if counts[g] > 1]
+    groups.sort(key=lambda g: int(g[0]))
+    return groups
+
+
+def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters: int,
+                   max_rounds: int = 30, threads: Optional[int] = None) -> Tuple[np.ndarray, dict]:
+    """The encode driver of infer.py:88-177 / generate_code.py:82-178: pass 1 (argmin codes),
+    ≤30 rounds of per-group re-encoding with Sinkhorn on the last level only (infer.py:109-130),
+    then the suffix column.  Returns ([N, L+1] int64, stats)."""
+    L = len(codebooks)
+    if L > 5:
+        raise IndexError("list index out of range")      # prefix list has 5 entries (infer.py:90)
+    z = mlp(x, enc_w, enc_b, threads=threads)
+    codes = quantize(z, codebooks, want_xq=False, threads=threads)[0]
+    eps = [0.0] * (L - 1) + [float(sk_epsilons[-1])]
+    rounds = 0
+    while rounds < max_rounds:
+        groups = collision_groups(codes)
+        if not groups:
+            break
+        new = codes.copy()
+        for g in groups:
+            new[g] = quantize_sk(z[g], codebooks, eps, sk_iters)
+        codes = new
+        rounds += 1
+    uniq, counts = np.unique(codes, axis=0, return_counts=True)
+    stats = {"rounds": rounds, "max_conflicts": int(counts.max()),
+             "collision_rate": (len(codes) - len(uniq)) / len(codes)}
+    return suffix_dedup(codes), stats
+
+
+# --------------------------------------------------------------------------- k-means (Lloyd)
+
+def kmeans_lloyd(x: np.ndarray, init: np.ndarray, iters: int, tol: float = 1e-4) -> np.ndarray:
+    """Lloyd iterations from given initial centres — the algorithm scikit-learn's ``KMeans``
+    (third-party, pinned scikit-learn==1.7.1 in the reference's requirements.txt:7; call site
+    layers.py:77) runs after seeding.  PARITY UNPINNED for seeding: sklearn's k-means++ consumes
+    numpy's global RNG, so only 'same init ⇒ same centres' is checked.  fp64 accumulation."""
+    x = np.asarray(x, dtype=np.float32)
+    c = np.asarray(init, dtype=np.float32).copy()
+    xv = float(np.mean(np.var(x.astype(np.float64), axis=0)))
+    for _ in range(iters):
+        d = (x.astype(np.float64) ** 2).sum(1)[:, None] + (c.astype(np.float64) ** 2).sum(1)[None] \
+            - 2.0 * x.astype(np.float64) @ c.astype(np.float64).T
+        a = d.argmin(1)
+        new = c.copy()
+        for k in range(c.shape[0]):
+            m = a == k
+            if m.any():
+                new[k] = x[m].astype(np.float64).mean(0).astype(np.float32)
+        shift = float(((new.astype(np.float64) - c.astype(np.float64)) ** 2).sum())
+        c = new
+        if shift <= tol * xv:
+            break
+    return c

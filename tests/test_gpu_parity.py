@@ -1,0 +1,309 @@
+"""GPU: the CUDA path (through the C ABI) against the golden vectors and the CPU oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_model, load_golden, synth_weights
+from ai_education_generative_recommendation_b200 import _cabi, synth
+import ai_education_generative_recommendation_b200 as rq
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gpu_synth(seed, first, n, dim, n_total):
+    x = torch.empty((n, dim), dtype=torch.float32, device=DEV)
+    _cabi.check(_cabi.lib().rqb200_synth_items(seed, first, n, dim, n_total, x.data_ptr(), _cabi.stream_ptr()))
+    return x
+
+
+def test_native_library_is_loaded_and_sees_the_gpu():
+    assert _cabi.lib().rqb200_device_count() >= 1
+    assert os.path.basename(_cabi.LIB_PATH) == "librqvae_b200.so"
+
+
+def test_synth_kernel_matches_numpy_twin():
+    for (first, n, dim, tot) in [(0, 4096, 768, 1_000_000), (999_000, 1000, 768, 1_000_000), (12345, 777, 1024, 10 ** 8)]:
+        got = gpu_synth(2024, first, n, dim, tot).cpu().numpy()
+        ref = synth.synth_items(2024, first, n, dim, tot)
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+
+
+@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice"])
+def test_get_indices_and_forward_match_reference_golden(oracle, name):
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n = int(g["n_rows"])
+    x = synth.synth_items(int(g["seed"]), 0, n, cfg["in_dim"], int(g["n_total"]))
+    xt = torch.from_numpy(x).to(DEV)
+    codes = m.get_indices(xt, use_sk=False)
+    assert codes.dtype == torch.int64 and tuple(codes.shape) == (n, len(cbs))
+    assert np.array_equal(codes.cpu().numpy(), g["codes"].astype(np.int64))              # bit-exact codes
+    z = m.encoder(xt).cpu().numpy()
+    keep = g["z_head"].shape[0]
+    assert np.array_equal(z[:keep].view(np.int32), g["z_head"].view(np.int32))           # bit-exact latent
+    out, rq_loss, idx = m(xt, use_sk=False)
+    assert np.array_equal(idx.cpu().numpy(), g["codes"].astype(np.int64))
+    assert np.array_equal(out[:8].cpu().numpy().view(np.int32), g["out_head"].view(np.int32))
+    assert abs(float(rq_loss) - float(g["rq_loss"])) <= 1e-4 * abs(float(g["rq_loss"]))  # tolerance: 1e-4 rel
+    total, recon = m.compute_loss(out, rq_loss, xs=xt)
+    assert abs(float(recon) - float(g["recon_loss"])) <= 1e-4 * float(g["recon_loss"])
+    assert abs(float(total) - float(g["total_loss"])) <= 1e-4 * float(g["total_loss"])
+    out2, rq2, idx2, total2, recon2 = m.forward_losses(xt)
+    assert torch.equal(out2, out) and torch.equal(idx2, idx)
+    assert abs(float(recon2) - float(g["recon_loss"])) <= 1e-4 * float(g["recon_loss"])
+    x_q, _, _ = m.rq(m.encoder(xt), use_sk=False)
+    assert np.array_equal(x_q[:keep].cpu().numpy().view(np.int32), g["xq_head"].view(np.int32))
+    # whole-slice check against the oracle as well (latent, x_q, decoded rows)
+    _, (ew, eb), (dw, db) = synth_weights(cfg)
+    zo = oracle.mlp(x, ew, eb)
+    assert np.array_equal(z.view(np.int32), zo.view(np.int32))
+    _, xqo, _, _ = oracle.quantize(zo, cbs)
+    assert np.array_equal(x_q.cpu().numpy().view(np.int32), xqo.view(np.int32))
+    assert np.array_equal(out.cpu().numpy().view(np.int32), oracle.mlp(xqo, dw, db).view(np.int32))
+
+
+def test_ragged_and_empty_batches(oracle):
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    _, (ew, eb), _ = synth_weights(cfg)
+    for n in (0, 1, 2, 3, 15, 16, 127, 128, 129, 1000):
+        x = synth.synth_items(7, 1, n, cfg["in_dim"], 5000) if n else np.zeros((0, cfg["in_dim"]), np.float32)
+        got = m.get_indices(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        assert got.shape == (n, 3)
+        if n:
+            assert np.array_equal(got, oracle.get_indices(x, ew, eb, cbs))
+    x3 = torch.from_numpy(synth.synth_items(7, 1, 24, cfg["in_dim"], 5000)).to(DEV).view(2, 3, 4, -1)
+    assert tuple(m.get_indices(x3).shape) == (2, 3, 4, 3)                                 # leading dims kept
+
+
+def test_exact_integer_lane_with_ties(oracle):
+    """Small-integer inputs/weights: every partial sum is exact in fp32, ties are abundant, so any
+    summation order gives the same bits and only first-index tie breaking decides."""
+    rng = np.random.default_rng(5)
+    cfg = dict(in_dim=768, num_emb_list=[256, 256, 256], e_dim=32, layers=[256, 128], sk_epsilons=[0.0] * 3, sk_iters=5)
+    n = 4096
+    x = rng.integers(-2, 3, size=(n, 768)).astype(np.float32)
+    def sparse(o, i, dens):
+        return (rng.integers(-1, 2, size=(o, i)) * (rng.random((o, i)) < dens)).astype(np.float32)
+    ew = [sparse(256, 768, 0.10), sparse(128, 256, 0.10), sparse(32, 128, 0.25)]
+    eb = [rng.integers(-1, 2, size=o).astype(np.float32) for o in (256, 128, 32)]
+    z = oracle.mlp(x, ew, eb)
+    cbs = []
+    r = z.copy()
+    for lvl in range(3):
+        cb = r[rng.integers(0, n, size=256)].copy()
+        cb[128:] = cb[:128]                                   # duplicated codebook rows force exact ties
+        cbs.append(cb)
+        idx, _, _, _ = oracle.quantize(r, [cb], want_xq=False)
+        r = r - (r + (cb[idx[:, 0]] - r))
+    ref = oracle.quantize(z, cbs, want_xq=False)[0]
+    assert (ref < 128).all()                                  # first index always wins
+    m = rq.RQVAE(in_dim=768, num_emb_list=[256] * 3, e_dim=32, layers=[256, 128], sk_epsilons=[0.0] * 3).to(DEV).eval()
+    with torch.no_grad():
+        for i, lin in enumerate([m.encoder.mlp_layers[1], m.encoder.mlp_layers[4], m.encoder.mlp_layers[7]]):
+            lin.weight.copy_(torch.from_numpy(ew[i])); lin.bias.copy_(torch.from_numpy(eb[i]))
+        for lvl in range(3):
+            m.rq.vq_layers[lvl].embedding.weight.copy_(torch.from_numpy(cbs[lvl]))
+    got = m.get_indices(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_distances_match_oracle(oracle):
+    g, cfg, cbs = load_golden("c3_slice")
+    m = build_model(cfg, cbs)
+    m._sync()
+    rng = np.random.default_rng(1)
+    r = (rng.standard_normal((300, cfg["e_dim"])) * 0.4).astype(np.float32)
+    for lvl in (0, 3):
+        d = m._distances(lvl, torch.from_numpy(r).to(DEV)).cpu().numpy()
+        ref = oracle.quantize(r, [cbs[lvl]], want_xq=False, dist_level=0, threads=1)[3]
+        assert np.array_equal(d.view(np.int32), ref.view(np.int32))
+
+
+@pytest.mark.parametrize("n,L,K", [(0, 3, 8), (1, 3, 8), (5000, 3, 8), (100_000, 3, 256), (70_001, 4, 1024), (3000, 1, 2),
+                                   (200_000, 5, 16)])
+def test_suffix_dedup_bit_exact(oracle, n, L, K):
+    rng = np.random.default_rng(n + L)
+    codes = rng.integers(0, K, size=(n, L)).astype(np.int64)
+    if n > 10:
+        codes[rng.integers(0, n, size=n // 3)] = codes[rng.integers(0, n, size=n // 3)]      # many duplicates
+    ct = torch.from_numpy(codes).to(DEV)
+    out, stats = rq.suffix_dedup(None, ct, [K] * L)
+    ref = oracle.suffix_dedup(codes) if n else np.zeros((0, L + 1), np.int64)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    if n:
+        assert stats["distinct"] == len(np.unique(codes, axis=0))
+        assert stats["max_conflicts"] == int(ref[:, -1].max()) + 1
+        out2, _ = rq.suffix_dedup(None, ct, None)               # column ranges scanned on the device
+        assert np.array_equal(out2.cpu().numpy(), ref)
+
+
+def test_suffix_dedup_shipped_artifact():
+    arr = np.load(os.path.join(os.path.dirname(__file__), "golden", "course_semantic_ids.npy")).astype(np.int64)
+    out, stats = rq.suffix_dedup(None, torch.from_numpy(arr[:, :3].copy()).to(DEV), [8, 8, 8])
+    assert np.array_equal(out.cpu().numpy(), arr)
+    assert stats["distinct"] == 167 and stats["max_conflicts"] == 18
+
+
+def test_collision_groups_match_oracle(oracle):
+    g, cfg, cbs = load_golden("c1_slice")
+    m = build_model(cfg, cbs)
+    m._sync()
+    codes = g["codes"].astype(np.int64)
+    items, offsets, max_group = rq.collision_groups(m, torch.from_numpy(codes).to(DEV))
+    items, offsets = items.cpu().numpy(), offsets.cpu().numpy()
+    mine = sorted(tuple(items[offsets[i]:offsets[i + 1]]) for i in range(len(offsets) - 1))
+    ref = sorted(tuple(int(v) for v in grp) for grp in oracle.collision_groups(codes))
+    assert mine == ref
+    assert max_group == max(len(grp) for grp in ref)
+
+
+def test_sinkhorn_cases_match_reference_golden(oracle):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sinkhorn_cases.npz"))
+    lib = _cabi.lib()
+    for i in range(int(g["n_cases"])):
+        B, K, iters = [int(v) for v in g[f"meta{i}"]]
+        eps = float(g[f"eps{i}"])
+        d = oracle.quantize(g[f"r{i}"], [g[f"cb{i}"]], want_xq=False, dist_level=0, threads=1)[3]
+        dt = torch.from_numpy(d).to(DEV)
+        scratch = torch.empty((B, K), dtype=torch.float64, device=DEV)
+        idx = torch.empty((B,), dtype=torch.int64, device=DEV)
+        _cabi.check(lib.rqb200_sinkhorn_assign(dt.data_ptr(), B, K, eps, iters, scratch.data_ptr(), idx.data_ptr(),
+                                               _cabi.stream_ptr()))
+        assert np.array_equal(idx.cpu().numpy(), g[f"idx{i}"].astype(np.int64)), i
+        # sinkhorn_algorithm drop-in: Q close to the fp64 oracle
+        c = oracle.center_distance(d).astype(np.float64)
+        Q = rq.sinkhorn_algorithm(torch.from_numpy(c).to(DEV), eps, iters).cpu().numpy()
+        Qo = oracle.sinkhorn(c, eps, iters)
+        assert np.allclose(Q, Qo, rtol=1e-9, atol=1e-300)
+
+
+def test_generate_codes_against_reference_infer(oracle):
+    """BASELINE config 1 end to end: 707 items, K=8, 30 Sinkhorn rounds, suffix column."""
+    g, cfg, cbs = load_golden("c1_infer")
+    m = build_model(cfg, cbs)
+    n = int(g["n_total"])
+    x = synth.synth_items(int(g["seed"]), 0, n, cfg["in_dim"], n)
+    golden = g["semantic_ids"].astype(np.int64)
+    trace = g["trace"].astype(np.int64)
+    out, stats = rq.generate_codes(m, x)
+    out = out.cpu().numpy()
+    assert out.shape == (n, 4) and out.dtype == np.int64
+    assert len(np.unique(out, axis=0)) == n                                   # ids are unique
+    assert np.array_equal(out[:, 3], oracle.suffix_dedup(out[:, :3])[:, 3])   # suffix rule
+    assert np.array_equal(out[:, :2], golden[:, :2])                          # argmin levels: bit-exact
+    assert stats["rounds"] == int(g["rounds"])
+    # the reference re-encodes groups with its small-batch GEMM order; 6/707 rows differ even for the CPU oracle
+    assert (out != golden).any(1).mean() <= 0.03
+    # one round as a pure function of the previous round's codes, against the reference trace
+    lib = _cabi.lib()
+    z = rq.encode_latents(m, x)
+    residual = torch.empty_like(z)
+    tmp = torch.empty((n, 3), dtype=torch.int64, device=DEV)
+    _cabi.check(lib.rqb200_quantize(m._handle, z.data_ptr(), n, tmp.data_ptr(), 0, 0, 0, residual.data_ptr(), _cabi.stream_ptr()))
+    assert np.array_equal(tmp.cpu().numpy(), trace[0])
+    bad_rows = 0
+    for t in range(len(trace) - 1):
+        codes = torch.from_numpy(trace[t].copy()).to(DEV)
+        items, offsets, mg = rq.collision_groups(m, codes)
+        new = codes.clone()
+        _cabi.check(lib.rqb200_sinkhorn_regroup(m._handle, residual.data_ptr(), items.data_ptr(), offsets.data_ptr(),
+                                                offsets.numel() - 1, mg, cfg["sk_epsilons"][-1], cfg["sk_iters"],
+                                                new.data_ptr(), _cabi.stream_ptr()))
+        bad_rows += int((new.cpu().numpy() != trace[t + 1]).any(1).sum())
+    assert bad_rows <= 12
+
+
+def test_generate_codes_matches_oracle_driver_at_scale(oracle):
+    g, cfg, cbs = load_golden("c2_slice")
+    cfg = dict(cfg, sk_epsilons=[0.0, 0.0, 0.003])
+    m = build_model(cfg, cbs)
+    _, (ew, eb), _ = synth_weights(cfg)
+    n = 6000
+    x = synth.synth_items(2024, 0, n, 768, 1_000_000)
+    x[3000:3040] = x[100:140]                                                  # exact duplicates → real collision groups
+    out, stats = rq.generate_codes(m, x)
+    ref, rstats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"])
+    assert stats["rounds"] == rstats["rounds"]
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert len(np.unique(ref, axis=0)) == n
+
+
+def test_kmeans_lloyd_matches_oracle(oracle):
+    rng = np.random.default_rng(3)
+    centres = rng.standard_normal((16, 32)).astype(np.float32)
+    x = (centres[rng.integers(0, 16, size=20000)] + 0.1 * rng.standard_normal((20000, 32))).astype(np.float32)
+    init = x[rng.choice(20000, size=16, replace=False)].copy()
+    got = rq.kmeans(torch.from_numpy(x).to(DEV), 16, 10, init=torch.from_numpy(init)).cpu().numpy()
+    ref = oracle.kmeans_lloyd(x, init, 10)
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-6)                          # tolerance: fp64 sums, fp32 centres
+    seeded = rq.kmeans(torch.from_numpy(x).to(DEV), 16, 20, seed=1)
+    assert tuple(seeded.shape) == (16, 32) and seeded.is_cuda
+    d = ((x[:, None, :] - seeded.cpu().numpy()[None]) ** 2).sum(-1).min(1).mean()
+    assert d < 0.01 * 32 * 2                                                    # found the planted clusters
+    with pytest.raises(ValueError, match="should be >= n_clusters"):
+        rq.kmeans(torch.from_numpy(x[:10]).to(DEV), 16, 5)
+
+
+def test_kmeans_init_path_of_the_model():
+    cfg = dict(in_dim=768, num_emb_list=[64, 64], e_dim=32, layers=[256, 128], sk_epsilons=[0.0, 0.0], sk_iters=5)
+    m = rq.RQVAE(in_dim=768, num_emb_list=[64, 64], e_dim=32, layers=[256, 128], kmeans_init=True, kmeans_iters=5,
+                 sk_epsilons=[0.0, 0.0]).to(DEV)
+    m.train()
+    x = torch.from_numpy(synth.synth_items(1, 1, 2048, 768, 100000)).to(DEV)
+    out, loss, idx = m(x, use_sk=False)
+    assert all(q.initted for q in m.rq.vq_layers)
+    assert float(m.rq.vq_layers[0].embedding.weight.abs().sum()) > 0
+    m.eval()
+    assert tuple(m.get_indices(x).shape) == (2048, 2)
+
+
+def test_host_buffer_end_to_end_call(oracle):
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    m._sync()
+    _, (ew, eb), _ = synth_weights(cfg)
+    n = 5000
+    x = synth.synth_items(2024, 0, n, 768, 1_000_000)
+    xh = torch.from_numpy(x).pin_memory()
+    out = torch.empty((n, 4), dtype=torch.int64).pin_memory()
+    stats = (ctypes.c_int64 * 4)()
+    _cabi.check(_cabi.lib().rqb200_generate_codes_host(m._handle, _cabi.ENCODE_EXACT, xh.data_ptr(), n, 1024,
+                                                       out.data_ptr(), stats))
+    ref = oracle.suffix_dedup(oracle.get_indices(x, ew, eb, cbs))
+    assert np.array_equal(out.numpy(), ref)
+    assert stats[1] == len(np.unique(ref[:, :3], axis=0))
+
+
+def test_full_size_properties_c2(oracle):
+    """BASELINE config 2 at full size (1M x 768, 3 x 256, e 32): sampled parity + size-independent properties."""
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    _, (ew, eb), _ = synth_weights(cfg)
+    n = 1_000_000
+    x = gpu_synth(2024, 0, n, 768, n)
+    codes = m.get_indices(x)
+    out, stats = rq.suffix_dedup(m, codes)
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:8192, :3], g["codes"].astype(np.int64))             # golden head of the same catalogue
+    sel = np.random.default_rng(0).choice(n, size=20000, replace=False)
+    sel.sort()
+    xs = x[torch.from_numpy(sel).to(DEV)].cpu().numpy()
+    assert np.array_equal(o[sel, :3], oracle.get_indices(xs, ew, eb, cbs))       # sampled bit-exact parity
+    # uniqueness, suffix rule via checksums: per-key count == max suffix + 1
+    key = (o[:, 0] * 256 + o[:, 1]) * 256 + o[:, 2]
+    full = key * (int(o[:, 3].max()) + 1) + o[:, 3]
+    assert len(np.unique(full)) == n
+    uk, cnt = np.unique(key, return_counts=True)
+    assert stats["distinct"] == len(uk) and stats["max_conflicts"] == cnt.max()
+    order = np.argsort(key, kind="stable")
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    expect = np.arange(n) - np.repeat(starts, cnt)
+    assert np.array_equal(o[order, 3], expect)
+    # idempotence: re-encoding a shuffled copy gives the permuted codes
+    perm = torch.randperm(n, device=DEV)[:200_000]
+    assert torch.equal(m.get_indices(x[perm]), codes[perm])

@@ -1,0 +1,116 @@
+"""CPU: the oracle against the committed golden vectors (made by oracle/make_golden.py from the reference)."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from conftest import load_golden, synth_weights
+from ai_education_generative_recommendation_b200 import synth
+
+
+@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice"])
+def test_oracle_matches_reference_slices(oracle, name):
+    g, cfg, cbs = load_golden(name)
+    _, (ew, eb), (dw, db) = synth_weights(cfg)
+    n = int(g["n_rows"])
+    x = synth.synth_items(int(g["seed"]), 0, n, cfg["in_dim"], int(g["n_total"]))
+    z = oracle.mlp(x, ew, eb)
+    keep = g["z_head"].shape[0]
+    assert np.array_equal(z[:keep].view(np.int32), g["z_head"].view(np.int32))          # bit-exact latent
+    idx, xq, ssq, _ = oracle.quantize(z, cbs)
+    assert np.array_equal(idx, g["codes"].astype(np.int64))                             # bit-exact codes
+    assert np.array_equal(xq[:keep].view(np.int32), g["xq_head"].view(np.int32))
+    out = oracle.mlp(xq[:8], dw, db) if n >= 16 else None
+    loss = oracle.rq_loss(ssq, n, cfg["e_dim"], 0.25)
+    assert abs(loss - float(g["rq_loss"])) <= 1e-5 * abs(float(g["rq_loss"]))
+    full = oracle.mlp(xq, dw, db)
+    assert np.array_equal(full[:8].view(np.int32), g["out_head"].view(np.int32))
+    recon = float(np.mean((full.astype(np.float64) - x.astype(np.float64)) ** 2))
+    assert abs(recon - float(g["recon_loss"])) <= 1e-5 * float(g["recon_loss"])
+
+
+def test_oracle_suffix_reproduces_shipped_artifact(oracle):
+    import os
+    arr = np.load(os.path.join(os.path.dirname(__file__), "golden", "course_semantic_ids.npy")).astype(np.int64)
+    assert arr.shape == (707, 4)
+    got = oracle.suffix_dedup(arr[:, :3])
+    assert np.array_equal(got, arr)
+    assert len(np.unique(got, axis=0)) == 707
+
+
+def test_oracle_sinkhorn_cases(oracle):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sinkhorn_cases.npz"))
+    for i in range(int(g["n_cases"])):
+        B, K, iters = [int(v) for v in g[f"meta{i}"]]
+        d = oracle.quantize(g[f"r{i}"], [g[f"cb{i}"]], want_xq=False, dist_level=0, threads=1)[3]
+        got = oracle.sinkhorn_assign(d, float(g[f"eps{i}"]), iters)
+        assert np.array_equal(got, g[f"idx{i}"].astype(np.int64)), i
+
+
+def test_oracle_driver_against_reference_infer(oracle):
+    g, cfg, cbs = load_golden("c1_infer")
+    _, (ew, eb), _ = synth_weights(cfg)
+    n = int(g["n_total"])
+    x = synth.synth_items(int(g["seed"]), 0, n, cfg["in_dim"], n)
+    golden = g["semantic_ids"].astype(np.int64)
+    trace = g["trace"].astype(np.int64)
+    assert golden.shape == (707, 4) and len(np.unique(golden, axis=0)) == 707
+    z = oracle.mlp(x, ew, eb)
+    assert np.array_equal(oracle.quantize(z, cbs, want_xq=False)[0], trace[0])          # pass 1 is bit-exact
+    # every round is a pure function of the previous round's codes (infer.py:117-129)
+    bad = 0
+    for t in range(len(trace) - 1):
+        for grp in oracle.collision_groups(trace[t]):
+            mine = oracle.quantize_sk(z[grp], cbs, [0.0, 0.0, cfg["sk_epsilons"][-1]], cfg["sk_iters"])
+            bad += int(not np.array_equal(mine, trace[t + 1][grp]))
+    assert bad <= 3          # reference re-runs its encoder on <16-row batches (another GEMM order)
+    assert np.array_equal(oracle.suffix_dedup(trace[-1]), golden)
+    got, stats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"])
+    assert (got != golden).any(1).mean() <= 0.02
+    assert len(np.unique(got, axis=0)) == n
+
+
+def brute_suffix(codes):
+    out = []
+    for i in range(len(codes)):
+        out.append(sum(1 for j in range(i) if (codes[j] == codes[i]).all()))
+    return np.array(out, dtype=np.int64)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 60), st.integers(1, 5), st.integers(1, 4), st.integers(0, 2 ** 31 - 1))
+def test_oracle_suffix_property(oracle, n, L, K, seed):
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, K, size=(n, L)).astype(np.int64)
+    got = oracle.suffix_dedup(codes) if n else np.zeros((0, L + 1), dtype=np.int64)
+    assert np.array_equal(got[:, :L], codes)
+    assert np.array_equal(got[:, L], brute_suffix(codes)) if n else True
+
+
+def test_sumsq_order_is_not_plain_sum(oracle):
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((2000, 64)).astype(np.float32)
+    got = oracle.sumsq(v)
+    seq = np.zeros(2000, dtype=np.float32)
+    for k in range(64):
+        seq = seq + v[:, k] * v[:, k]
+    assert np.allclose(got, seq, rtol=1e-5)
+    assert (got != seq).any()          # the ATen order differs from a left-to-right sum in the last bit
+
+
+def test_synth_generator_known_answers():
+    x = synth.synth_items(2024, 0, 2048, 768, 1_000_000)
+    assert x.dtype == np.float32 and x.shape == (2048, 768)
+    assert not x[0].any()                                   # padding row
+    assert np.array_equal(x[5:9], synth.synth_items(2024, 5, 4, 768, 1_000_000))   # row ranges compose
+    assert abs(float(x[1:].std()) - 0.51) < 0.02
+    big = synth.synth_items(2024, 0, 20000, 8, 20000)
+    uniq = len(np.unique(big, axis=0))
+    assert 20000 - 60 < uniq < 20000                        # ~0.1 % exact duplicates
+
+
+def test_kblock_rule(oracle):
+    assert oracle.mkl_kblocks(768) == [384, 384]
+    assert oracle.mkl_kblocks(256) == [256]
+    assert oracle.mkl_kblocks(1024) == [384, 384, 256]
+    assert oracle.mkl_kblocks(400) == [200, 200]
