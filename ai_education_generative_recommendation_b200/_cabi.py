@@ -38,6 +38,8 @@ _PROTOS = {
     "rqb200_model_set_linear": (c_int, [c_void_p, c_int, c_int, _P, _P, POINTER(c_int), c_int]),
     "rqb200_model_set_codebook": (c_int, [c_void_p, c_int, _P]),
     "rqb200_model_get_codebook": (c_int, [c_void_p, c_int, _P]),
+    "rqb200_model_set_gate": (c_int, [c_void_p, c_float, c_float]),
+    "rqb200_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P]),
     "rqb200_mlp_exact": (c_int, [c_void_p, c_int, _P, _P, c_int64, _P, _P]),
     "rqb200_quantize": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P, _P]),
     "rqb200_get_indices": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P, POINTER(c_int64), _P]),

@@ -203,7 +203,8 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
         if (m->cb[l]) cudaFree(m->cb[l]);
         if (m->cc[l]) cudaFree(m->cc[l]);
     }
-    Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1]};
+    Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1],
+                       &m->rescue, &m->rescue_act[0], &m->rescue_act[1]};
     for (Workspace *w : ws)
         if (w->ptr) cudaFree(w->ptr);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -254,6 +255,25 @@ extern "C" int rqb200_model_set_codebook(rqb200_model *m, int level, const float
     RQB_CUDA(cudaStreamSynchronize(0));
     m->cb_set[level] = true;
     return 0;
+}
+
+extern "C" int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_abs) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(gamma >= 0.0f && floor_abs >= 0.0f, "gate parameters must be non-negative");
+    m->gate_gamma = gamma;
+    m->gate_floor = floor_abs;
+    return 0;
+}
+
+extern "C" int rqb200_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(which == 0 || which == 1, "which must be 0 or 1");
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && y_dev != nullptr, "NULL buffer");
+    for (int i = 0; i < m->n_layers; ++i)
+        if (!(which == 0 ? m->enc[i].set : m->dec[i].set)) { set_error("layer %d not loaded", i); return RQB200_ESTATE; }
+    RQB_CUDA(cudaSetDevice(m->device));
+    return mlp_tc(m, which, x_dev, n, y_dev, (cudaStream_t)stream);
 }
 
 extern "C" int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out) {

@@ -61,6 +61,7 @@ struct Linear {
     void *W_tc = nullptr;
     size_t W_tc_bytes = 0;
     float *absW_rowmax = nullptr;
+    int tc_scale_exp = 0;    // W_tc holds W * 2^tc_scale_exp
 };
 
 struct Workspace {
@@ -86,6 +87,10 @@ struct rqb200_model {
     rqb::Workspace sortws;          // radix sort scratch
     rqb::Workspace misc;            // rescue lists, counters
     rqb::Workspace hostpipe[2];     // device chunks of the host-buffer pipeline
+    rqb::Workspace rescue;          // exact latent of gated rows
+    rqb::Workspace rescue_act[2];
+    float gate_gamma = 3.0517578125e-05f;   // 2^-15: bound on |z~ - z| / |z| of the tensor-core encoder
+    float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -97,6 +102,9 @@ int ws_reserve(Workspace &w, size_t bytes);
 // linear_exact.cu
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
                  bool relu, cudaStream_t s);
+// encode_tc.cu
+int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
+int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s);
 // quantize.cu
 int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,

@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(QT)
 quantize_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
                 const int64_t *__restrict__ rows_out, float *__restrict__ xq_out,
                 double *__restrict__ sumsq_out, float *__restrict__ last_residual,
-                float *__restrict__ margin_out, float *__restrict__ dist_out, int dist_level) {
+                float *__restrict__ margin_out, float *__restrict__ dist_out, int dist_level,
+                float gate_gamma, float gate_floor) {
     extern __shared__ __align__(16) float smem[];
     constexpr int CH = CHUNK_FLOATS / E;    // codes per chunk
     float *s_cb = smem;                     // [CH][E]
@@ -113,6 +114,7 @@ quantize_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *_
         r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
     }
     float min_margin = __int_as_float(0x7f800000);
+    float gate_eps = 0.0f;      // bound on |z~ - z| for this row (tensor-core route only)
 
     const int L = (MODE == 1) ? 1 : qa.L;
     for (int l0 = 0; l0 < L; ++l0) {
@@ -127,6 +129,7 @@ quantize_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *_
                     make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]);
         }
         const float xx = sumsq_aten<E>(r);
+        if (MODE == 0 && l0 == 0) gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
         int best = 0;
         float bestd = 0.0f, second = __int_as_float(0x7f800000);
         for (int c0 = 0; c0 < K; c0 += CH) {
@@ -189,7 +192,15 @@ quantize_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *_
             int64_t orow = rows_out ? rows_out[row] : row;
             codes[orow * qa.L + l] = best;
         }
-        min_margin = fminf(min_margin, __fsub_rn(second, bestd));
+        {
+            // A code j can overtake `best` only if |c_j - c_best| <= 2*rho + 2*eps (rho = |r - c_best|), and then the
+            // error of (d_j - d_best) caused by |dr| <= eps is at most 2*eps*(2*rho + 2*eps); plus fp32 rounding of d.
+            const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
+            const float tau = 4.0f * gate_eps * (rho + gate_eps) + 1.0e-6f * (xx + fabsf(cc[best]));
+            const float mg = (second - bestd) - tau;
+            min_margin = (mg == mg) ? fminf(min_margin, mg) : mg;      // NaN sticks
+            if (min_margin != min_margin) min_margin = __int_as_float(0x7fc00000);
+        }
         // gather q, losses, straight-through residual update
         double lsum = 0.0;
         const float4 *q4 = reinterpret_cast<const float4 *>(cb + (int64_t)best * E);
@@ -254,7 +265,7 @@ int launch_quant(const rqb200_model *m, const float *z, int64_t n, int64_t *code
     unsigned grid = (unsigned)((n + QT - 1) / QT);
     rqb::count_launch();
     kern<<<grid, QT, smem, s>>>(z, n, make_args(m), codes, rows_out, xq, sumsq, last_residual, margin,
-                               dist, dist_level);
+                               dist, dist_level, m->gate_gamma, m->gate_floor);
     RQB_LAUNCH_CHECK();
     return 0;
 }

@@ -138,6 +138,6 @@ def kmeans_fit(samples: torch.Tensor, num_clusters: int, num_iters: int = 10, se
         info["inertia"] = float(packed[-1].item())
         shift = ops.update(centers, sums, counts)
         info["iters"] = it + 1
-        if float(shift.item()) <= tol * var:
+        if tol > 0 and float(shift.item()) <= tol * var:
             break
     return (centers, info) if return_info else centers

@@ -326,6 +326,21 @@ class RQVAE(nn.Module):
                 check(L.rqb200_model_set_codebook(self._handle, lvl, ptr(w.detach().float().contiguous())))
                 self._synced[("cb", lvl)] = sig
 
+    def set_gate(self, gamma: float, floor_abs: float = 1e-3):
+        """Margin-gate parameters of the tensor-core route (see rqb200_model_set_gate)."""
+        self._ensure_handle()
+        check(_cabi.lib().rqb200_model_set_gate(self._handle, float(gamma), float(floor_abs)))
+
+    @torch.no_grad()
+    def encode_tc(self, x: torch.Tensor) -> torch.Tensor:
+        """Encoder MLP on the tensor cores (fp32-class accuracy, not bit-exact) — diagnostic / building block."""
+        _require_cuda_tensor(x, "input")
+        self._sync()
+        x2 = x.reshape(-1, self.in_dim).contiguous()
+        y = torch.empty((x2.shape[0], self.e_dim), dtype=torch.float32, device=x.device)
+        check(_cabi.lib().rqb200_mlp_tc(self._handle, 0, ptr(x2), x2.shape[0], ptr(y), stream_ptr(x.device)))
+        return y
+
     # ---- building blocks -----------------------------------------------------------------
     @torch.no_grad()
     def _mlp(self, which: int, x: torch.Tensor) -> torch.Tensor:

@@ -74,6 +74,10 @@ int rqb200_model_set_linear(rqb200_model *m, int which, int layer, const float *
                             const int *kblocks, int nblk);
 /* Upload codebook `level` ([K[level], e_dim], nn.Embedding.weight, vq.py:21). */
 int rqb200_model_set_codebook(rqb200_model *m, int level, const float *E);
+/* Margin-gate parameters of RQB200_ENCODE_FAST: the tensor-core latent z~ is assumed to satisfy
+ * |z~ - z| <= gamma * (|z| + floor_abs) per row; rows whose top-2 distance gap could be closed by
+ * such an error are re-run by the exact kernels.  Defaults: gamma = 2^-15, floor_abs = 1e-3.       */
+int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_abs);
 /* Copy the current codebook of `level` back (host or device destination). */
 int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out);
 
@@ -82,6 +86,10 @@ int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out);
  * rows (device int64, may be NULL) gathers input rows x[rows[i]] for i < n.            */
 int rqb200_mlp_exact(rqb200_model *m, int which, const float *x_dev, const int64_t *rows_dev,
                      int64_t n, float *y_dev, void *stream);
+
+/* Same MLP on the tensor cores (tcgen05 split-fp16 GEMMs, fp32-class accuracy, NOT bit-exact):
+ * the building block of RQB200_ENCODE_FAST, exposed for tests and for the decoder (1e-4 tolerance). */
+int rqb200_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, void *stream);
 
 /* ---- residual quantizer, use_sk=False (rq.py:39-56, vq.py:63-99) --------------------
  * z[n,e] → codes[n,L] int64; optional x_q[n,e] (Σ of straight-through outputs, rq.py:48),

@@ -298,6 +298,6 @@ def kmeans_lloyd(x: np.ndarray, init: np.ndarray, iters: int, tol: float = 1e-4)
                 new[k] = x[m].astype(np.float64).mean(0).astype(np.float32)
         shift = float(((new.astype(np.float64) - c.astype(np.float64)) ** 2).sum())
         c = new
-        if shift <= tol * xv:
+        if tol > 0 and shift <= tol * xv:
             break
     return c

@@ -1,0 +1,61 @@
+"""GPU: the tcgen05 encoder and the margin-gated fast route give the same codes as the exact route."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_model, load_golden, synth_weights
+from ai_education_generative_recommendation_b200 import _cabi, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gpu_synth(seed, first, n, dim, n_total):
+    x = torch.empty((n, dim), dtype=torch.float32, device=DEV)
+    _cabi.check(_cabi.lib().rqb200_synth_items(seed, first, n, dim, n_total, x.data_ptr(), _cabi.stream_ptr()))
+    return x
+
+
+@pytest.mark.parametrize("name", ["c2_slice", "c3_slice", "c5_slice"])
+def test_tensor_core_encoder_is_fp32_class(name):
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n = 50_000 + 77                                   # ragged last tile
+    x = gpu_synth(2024, 0, n, cfg["in_dim"], int(g["n_total"]))
+    z = m.encoder(x)                                  # exact SIMT route (bit-equal to the reference)
+    zt = m.encode_tc(x)
+    err = (zt - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
+    assert torch.isfinite(zt).all()
+    assert float(err.max()) < 2.0 ** -17, float(err.max())     # tolerance: split-fp16 GEMM, ~22-bit operands
+
+
+@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice"])
+def test_fast_route_codes_equal_exact_route(name):
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n_gold = int(g["n_rows"])
+    xg = torch.from_numpy(synth.synth_items(int(g["seed"]), 0, n_gold, cfg["in_dim"], int(g["n_total"]))).to(DEV)
+    m.encode_mode = _cabi.ENCODE_FAST
+    got = m.get_indices(xg)
+    assert np.array_equal(got.cpu().numpy(), g["codes"].astype(np.int64))       # reference golden, bit-exact codes
+    n = 300_000
+    x = gpu_synth(2024, 0, n, cfg["in_dim"], int(g["n_total"]))
+    fast = m.get_indices(x)
+    rescued = m.last_stats["rescued_rows"]
+    m.encode_mode = _cabi.ENCODE_EXACT
+    exact = m.get_indices(x)
+    assert torch.equal(fast, exact)
+    if name != "c1_slice":                      # K=8 codebooks on 707-item clusters: many near-ties by construction
+        assert rescued <= 0.05 * n, rescued
+
+
+def test_fast_route_handles_overflowing_rows():
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    x = gpu_synth(2024, 0, 4096, 768, 1_000_000)
+    x[5] *= 1.0e6                                   # beyond fp16 range → must be rescued, not mis-coded
+    x[77, 3] = float("inf")
+    m.encode_mode = _cabi.ENCODE_FAST
+    fast = m.get_indices(x)
+    m.encode_mode = _cabi.ENCODE_EXACT
+    assert torch.equal(fast, m.get_indices(x))

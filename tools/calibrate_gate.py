@@ -1,0 +1,33 @@
+"""Measures the tensor-core encoder's error and the margin gate's behaviour on the GPU (diagnostic)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import build_model, load_golden          # noqa: E402
+from ai_education_generative_recommendation_b200 import _cabi   # noqa: E402
+
+DEV = "cuda:0"
+for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n = 1_000_000 if cfg["in_dim"] == 768 else 400_000
+    x = torch.empty((n, cfg["in_dim"]), dtype=torch.float32, device=DEV)
+    _cabi.check(_cabi.lib().rqb200_synth_items(2024, 0, n, cfg["in_dim"], int(g["n_total"]), x.data_ptr(), _cabi.stream_ptr()))
+    z = m.encoder(x)
+    zt = m.encode_tc(x)
+    rel = (zt - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
+    exact = m.get_indices(x)
+    out = {"config": name, "rows": n, "rel_err_max": float(rel.max()), "rel_err_mean": float(rel.mean()),
+           "rel_err_log2_max": float(torch.log2(rel.max()))}
+    m.encode_mode = _cabi.ENCODE_FAST
+    for gamma_log2 in (-30, -19, -17, -16, -15, -14):
+        m.set_gate(2.0 ** gamma_log2 if gamma_log2 > -30 else 0.0, 1e-3)
+        fast = m.get_indices(x)
+        out[f"gamma=2^{gamma_log2}"] = {"rescued": m.last_stats["rescued_rows"],
+                                        "mismatching_rows": int((fast != exact).any(1).sum())}
+    print(json.dumps(out))
