@@ -202,7 +202,9 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
     for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
         if (m->cb[l]) cudaFree(m->cb[l]);
         if (m->cc[l]) cudaFree(m->cc[l]);
+        if (m->cb_tc[l]) cudaFree(m->cb_tc[l]);
     }
+    if (m->cc_tc) cudaFree(m->cc_tc);
     Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1],
                        &m->rescue, &m->rescue_act[0], &m->rescue_act[1]};
     for (Workspace *w : ws)
@@ -253,6 +255,7 @@ extern "C" int rqb200_model_set_codebook(rqb200_model *m, int level, const float
     RQB_CUDA(cudaMemcpy(m->cb[level], E, sizeof(float) * (size_t)m->K[level] * m->e, cudaMemcpyDefault));
     RQB_TRY(codebook_norms(m->cb[level], m->K[level], m->e, m->cc[level], 0));
     RQB_CUDA(cudaStreamSynchronize(0));
+    if (m->cb_tc[level]) { cudaFree(m->cb_tc[level]); m->cb_tc[level] = nullptr; }     // stale tensor-core image
     m->cb_set[level] = true;
     return 0;
 }

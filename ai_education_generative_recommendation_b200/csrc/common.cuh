@@ -83,6 +83,10 @@ struct rqb200_model {
     float *cb[RQB200_MAX_LEVELS];   // [K, e]
     float *cc[RQB200_MAX_LEVELS];   // [K]  sum of squares in the reference's order
     bool cb_set[RQB200_MAX_LEVELS];
+    void *cb_tc[RQB200_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // packed fp16 hi/lo chunks
+    int cb_tc_scale_exp[RQB200_MAX_LEVELS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float *cc_tc = nullptr;         // padded code norms of all levels
+    int cc_tc_total = 0;
     rqb::Workspace act[2];          // ping-pong activations for the MLP
     rqb::Workspace sortws;          // radix sort scratch
     rqb::Workspace misc;            // rescue lists, counters
@@ -90,6 +94,7 @@ struct rqb200_model {
     rqb::Workspace rescue;          // exact latent of gated rows
     rqb::Workspace rescue_act[2];
     float gate_gamma = 3.0517578125e-05f;   // 2^-15: bound on |z~ - z| / |z| of the tensor-core encoder
+    bool force_simt_quantizer = false;      // diagnostics: keep the SIMT quantizer behind the tensor-core encoder
     float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -105,6 +110,10 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
 int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s);
+// quantize_tc.cu
+bool quantize_tc_supported(const rqb200_model *m);
+int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list, unsigned long long *count,
+                cudaStream_t s);
 // quantize.cu
 int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,

@@ -87,19 +87,21 @@ radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint3
     hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
 }
 
-// exclusive prefix sum over `count` uint32 values, single CTA (count is 256 * nblocks: small)
-__global__ void __launch_bounds__(1024) scan_u32_single_cta_kernel(uint32_t *__restrict__ data, int64_t count) {
-    __shared__ uint32_t s_warp[32];
+// per-digit exclusive scan over blocks (one CTA per digit) + digit totals; then a 256-wide scan of the totals
+__global__ void __launch_bounds__(256) radix_scan_rows_kernel(uint32_t *__restrict__ hist, int nblocks,
+                                                              uint32_t *__restrict__ digit_total) {
+    __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_carry;
+    uint32_t *row = hist + (int64_t)blockIdx.x * nblocks;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int64_t base = 0; base < count; base += 1024 * 4) {
-        int64_t i0 = base + (int64_t)threadIdx.x * 4;
+    for (int base = 0; base < nblocks; base += 256 * 4) {
+        const int i0 = base + threadIdx.x * 4;
         uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < count) ? data[i0 + j] : 0u;
-        uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nblocks) ? row[i0 + j] : 0u;
+        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
         uint32_t inc = tsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -108,27 +110,37 @@ __global__ void __launch_bounds__(1024) scan_u32_single_cta_kernel(uint32_t *__r
         }
         if (lane == 31) s_warp[wid] = inc;
         __syncthreads();
-        if (wid == 0) {
-            uint32_t w = s_warp[lane];
-            uint32_t winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            s_warp[lane] = winc - w;   // exclusive per-warp offset
-        }
-        __syncthreads();
-        uint32_t excl = s_carry + s_warp[wid] + inc - tsum;
+        uint32_t woff = 0;
+        for (int w = 0; w < wid; ++w) woff += s_warp[w];
+        uint32_t excl = s_carry + woff + inc - tsum;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (i0 + j < count) data[i0 + j] = excl;
+            if (i0 + j < nblocks) row[i0 + j] = excl;
             excl += v[j];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl;
+        if (threadIdx.x == 255) s_carry = excl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) radix_scan_digits_kernel(const uint32_t *__restrict__ digit_total,
+                                                                uint32_t *__restrict__ digit_base) {
+    __shared__ uint32_t s_warp[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t v = digit_total[threadIdx.x];
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    digit_base[threadIdx.x] = woff + inc - v;
 }
 
 // stable scatter: warp w owns keys [base + w*WARP_CHUNK, +WARP_CHUNK) in rounds of 32 lanes, so the
@@ -136,7 +148,8 @@ __global__ void __launch_bounds__(1024) scan_u32_single_cta_kernel(uint32_t *__r
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                     int shift, const uint32_t *__restrict__ hist, int nblocks) {
+                     int shift, const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_base,
+                     int nblocks) {
     __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
@@ -160,7 +173,7 @@ radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__res
     __syncthreads();
     // phase B: thread d turns counts into start offsets per warp
     {
-        uint32_t run = hist[(int64_t)tid * nblocks + blockIdx.x];
+        uint32_t run = digit_base[tid] + hist[(int64_t)tid * nblocks + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
             uint32_t c = s_cnt[w][tid];
@@ -473,7 +486,7 @@ int carve(rqb200_model *m, int64_t n, SortScratch &sc) {
     size_t o_k1 = need; need += align256(sizeof(uint64_t) * n);
     size_t o_v0 = need; need += align256(sizeof(uint32_t) * n);
     size_t o_v1 = need; need += align256(sizeof(uint32_t) * n);
-    size_t o_h = need; need += align256(sizeof(uint32_t) * (size_t)RADIX * nblocks);
+    size_t o_h = need; need += align256(sizeof(uint32_t) * ((size_t)RADIX * nblocks + 2 * RADIX));
     size_t o_tl = need; need += align256(sizeof(long long) * (ntiles + 2));
     size_t o_c = need; need += align256(sizeof(long long) * (ntiles + 2));
     size_t o_f = need; need += align256(sizeof(uint64_t) * n);
@@ -497,11 +510,15 @@ int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *re
     for (int shift = 0; shift < key_bits; shift += 8) {
         rqb::count_launch();
         radix_hist_kernel<<<sc.nblocks, SORT_THREADS, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sc.nblocks);
+        uint32_t *digit_total = sc.hist + (size_t)RADIX * sc.nblocks;
+        uint32_t *digit_base = digit_total + RADIX;
         rqb::count_launch();
-        scan_u32_single_cta_kernel<<<1, 1024, 0, s>>>(sc.hist, (int64_t)RADIX * sc.nblocks);
+        radix_scan_rows_kernel<<<RADIX, 256, 0, s>>>(sc.hist, sc.nblocks, digit_total);
+        rqb::count_launch();
+        radix_scan_digits_kernel<<<1, 256, 0, s>>>(digit_total, digit_base);
         rqb::count_launch();
         radix_scatter_kernel<<<sc.nblocks, SORT_THREADS, 0, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1],
-                                                               sc.vals[cur ^ 1], n, shift, sc.hist, sc.nblocks);
+                                                               sc.vals[cur ^ 1], n, shift, sc.hist, digit_base, sc.nblocks);
         cur ^= 1;
     }
     RQB_LAUNCH_CHECK();

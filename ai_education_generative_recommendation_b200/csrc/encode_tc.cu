@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace rqb {
 
@@ -33,97 +34,6 @@ constexpr int TC_THREADS = 448;
 constexpr int EPI_WARPS = 4, CONV_WARPS = 8;
 constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int A_TILE_BYTES = TM * BK * 2;          // 16 KB (one of hi / lo)
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (dense tile)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
-
-// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t umma_idesc(int n) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// fp32 pair → packed fp16 hi and fp16 lo (x ≈ hi + lo, |x - hi - lo| ≲ 2^-22 |x|)
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t *>(&h);
-    lo = *reinterpret_cast<uint32_t *>(&l);
-}
 
 template <int N>
 struct TcCfg {
@@ -211,64 +121,64 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
     } else if (warp < EPI_WARPS + CONV_WARPS) {
         // ===================== A producers =====================
         const int ct = threadIdx.x - EPI_WARPS * 32;        // 0..255
-        // unit u = ct + 256*i (i<4): row = u / 8, c8 = u % 8  → 8 consecutive floats of one row
-        const int c8 = ct & 7;
-        const int rbase = ct >> 3;                           // 0..31, rows rbase + 32*i
-        float4 cur[8], nxt[8];
+        // unit u = ct + 256*i (i<8): row = u / 16, c4 = u % 16 → one float4 (4 consecutive k) of one row.
+        // A half-warp covers 256 contiguous bytes of one row (full 32-byte sectors per LDG.128) and stores
+        // 128 contiguous (swizzled) bytes of fp16 — conflict-free STS.64.
+        const int c4 = ct & 15;
+        const int rbase = ct >> 4;                           // 0..15, rows rbase + 16*i
         auto load_slab = [&](int64_t tile, int slab, float4 (&dst)[8]) {
-            const int k0 = slab * BK + c8 * 8;
+            const int k0 = slab * BK + c4 * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int64_t row = tile * TM + rbase + 32 * i;
-                if (row < n && k0 < K) {
-                    const float4 *p = reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0);
-                    dst[2 * i] = __ldg(p);
-                    dst[2 * i + 1] = __ldg(p + 1);
-                } else {
-                    dst[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    dst[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = tile * TM + rbase + 16 * i;
+                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
+                else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         int stage = 0;
         uint32_t phase = 0;
-        int64_t tile = blockIdx.x;
-        int slab = 0;
-        if (tile < ntiles) load_slab(tile, 0, cur);
-        while (tile < ntiles) {
-            // next (tile, slab)
-            int64_t ntile = tile;
-            int nslab = slab + 1;
-            if (nslab == KS) { nslab = 0; ntile += gridDim.x; }
-            if (ntile < ntiles) load_slab(ntile, nslab, nxt);
+        auto convert_slab = [&](const float4 (&src)[8]) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char *a_hi = smem + stage * Cfg::STAGE_BYTES;
             unsigned char *a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = rbase + 32 * i;
-                uint4 hi, lo;
-                split2(cur[2 * i].x, cur[2 * i].y, hi.x, lo.x);
-                split2(cur[2 * i].z, cur[2 * i].w, hi.y, lo.y);
-                split2(cur[2 * i + 1].x, cur[2 * i + 1].y, hi.z, lo.z);
-                split2(cur[2 * i + 1].z, cur[2 * i + 1].w, hi.w, lo.w);
-                const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                uint2 hi, lo;
+                split2(src[i].x, src[i].y, hi.x, lo.x);
+                split2(src[i].z, src[i].w, hi.y, lo.y);
+                const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
+                *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint2 *>(a_lo + off) = lo;
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_a[stage]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
-            tile = ntile;
-            slab = nslab;
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        };
+        // flattened (tile, slab) sequence, two register buffers used alternately: the loads of step i+1 are in
+        // flight while step i is converted, and no register copies force an early wait on them.
+        const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t steps = my_tiles * KS;
+        float4 bufA[8], bufB[8];
+        auto coords = [&](int64_t st, int64_t &tile, int &slab) {
+            tile = blockIdx.x + (st / KS) * (int64_t)gridDim.x;
+            slab = (int)(st % KS);
+        };
+        int64_t t0; int s0;
+        if (steps > 0) { coords(0, t0, s0); load_slab(t0, s0, bufA); }
+        for (int64_t st = 0; st < steps; st += 2) {
+            if (st + 1 < steps) { coords(st + 1, t0, s0); load_slab(t0, s0, bufB); }
+            convert_slab(bufA);
+            if (st + 1 < steps) {
+                if (st + 2 < steps) { coords(st + 2, t0, s0); load_slab(t0, s0, bufA); }
+                convert_slab(bufB);
+            }
         }
     } else if (warp == 12) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(N);
+            constexpr uint32_t idesc = umma_idesc(TM, N);
             int stage = 0;
             uint32_t phase = 0;
             int64_t it = 0;
@@ -491,11 +401,15 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
         ProfScope ps(PROF_TC_ENCODER, s);
         RQB_TRY(mlp_tc(m, 0, x, n, z, s));
     }
-    RQB_TRY(quantize_exact(m, z, n, codes, nullptr, nullptr, nullptr, nullptr, margin, s));   // margin - threshold
     RQB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), s));
-    count_launch();
-    gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(margin, n, list, count);
-    RQB_LAUNCH_CHECK();
+    if (quantize_tc_supported(m) && !m->force_simt_quantizer) {
+        RQB_TRY(quantize_tc(m, z, n, codes, list, count, s));          // distances on the tensor cores, gate fused
+    } else {
+        RQB_TRY(quantize_exact(m, z, n, codes, nullptr, nullptr, nullptr, nullptr, margin, s));   // margin - threshold
+        count_launch();
+        gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(margin, n, list, count);
+        RQB_LAUNCH_CHECK();
+    }
     unsigned long long h = 0;
     RQB_CUDA(cudaMemcpyAsync(&h, count, sizeof(h), cudaMemcpyDeviceToHost, s));
     RQB_CUDA(cudaStreamSynchronize(s));

@@ -1,0 +1,397 @@
+// quantize_tc.cu — residual quantizer on the tensor cores, with the margin gate fused in.
+//
+// Fast-route twin of quantize.cu for `ResidualVectorQuantizer.forward(use_sk=False)` (reference
+// RQ-VAE/models/rq.py:39-56, RQ-VAE/models/vq.py:63-99): per level the codebook-distance contraction
+// r·Cᵀ (vq.py:73) runs as split-fp16 tcgen05 MMAs (codebook chunk staged in shared memory by
+// cp.async.bulk, residual tile written by the row warps), the accumulator is read back from TMEM and
+// reduced to the top-2 distances per row, the chosen code is gathered and the residual is updated in
+// registers (vq.py:95, rq.py:47) — the residual never leaves the SM between levels.
+//
+// Results here are APPROXIMATE by construction (the input z~ comes from the tensor-core encoder), so
+// the kernel also decides which rows can be trusted: a row is appended to the rescue list when, at any
+// level, the gap between its two smallest distances is within the error bound of the approximate
+// arithmetic (see the derivation at `tau` below).  Rows on the list are recomputed by the exact
+// kernels; all other rows provably have the reference's codes.
+//
+// CTA = 320 threads: warps 0-3 and 4-7 are two independent "row groups" (one 128-row tile each, thread
+// = row), warp 8 issues the MMAs for both groups, warp 9 streams codebook chunks.  While one group is
+// in its top-2 epilogue the tensor core works for the other.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rqb {
+
+namespace {
+
+constexpr int QTM = 128;                   // rows per group tile
+constexpr int QCH = 256;                   // codes per MMA (UMMA N)
+constexpr int QTC_THREADS = 320;
+constexpr int Q_STAGES = 2;
+constexpr int Q_A_BYTES = QTM * 128;       // one of hi / lo, one 64-wide K slab
+constexpr int Q_CB_TILE = QCH * 128;       // one of hi / lo
+constexpr int Q_STAGE_BYTES = 2 * Q_CB_TILE;               // hi | lo
+constexpr int Q_CC_MAX = 6144;                             // padded code norms of all levels, resident in smem
+constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + Q_CC_MAX * 4 + 1024 + 256;
+
+struct QtcArgs {
+    const unsigned char *cbp[RQB200_MAX_LEVELS];   // packed chunks: [hi tile | lo tile]
+    const float *ccp;                              // code norms, padded per level to 256-code chunks with +inf
+    int cc_total;
+    const float *cb[RQB200_MAX_LEVELS];            // fp32 codebooks for the gather
+    const float *cc[RQB200_MAX_LEVELS];
+    int K[RQB200_MAX_LEVELS];
+    float inv_scale[RQB200_MAX_LEVELS];
+    int L;
+};
+
+template <int E>
+__device__ __forceinline__ float sumsq_plain(const float (&v)[E]) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {
+        s0 = fmaf(v[k], v[k], s0); s1 = fmaf(v[k + 1], v[k + 1], s1);
+        s2 = fmaf(v[k + 2], v[k + 2], s2); s3 = fmaf(v[k + 3], v[k + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
+template <int E>
+__global__ void __launch_bounds__(QTC_THREADS, 1)
+quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *__restrict__ codes,
+                   int64_t *__restrict__ list, unsigned long long *__restrict__ list_count, float gate_gamma,
+                   float gate_floor) {
+    static_assert(E % 8 == 0 && E <= 64, "tensor-core quantizer supports e_dim <= 64");
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *a_base = smem;                                     // [group][hi|lo] 16 KB each
+    unsigned char *cb_base = smem + 4 * Q_A_BYTES;                    // [stage] hi | lo | cc
+    float *s_ccall = reinterpret_cast<float *>(cb_base + Q_STAGES * Q_STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_ccall + Q_CC_MAX);
+    uint64_t *a_full = bars;            // [2]  row warps → MMA   (count 4)
+    uint64_t *d_full = bars + 2;        // [2]  MMA → row warps   (count 1, tcgen05.commit)
+    uint64_t *d_empty = bars + 4;       // [2]  row warps → MMA   (count 128)
+    uint64_t *cb_full = bars + 6;       // [Q_STAGES] loader → MMA (tx)
+    uint64_t *cb_empty = bars + 8;      // [Q_STAGES] MMA → loader (commit)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (n + QTM - 1) / QTM;
+
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < 2; ++g) { mbar_init(&a_full[g], 4); mbar_init(&d_full[g], 1); mbar_init(&d_empty[g], 128); }
+        for (int s = 0; s < Q_STAGES; ++s) { mbar_init(&cb_full[s], 1); mbar_init(&cb_empty[s], 1); }
+        fence_barrier_init();
+    }
+    // zero the A tiles once: columns >= E of the 64-wide K slab stay zero for the whole kernel
+    for (int i = threadIdx.x; i < 4 * Q_A_BYTES / 16; i += QTC_THREADS) reinterpret_cast<uint4 *>(a_base)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < qa.cc_total; i += QTC_THREADS) s_ccall[i] = qa.ccp[i];
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== row groups =====================
+        const int g = warp >> 2;
+        const int rloc = (warp & 3) * 32 + lane;
+        unsigned char *a_hi = a_base + g * 2 * Q_A_BYTES;
+        unsigned char *a_lo = a_hi + Q_A_BYTES;
+        const uint32_t t_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * QCH);
+        uint32_t round = 0;                       // MMA rounds consumed by this group so far
+        uint32_t cb_round = 0;                    // chunks consumed so far (all groups see the same sequence)
+        for (int64_t pair = blockIdx.x;; pair += gridDim.x) {
+            const int64_t tile = pair * 2 + g;
+            if (pair * 2 >= ntiles) break;
+            const bool active = tile < ntiles;
+            // chunk bookkeeping must advance identically in both groups even if this one is idle
+            int nchunks_total = 0;
+            for (int l = 0; l < qa.L; ++l) nchunks_total += (qa.K[l] + QCH - 1) / QCH;
+            if (!active) { cb_round += nchunks_total; continue; }
+            const int64_t row = tile * QTM + rloc;
+            const bool live = row < n;
+            float r[E];
+#pragma unroll
+            for (int k = 0; k < E; k += 4) {
+                float4 v = live ? *reinterpret_cast<const float4 *>(z + row * E + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+            }
+            float min_margin = __int_as_float(0x7f800000);
+            float gate_eps = 0.0f;
+            for (int l = 0; l < qa.L; ++l) {
+                const float xx = sumsq_plain<E>(r);
+                if (l == 0) gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
+                // residual tile → split fp16, UMMA K-major SWIZZLE_128B (row = 128 B, chunk c of 8 halves)
+#pragma unroll
+                for (int c = 0; c < E / 8; ++c) {
+                    uint4 hi, lo;
+                    split2(r[8 * c], r[8 * c + 1], hi.x, lo.x);
+                    split2(r[8 * c + 2], r[8 * c + 3], hi.y, lo.y);
+                    split2(r[8 * c + 4], r[8 * c + 5], hi.z, lo.z);
+                    split2(r[8 * c + 6], r[8 * c + 7], hi.w, lo.w);
+                    const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
+                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[g]);
+                const float m2s = -2.0f * qa.inv_scale[l];
+                float bestd = __int_as_float(0x7f800000), second = __int_as_float(0x7f800000);
+                int best = 0;
+                const int K = qa.K[l];
+                int cc_off = 0;
+                for (int ll = 0; ll < l; ++ll) cc_off += ((qa.K[ll] + QCH - 1) / QCH) * QCH;
+                for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
+                    const int ncols = min(QCH, ((K - c0) + 31) & ~31);
+                    const float *s_cc = s_ccall + cc_off + c0;
+                    mbar_wait(&d_full[g], round & 1);
+                    ++round;
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int cc0 = 0; cc0 < ncols; cc0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + (uint32_t)cc0, v);
+#pragma unroll
+                        for (int t = 0; t < 32; ++t) {
+                            const float d = fmaf(__uint_as_float(v[t]), m2s, xx + s_cc[cc0 + t]);     // +inf on padded codes
+                            second = fminf(second, fmaxf(d, bestd));
+                            if (d < bestd) { bestd = d; best = c0 + cc0 + t; }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&d_empty[g]);
+                }
+                if (live) codes[row * qa.L + l] = best;
+                {
+                    // Let eps bound |r~ - r| (tensor-core encoder) and rho = |r - c_best|.  A code j can overtake `best`
+                    // only if |c_j - c_best| <= 2 rho + 2 eps, and then (d_j - d_best) moves by at most
+                    // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM
+                    // and of the reference's own fp32 evaluation of d.
+                    const float ccb = __ldg(qa.cc[l] + best);
+                    const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
+                    const float tau = 4.0f * gate_eps * (rho + gate_eps) + 4.0e-6f * (xx + fabsf(ccb));
+                    const float mg = (second - bestd) - tau;
+                    min_margin = (mg == mg && min_margin == min_margin) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
+                }
+                // gather + straight-through residual update, same operations as vq.py:95 / rq.py:47
+                const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
+#pragma unroll
+                for (int k = 0; k < E; k += 4) {
+                    const float4 q = __ldg(q4 + k / 4);
+                    const float qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float xres = __fadd_rn(r[k + t], __fsub_rn(qv[t], r[k + t]));
+                        r[k + t] = __fsub_rn(r[k + t], xres);
+                    }
+                }
+            }
+            // rows that cannot be certified → rescue list (warp-aggregated append)
+            const bool flag = live && !(min_margin > 0.0f);
+            const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+            if (ballot) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(list_count, (unsigned long long)__popc(ballot));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = row;
+            }
+        }
+    } else if (warp == 8) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t a_round[2] = {0, 0}, d_round[2] = {0, 0};
+            uint32_t cb_round = 0;
+            for (int64_t pair = blockIdx.x; pair * 2 < ntiles; pair += gridDim.x) {
+                const bool act[2] = {true, pair * 2 + 1 < ntiles};
+                for (int l = 0; l < qa.L; ++l) {
+                    const int K = qa.K[l];
+                    for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
+                        const int ncols = min(QCH, ((K - c0) + 31) & ~31);
+                        const int st = cb_round % Q_STAGES;
+                        mbar_wait(&cb_full[st], (cb_round / Q_STAGES) & 1);
+                        const uint32_t w_hi = smem_u32(cb_base + st * Q_STAGE_BYTES);
+                        const uint32_t w_lo = w_hi + Q_CB_TILE;
+                        const uint32_t idesc = umma_idesc(QTM, ncols);
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if (!act[g]) continue;
+                            if (c0 == 0) { mbar_wait(&a_full[g], a_round[g] & 1); ++a_round[g]; }
+                            mbar_wait(&d_empty[g], (d_round[g] & 1) ^ 1);
+                            ++d_round[g];
+                            tc_fence_after();
+                            const uint32_t a_hi = smem_u32(a_base + g * 2 * Q_A_BYTES);
+                            const uint32_t a_lo = a_hi + Q_A_BYTES;
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(g * QCH);
+#pragma unroll
+                            for (int kk = 0; kk < (E + 15) / 16; ++kk) {
+                                const uint32_t ko = kk * 32;
+                                umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, kk != 0);
+                                umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
+                                umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                            }
+                            umma_commit(&d_full[g]);
+                        }
+                        umma_commit(&cb_empty[st]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== codebook loader =====================
+        if (lane == 0) {
+            uint32_t cb_round = 0;
+            for (int64_t pair = blockIdx.x; pair * 2 < ntiles; pair += gridDim.x) {
+                for (int l = 0; l < qa.L; ++l) {
+                    const int K = qa.K[l];
+                    int chunk = 0;
+                    for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round, ++chunk) {
+                        const int st = cb_round % Q_STAGES;
+                        mbar_wait(&cb_empty[st], ((cb_round / Q_STAGES) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&cb_full[st], (uint32_t)Q_STAGE_BYTES);
+                        bulk_g2s(cb_base + st * Q_STAGE_BYTES, qa.cbp[l] + (size_t)chunk * Q_STAGE_BYTES, (uint32_t)Q_STAGE_BYTES,
+                                 &cb_full[st]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
+// codebook [K,e] fp32 → per 256-code chunk: hi tile | lo tile (SW128 K-major, K padded to 64, codes padded with
+// zeros); code norms go to ccp (+inf on padded codes)
+__global__ void pack_codebook_kernel(const float *__restrict__ cb, const float *__restrict__ cc, int K, int e, float scale,
+                                     unsigned char *__restrict__ out, float *__restrict__ ccp) {
+    const int nchunks = (K + QCH - 1) / QCH;
+    const int64_t total = (int64_t)nchunks * QCH * 8;       // 16-byte units per (hi or lo)
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(u & 7);
+        const int rowc = (int)((u >> 3) % QCH);
+        const int chunk = (int)(u / (8 * QCH));
+        const int code = chunk * QCH + rowc;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = c8 * 8 + 2 * t;
+            const float a = (code < K && k < e) ? cb[(int64_t)code * e + k] * scale : 0.0f;
+            const float b = (code < K && k + 1 < e) ? cb[(int64_t)code * e + k + 1] * scale : 0.0f;
+            split2(a, b, hi[t], lo[t]);
+        }
+        unsigned char *base = out + (size_t)chunk * Q_STAGE_BYTES;
+        const size_t off = (size_t)(rowc >> 3) * 1024 + (rowc & 7) * 128 + ((c8 ^ (rowc & 7)) << 4);
+        *reinterpret_cast<uint4 *>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(base + Q_CB_TILE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (c8 == 0) ccp[chunk * QCH + rowc] = code < K ? cc[code] : __int_as_float(0x7f800000);
+    }
+}
+
+__global__ void absmax2_kernel(const float *__restrict__ w, int64_t count, float *__restrict__ out) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));
+}
+
+}  // namespace
+
+// (re)build the packed fp16 images of all codebooks
+int quantize_tc_prepare(rqb200_model *m, cudaStream_t s) {
+    int total = 0, off[RQB200_MAX_LEVELS];
+    for (int l = 0; l < m->L; ++l) { off[l] = total; total += ((m->K[l] + QCH - 1) / QCH) * QCH; }
+    RQB_CHECK(total <= Q_CC_MAX, "tensor-core quantizer: too many codes in total (%d > %d)", total, Q_CC_MAX);
+    if (!m->cc_tc) RQB_CUDA(cudaMalloc(&m->cc_tc, sizeof(float) * Q_CC_MAX));
+    m->cc_tc_total = total;
+    for (int l = 0; l < m->L; ++l) {
+        if (m->cb_tc[l]) continue;
+        const int nchunks = (m->K[l] + QCH - 1) / QCH;
+        float *dmax = nullptr;
+        RQB_CUDA(cudaMalloc(&dmax, sizeof(float)));
+        RQB_CUDA(cudaMemsetAsync(dmax, 0, sizeof(float), s));
+        count_launch();
+        absmax2_kernel<<<32, 256, 0, s>>>(m->cb[l], (int64_t)m->K[l] * m->e, dmax);
+        float hmax = 0.0f;
+        RQB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(float), cudaMemcpyDeviceToHost, s));
+        RQB_CUDA(cudaStreamSynchronize(s));
+        RQB_CUDA(cudaFree(dmax));
+        RQB_CHECK(hmax == hmax && hmax < 3.0e38f, "non-finite codebook entry");
+        int ex = 0;
+        if (hmax > 0.0f) { frexpf(hmax, &ex); ex = 14 - ex; }
+        if (ex > 40) ex = 40;
+        if (ex < -20) ex = -20;
+        m->cb_tc_scale_exp[l] = ex;
+        void *p = nullptr;
+        RQB_CUDA(cudaMalloc(&p, (size_t)nchunks * Q_STAGE_BYTES));
+        count_launch();
+        pack_codebook_kernel<<<64, 256, 0, s>>>(m->cb[l], m->cc[l], m->K[l], m->e, ldexpf(1.0f, ex), (unsigned char *)p,
+                                                m->cc_tc + off[l]);
+        RQB_LAUNCH_CHECK();
+        m->cb_tc[l] = p;
+    }
+    return 0;
+}
+
+bool quantize_tc_supported(const rqb200_model *m) {
+    int total = 0;
+    for (int l = 0; l < m->L; ++l) total += ((m->K[l] + QCH - 1) / QCH) * QCH;
+    return (m->e == 32 || m->e == 64 || m->e == 16 || m->e == 48) && total <= Q_CC_MAX;
+}
+
+template <int E>
+static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list,
+                      unsigned long long *count, cudaStream_t s) {
+    auto kern = quantize_tc_kernel<E>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
+        attr_done = true;
+    }
+    QtcArgs qa;
+    qa.L = m->L;
+    qa.ccp = m->cc_tc;
+    qa.cc_total = m->cc_tc_total;
+    for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
+        const bool on = l < m->L;
+        qa.cbp[l] = on ? (const unsigned char *)m->cb_tc[l] : nullptr;
+        qa.cb[l] = on ? m->cb[l] : nullptr;
+        qa.cc[l] = on ? m->cc[l] : nullptr;
+        qa.K[l] = on ? m->K[l] : 0;
+        qa.inv_scale[l] = on ? ldexpf(1.0f, -m->cb_tc_scale_exp[l]) : 0.0f;
+    }
+    const int64_t npairs = ((n + QTM - 1) / QTM + 1) / 2;
+    const unsigned grid = (unsigned)(npairs < kNumSMs ? npairs : kNumSMs);
+    count_launch();
+    kern<<<grid, QTC_THREADS, Q_SMEM, s>>>(z, n, qa, codes, list, count, m->gate_gamma, m->gate_floor);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+// z~[n,e] → codes[n,L] (approximate route) + list of rows that need the exact route
+int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list, unsigned long long *count,
+                cudaStream_t s) {
+    if (n == 0) return 0;
+    RQB_TRY(quantize_tc_prepare(m, s));
+    ProfScope ps(PROF_QUANTIZE, s);
+    switch (m->e) {
+        case 16: return launch_qtc<16>(m, z, n, codes, list, count, s);
+        case 32: return launch_qtc<32>(m, z, n, codes, list, count, s);
+        case 48: return launch_qtc<48>(m, z, n, codes, list, count, s);
+        case 64: return launch_qtc<64>(m, z, n, codes, list, count, s);
+    }
+    set_error("tensor-core quantizer: e_dim %d not supported", m->e);
+    return RQB200_EINVAL;
+}
+
+}  // namespace rqb

@@ -26,7 +26,8 @@ def test_tensor_core_encoder_is_fp32_class(name):
     zt = m.encode_tc(x)
     err = (zt - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
     assert torch.isfinite(zt).all()
-    assert float(err.max()) < 2.0 ** -17, float(err.max())     # tolerance: split-fp16 GEMM, ~22-bit operands
+    # tolerance: split-fp16 GEMM with truncating fp32 accumulation; must stay well inside the gate's 2^-15 bound
+    assert float(err.max()) < 2.0 ** -16, float(err.max())
 
 
 @pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice"])
