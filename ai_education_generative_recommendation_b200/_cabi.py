@@ -32,6 +32,8 @@ _PROTOS = {
     "rqb200_device_count": (c_int, []),
     "rqb200_launch_count": (ctypes.c_longlong, []),
     "rqb200_profile_enable": (c_int, [c_int]),
+    "rqb200_debug_tc_trace": (c_int, [_P]),
+    "rqb200_debug_tc_flags": (c_int, [c_int]),
     "rqb200_profile_read": (c_int, [POINTER(c_double), POINTER(ctypes.c_longlong), c_int]),
     "rqb200_model_create": (c_int, [POINTER(c_void_p), c_int, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     "rqb200_model_destroy": (None, [c_void_p]),

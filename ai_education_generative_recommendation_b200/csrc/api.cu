@@ -268,6 +268,11 @@ extern "C" int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_a
     return 0;
 }
 
+namespace rqb { int tc_set_trace(long long *buf); int tc_set_debug(int flags); }
+extern "C" int rqb200_debug_tc_flags(int flags) { return rqb::tc_set_debug(flags); }
+// diagnostics: device buffer of 8*256 int64 that CTA 0 of the tensor-core linear kernel fills with clock64() stamps
+extern "C" int rqb200_debug_tc_trace(long long *buf_dev) { return rqb::tc_set_trace(buf_dev); }
+
 extern "C" int rqb200_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, void *stream) {
     RQB_CHECK(m != nullptr, "model is NULL");
     RQB_CHECK(which == 0 || which == 1, "which must be 0 or 1");

@@ -35,6 +35,10 @@ constexpr int EPI_WARPS = 4, CONV_WARPS = 8;
 constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int A_TILE_BYTES = TM * BK * 2;          // 16 KB (one of hi / lo)
 
+// ---- ablation switches for tools/ablate_tc.py (0 in production): bit0 no epilogue stores, bit1 no MMA,
+// bit2 no producer smem stores, bit3 no W bulk loads, bit4 no producer global loads
+__device__ int g_tc_debug = 0;
+
 template <int N>
 struct TcCfg {
     static constexpr int W_TILE_BYTES = N * BK * 2;                    // one of hi / lo
@@ -63,6 +67,7 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dbg = g_tc_debug;
     const int KS = (K + BK - 1) / BK;
     const int64_t ntiles = (n + TM - 1) / TM;
 
@@ -101,7 +106,7 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
             for (int c = 0; c < N; c += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N + c), v);
-                if (row < n) {
+                if (row < n && !(dbg & 1)) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float o[4];
@@ -131,7 +136,7 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int64_t row = tile * TM + rbase + 16 * i;
-                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
+                if (row < n && k0 < K && !(dbg & 16)) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
                 else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -148,8 +153,10 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
                 split2(src[i].x, src[i].y, hi.x, lo.x);
                 split2(src[i].z, src[i].w, hi.y, lo.y);
                 const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
-                *reinterpret_cast<uint2 *>(a_hi + off) = hi;
-                *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                if (!(dbg & 4)) {
+                    *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                    *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -195,6 +202,7 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
                     const uint32_t a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
                     const uint32_t w_lo = w_hi + Cfg::W_TILE_BYTES;
+                    if (!(dbg & 2))
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint32_t ko = kk * 32;       // 16 fp16 = 32 bytes along K inside the swizzle row
@@ -218,9 +226,13 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_w[stage], slab_bytes);
-                    bulk_g2s(smem + stage * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES, Wp + (size_t)slab * slab_bytes, slab_bytes,
-                             &full_w[stage]);
+                    if (dbg & 8) {
+                        mbar_arrive(&full_w[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_w[stage], slab_bytes);
+                        bulk_g2s(smem + stage * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES, Wp + (size_t)slab * slab_bytes, slab_bytes,
+                                 &full_w[stage]);
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -334,6 +346,17 @@ __global__ void gate_kernel(const float *__restrict__ margin, int64_t n, int64_t
 }
 
 }  // namespace
+
+int tc_set_debug(int flags) {
+    RQB_CUDA(cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(flags)));
+    return 0;
+}
+
+int tc_set_trace(long long *buf) {
+    (void)buf;
+    set_error("timeline trace is not compiled into this build");
+    return RQB200_EINVAL;
+}
 
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s) {
     if (n == 0) return 0;

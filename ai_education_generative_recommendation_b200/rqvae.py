@@ -107,7 +107,7 @@ def kmeans(samples, num_clusters, num_iters=10, seed: Optional[int] = None, init
     ``group``: optional torch.distributed process group — samples are then one shard per rank and the
     per-cluster sums / counts are all-reduced every iteration (NCCL over NVLink).
     Parity with scikit-learn is statistical only (its seeding consumes numpy's global RNG)."""
-    from .kmeans import kmeans_fit
+    from .kmeans_gpu import kmeans_fit
     return kmeans_fit(samples, num_clusters, num_iters, seed=seed, init=init, group=group, tol=tol)
 
 

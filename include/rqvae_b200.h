@@ -57,6 +57,11 @@ int         rqb200_device_count(void);
 long long rqb200_launch_count(void);
 int rqb200_profile_enable(int on);
 int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
+/* Diagnostics: CTA 0 of the tensor-core linear kernel records clock64() at pipeline events into
+ * buf_dev[8][256] (NULL switches the trace off).  Used by tools/trace_tc.py.                      */
+int rqb200_debug_tc_trace(long long *buf_dev);
+/* Diagnostics: ablation switches of the tensor-core linear kernel (tools/ablate_tc.py); 0 = production. */
+int rqb200_debug_tc_flags(int flags);
 
 /* ---- model lifetime ---------------------------------------------------------------
  * Replaces the module tree RQVAE.__init__ builds (rqvae.py:45-58): an encoder MLP
