@@ -1,0 +1,132 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (global suffix dedup exchange, sharded k-means
+statistics all-reduce).  The per-rank kernels are replaced by oracle-backed numpy twins — only here, in tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ai_education_generative_recommendation_b200 import sharding
+from ai_education_generative_recommendation_b200.kmeans_gpu import kmeans_fit
+
+
+class NumpyShardOps:
+    def pack_keys(self, codes, num_emb_list):
+        bits = sharding.key_bits(num_emb_list)
+        keys = torch.zeros(codes.shape[0], dtype=torch.int64)
+        shift = 0
+        for l in range(len(num_emb_list) - 1, -1, -1):
+            keys |= codes[:, l] << shift
+            shift += bits[l]
+        return keys
+
+    def rank_among_equal(self, keys, bits):
+        from oracle import oracle as O
+        if keys.numel() == 0:
+            return torch.zeros(0, dtype=torch.int64)
+        return torch.from_numpy(O.suffix_dedup(keys.numpy()[:, None])[:, 1].copy())
+
+
+class NumpyKMeansOps:
+    def assign(self, x, centers):
+        d = ((x[:, None, :].double() - centers[None].double()) ** 2).sum(-1)
+        return d.argmin(1)
+
+    def accumulate(self, x, assign, centers):
+        K, e = centers.shape
+        sums = torch.zeros((K, e), dtype=torch.float64).index_add_(0, assign, x.double())
+        counts = torch.bincount(assign, minlength=K).to(torch.int64)
+        inertia = ((x.double() - centers[assign].double()) ** 2).sum().reshape(1)
+        return sums, counts, inertia
+
+    def update(self, centers, sums, counts):
+        new = centers.clone()
+        m = counts > 0
+        new[m] = (sums[m] / counts[m][:, None].double()).float()
+        shift = ((new.double() - centers.double()) ** 2).sum().reshape(1)
+        centers.copy_(new)
+        return shift
+
+    def min_sqdist(self, x, center, cur):
+        d = ((x - center[None, :]) ** 2).sum(1)
+        return d if cur is None else torch.minimum(cur, d)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, args, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = fn(rank, world, *args)
+        torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_world(fn, args, tmp_path, world=2):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, fn, args, str(tmp_path)), nprocs=world, join=True)
+    return [torch.load(os.path.join(str(tmp_path), f"r{r}.pt")) for r in range(world)]
+
+
+def _suffix_job(rank, world, codes_all, Ks):
+    lo, hi = sharding.shard_range(codes_all.shape[0], rank, world)
+    out = sharding.global_suffix(codes_all[lo:hi].clone(), Ks, NumpyShardOps(), dist.group.WORLD)
+    stats = sharding.global_stats(out, dist.group.WORLD)
+    return out, stats
+
+
+@pytest.mark.parametrize("n,Ks", [(5000, [8, 8, 8]), (20001, [256, 256, 256]), (3, [4, 4]), (4097, [1024] * 4)])
+def test_global_suffix_matches_single_process(tmp_path, oracle, n, Ks):
+    rng = np.random.default_rng(n)
+    codes = np.stack([rng.integers(0, min(k, 6), size=n) for k in Ks], axis=1).astype(np.int64)
+    codes[rng.integers(0, n, size=n // 2)] = codes[rng.integers(0, n, size=n // 2)]
+    res = run_world(_suffix_job, (torch.from_numpy(codes), Ks), tmp_path)
+    got = torch.cat([r[0] for r in res]).numpy()
+    ref = oracle.suffix_dedup(codes)
+    assert np.array_equal(got, ref)                       # identical to the single-GPU / reference rule
+    assert res[0][1] == res[1][1]
+    assert res[0][1]["distinct"] == len(np.unique(codes, axis=0))
+    assert res[0][1]["max_conflicts"] == int(ref[:, -1].max()) + 1
+
+
+def _kmeans_job(rank, world, x_all, init):
+    lo, hi = sharding.shard_range(x_all.shape[0], rank, world)
+    c, info = kmeans_fit(x_all[lo:hi], init.shape[0], 8, init=init, group=dist.group.WORLD, ops=NumpyKMeansOps(),
+                         return_info=True, tol=0.0)
+    seeded = kmeans_fit(x_all[lo:hi], init.shape[0], 3, seed=7, group=dist.group.WORLD, ops=NumpyKMeansOps())
+    return c, info, seeded
+
+
+def test_sharded_kmeans_equals_single_process(tmp_path, oracle):
+    rng = np.random.default_rng(11)
+    centres = rng.standard_normal((8, 16)).astype(np.float32)
+    x = (centres[rng.integers(0, 8, size=4001)] + 0.05 * rng.standard_normal((4001, 16))).astype(np.float32)
+    init = x[rng.choice(4001, size=8, replace=False)].copy()
+    res = run_world(_kmeans_job, (torch.from_numpy(x), torch.from_numpy(init)), tmp_path)
+    assert torch.equal(res[0][0], res[1][0])              # every rank applies the same update
+    single = kmeans_fit(torch.from_numpy(x), 8, 8, init=torch.from_numpy(init), ops=NumpyKMeansOps(), tol=0.0)
+    assert torch.allclose(res[0][0], single, rtol=0, atol=1e-6)
+    ref = oracle.kmeans_lloyd(x, init, 8, tol=0.0)
+    assert np.allclose(res[0][0].numpy(), ref, atol=1e-5)
+    assert torch.equal(res[0][2], res[1][2])              # sharded k-means++ seeding is rank-consistent
+    with pytest.raises(ValueError, match="should be >= n_clusters"):
+        kmeans_fit(torch.from_numpy(x[:4]), 8, 2, ops=NumpyKMeansOps())
+
+
+def test_shard_ranges_cover_the_catalogue():
+    for n in (0, 1, 7, 1000003):
+        for w in (1, 2, 3, 8):
+            r = [sharding.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
