@@ -111,6 +111,7 @@ static void free_linear(Linear &l) {
     if (l.W) cudaFree(l.W);
     if (l.b) cudaFree(l.b);
     if (l.W_tc) cudaFree(l.W_tc);
+    if (l.W_tc2) cudaFree(l.W_tc2);
     if (l.absW_rowmax) cudaFree(l.absW_rowmax);
     l = Linear();
 }
@@ -243,7 +244,8 @@ extern "C" int rqb200_model_set_linear(rqb200_model *m, int which, int layer, co
         l.nblk = default_kblocks(in, l.kblocks);
         RQB_CHECK(l.nblk >= 1 && l.nblk <= 8, "in_features=%d needs more than 8 K-blocks", in);
     }
-    if (l.W_tc) { cudaFree(l.W_tc); l.W_tc = nullptr; l.W_tc_bytes = 0; }   // stale tensor-core image
+    if (l.W_tc) { cudaFree(l.W_tc); l.W_tc = nullptr; l.W_tc_bytes = 0; }   // stale tensor-core images
+    if (l.W_tc2) { cudaFree(l.W_tc2); l.W_tc2 = nullptr; }
     l.set = true;
     return 0;
 }

@@ -62,6 +62,7 @@ struct Linear {
     size_t W_tc_bytes = 0;
     float *absW_rowmax = nullptr;
     int tc_scale_exp = 0;    // W_tc holds W * 2^tc_scale_exp
+    void *W_tc2 = nullptr;   // image for the 2-CTA kernel (each CTA of a pair stages half of the output features)
 };
 
 struct Workspace {
@@ -94,6 +95,7 @@ struct rqb200_model {
     rqb::Workspace rescue;          // exact latent of gated rows
     rqb::Workspace rescue_act[2];
     float gate_gamma = 3.0517578125e-05f;   // 2^-15: bound on |z~ - z| / |z| of the tensor-core encoder
+    int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced
     bool force_simt_quantizer = false;      // diagnostics: keep the SIMT quantizer behind the tensor-core encoder
     float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
     cudaStream_t copy_stream = nullptr;
@@ -107,6 +109,9 @@ int ws_reserve(Workspace &w, size_t bytes);
 // linear_exact.cu
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
                  bool relu, cudaStream_t s);
+// encode_tc2.cu
+bool linear_tc2_supported(const Linear &l);
+int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
 int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s);

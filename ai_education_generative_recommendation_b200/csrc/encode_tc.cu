@@ -21,8 +21,14 @@
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
+
+#ifndef RQB200_TC2_DEFAULT
+#define RQB200_TC2_DEFAULT 1      // 2-CTA kernel for 256-wide layers (RQB200_TC2=0 selects the 1-CTA kernel)
+#endif
 
 namespace rqb {
 
@@ -45,7 +51,7 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
     static constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;         // two accumulator buffers
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4;
     static_assert(STAGES >= 2, "need at least two smem stages");
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N must be a multiple of 16 in [16,256]");
 };
@@ -95,31 +101,14 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
 
     if (warp < EPI_WARPS) {
         // ===================== epilogue =====================
+        float *patch = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256) + warp * (32 * EPI_LD);
         int64_t it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int buf = (int)(it & 1);
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            const int64_t row = tile * TM + warp * 32 + lane;
-            float *yrow = Y + row * (int64_t)N;
-#pragma unroll 1
-            for (int c = 0; c < N; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N + c), v);
-                if (row < n && !(dbg & 1)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float o[4];
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float f = fmaf(__uint_as_float(v[j + t]), inv_scale, bias[c + j + t]);
-                            if (relu) f = (f != f) ? f : fmaxf(f, 0.0f);
-                            o[t] = f;
-                        }
-                        *reinterpret_cast<float4 *>(yrow + c + j) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-            }
+            epilogue_rows<N>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N), patch, lane, bias, inv_scale, relu,
+                             Y, tile * TM + warp * 32, n, !(dbg & 1));
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);
         }
@@ -358,9 +347,16 @@ int tc_set_trace(long long *buf) {
     return RQB200_EINVAL;
 }
 
+static bool env_tc2() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("RQB200_TC2"); v = (e && e[0] == '0') ? 0 : ((e && e[0] == '1') ? 1 : RQB200_TC2_DEFAULT); }
+    return v == 1;
+}
+
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s) {
     if (n == 0) return 0;
     RQB_TRY(ensure_packed(l, s));
+    if (linear_tc2_supported(l) && env_tc2()) return linear_tc2(l, x, n, y, relu, s);
     switch (l.out) {
         case 32: return launch_tc<32>(l, x, n, y, relu, s);
         case 64: return launch_tc<64>(l, x, n, y, relu, s);

@@ -143,14 +143,17 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
                 const float m2s = -2.0f * qa.inv_scale[l];
-                float bestd = __int_as_float(0x7f800000), second = __int_as_float(0x7f800000);
-                int best = 0;
+                // four independent (best, second) trackers (column mod 4) keep the compare chains short
+                float bd[4], sd[4];
+                int bi[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { bd[u] = __int_as_float(0x7f800000); sd[u] = __int_as_float(0x7f800000); bi[u] = 0; }
                 const int K = qa.K[l];
                 int cc_off = 0;
                 for (int ll = 0; ll < l; ++ll) cc_off += ((qa.K[ll] + QCH - 1) / QCH) * QCH;
                 for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
                     const int ncols = min(QCH, ((K - c0) + 31) & ~31);
-                    const float *s_cc = s_ccall + cc_off + c0;
+                    const float4 *s_cc4 = reinterpret_cast<const float4 *>(s_ccall + cc_off + c0);
                     mbar_wait(&d_full[g], round & 1);
                     ++round;
                     tc_fence_after();
@@ -159,14 +162,28 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                         uint32_t v[32];
                         tmem_ld32(t_addr + (uint32_t)cc0, v);
 #pragma unroll
-                        for (int t = 0; t < 32; ++t) {
-                            const float d = fmaf(__uint_as_float(v[t]), m2s, xx + s_cc[cc0 + t]);     // +inf on padded codes
-                            second = fminf(second, fmaxf(d, bestd));
-                            if (d < bestd) { bestd = d; best = c0 + cc0 + t; }
+                        for (int t4 = 0; t4 < 8; ++t4) {
+                            const float4 ccv = s_cc4[(cc0 >> 2) + t4];                 // +inf on padded codes
+                            const float cv[4] = {ccv.x, ccv.y, ccv.z, ccv.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float d = fmaf(__uint_as_float(v[4 * t4 + u]), m2s, xx + cv[u]);
+                                sd[u] = fminf(sd[u], fmaxf(d, bd[u]));
+                                if (d < bd[u]) { bd[u] = d; bi[u] = c0 + cc0 + 4 * t4 + u; }
+                            }
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&d_empty[g]);
+                }
+                // merge the trackers: global best, and second = min(other bests, all seconds)
+                float bestd = bd[0], second = sd[0];
+                int best = bi[0];
+#pragma unroll
+                for (int u = 1; u < 4; ++u) {
+                    second = fminf(second, sd[u]);
+                    if (bd[u] < bestd || (bd[u] == bestd && bi[u] < best)) { second = fminf(second, bestd); bestd = bd[u]; best = bi[u]; }
+                    else second = fminf(second, bd[u]);
                 }
                 if (live) codes[row * qa.L + l] = best;
                 {

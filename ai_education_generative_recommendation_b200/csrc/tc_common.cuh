@@ -100,5 +100,42 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
 }
 
 
+constexpr int EPI_LD = 36;     // floats per row of the per-warp transpose patch (16-byte aligned, conflict-free)
+
+// Epilogue for one 128 x N accumulator (this warp: TMEM lanes 32*w .. 32*w+31 = rows row0 .. row0+31).
+// TMEM gives lane = row; each 32x32 chunk is transposed through a per-warp shared-memory patch so that the global
+// stores are 128 contiguous bytes per row (4 rows per STG.128 instruction, 4 L1 wavefronts) instead of 32
+// scattered 16-byte pieces (32 wavefronts).  Scale / bias / ReLU are applied after the transpose.
+template <int N>
+__device__ __forceinline__ void epilogue_rows(uint32_t taddr, float *patch, int lane, const float *__restrict__ bias,
+                                              float inv_scale, int relu, float *__restrict__ Y, int64_t row0, int64_t n,
+                                              bool store) {
+    const int sub = lane >> 3, q = lane & 7;
+#pragma unroll 1
+    for (int c = 0; c < N; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4 *>(patch + lane * EPI_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c) + q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + sub;
+            const float4 a = *reinterpret_cast<const float4 *>(patch + r * EPI_LD + 4 * q);
+            float4 o;
+            o.x = fmaf(a.x, inv_scale, b4.x); o.y = fmaf(a.y, inv_scale, b4.y);
+            o.z = fmaf(a.z, inv_scale, b4.z); o.w = fmaf(a.w, inv_scale, b4.w);
+            if (relu) {
+                o.x = (o.x != o.x) ? o.x : fmaxf(o.x, 0.0f); o.y = (o.y != o.y) ? o.y : fmaxf(o.y, 0.0f);
+                o.z = (o.z != o.z) ? o.z : fmaxf(o.z, 0.0f); o.w = (o.w != o.w) ? o.w : fmaxf(o.w, 0.0f);
+            }
+            if (store && row0 + r < n) *reinterpret_cast<float4 *>(Y + (row0 + r) * (int64_t)N + c + 4 * q) = o;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 }  // namespace rqb

@@ -45,6 +45,18 @@ class CudaShardOps:
                                            stream_ptr(codes.device)))
         return keys
 
+    def bucket_by_owner(self, owner: torch.Tensor, world: int):
+        """Stable bucketing by destination rank: one radix pass of the library's sort (keys = owner)."""
+        n = owner.numel()
+        self.model._ensure_handle()
+        sk = owner.clone()
+        pos = torch.arange(n, dtype=torch.int64, device=owner.device)
+        if n:
+            check(_cabi.lib().rqb200_sort_pairs(self.model._handle, ptr(sk), ptr(pos), n,
+                                                max(1, (world - 1).bit_length()), stream_ptr(owner.device)))
+        bounds = torch.searchsorted(sk, torch.arange(world + 1, dtype=torch.int64, device=owner.device))
+        return pos, (bounds[1:] - bounds[:-1]).to(torch.int64)
+
     def rank_among_equal(self, keys: torch.Tensor, bits: int) -> torch.Tensor:
         """out[i] = #{j < i : keys[j] == keys[i]} — stable radix sort + segmented rank."""
         n = keys.numel()
@@ -70,17 +82,18 @@ def owner_of(keys: torch.Tensor, world: int) -> torch.Tensor:
     return h % world
 
 
-def _all_to_all(send: torch.Tensor, send_counts: torch.Tensor, group) -> Tuple[torch.Tensor, List[int]]:
-    world = dist.get_world_size(group)
+def _exchange_counts(send_counts: torch.Tensor, group) -> Tuple[List[int], List[int]]:
+    """One small all-to-all of the per-destination counts; returns (send, recv) split sizes as host lists."""
     recv_counts = torch.empty_like(send_counts)
     dist.all_to_all_single(recv_counts, send_counts, group=group)
-    sc = send_counts.cpu().tolist()
-    rc = recv_counts.cpu().tolist()
-    tail = send.shape[1:]
-    recv = torch.empty((sum(rc),) + tuple(tail), dtype=send.dtype, device=send.device)
+    both = torch.stack([send_counts, recv_counts]).cpu().tolist()      # single device→host sync
+    return both[0], both[1]
+
+
+def _all_to_all(send: torch.Tensor, sc: List[int], rc: List[int], group) -> torch.Tensor:
+    recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
     dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
-    assert len(rc) == world
-    return recv, rc
+    return recv
 
 
 def global_suffix(codes: torch.Tensor, num_emb_list, ops, group=None) -> torch.Tensor:
@@ -95,15 +108,16 @@ def global_suffix(codes: torch.Tensor, num_emb_list, ops, group=None) -> torch.T
         return torch.cat([codes, suffix[:, None]], dim=1)
     world = dist.get_world_size(group)
     owner = owner_of(keys, world)
-    order = torch.sort(owner, stable=True).indices            # bucket by destination, ascending item index inside
-    send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
-    recv_keys, rc = _all_to_all(keys[order], send_counts, group)
+    order, send_counts = ops.bucket_by_owner(owner, world)    # stable: ascending item index inside a bucket
+    sc, rc = _exchange_counts(send_counts, group)
+    recv_keys = _all_to_all(keys[order], sc, rc, group)
     # arrivals are ordered (source rank, local index) == ascending global item index
     rk = ops.rank_among_equal(recv_keys, bits)
-    back, _ = _all_to_all(rk, torch.tensor(rc, dtype=torch.int64, device=codes.device), group)
-    suffix = torch.empty_like(back)
-    suffix[order] = back
-    return torch.cat([codes, suffix[:, None]], dim=1)
+    back = _all_to_all(rk, rc, sc, group)                     # same split sizes, reversed roles
+    out = torch.empty((codes.shape[0], codes.shape[1] + 1), dtype=torch.int64, device=codes.device)
+    out[:, :-1] = codes
+    out[order, -1] = back
+    return out
 
 
 def global_stats(codes_with_suffix: torch.Tensor, group=None) -> dict:

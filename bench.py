@@ -215,6 +215,20 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # nvidia-smi needs ~100 ms to start: begin during the warm-up, keep sampling through the timed steps
+    multi_check = None
+    if world > 1:
+        # one-off verification: the N-GPU ids equal a single-GPU dedup of the gathered catalogue
+        codes = model.get_indices(x, use_sk=False)
+        mine = sharding.global_suffix(codes, Ks, ops, group)
+        gathered = [torch.empty_like(codes) for _ in range(world)]
+        gathered_ids = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, codes)
+        dist.all_gather(gathered_ids, mine)
+        if rank == 0:
+            ref, _ = rq.suffix_dedup(model, torch.cat(gathered))
+            multi_check = bool(torch.equal(ref, torch.cat(gathered_ids)))
+            assert multi_check, "multi-GPU semantic ids differ from the single-GPU result"
+        del gathered, gathered_ids
     for _ in range(max(args.warmup, 3)):
         out = step()
     t_w = time.perf_counter()
@@ -296,7 +310,8 @@ def main():
                 "config": {"workload": WORKLOAD, "items_per_gpu": n, "global_items": n_total, "encode_mode": mode_name,
                            "step": "get_indices(use_sk=False) + suffix dedup" + (" (global, all-to-all)" if world > 1 else ""),
                            "l2": "inputs 3.07 GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
-                           "parallelism": f"items sharded x{world}, codebooks replicated"},
+                           "parallelism": f"items sharded x{world}, codebooks replicated",
+                           "multi_gpu_ids_equal_single_gpu": multi_check},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 768 * 4),
                         "d2h_bytes_per_step": int(n * (len(Ks) + 1) * 8), "api": "rqb200_generate_codes_host (pinned host buffers)"},

@@ -60,3 +60,22 @@ def test_fast_route_handles_overflowing_rows():
     fast = m.get_indices(x)
     m.encode_mode = _cabi.ENCODE_EXACT
     assert torch.equal(fast, m.get_indices(x))
+
+
+def test_one_cta_and_two_cta_kernels_agree():
+    """The 2-CTA (cta_group::2) first-layer kernel and the 1-CTA kernel implement the same arithmetic."""
+    import os, subprocess, sys
+    code = ("import sys, torch; sys.path.insert(0, 'tests'); from conftest import build_model, load_golden;"
+            "from ai_education_generative_recommendation_b200 import _cabi;"
+            "g, cfg, cbs = load_golden('c2_slice'); m = build_model(cfg, cbs);"
+            "x = torch.empty((70001, 768), device='cuda:0');"
+            "_cabi.check(_cabi.lib().rqb200_synth_items(2024, 0, 70001, 768, 1000000, x.data_ptr(), _cabi.stream_ptr()));"
+            "z = m.encode_tc(x); torch.cuda.synchronize(); print(float(z.double().sum()), float(z.double().abs().sum()))")
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, RQB200_TC2=flag)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs

@@ -23,6 +23,10 @@ class NumpyShardOps:
             shift += bits[l]
         return keys
 
+    def bucket_by_owner(self, owner, world):
+        order = torch.sort(owner, stable=True).indices
+        return order, torch.bincount(owner, minlength=world).to(torch.int64)
+
     def rank_among_equal(self, keys, bits):
         from oracle import oracle as O
         if keys.numel() == 0:
