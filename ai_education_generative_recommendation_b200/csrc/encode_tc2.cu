@@ -26,8 +26,13 @@ constexpr int TM2 = 128;                   // rows per CTA (256 per pair)
 constexpr int BK2 = 64;
 constexpr int N2 = 256;                    // output features of the pair tile
 constexpr int NH2 = N2 / 2;                // W rows staged per CTA
-constexpr int T2_EPI = 4, T2_CONV = 8;
-constexpr int T2_THREADS = (T2_EPI + T2_CONV + 2) * 32;     // 448
+#ifndef T2_CONV_WARPS
+#define T2_CONV_WARPS 16
+#endif
+constexpr int T2_EPI = 4, T2_CONV = T2_CONV_WARPS;       // 16 producer warps: more independent load streams per SM
+constexpr int T2_THREADS = (T2_EPI + T2_CONV + 2) * 32;
+constexpr int T2_NF4 = TM2 * BK2 / 4 / (T2_CONV * 32);      // float4 per producer thread per slab
+constexpr int T2_RSTEP = T2_CONV * 32 / 16;                 // rows covered by one pass of the producers
 constexpr int T2_MMA_WARP = T2_EPI + T2_CONV, T2_LOAD_WARP = T2_MMA_WARP + 1;
 constexpr int T2_A_TILE = TM2 * BK2 * 2;   // 16 KB (hi or lo)
 constexpr int T2_W_TILE = NH2 * BK2 * 2;   // 16 KB (hi or lo, this CTA's half)
@@ -151,30 +156,30 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
         }
     } else if (warp < T2_EPI + T2_CONV) {
         // ===================== A producers (own 128 rows) =====================
-        const int ct = threadIdx.x - T2_EPI * 32;            // 0..255
+        const int ct = threadIdx.x - T2_EPI * 32;
         const int c4 = ct & 15;
-        const int rbase = ct >> 4;                           // rows rbase + 16*i
+        const int rbase = ct >> 4;                           // rows rbase + T2_RSTEP*i
         const int64_t my_tiles = pair0 < npt ? (npt - pair0 + npairs - 1) / npairs : 0;
         const int64_t steps = my_tiles * KS;
-        auto load_slab = [&](int64_t st, float4 (&dst)[8]) {
+        auto load_slab = [&](int64_t st, float4 (&dst)[T2_NF4]) {
             const int64_t pt = pair0 + (st / KS) * npairs;
             const int k0 = (int)(st % KS) * BK2 + c4 * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t row = pt * (2 * TM2) + rank * TM2 + rbase + 16 * i;
+            for (int i = 0; i < T2_NF4; ++i) {
+                const int64_t row = pt * (2 * TM2) + rank * TM2 + rbase + T2_RSTEP * i;
                 if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
                 else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         int stage = 0;
         uint32_t phase = 0;
-        auto convert_slab = [&](const float4 (&src)[8]) {
+        auto convert_slab = [&](const float4 (&src)[T2_NF4]) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char *a_hi = smem + stage * T2_STAGE;
             unsigned char *a_lo = a_hi + T2_A_TILE;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
+            for (int i = 0; i < T2_NF4; ++i) {
+                const int r = rbase + T2_RSTEP * i;
                 uint2 hi, lo;
                 split2(src[i].x, src[i].y, hi.x, lo.x);
                 split2(src[i].z, src[i].w, hi.y, lo.y);
@@ -189,7 +194,7 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
         };
         // T2_PREFETCH register buffers in rotation; a buffer is refilled right after it has been converted.
         // (Measured: 3 buffers or an L2 bulk prefetch of the next tile are both slower than 2 buffers.)
-        float4 buf[T2_PREFETCH][8];
+        float4 buf[T2_PREFETCH][T2_NF4];
 #pragma unroll
         for (int d = 0; d < T2_PREFETCH; ++d)
             if (d < steps) load_slab(d, buf[d]);
