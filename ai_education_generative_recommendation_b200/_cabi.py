@@ -59,6 +59,7 @@ _PROTOS = {
     "rqb200_sort_pairs": (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     "rqb200_segment_rank": (c_int, [c_void_p, _P, c_int64, _P, _P]),
     "rqb200_kmeans_assign": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
+    "rqb200_kmeans_distances": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
     "rqb200_kmeans_accumulate": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P]),
     "rqb200_kmeans_update": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "rqb200_synth_items": (c_int, [c_uint64, c_int64, c_int64, c_int, c_int64, _P, _P]),

@@ -204,8 +204,8 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
         if (m->cb[l]) cudaFree(m->cb[l]);
         if (m->cc[l]) cudaFree(m->cc[l]);
         if (m->cb_tc[l]) cudaFree(m->cb_tc[l]);
+        if (m->ccs_tc[l]) cudaFree(m->ccs_tc[l]);
     }
-    if (m->cc_tc) cudaFree(m->cc_tc);
     Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1],
                        &m->rescue, &m->rescue_act[0], &m->rescue_act[1]};
     for (Workspace *w : ws)

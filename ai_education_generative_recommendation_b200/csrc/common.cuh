@@ -16,7 +16,7 @@ void count_launch();          // bumps the process-wide kernel-launch counter (r
 
 // per-kernel device timing (cudaEvent pairs on the launching stream), enabled by rqb200_profile_enable
 enum ProfSlot { PROF_LINEAR0 = 0, PROF_LINEAR_REST = 1, PROF_QUANTIZE = 2, PROF_DEDUP = 3, PROF_TC_ENCODER = 4,
-                PROF_SINKHORN = 5, PROF_NSLOTS = 8 };
+                PROF_SINKHORN = 5, PROF_TC_REST = 6, PROF_NSLOTS = 8 };
 void prof_begin(int slot, cudaStream_t s);
 void prof_end(int slot, cudaStream_t s);
 struct ProfScope {
@@ -86,8 +86,8 @@ struct rqb200_model {
     bool cb_set[RQB200_MAX_LEVELS];
     void *cb_tc[RQB200_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // packed fp16 hi/lo chunks
     int cb_tc_scale_exp[RQB200_MAX_LEVELS] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float *cc_tc = nullptr;         // padded code norms of all levels
-    int cc_tc_total = 0;
+    int cb_tc_aug_exp[RQB200_MAX_LEVELS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float *ccs_tc[RQB200_MAX_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // e == 64: scaled norms
     rqb::Workspace act[2];          // ping-pong activations for the MLP
     rqb::Workspace sortws;          // radix sort scratch
     rqb::Workspace misc;            // rescue lists, counters

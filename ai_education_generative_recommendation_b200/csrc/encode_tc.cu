@@ -379,7 +379,10 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
     for (int i = 0; i < m->n_layers; ++i) {
         const bool last = i == m->n_layers - 1;
         float *dst = last ? y : (float *)m->act[i & 1].ptr;
-        RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s));
+        {
+            ProfScope ps(i == 0 ? PROF_TC_ENCODER : PROF_TC_REST, s);      // slot 4 = the wide first layer alone
+            RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s));
+        }
         cur = dst;
     }
     return 0;
@@ -416,10 +419,7 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
     float *margin = (float *)(base + off_m);
     int64_t *list = (int64_t *)(base + off_l);
     unsigned long long *count = (unsigned long long *)(base + off_c);
-    {
-        ProfScope ps(PROF_TC_ENCODER, s);
-        RQB_TRY(mlp_tc(m, 0, x, n, z, s));
-    }
+    RQB_TRY(mlp_tc(m, 0, x, n, z, s));
     RQB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), s));
     if (quantize_tc_supported(m) && !m->force_simt_quantizer) {
         RQB_TRY(quantize_tc(m, z, n, codes, list, count, s));          // distances on the tensor cores, gate fused

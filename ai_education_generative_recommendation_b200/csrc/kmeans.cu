@@ -96,6 +96,20 @@ extern "C" int rqb200_kmeans_assign(const float *x_dev, int64_t n, int e, const 
     return quantize_exact(&tmp, x_dev, n, assign_dev, nullptr, nullptr, nullptr, nullptr, nullptr, s);
 }
 
+extern "C" int rqb200_kmeans_distances(const float *x_dev, int64_t n, int e, const float *centers_dev, int K,
+                                       float *cnorm_scratch_dev, float *d_dev, void *stream) {
+    // d[n, K] = squared distances to K candidate centres (used by the k-means++ seeding), quantizer arithmetic
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev && centers_dev && cnorm_scratch_dev && d_dev, "NULL buffer");
+    rqb200_model tmp;
+    tmp.L = 1; tmp.e = e; tmp.K[0] = K;
+    tmp.cb[0] = const_cast<float *>(centers_dev);
+    tmp.cc[0] = cnorm_scratch_dev;
+    RQB_TRY(codebook_norms(centers_dev, K, e, cnorm_scratch_dev, s));
+    return distances_exact(&tmp, 0, x_dev, n, d_dev, s);
+}
+
 extern "C" int rqb200_kmeans_accumulate(const float *x_dev, int64_t n, int e, const int64_t *assign_dev,
                                         const float *centers_dev, int K, double *sums_dev,
                                         int64_t *counts_dev, double *inertia_dev, void *stream) {

@@ -32,13 +32,12 @@ constexpr int Q_STAGES = 2;
 constexpr int Q_A_BYTES = QTM * 128;       // one of hi / lo, one 64-wide K slab
 constexpr int Q_CB_TILE = QCH * 128;       // one of hi / lo
 constexpr int Q_STAGE_BYTES = 2 * Q_CB_TILE;               // hi | lo
-constexpr int Q_CC_MAX = 6144;                             // padded code norms of all levels, resident in smem
-constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + Q_CC_MAX * 4 + 1024 + 256;
+constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + 1024 + 256;
 
 struct QtcArgs {
     const unsigned char *cbp[RQB200_MAX_LEVELS];   // packed chunks: [hi tile | lo tile]
-    const float *ccp;                              // code norms, padded per level to 256-code chunks with +inf
-    int cc_total;
+    const float *ccs[RQB200_MAX_LEVELS];           // E == 64 only (no room for the augmented column): |c_j|^2 2^s, +huge on padding
+    uint32_t aug_half[RQB200_MAX_LEVELS];          // fp16 bits of 2^t: value of the augmented A column (see pack_codebook_kernel)
     const float *cb[RQB200_MAX_LEVELS];            // fp32 codebooks for the gather
     const float *cc[RQB200_MAX_LEVELS];
     int K[RQB200_MAX_LEVELS];
@@ -67,8 +66,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *a_base = smem;                                     // [group][hi|lo] 16 KB each
     unsigned char *cb_base = smem + 4 * Q_A_BYTES;                    // [stage] hi | lo | cc
-    float *s_ccall = reinterpret_cast<float *>(cb_base + Q_STAGES * Q_STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_ccall + Q_CC_MAX);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cb_base + Q_STAGES * Q_STAGE_BYTES);
     uint64_t *a_full = bars;            // [2]  row warps → MMA   (count 4)
     uint64_t *d_full = bars + 2;        // [2]  MMA → row warps   (count 1, tcgen05.commit)
     uint64_t *d_empty = bars + 4;       // [2]  row warps → MMA   (count 128)
@@ -86,7 +84,6 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     }
     // zero the A tiles once: columns >= E of the 64-wide K slab stay zero for the whole kernel
     for (int i = threadIdx.x; i < 4 * Q_A_BYTES / 16; i += QTC_THREADS) reinterpret_cast<uint4 *>(a_base)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < qa.cc_total; i += QTC_THREADS) s_ccall[i] = qa.ccp[i];
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -139,21 +136,26 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     *reinterpret_cast<uint4 *>(a_hi + off) = hi;
                     *reinterpret_cast<uint4 *>(a_lo + off) = lo;
                 }
+                constexpr bool AUG = E < 64;          // the 64-wide K slab has a free column for the code norm
+                if (AUG) {
+                    // augmented K column E: A = 2^t, B = |c_j|^2 * 2^(s-t)  ⇒  the MMA itself adds the code norm
+                    const int c = E / 8;
+                    const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(qa.aug_half[l], 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(0, 0, 0, 0);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
-                const float m2s = -2.0f * qa.inv_scale[l];
+                const float inv_s = qa.inv_scale[l];
                 // four independent (best, second) trackers (column mod 4) keep the compare chains short
                 float bd[4], sd[4];
                 int bi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { bd[u] = __int_as_float(0x7f800000); sd[u] = __int_as_float(0x7f800000); bi[u] = 0; }
                 const int K = qa.K[l];
-                int cc_off = 0;
-                for (int ll = 0; ll < l; ++ll) cc_off += ((qa.K[ll] + QCH - 1) / QCH) * QCH;
                 for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
                     const int ncols = min(QCH, ((K - c0) + 31) & ~31);
-                    const float4 *s_cc4 = reinterpret_cast<const float4 *>(s_ccall + cc_off + c0);
                     mbar_wait(&d_full[g], round & 1);
                     ++round;
                     tc_fence_after();
@@ -163,11 +165,11 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                         tmem_ld32(t_addr + (uint32_t)cc0, v);
 #pragma unroll
                         for (int t4 = 0; t4 < 8; ++t4) {
-                            const float4 ccv = s_cc4[(cc0 >> 2) + t4];                 // +inf on padded codes
-                            const float cv[4] = {ccv.x, ccv.y, ccv.z, ccv.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const float d = fmaf(__uint_as_float(v[4 * t4 + u]), m2s, xx + cv[u]);
+                                // accumulator = 2^s (|c_j|^2 - 2 r.c_j): the distance up to the row constant |r|^2, scaled
+                                float d = __uint_as_float(v[4 * t4 + u]);
+                                if (!AUG) d += __ldg(qa.ccs[l] + c0 + cc0 + 4 * t4 + u);
                                 sd[u] = fminf(sd[u], fmaxf(d, bd[u]));
                                 if (d < bd[u]) { bd[u] = d; bi[u] = c0 + cc0 + 4 * t4 + u; }
                             }
@@ -185,6 +187,11 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     if (bd[u] < bestd || (bd[u] == bestd && bi[u] < best)) { second = fminf(second, bestd); bestd = bd[u]; best = bi[u]; }
                     else second = fminf(second, bd[u]);
                 }
+                // back to distance units: d = acc * 2^-s + |r|^2
+                const bool bad_index = best >= K;                 // a padded code won: only possible for wild inputs
+                if (bad_index) best = 0;
+                second = fmaf(second, inv_s, xx);
+                bestd = fmaf(bestd, inv_s, xx);
                 if (live) codes[row * qa.L + l] = best;
                 {
                     // Let eps bound |r~ - r| (tensor-core encoder) and rho = |r - c_best|.  A code j can overtake `best`
@@ -195,7 +202,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
                     const float tau = 4.0f * gate_eps * (rho + gate_eps) + 4.0e-6f * (xx + fabsf(ccb));
                     const float mg = (second - bestd) - tau;
-                    min_margin = (mg == mg && min_margin == min_margin) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
+                    min_margin = (mg == mg && min_margin == min_margin && !bad_index) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
                 }
                 // gather + straight-through residual update, same operations as vq.py:95 / rq.py:47
                 const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
@@ -247,7 +254,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                             const uint32_t a_lo = a_hi + Q_A_BYTES;
                             const uint32_t d_tmem = tmem_base + (uint32_t)(g * QCH);
 #pragma unroll
-                            for (int kk = 0; kk < (E + 15) / 16; ++kk) {
+                            for (int kk = 0; kk < (E + (E < 64 ? 1 : 0) + 15) / 16; ++kk) {      // E residual columns (+ the augmented norm column)
                                 const uint32_t ko = kk * 32;
                                 umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, kk != 0);
                                 umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
@@ -287,10 +294,10 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     }
 }
 
-// codebook [K,e] fp32 → per 256-code chunk: hi tile | lo tile (SW128 K-major, K padded to 64, codes padded with
-// zeros); code norms go to ccp (+inf on padded codes)
+// codebook [K,e] fp32 → per 256-code chunk: hi tile | lo tile (SW128 K-major, 64-wide K slab).  Column k < e holds
+// -2 c_jk 2^s, column e holds |c_j|^2 2^(s-t) (the A operand carries 2^t there), padded codes get a huge norm.
 __global__ void pack_codebook_kernel(const float *__restrict__ cb, const float *__restrict__ cc, int K, int e, float scale,
-                                     unsigned char *__restrict__ out, float *__restrict__ ccp) {
+                                     float cc_scale, unsigned char *__restrict__ out, float *__restrict__ ccs) {
     const int nchunks = (K + QCH - 1) / QCH;
     const int64_t total = (int64_t)nchunks * QCH * 8;       // 16-byte units per (hi or lo)
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
@@ -301,16 +308,22 @@ __global__ void pack_codebook_kernel(const float *__restrict__ cb, const float *
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const int k = c8 * 8 + 2 * t;
-            const float a = (code < K && k < e) ? cb[(int64_t)code * e + k] * scale : 0.0f;
-            const float b = (code < K && k + 1 < e) ? cb[(int64_t)code * e + k + 1] * scale : 0.0f;
-            split2(a, b, hi[t], lo[t]);
+            float ab[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = c8 * 8 + 2 * t + h;
+                float v = 0.0f;
+                if (k < e) v = code < K ? -2.0f * cb[(int64_t)code * e + k] * scale : 0.0f;
+                else if (k == e) v = code < K ? cc[code] * cc_scale : 60000.0f;
+                ab[h] = v;
+            }
+            split2(ab[0], ab[1], hi[t], lo[t]);
         }
         unsigned char *base = out + (size_t)chunk * Q_STAGE_BYTES;
         const size_t off = (size_t)(rowc >> 3) * 1024 + (rowc & 7) * 128 + ((c8 ^ (rowc & 7)) << 4);
         *reinterpret_cast<uint4 *>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4 *>(base + Q_CB_TILE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        if (c8 == 0) ccp[chunk * QCH + rowc] = code < K ? cc[code] : __int_as_float(0x7f800000);
+        if (ccs && c8 == 0) ccs[chunk * QCH + rowc] = code < K ? cc[code] * scale : 3.0e38f;
     }
 }
 
@@ -326,45 +339,45 @@ __global__ void absmax2_kernel(const float *__restrict__ w, int64_t count, float
 
 // (re)build the packed fp16 images of all codebooks
 int quantize_tc_prepare(rqb200_model *m, cudaStream_t s) {
-    int total = 0, off[RQB200_MAX_LEVELS];
-    for (int l = 0; l < m->L; ++l) { off[l] = total; total += ((m->K[l] + QCH - 1) / QCH) * QCH; }
-    RQB_CHECK(total <= Q_CC_MAX, "tensor-core quantizer: too many codes in total (%d > %d)", total, Q_CC_MAX);
-    if (!m->cc_tc) RQB_CUDA(cudaMalloc(&m->cc_tc, sizeof(float) * Q_CC_MAX));
-    m->cc_tc_total = total;
     for (int l = 0; l < m->L; ++l) {
         if (m->cb_tc[l]) continue;
         const int nchunks = (m->K[l] + QCH - 1) / QCH;
         float *dmax = nullptr;
-        RQB_CUDA(cudaMalloc(&dmax, sizeof(float)));
-        RQB_CUDA(cudaMemsetAsync(dmax, 0, sizeof(float), s));
+        RQB_CUDA(cudaMalloc(&dmax, 2 * sizeof(float)));
+        RQB_CUDA(cudaMemsetAsync(dmax, 0, 2 * sizeof(float), s));
         count_launch();
         absmax2_kernel<<<32, 256, 0, s>>>(m->cb[l], (int64_t)m->K[l] * m->e, dmax);
-        float hmax = 0.0f;
-        RQB_CUDA(cudaMemcpyAsync(&hmax, dmax, sizeof(float), cudaMemcpyDeviceToHost, s));
+        count_launch();
+        absmax2_kernel<<<8, 256, 0, s>>>(m->cc[l], (int64_t)m->K[l], dmax + 1);
+        float hmax[2] = {0.0f, 0.0f};
+        RQB_CUDA(cudaMemcpyAsync(hmax, dmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
         RQB_CUDA(cudaStreamSynchronize(s));
         RQB_CUDA(cudaFree(dmax));
-        RQB_CHECK(hmax == hmax && hmax < 3.0e38f, "non-finite codebook entry");
+        RQB_CHECK(hmax[0] == hmax[0] && hmax[0] < 1.0e18f && hmax[1] == hmax[1] && hmax[1] < 1.0e36f, "non-finite codebook entry");
+        // s: max|2 c| 2^s in [2^13, 2^14);  t: |c|^2 2^(s-t) < 2^14 with the A column carrying 2^t (t in [0, 15])
         int ex = 0;
-        if (hmax > 0.0f) { frexpf(hmax, &ex); ex = 14 - ex; }
+        if (hmax[0] > 0.0f) { frexpf(2.0f * hmax[0], &ex); ex = 14 - ex; }
         if (ex > 40) ex = 40;
         if (ex < -20) ex = -20;
+        int t = 0;
+        if (hmax[1] > 0.0f) { int ec = 0; frexpf(hmax[1], &ec); t = ec + ex - 14; }
+        if (t < 0) t = 0;
+        RQB_CHECK(t <= 15, "codebook %d: norms too large relative to entries for the fp16 tensor-core quantizer", l);
         m->cb_tc_scale_exp[l] = ex;
+        m->cb_tc_aug_exp[l] = t;
         void *p = nullptr;
         RQB_CUDA(cudaMalloc(&p, (size_t)nchunks * Q_STAGE_BYTES));
+        if (m->e >= 64 && !m->ccs_tc[l]) RQB_CUDA(cudaMalloc(&m->ccs_tc[l], sizeof(float) * (size_t)nchunks * QCH));
         count_launch();
-        pack_codebook_kernel<<<64, 256, 0, s>>>(m->cb[l], m->cc[l], m->K[l], m->e, ldexpf(1.0f, ex), (unsigned char *)p,
-                                                m->cc_tc + off[l]);
+        pack_codebook_kernel<<<64, 256, 0, s>>>(m->cb[l], m->cc[l], m->K[l], m->e, ldexpf(1.0f, ex), ldexpf(1.0f, ex - t),
+                                                (unsigned char *)p, m->e >= 64 ? m->ccs_tc[l] : nullptr);
         RQB_LAUNCH_CHECK();
         m->cb_tc[l] = p;
     }
     return 0;
 }
 
-bool quantize_tc_supported(const rqb200_model *m) {
-    int total = 0;
-    for (int l = 0; l < m->L; ++l) total += ((m->K[l] + QCH - 1) / QCH) * QCH;
-    return (m->e == 32 || m->e == 64 || m->e == 16 || m->e == 48) && total <= Q_CC_MAX;
-}
+bool quantize_tc_supported(const rqb200_model *m) { return m->e == 16 || m->e == 32 || m->e == 48 || m->e == 64; }
 
 template <int E>
 static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list,
@@ -377,8 +390,6 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
     }
     QtcArgs qa;
     qa.L = m->L;
-    qa.ccp = m->cc_tc;
-    qa.cc_total = m->cc_tc_total;
     for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
         const bool on = l < m->L;
         qa.cbp[l] = on ? (const unsigned char *)m->cb_tc[l] : nullptr;
@@ -386,6 +397,8 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
         qa.cc[l] = on ? m->cc[l] : nullptr;
         qa.K[l] = on ? m->K[l] : 0;
         qa.inv_scale[l] = on ? ldexpf(1.0f, -m->cb_tc_scale_exp[l]) : 0.0f;
+        qa.ccs[l] = on ? m->ccs_tc[l] : nullptr;
+        qa.aug_half[l] = on ? (uint32_t)__half_as_ushort(__float2half(ldexpf(1.0f, m->cb_tc_aug_exp[l]))) : 0u;
     }
     const int64_t npairs = ((n + QTM - 1) / QTM + 1) / 2;
     const unsigned grid = (unsigned)(npairs < kNumSMs ? npairs : kNumSMs);

@@ -43,10 +43,16 @@ class CudaKMeansOps:
                                                stream_ptr(centers.device)))
         return shift
 
-    def min_sqdist(self, x, center, cur):
-        """cur = min(cur, ||x - center||²) — elementwise plumbing for the seeding only."""
-        d = ((x - center[None, :]) ** 2).sum(1)
-        return d if cur is None else torch.minimum(cur, d)
+    def sqdist(self, x, cands):
+        """[n, T] squared distances to T candidate centres (seeding) — the quantizer's distance kernel."""
+        n, e = x.shape
+        T = cands.shape[0]
+        cn = torch.empty((T,), dtype=torch.float32, device=x.device)
+        d = torch.empty((n, T), dtype=torch.float32, device=x.device)
+        if n:
+            check(_cabi.lib().rqb200_kmeans_distances(ptr(x), n, e, ptr(cands.contiguous()), T, ptr(cn), ptr(d),
+                                                      stream_ptr(x.device)))
+        return d.clamp_min_(0.0)
 
 
 def _all_reduce(t, group):
@@ -57,48 +63,56 @@ def _all_reduce(t, group):
 
 
 def kmeans_pp_seed(x: torch.Tensor, K: int, gen: torch.Generator, ops, group=None) -> torch.Tensor:
-    """k-means++ seeding.  Sharded mode: every rank draws the same uniform numbers; the rank that owns the
-    selected global position broadcasts the chosen row through an all-reduce of a one-hot contribution."""
+    """Greedy k-means++ seeding (like scikit-learn: 2 + log K candidates per step, keep the one that lowers the
+    potential most).  Sharded mode: every rank draws the same uniform numbers; the rank that owns a selected
+    global position contributes the row through an all-reduce, potentials are all-reduced."""
+    import math
     n, e = x.shape
+    dev = x.device
     if group is not None:
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        sizes = torch.zeros(world, dtype=torch.float64, device=x.device)
-        sizes[rank] = n
-        _all_reduce(sizes, group)
     else:
         rank, world = 0, 1
-        sizes = torch.tensor([float(n)], dtype=torch.float64, device=x.device)
-    centers = torch.empty((K, e), dtype=torch.float32, device=x.device)
-    mind = None
+    trials = 2 + int(math.log(K)) if K > 1 else 1
+    centers = torch.empty((K, e), dtype=torch.float32, device=dev)
+    mind = None                                   # current min squared distance of every local sample
     for k in range(K):
-        u = torch.rand((), generator=gen, dtype=torch.float64).item()
-        if mind is None:
-            w_local = torch.ones((n,), dtype=torch.float64, device=x.device)
-        else:
-            w_local = mind.to(torch.float64)
-        tot = torch.zeros(world, dtype=torch.float64, device=x.device)
+        T = 1 if k == 0 else trials
+        u = torch.rand((T,), generator=gen, dtype=torch.float64).to(dev)
+        w_local = torch.ones((n,), dtype=torch.float64, device=dev) if mind is None else mind.to(torch.float64)
+        tot = torch.zeros(world, dtype=torch.float64, device=dev)
         tot[rank] = w_local.sum()
         _all_reduce(tot, group)
-        total = float(tot.sum().item())
-        if not (total > 0.0):                 # all remaining points coincide with a centre
-            w_local = torch.ones((n,), dtype=torch.float64, device=x.device)
-            tot = sizes.clone()
-            total = float(tot.sum().item())
-        target = u * total
-        before = float(tot[:rank].sum().item())
-        row = torch.zeros((e,), dtype=torch.float32, device=x.device)
-        mine = float(tot[rank].item())
-        last_nonempty = max((r for r in range(world) if float(tot[r].item()) > 0.0), default=0)
-        if n > 0 and mine > 0.0 and (before <= target < before + mine or
-                                     (rank == last_nonempty and target >= before + mine)):
+        total = tot.sum()
+        if not bool(total > 0):                   # all remaining samples coincide with a centre
+            w_local = torch.ones((n,), dtype=torch.float64, device=dev)
+            tot = torch.zeros(world, dtype=torch.float64, device=dev)
+            tot[rank] = float(n)
+            _all_reduce(tot, group)
+            total = tot.sum()
+        target = u * total                        # [T] positions in the global cumulative weight
+        before = tot[:rank].sum()
+        mine = tot[rank]
+        last_nonempty = int(torch.nonzero(tot > 0).max().item()) if bool((tot > 0).any()) else 0
+        cands = torch.zeros((T, e), dtype=torch.float32, device=dev)
+        if n > 0 and bool(mine > 0):
             cs = torch.cumsum(w_local, 0)
-            j = int(torch.searchsorted(cs, torch.tensor(target - before, dtype=torch.float64, device=x.device)).item())
-            j = min(max(j, 0), n - 1)
-            row = x[j].clone()
-        _all_reduce(row, group)
-        centers[k] = row
-        mind = ops.min_sqdist(x, row, mind)
+            local_t = target - before
+            own = (local_t >= 0) & (local_t < mine)
+            if rank == last_nonempty:
+                own = own | (local_t >= mine)
+            j = torch.searchsorted(cs, local_t.clamp(min=0)).clamp(0, n - 1)
+            cands[own] = x[j[own]]
+        _all_reduce(cands, group)
+        d = ops.sqdist(x, cands)                  # [n, T]
+        if mind is not None:
+            d = torch.minimum(d, mind[:, None])
+        pot = d.to(torch.float64).sum(0)
+        _all_reduce(pot, group)
+        best = int(torch.argmin(pot).item())
+        centers[k] = cands[best]
+        mind = d[:, best].contiguous()
     return centers
 
 

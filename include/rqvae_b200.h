@@ -53,7 +53,7 @@ int         rqb200_device_count(void);
  * rqb200_profile_enable(1) makes the library record cudaEvent pairs around its main kernels on the
  * launching stream; rqb200_profile_read waits for them and returns accumulated milliseconds and
  * launch counts per slot: 0 first Linear (exact), 1 other Linears (exact), 2 quantizer, 3 dedup
- * (sort + segmented rank), 4 tensor-core encoder, 5 Sinkhorn regroup.                        */
+ * (sort + segmented rank), 4 tensor-core first Linear, 5 Sinkhorn regroup, 6 other tensor-core Linears.                        */
 long long rqb200_launch_count(void);
 int rqb200_profile_enable(int on);
 int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
@@ -180,6 +180,9 @@ int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_dev, int64_
  * previous centre) and adds the squared centre shift to *shift_dev.                       */
 int rqb200_kmeans_assign(const float *x_dev, int64_t n, int e, const float *centers_dev, int K,
                          float *cnorm_scratch_dev /*[K]*/, int64_t *assign_dev, void *stream);
+/* d[n,K]: squared distances of every sample to K candidate centres (k-means++ seeding). */
+int rqb200_kmeans_distances(const float *x_dev, int64_t n, int e, const float *centers_dev, int K,
+                            float *cnorm_scratch_dev /*[K]*/, float *d_dev, void *stream);
 int rqb200_kmeans_accumulate(const float *x_dev, int64_t n, int e, const int64_t *assign_dev,
                              const float *centers_dev, int K, double *sums_dev, int64_t *counts_dev,
                              double *inertia_dev, void *stream);

@@ -54,9 +54,8 @@ class NumpyKMeansOps:
         centers.copy_(new)
         return shift
 
-    def min_sqdist(self, x, center, cur):
-        d = ((x - center[None, :]) ** 2).sum(1)
-        return d if cur is None else torch.minimum(cur, d)
+    def sqdist(self, x, cands):
+        return ((x[:, None, :].double() - cands[None].double()) ** 2).sum(-1).float()
 
 
 def _free_port():
