@@ -58,6 +58,12 @@ _PROTOS = {
     "rqb200_pack_keys": (c_int, [_P, c_int64, c_int, POINTER(c_int), _P, _P]),
     "rqb200_sort_pairs": (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     "rqb200_segment_rank": (c_int, [c_void_p, _P, c_int64, _P, _P]),
+    "rqb200_shard_create": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int, c_int64, c_int64]),
+    "rqb200_shard_handle_bytes": (c_int, []),
+    "rqb200_shard_get_handle": (c_int, [c_void_p, _P]),
+    "rqb200_shard_connect": (c_int, [c_void_p, _P]),
+    "rqb200_shard_suffix_dedup": (c_int, [c_void_p, _P, c_int64, c_int, POINTER(c_int), _P, _P]),
+    "rqb200_shard_destroy": (None, [c_void_p]),
     "rqb200_kmeans_assign": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
     "rqb200_kmeans_distances": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
     "rqb200_kmeans_accumulate": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P]),

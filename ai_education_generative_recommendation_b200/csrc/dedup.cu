@@ -10,6 +10,10 @@
 // position of an item inside its run of equal keys IS the number of equal codes with a smaller
 // item index.  Everything is HBM-bound integer work: coalesced loads, shared-memory ranking, grids
 // sized from the SM count.
+#include <string.h>
+
+#include <new>
+
 #include "common.cuh"
 
 namespace rqb {
@@ -282,7 +286,8 @@ __global__ void __launch_bounds__(SEG_THREADS)
 seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ perm, int64_t n,
                 const long long *__restrict__ carry, int64_t *__restrict__ rank_out,
                 const int64_t *__restrict__ codes, int L, int64_t *__restrict__ out,
-                unsigned long long *__restrict__ stats /* [0]=runs [1]=max run */) {
+                unsigned long long *__restrict__ stats /* [0]=runs [1]=max run */,
+                uint32_t *__restrict__ rank_by_item /* rank_by_item[perm[i]] = rank, may be NULL */) {
     __shared__ long long s_warp[SEG_THREADS / 32];
     __shared__ unsigned long long s_runs, s_maxrun;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -320,6 +325,7 @@ seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ pe
         long long st = start[i] >= 0 ? start[i] : before;
         long long rk = idx - st;
         if (rank_out) rank_out[idx] = rk;
+        if (rank_by_item) rank_by_item[perm[idx]] = (uint32_t)rk;
         if (out) {
             int64_t item = perm[idx];
             for (int l = 0; l < L; ++l) out[item * (L + 1) + l] = codes[item * L + l];
@@ -583,7 +589,7 @@ int sort_codes(rqb200_model *m, const int64_t *codes, int64_t n, int L, const in
 }
 
 int run_seg_rank(SortScratch &sc, int buf, int64_t n, int64_t *rank_out, const int64_t *codes, int L,
-                 int64_t *out, bool want_stats, cudaStream_t s) {
+                 int64_t *out, bool want_stats, cudaStream_t s, uint32_t *rank_by_item = nullptr) {
     const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
     if (want_stats) RQB_CUDA(cudaMemsetAsync(sc.stats, 0, 2 * sizeof(unsigned long long), s));
     rqb::count_launch();
@@ -592,9 +598,232 @@ int run_seg_rank(SortScratch &sc, int buf, int64_t n, int64_t *rank_out, const i
     seg_carry_kernel<<<1, 1024, 0, s>>>(sc.tile_last, sc.carry, ntiles);
     rqb::count_launch();
     seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sc.keys[buf], sc.vals[buf], n, sc.carry, rank_out, codes, L,
-                                                   out, want_stats ? sc.stats : nullptr);
+                                                   out, want_stats ? sc.stats : nullptr, rank_by_item);
     RQB_LAUNCH_CHECK();
     return 0;
+}
+
+
+// ---------------------------------------------------------------- sharded suffix dedup over NVLink peer memory
+//
+// New design (the reference is single-process): the catalogue is sharded by contiguous
+// item ranges, one process per GPU.  The suffix of an item is its rank among ALL items with the same code in
+// ascending GLOBAL item order, so equal keys have to meet: every key is routed to owner = hash(key) mod G.
+// The exchange is done by the kernels themselves over peer memory (cudaIpc mappings of one symmetric block
+// per rank, NVLink/NVSwitch underneath) instead of NCCL calls with host-side split sizes:
+//   1. histogram of owners per CTA, scanned (the radix machinery above with the owner as the digit);
+//   2. every rank stores its count row into every peer's count matrix, system-scope fence, signal, spin
+//      until all rows are in → each rank knows where its keys start in every owner's receive buffer;
+//   3. stable partition scatter that writes each key DIRECTLY into the owner's receive buffer (P2P stores);
+//      arrival order = (source rank, local index) = ascending global item index;
+//   4. signal/spin; the owner stable-sorts (key, slot) and ranks every slot inside its run of equal keys;
+//   5. the owner writes the ranks back as contiguous blocks into each source's return buffer (P2P stores);
+//   6. signal/spin; out[i] = (codes[i], ret[slot position of i]).
+// The result is bit-identical to rqb200_suffix_dedup on the concatenated catalogue.
+
+constexpr int SHARD_MAX_WORLD = 16;
+constexpr unsigned long long SHARD_SPIN_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct ShardPeers { unsigned char *base[SHARD_MAX_WORLD]; };
+
+struct ShardPlan {                         // device-resident, written by shard_exchange_counts_kernel
+    uint32_t dest_off[SHARD_MAX_WORLD];    // where my keys start in owner d's receive buffer
+    uint32_t send_off[SHARD_MAX_WORLD];    // where the block for owner d starts in my own return buffer
+    uint32_t src_off[SHARD_MAX_WORLD + 1]; // receive buffer: slots [src_off[r], src_off[r+1]) came from rank r
+    uint32_t ret_off[SHARD_MAX_WORLD];     // where my block starts in source r's return buffer
+    unsigned long long recv_total;
+    int status;                            // 0 ok, 1 receive capacity exceeded, 2 peer timeout
+};
+
+__device__ __forceinline__ uint32_t shard_owner(uint64_t key, int world) {
+    uint64_t h = key * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)((h >> 33) % (uint64_t)world);
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// signal every peer with `epoch` and wait until every peer has signalled at least `epoch` (thread r <-> rank r)
+__device__ __forceinline__ void shard_signal_and_wait(ShardPeers peers, size_t sig_off, int rank, int world,
+                                                      unsigned long long epoch, int *status) {
+    const int r = threadIdx.x;
+    __threadfence_system();
+    if (r < world) {
+        st_release_sys(reinterpret_cast<unsigned long long *>(peers.base[r] + sig_off) + rank, epoch);
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(peers.base[rank] + sig_off) + r;
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(mine) < epoch) {
+            if (globaltimer_ns() - t0 > SHARD_SPIN_TIMEOUT_NS) { atomicMax(status, 2); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+shard_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int world, uint32_t *__restrict__ hist, int nblocks) {
+    __shared__ uint32_t s_hist[SHARD_MAX_WORLD];
+    if (threadIdx.x < SHARD_MAX_WORLD) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    uint32_t local[SHARD_MAX_WORLD];
+#pragma unroll
+    for (int d = 0; d < SHARD_MAX_WORLD; ++d) local[d] = 0;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int64_t idx = base + i * SORT_THREADS + threadIdx.x;
+        if (idx < n) {
+            const uint32_t o = shard_owner(keys[idx], world);
+#pragma unroll
+            for (int d = 0; d < SHARD_MAX_WORLD; ++d) local[d] += (o == (uint32_t)d);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < SHARD_MAX_WORLD; ++d) {
+        uint32_t v = local[d];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_hist[d], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// one CTA of 32 threads: publish my counts row, barrier, derive the plan
+__global__ void __launch_bounds__(32)
+shard_exchange_counts_kernel(ShardPeers peers, size_t sig_off, size_t counts_off, int rank, int world,
+                             unsigned long long epoch, const uint32_t *__restrict__ my_counts /* digit totals */,
+                             unsigned long long cap_recv, ShardPlan *__restrict__ plan) {
+    __shared__ uint32_t M[SHARD_MAX_WORLD][SHARD_MAX_WORLD];
+    const int t = threadIdx.x;
+    if (t == 0) plan->status = 0;
+    __syncthreads();
+    if (t < world) {
+        uint32_t *row = reinterpret_cast<uint32_t *>(peers.base[t] + counts_off) + rank * SHARD_MAX_WORLD;
+        for (int d = 0; d < world; ++d) row[d] = my_counts[d];
+    }
+    shard_signal_and_wait(peers, sig_off, rank, world, epoch, &plan->status);
+    const volatile uint32_t *mat = reinterpret_cast<const volatile uint32_t *>(peers.base[rank] + counts_off);
+    for (int i = t; i < world * world; i += 32) M[i / world][i % world] = mat[(i / world) * SHARD_MAX_WORLD + (i % world)];
+    __syncthreads();
+    if (t < world) {
+        uint32_t a = 0;
+        for (int r = 0; r < rank; ++r) a += M[r][t];
+        plan->dest_off[t] = a;                                   // my keys in owner t's buffer
+        uint32_t b = 0;
+        for (int d = 0; d < t; ++d) b += M[rank][d];
+        plan->send_off[t] = b;                                   // block for owner t in my return buffer
+        uint32_t c = 0;
+        for (int r = 0; r < t; ++r) c += M[r][rank];
+        plan->src_off[t] = c;                                    // slots of source t in my receive buffer
+        uint32_t e = 0;
+        for (int d = 0; d < rank; ++d) e += M[t][d];
+        plan->ret_off[t] = e;                                    // my block in source t's return buffer
+        unsigned long long col = 0;
+        for (int r = 0; r < world; ++r) col += M[r][t];
+        if (col > cap_recv) atomicMax(&plan->status, 1);         // same verdict on every rank (same matrix)
+    }
+    if (t == 0) {
+        unsigned long long tot = 0;
+        for (int r = 0; r < world; ++r) tot += M[r][rank];
+        plan->src_off[world] = (uint32_t)tot;
+        plan->recv_total = tot;
+    }
+}
+
+// stable partition by owner, written straight into the owners' receive buffers (peer memory)
+__global__ void __launch_bounds__(SORT_THREADS)
+shard_scatter_kernel(const uint64_t *__restrict__ keys_in, int64_t n, int world, ShardPeers peers, size_t recv_off,
+                     const uint32_t *__restrict__ hist, int nblocks, const ShardPlan *__restrict__ plan,
+                     uint32_t *__restrict__ slotpos) {
+    __shared__ uint32_t s_cnt[SORT_WARPS][SHARD_MAX_WORLD];
+    __shared__ uint32_t s_dest[SHARD_MAX_WORLD], s_send[SHARD_MAX_WORLD];
+    if (plan->status != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid < SORT_WARPS * SHARD_MAX_WORLD) (&s_cnt[0][0])[tid] = 0;
+    if (tid < SHARD_MAX_WORLD) { s_dest[tid] = tid < world ? plan->dest_off[tid] : 0; s_send[tid] = tid < world ? plan->send_off[tid] : 0; }
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + wid * WARP_CHUNK;
+    uint64_t k[SORT_ITEMS];
+    uint32_t own[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int64_t idx = wbase + i * 32 + lane;
+        const bool ok = idx < n;
+        k[i] = ok ? keys_in[idx] : 0;
+        own[i] = ok ? shard_owner(k[i], world) : 0xffu;
+        uint32_t peers_m = __match_any_sync(0xffffffffu, own[i]);
+        if (ok && lane == (__ffs(peers_m) - 1)) s_cnt[wid][own[i]] += __popc(peers_m);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < world) {
+        uint32_t run = hist[(int64_t)tid * nblocks + blockIdx.x];       // exclusive scan over CTAs of this owner
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = s_cnt[w][tid];
+            s_cnt[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int64_t idx = wbase + i * 32 + lane;
+        const bool ok = idx < n;
+        uint32_t peers_m = __match_any_sync(0xffffffffu, own[i]);
+        uint32_t below = __popc(peers_m & ((1u << lane) - 1u));
+        uint32_t rel = 0;
+        if (ok) rel = s_cnt[wid][own[i]] + below;
+        __syncwarp();
+        if (ok && lane == (__ffs(peers_m) - 1)) s_cnt[wid][own[i]] += __popc(peers_m);
+        __syncwarp();
+        if (ok) {
+            uint64_t *dst = reinterpret_cast<uint64_t *>(peers.base[own[i]] + recv_off);
+            dst[s_dest[own[i]] + rel] = k[i];
+            slotpos[idx] = s_send[own[i]] + rel;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+shard_barrier_kernel(ShardPeers peers, size_t sig_off, int rank, int world, unsigned long long epoch,
+                     ShardPlan *__restrict__ plan) {
+    shard_signal_and_wait(peers, sig_off, rank, world, epoch, &plan->status);
+}
+
+// the owner returns the ranks: slot s of source r → r's return buffer at ret_off[r] + (s - src_off[r])
+__global__ void shard_return_kernel(const uint32_t *__restrict__ rank_slot, int world, ShardPeers peers, size_t ret_off_bytes,
+                                    const ShardPlan *__restrict__ plan) {
+    if (plan->status != 0) return;
+    const unsigned long long total = plan->recv_total;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < total;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        int r = 0;
+        while (r + 1 < world && s >= plan->src_off[r + 1]) ++r;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(peers.base[r] + ret_off_bytes);
+        dst[plan->ret_off[r] + (uint32_t)(s - plan->src_off[r])] = rank_slot[s];
+    }
+}
+
+__global__ void shard_finalize_kernel(const int64_t *__restrict__ codes, int64_t n, int L, const uint32_t *__restrict__ ret,
+                                      const uint32_t *__restrict__ slotpos, const ShardPlan *__restrict__ plan,
+                                      int64_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int l = 0; l < L; ++l) out[i * (L + 1) + l] = codes[i * L + l];
+    out[i * (L + 1) + L] = plan->status == 0 ? (int64_t)ret[slotpos[i]] : -1;
 }
 
 }  // namespace
@@ -732,7 +961,171 @@ extern "C" int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_
     seg_carry_kernel<<<1, 1024, 0, s>>>(tile_last, carry, ntiles);
     rqb::count_launch();
     seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, nullptr, n, carry, rank_dev, nullptr, 0,
-                                                   nullptr, nullptr);
+                                                   nullptr, nullptr, nullptr);
     RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------- sharded dedup: C ABI
+
+struct rqb200_shard {
+    rqb200_model *m = nullptr;
+    int rank = 0, world = 1;
+    int64_t cap_local = 0, cap_recv = 0;
+    unsigned char *block = nullptr;          // this rank's symmetric block (cudaMalloc, exported by cudaIpc)
+    size_t block_bytes = 0;
+    size_t sig_off = 0, counts_off = 0, recv_off = 0, ret_off = 0;
+    rqb::ShardPeers peers;
+    bool connected = false;
+    unsigned long long epoch = 0;
+    rqb::ShardPlan *plan = nullptr;          // device
+};
+
+extern "C" int rqb200_shard_create(rqb200_shard **out, rqb200_model *m, int rank, int world,
+                                   int64_t max_local_items, int64_t max_recv_items) {
+    RQB_CHECK(out != nullptr && m != nullptr, "NULL argument");
+    RQB_CHECK(world >= 1 && world <= SHARD_MAX_WORLD, "world=%d out of range (1..%d)", world, SHARD_MAX_WORLD);
+    RQB_CHECK(rank >= 0 && rank < world, "rank %d out of range", rank);
+    RQB_CHECK(max_local_items >= 0 && max_local_items < ((int64_t)1 << 32), "max_local_items out of range");
+    if (max_recv_items <= 0) max_recv_items = 2 * max_local_items + 65536;
+    RQB_CHECK(max_recv_items < ((int64_t)1 << 32), "max_recv_items out of range");
+    RQB_CUDA(cudaSetDevice(m->device));
+    rqb200_shard *sh = new (std::nothrow) rqb200_shard();
+    if (!sh) { set_error("out of host memory"); return RQB200_ENOMEM; }
+    sh->m = m; sh->rank = rank; sh->world = world;
+    sh->cap_local = max_local_items; sh->cap_recv = max_recv_items;
+    sh->sig_off = 0;
+    sh->counts_off = 256;
+    sh->recv_off = 4096;
+    sh->ret_off = sh->recv_off + align256(sizeof(uint64_t) * (size_t)max_recv_items);
+    sh->block_bytes = sh->ret_off + align256(sizeof(uint32_t) * (size_t)max_local_items) + 256;
+    for (int r = 0; r < SHARD_MAX_WORLD; ++r) sh->peers.base[r] = nullptr;
+    if (cudaMalloc(&sh->block, sh->block_bytes) != cudaSuccess || cudaMalloc(&sh->plan, sizeof(rqb::ShardPlan)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc(%zu) for the symmetric block failed", sh->block_bytes);
+        if (sh->block) cudaFree(sh->block);
+        delete sh;
+        return RQB200_ENOMEM;
+    }
+    RQB_CUDA(cudaMemset(sh->block, 0, sh->block_bytes));
+    RQB_CUDA(cudaMemset(sh->plan, 0, sizeof(rqb::ShardPlan)));
+    RQB_CUDA(cudaDeviceSynchronize());
+    sh->peers.base[rank] = sh->block;
+    sh->connected = world == 1;
+    *out = sh;
+    return 0;
+}
+
+extern "C" int rqb200_shard_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int rqb200_shard_get_handle(rqb200_shard *sh, void *handle_out) {
+    RQB_CHECK(sh != nullptr && handle_out != nullptr, "NULL argument");
+    RQB_CUDA(cudaSetDevice(sh->m->device));
+    cudaIpcMemHandle_t h;
+    RQB_CUDA(cudaIpcGetMemHandle(&h, sh->block));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int rqb200_shard_connect(rqb200_shard *sh, const void *all_handles) {
+    RQB_CHECK(sh != nullptr && all_handles != nullptr, "NULL argument");
+    RQB_CUDA(cudaSetDevice(sh->m->device));
+    for (int r = 0; r < sh->world; ++r) {
+        if (r == sh->rank || sh->peers.base[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)all_handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        RQB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        sh->peers.base[r] = (unsigned char *)p;
+    }
+    sh->connected = true;
+    return 0;
+}
+
+extern "C" void rqb200_shard_destroy(rqb200_shard *sh) {
+    if (!sh) return;
+    cudaSetDevice(sh->m->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < sh->world; ++r)
+        if (r != sh->rank && sh->peers.base[r]) cudaIpcCloseMemHandle(sh->peers.base[r]);
+    if (sh->block) cudaFree(sh->block);
+    if (sh->plan) cudaFree(sh->plan);
+    (void)cudaGetLastError();
+    delete sh;
+}
+
+extern "C" int rqb200_shard_suffix_dedup(rqb200_shard *sh, const int64_t *codes_dev, int64_t n, int L,
+                                         const int *K_host, int64_t *out_dev, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_CHECK(sh != nullptr && K_host != nullptr, "NULL argument");
+    RQB_CHECK(sh->connected, "rqb200_shard_connect has not been called");
+    RQB_CHECK(n >= 0 && n <= sh->cap_local, "n=%lld exceeds the shard capacity %lld", (long long)n, (long long)sh->cap_local);
+    RQB_CHECK(n == 0 || (codes_dev != nullptr && out_dev != nullptr), "NULL buffer");
+    rqb200_model *m = sh->m;
+    RQB_CUDA(cudaSetDevice(m->device));
+    ProfScope ps(PROF_DEDUP, s);
+    SortScratch sc;
+    const int64_t nmax = (n > sh->cap_recv ? n : sh->cap_recv) + 1;
+    RQB_TRY(carve(m, nmax, sc));
+    const int nblocks_max = sc.nblocks;
+    PackArgs pa;
+    int key_bits = 0;
+    RQB_TRY(plan_pack(sc, codes_dev, n, L, K_host, pa, &key_bits, s));
+    uint32_t *digit_total = sc.hist + (size_t)RADIX * nblocks_max;
+    uint32_t *slotpos = reinterpret_cast<uint32_t *>(sc.flags);
+    uint32_t *rank_slot = slotpos + (size_t)nmax;
+    const int world = sh->world, rank = sh->rank;
+    const int nb1 = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    RQB_CUDA(cudaMemsetAsync(digit_total, 0, sizeof(uint32_t) * RADIX, s));
+    if (n > 0) {
+        rqb::count_launch();
+        pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(codes_dev, n, pa, sc.keys[0], nullptr);
+        rqb::count_launch();
+        shard_hist_kernel<<<nb1, SORT_THREADS, 0, s>>>(sc.keys[0], n, world, sc.hist, nb1);
+        rqb::count_launch();
+        radix_scan_rows_kernel<<<world, 256, 0, s>>>(sc.hist, nb1, digit_total);
+    }
+    rqb::count_launch();
+    shard_exchange_counts_kernel<<<1, 32, 0, s>>>(sh->peers, sh->sig_off, sh->counts_off, rank, world, ++sh->epoch, digit_total,
+                                                  (unsigned long long)sh->cap_recv, sh->plan);
+    if (n > 0) {
+        rqb::count_launch();
+        shard_scatter_kernel<<<nb1, SORT_THREADS, 0, s>>>(sc.keys[0], n, world, sh->peers, sh->recv_off, sc.hist, nb1, sh->plan,
+                                                         slotpos);
+    }
+    rqb::count_launch();
+    shard_barrier_kernel<<<1, 32, 0, s>>>(sh->peers, sh->sig_off, rank, world, ++sh->epoch, sh->plan);
+    RQB_LAUNCH_CHECK();
+    rqb::ShardPlan hp;
+    RQB_CUDA(cudaMemcpyAsync(&hp, sh->plan, sizeof(hp), cudaMemcpyDeviceToHost, s));
+    RQB_CUDA(cudaStreamSynchronize(s));
+    const int64_t R = hp.status == 0 ? (int64_t)hp.recv_total : 0;
+    if (R > 0) {
+        RQB_CUDA(cudaMemcpyAsync(sc.keys[0], sh->block + sh->recv_off, sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+        rqb::count_launch();
+        iota_u32_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(sc.vals[0], R);
+        sc.nblocks = (int)((R + SORT_TILE - 1) / SORT_TILE);
+        int buf = 0;
+        RQB_TRY(radix_sort(sc, R, key_bits, s, &buf));
+        RQB_TRY(run_seg_rank(sc, buf, R, nullptr, nullptr, 0, nullptr, false, s, rank_slot));
+        int blocks = (int)((R + 255) / 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        rqb::count_launch();
+        shard_return_kernel<<<blocks, 256, 0, s>>>(rank_slot, world, sh->peers, sh->ret_off, sh->plan);
+    }
+    rqb::count_launch();
+    shard_barrier_kernel<<<1, 32, 0, s>>>(sh->peers, sh->sig_off, rank, world, ++sh->epoch, sh->plan);
+    if (n > 0) {
+        rqb::count_launch();
+        shard_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(codes_dev, n, L, reinterpret_cast<const uint32_t *>(sh->block + sh->ret_off),
+                                                                         slotpos, sh->plan, out_dev);
+    }
+    RQB_LAUNCH_CHECK();
+    int status = 0;
+    RQB_CUDA(cudaMemcpyAsync(&status, &sh->plan->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RQB_CUDA(cudaStreamSynchronize(s));
+    if (hp.status != 0) status = hp.status;
+    if (status == 1) { set_error("sharded dedup: a key owner would receive more than max_recv_items=%lld keys", (long long)sh->cap_recv); return RQB200_ENOMEM; }
+    if (status != 0) { set_error("sharded dedup: timed out waiting for a peer rank"); return RQB200_ESTATE; }
     return 0;
 }

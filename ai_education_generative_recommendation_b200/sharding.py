@@ -75,6 +75,65 @@ class CudaShardOps:
         return out
 
 
+class PeerShardDedup:
+    """Global suffix column over NVLink peer memory (`rqb200_shard_*`, csrc/dedup.cu): the production path on
+    the GPU box.  torch.distributed is used once, to pass the cudaIpc handles around; the data path is the
+    library's own kernels storing into peer memory — no NCCL call per step.
+
+    `max_local_items` bounds n of every later call on this rank; an owner may receive up to `max_recv_items`
+    keys (default 2 * max_local_items + 65536; RQB200 raises MemoryError on every rank beyond that)."""
+
+    def __init__(self, model, group=None, max_local_items: int = 0, max_recv_items: int = 0):
+        self.model = model
+        self.group = group
+        model._ensure_handle()
+        lib = _cabi.lib()
+        if group is not None and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        caps = [int(max_local_items)]
+        if self.world > 1:
+            got = [None] * self.world
+            dist.all_gather_object(got, int(max_local_items), group=group)
+            caps = got
+        self.max_local = max(caps)            # symmetric layout: identical sizes on every rank
+        self._h = ctypes.c_void_p()
+        check(lib.rqb200_shard_create(ctypes.byref(self._h), model._handle, self.rank, self.world, self.max_local,
+                                      int(max_recv_items)))
+        if self.world > 1:
+            nb = lib.rqb200_shard_handle_bytes()
+            mine = ctypes.create_string_buffer(nb)
+            check(lib.rqb200_shard_get_handle(self._h, ctypes.cast(mine, ctypes.c_void_p)))
+            got = [None] * self.world
+            dist.all_gather_object(got, bytes(mine.raw), group=group)
+            blob = ctypes.create_string_buffer(b"".join(got), nb * self.world)
+            check(lib.rqb200_shard_connect(self._h, ctypes.cast(blob, ctypes.c_void_p)))
+            dist.barrier(group=group)
+
+    def __call__(self, codes: torch.Tensor, num_emb_list) -> torch.Tensor:
+        """[n_local, L] int64 codes of this rank's contiguous shard → [n_local, L+1] with the global suffix."""
+        if not codes.is_cuda or codes.dtype != torch.int64:
+            raise RuntimeError("PeerShardDedup needs int64 CUDA codes (there is no CPU fallback)")
+        codes = codes.contiguous()
+        n, Lv = codes.shape
+        out = torch.empty((n, Lv + 1), dtype=torch.int64, device=codes.device)
+        check(_cabi.lib().rqb200_shard_suffix_dedup(self._h, ptr(codes), n, Lv, _cabi.int_array(num_emb_list), ptr(out),
+                                                    stream_ptr(codes.device)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _cabi.lib().rqb200_shard_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def owner_of(keys: torch.Tensor, world: int) -> torch.Tensor:
     """Rank that owns a key: a multiplicative hash so clustered codes spread evenly."""
     h = keys * -7046029254386353131          # 0x9E3779B97F4A7C15 as int64 (wraps)

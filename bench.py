@@ -6,7 +6,8 @@ get_indices(use_sk=False) over every item (encoder MLP + residual quantizer) fol
 dedup, inputs resident in HBM → final [N, L+1] int64 semantic ids resident in HBM.
   N=1 workload: BASELINE configs[1] — 1M items x 768-d, 3 levels x 256 codes, e_dim 32.
   N>1: weak scaling, every rank encodes its own 1M-item shard of an N x 1M catalogue; the dedup is global
-       (packed codes all-to-all to the key owner over NCCL, ranks returned) so ids are unique catalogue-wide.
+       (packed codes stored into the key owner's buffer over NVLink peer memory by the partition kernel itself,
+       ranks written back the same way) so ids are unique catalogue-wide.
 `e2e` is the same work through the host-buffer C-ABI call (rqb200_generate_codes_host): pinned host
 embeddings in, host semantic ids out, H2D/D2H inside the timed region.
 `--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on a bounded
@@ -196,15 +197,17 @@ def main():
     lo = rank * n
     x = torch.empty((n, 768), dtype=torch.float32, device=dev)
     _cabi.check(lib.rqb200_synth_items(SEED, lo, n, 768, n_total, x.data_ptr(), _cabi.stream_ptr()))
-    ops = sharding.CudaShardOps(model)
     Ks = cfg["num_emb_list"]
+    # N > 1: the suffix column is global — keys travel to their owner rank through NVLink peer memory
+    # (rqb200_shard_suffix_dedup: the library's own kernels store into the peers' buffers, no NCCL call per step)
+    peer_dedup = sharding.PeerShardDedup(model, group, max_local_items=n) if world > 1 else None
 
     def step():
         codes = model.get_indices(x, use_sk=False)
         if world == 1:
             out, _ = rq.suffix_dedup(model, codes)
         else:
-            out = sharding.global_suffix(codes, Ks, ops, group)
+            out = peer_dedup(codes, Ks)
         return out
 
     def barrier():
@@ -219,7 +222,7 @@ def main():
     if world > 1:
         # one-off verification: the N-GPU ids equal a single-GPU dedup of the gathered catalogue
         codes = model.get_indices(x, use_sk=False)
-        mine = sharding.global_suffix(codes, Ks, ops, group)
+        mine = peer_dedup(codes, Ks)
         gathered = [torch.empty_like(codes) for _ in range(world)]
         gathered_ids = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, codes)
@@ -316,7 +319,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "items_per_gpu": n, "global_items": n_total, "encode_mode": mode_name,
-                           "step": "get_indices(use_sk=False) + suffix dedup" + (" (global, all-to-all)" if world > 1 else ""),
+                           "step": "get_indices(use_sk=False) + suffix dedup" + (" (global: keys routed to owner ranks over NVLink peer memory)" if world > 1 else ""),
                            "l2": "inputs 3.07 GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
                            "parallelism": f"items sharded x{world}, codebooks replicated",
                            "multi_gpu_ids_equal_single_gpu": multi_check},

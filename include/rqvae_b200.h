@@ -172,6 +172,31 @@ int rqb200_sort_pairs(rqb200_model *m, uint64_t *keys_dev, int64_t *vals_dev, in
 int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_dev, int64_t n,
                         int64_t *rank_dev, void *stream);
 
+/* ---- sharded suffix dedup over NVLink peer memory (new design; SURVEY.md §8e row "dedup") ------------
+ * One process per GPU, contiguous item shards.  Equal codes have to meet to be ranked in ascending GLOBAL
+ * item order, so every packed key travels to owner = hash(key) mod world — written by the partition kernel
+ * itself straight into the owner's receive buffer (peer memory mapped with cudaIpc, NVLink underneath); the
+ * owner ranks them with the same radix sort + segmented rank as rqb200_suffix_dedup and writes the ranks
+ * back into the sources' return buffers.  Cross-GPU ordering uses system-scope release/acquire flags; there
+ * is no NCCL call and one stream synchronisation (the owner needs its receive count to size the sort).
+ * Result: out[n_local, L+1], bit-identical to rqb200_suffix_dedup on the concatenated catalogue.
+ *
+ * Setup: every rank calls rqb200_shard_create, exchanges the rqb200_shard_handle_bytes()-byte handle of
+ * rqb200_shard_get_handle with all ranks (any transport: the Python host uses torch.distributed
+ * all_gather_object), then rqb200_shard_connect with the world*handle_bytes concatenation in rank order.
+ * max_recv_items <= 0 selects 2*max_local_items + 65536; if an owner would receive more keys than that,
+ * every rank returns RQB200_ENOMEM (nothing is written out of bounds).  All ranks must make the same
+ * sequence of rqb200_shard_suffix_dedup calls (it is a collective).                                   */
+typedef struct rqb200_shard rqb200_shard;
+int  rqb200_shard_create(rqb200_shard **out, rqb200_model *m, int rank, int world,
+                         int64_t max_local_items, int64_t max_recv_items);
+int  rqb200_shard_handle_bytes(void);
+int  rqb200_shard_get_handle(rqb200_shard *sh, void *handle_out);
+int  rqb200_shard_connect(rqb200_shard *sh, const void *all_handles);
+int  rqb200_shard_suffix_dedup(rqb200_shard *sh, const int64_t *codes_dev, int64_t n, int L,
+                               const int *K_host, int64_t *out_dev, void *stream);
+void rqb200_shard_destroy(rqb200_shard *sh);
+
 /* ---- k-means codebook init (layers.py:69-82 via vq.py:40-49) ------------------------
  * Lloyd steps on device.  kmeans_assign gives each sample its nearest centre (the quantizer's
  * distance / first-index argmin); kmeans_accumulate adds per-cluster sums[K,e] (fp64),
