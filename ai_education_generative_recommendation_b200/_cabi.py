@@ -41,6 +41,9 @@ _PROTOS = {
     "rqb200_model_set_codebook": (c_int, [c_void_p, c_int, _P]),
     "rqb200_model_get_codebook": (c_int, [c_void_p, c_int, _P]),
     "rqb200_model_set_gate": (c_int, [c_void_p, c_float, c_float]),
+    "rqb200_model_set_screen": (c_int, [c_void_p, c_int, c_float]),
+    "rqb200_model_last_tier_rows": (c_int, [c_void_p, POINTER(c_int64)]),
+    "rqb200_debug_linear_tc": (c_int, [c_void_p, c_int, c_int, _P, c_int64, _P, c_int, c_int, _P]),
     "rqb200_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P]),
     "rqb200_mlp_exact": (c_int, [c_void_p, c_int, _P, _P, c_int64, _P, _P]),
     "rqb200_quantize": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P, _P]),

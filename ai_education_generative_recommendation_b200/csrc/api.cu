@@ -47,14 +47,14 @@ static cudaEvent_t prof_get_event() {
     return e;
 }
 void prof_begin(int slot, cudaStream_t s) {
-    if (!g_prof.enabled) return;
+    if (!g_prof.enabled || slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e = prof_get_event();
     cudaEventRecord(e, s);
     g_prof.open_ev[slot] = e;
 }
 void prof_end(int slot, cudaStream_t s) {
-    if (!g_prof.enabled) return;
+    if (!g_prof.enabled || slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof.open_ev[slot]) return;
     cudaEvent_t e = prof_get_event();
@@ -270,6 +270,21 @@ extern "C" int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_a
     return 0;
 }
 
+extern "C" int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma1) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(gamma1 >= 0.0f, "gate parameters must be non-negative");
+    m->screen_enabled = enabled != 0;
+    if (gamma1 > 0.0f) m->screen_gamma = gamma1;
+    return 0;
+}
+
+extern "C" int rqb200_model_last_tier_rows(rqb200_model *m, int64_t *out2) {
+    RQB_CHECK(m != nullptr && out2 != nullptr, "NULL argument");
+    out2[0] = m->last_tier_rows[0];
+    out2[1] = m->last_tier_rows[1];
+    return 0;
+}
+
 namespace rqb { int tc_set_trace(long long *buf); int tc_set_debug(int flags); }
 extern "C" int rqb200_debug_tc_flags(int flags) { return rqb::tc_set_debug(flags); }
 // diagnostics: device buffer of 8*256 int64 that CTA 0 of the tensor-core linear kernel fills with clock64() stamps
@@ -284,6 +299,20 @@ extern "C" int rqb200_mlp_tc(rqb200_model *m, int which, const float *x_dev, int
         if (!(which == 0 ? m->enc[i].set : m->dec[i].set)) { set_error("layer %d not loaded", i); return RQB200_ESTATE; }
     RQB_CUDA(cudaSetDevice(m->device));
     return mlp_tc(m, which, x_dev, n, y_dev, (cudaStream_t)stream);
+}
+
+// diagnostics / tools: one tensor-core Linear of the model in isolation (passes = 1 or 3)
+extern "C" int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
+                                      int passes, int relu, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(which == 0 || which == 1, "which must be 0 or 1");
+    RQB_CHECK(layer >= 0 && layer < m->n_layers, "layer out of range");
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && y_dev != nullptr, "NULL buffer");
+    Linear &l = which == 0 ? m->enc[layer] : m->dec[layer];
+    RQB_CHECK(l.set, "layer not loaded");
+    RQB_CUDA(cudaSetDevice(m->device));
+    return linear_tc(l, x_dev, n, y_dev, relu != 0, (cudaStream_t)stream, passes);
 }
 
 extern "C" int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out) {

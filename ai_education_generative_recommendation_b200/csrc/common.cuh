@@ -16,7 +16,7 @@ void count_launch();          // bumps the process-wide kernel-launch counter (r
 
 // per-kernel device timing (cudaEvent pairs on the launching stream), enabled by rqb200_profile_enable
 enum ProfSlot { PROF_LINEAR0 = 0, PROF_LINEAR_REST = 1, PROF_QUANTIZE = 2, PROF_DEDUP = 3, PROF_TC_ENCODER = 4,
-                PROF_SINKHORN = 5, PROF_TC_REST = 6, PROF_NSLOTS = 8 };
+                PROF_SINKHORN = 5, PROF_TC_REST = 6, PROF_TIER2 = 7, PROF_RESCUE = 8, PROF_NSLOTS = 12 };
 void prof_begin(int slot, cudaStream_t s);
 void prof_end(int slot, cudaStream_t s);
 struct ProfScope {
@@ -98,6 +98,9 @@ struct rqb200_model {
     int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced
     bool force_simt_quantizer = false;      // diagnostics: keep the SIMT quantizer behind the tensor-core encoder
     float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
+    bool screen_enabled = false;            // tier 1 (opt-in): one fp16 pass over every row, only gated rows get the 3-pass run
+    float screen_gamma = 4.8828125e-04f;    // 2^-11: calibrated gate of the one-pass tier
+    int64_t last_tier_rows[2] = {0, 0};     // rows re-run by tier 2 / tier 3 in the last fast get_indices
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -111,14 +114,19 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
                  bool relu, cudaStream_t s);
 // encode_tc2.cu
 bool linear_tc2_supported(const Linear &l);
-int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
+int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
+               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr);
 // encode_tc.cu
-int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s);
-int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s);
+int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
+              const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr);
+int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s, int passes = 3,
+           const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool profile = true);
 // quantize_tc.cu
 bool quantize_tc_supported(const rqb200_model *m);
+// rows (may be NULL): row i of z is item rows[i] (codes / list entries use the item index); n_dev: device-resident
+// row count (n = upper bound); gamma: relative bound on |z~ - z| used by the margin gate of this tier.
 int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list, unsigned long long *count,
-                cudaStream_t s);
+                cudaStream_t s, float gamma, const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr);
 // quantize.cu
 int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,

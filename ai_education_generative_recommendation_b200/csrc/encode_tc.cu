@@ -45,11 +45,12 @@ constexpr int A_TILE_BYTES = TM * BK * 2;          // 16 KB (one of hi / lo)
 // bit2 no producer smem stores, bit3 no W bulk loads, bit4 no producer global loads
 __device__ int g_tc_debug = 0;
 
-template <int N>
+template <int N, int PASSES>
 struct TcCfg {
+    static constexpr int NSPLIT = PASSES == 1 ? 1 : 2;                 // tiles per operand: hi [, lo]
     static constexpr int W_TILE_BYTES = N * BK * 2;                    // one of hi / lo
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W_TILE_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int STAGE_BYTES = NSPLIT * (A_TILE_BYTES + W_TILE_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 6 ? 6 : ((200 * 1024) / STAGE_BYTES >= 4 ? 4 : (200 * 1024) / STAGE_BYTES);
     static constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;         // two accumulator buffers
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_LD * 4;
     static_assert(STAGES >= 2, "need at least two smem stages");
@@ -57,11 +58,15 @@ struct TcCfg {
 };
 
 // Y[n, N] = act((X[n, K] · W^T) * 2^-s + b);  W pre-packed per 64-wide K slab (hi tile | lo tile, swizzled)
-template <int N>
+// PASSES = 3: split-fp16 operands (hi+lo), three MMAs per K step; PASSES = 1: hi halves only (tier-1 screening pass).
+// n_dev (may be NULL): the row count lives on the device (written by the previous tier's gate); n is its upper bound.
+template <int N, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp,
-                 const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y) {
-    using Cfg = TcCfg<N>;
+                 const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y,
+                 const unsigned long long *__restrict__ n_dev) {
+    using Cfg = TcCfg<N, PASSES>;
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -138,13 +143,19 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = rbase + 16 * i;
-                uint2 hi, lo;
-                split2(src[i].x, src[i].y, hi.x, lo.x);
-                split2(src[i].z, src[i].w, hi.y, lo.y);
                 const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
-                if (!(dbg & 4)) {
-                    *reinterpret_cast<uint2 *>(a_hi + off) = hi;
-                    *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                if (PASSES == 1) {
+                    __half2 h0 = __floats2half2_rn(src[i].x, src[i].y), h1 = __floats2half2_rn(src[i].z, src[i].w);
+                    if (!(dbg & 4))
+                        *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                } else {
+                    uint2 hi, lo;
+                    split2(src[i].x, src[i].y, hi.x, lo.x);
+                    split2(src[i].z, src[i].w, hi.y, lo.y);
+                    if (!(dbg & 4)) {
+                        *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                        *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                    }
                 }
             }
             fence_proxy_async();
@@ -189,16 +200,20 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
+                    const uint32_t w_hi = a_hi + Cfg::NSPLIT * A_TILE_BYTES;
                     const uint32_t w_lo = w_hi + Cfg::W_TILE_BYTES;
                     if (!(dbg & 2))
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; ++kk) {
                         const uint32_t ko = kk * 32;       // 16 fp16 = 32 bytes along K inside the swizzle row
-                        // small cross terms first, the dominant hi*hi product last
-                        umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
-                        umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
-                        umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                        if (PASSES == 1) {
+                            umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                        } else {
+                            // small cross terms first, the dominant hi*hi product last
+                            umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                            umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
+                            umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                        }
                     }
                     umma_commit(&empty[stage]);            // smem stage reusable once these MMAs retire
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -211,15 +226,16 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            constexpr uint32_t slab_bytes = 2 * Cfg::W_TILE_BYTES;
+            constexpr uint32_t slab_bytes = 2 * Cfg::W_TILE_BYTES;               // packed image: hi tile | lo tile per slab
+            constexpr uint32_t copy_bytes = Cfg::NSPLIT * Cfg::W_TILE_BYTES;     // one pass needs the hi tile only
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (dbg & 8) {
                         mbar_arrive(&full_w[stage]);
                     } else {
-                        mbar_arrive_expect_tx(&full_w[stage], slab_bytes);
-                        bulk_g2s(smem + stage * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES, Wp + (size_t)slab * slab_bytes, slab_bytes,
+                        mbar_arrive_expect_tx(&full_w[stage], copy_bytes);
+                        bulk_g2s(smem + stage * Cfg::STAGE_BYTES + Cfg::NSPLIT * A_TILE_BYTES, Wp + (size_t)slab * slab_bytes, copy_bytes,
                                  &full_w[stage]);
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -302,10 +318,10 @@ int ensure_packed(Linear &l, cudaStream_t s) {
     return 0;
 }
 
-template <int N>
-int launch_tc(const Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s) {
-    using Cfg = TcCfg<N>;
-    auto kern = linear_tc_kernel<N>;
+template <int N, int PASSES>
+int launch_tc(const Linear &l, const float *x, int64_t n, float *y, bool relu, const unsigned long long *n_dev, cudaStream_t s) {
+    using Cfg = TcCfg<N, PASSES>;
+    auto kern = linear_tc_kernel<N, PASSES>;
     static bool attr_done = false;
     if (!attr_done) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -315,7 +331,7 @@ int launch_tc(const Linear &l, const float *x, int64_t n, float *y, bool relu, c
     const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);
     count_launch();
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(x, n, l.in, (const unsigned char *)l.W_tc, l.b, ldexpf(1.0f, -l.tc_scale_exp),
-                                                  relu ? 1 : 0, y);
+                                                  relu ? 1 : 0, y, n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -353,21 +369,30 @@ static bool env_tc2() {
     return v == 1;
 }
 
-int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s) {
+// passes: 3 (split-fp16, fp32-class) or 1 (fp16 screening pass).  rows: gather of the input rows (first layer of a
+// re-run tier; needs the 2-CTA kernel).  n_dev: device-resident row count, n = upper bound.
+int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes, const int64_t *rows,
+              const unsigned long long *n_dev) {
     if (n == 0) return 0;
+    RQB_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
     RQB_TRY(ensure_packed(l, s));
-    if (linear_tc2_supported(l) && env_tc2()) return linear_tc2(l, x, n, y, relu, s);
+    if (linear_tc2_supported(l) && (env_tc2() || rows)) return linear_tc2(l, x, n, y, relu, s, passes, rows, n_dev);
+    RQB_CHECK(rows == nullptr, "row gather needs the 2-CTA kernel (out_features 256)");
+#define RQB_TC_CASE(NN)                                                                              \
+    case NN: return passes == 1 ? launch_tc<NN, 1>(l, x, n, y, relu, n_dev, s) : launch_tc<NN, 3>(l, x, n, y, relu, n_dev, s);
     switch (l.out) {
-        case 32: return launch_tc<32>(l, x, n, y, relu, s);
-        case 64: return launch_tc<64>(l, x, n, y, relu, s);
-        case 128: return launch_tc<128>(l, x, n, y, relu, s);
-        case 256: return launch_tc<256>(l, x, n, y, relu, s);
+        RQB_TC_CASE(32)
+        RQB_TC_CASE(64)
+        RQB_TC_CASE(128)
+        RQB_TC_CASE(256)
     }
+#undef RQB_TC_CASE
     set_error("unsupported out_features %d", l.out);
     return RQB200_EINVAL;
 }
 
-int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s) {
+int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s, int passes,
+           const int64_t *rows, const unsigned long long *n_dev, bool profile) {
     Linear *ls = which == 0 ? m->enc : m->dec;
     int maxdim = 0;
     for (int i = 0; i + 1 < m->n_layers; ++i) maxdim = ls[i].out > maxdim ? ls[i].out : maxdim;
@@ -380,8 +405,8 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
         const bool last = i == m->n_layers - 1;
         float *dst = last ? y : (float *)m->act[i & 1].ptr;
         {
-            ProfScope ps(i == 0 ? PROF_TC_ENCODER : PROF_TC_REST, s);      // slot 4 = the wide first layer alone
-            RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s));
+            ProfScope ps(!profile ? -1 : (i == 0 ? PROF_TC_ENCODER : PROF_TC_REST), s);      // slot 4 = the wide first layer alone
+            RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev));
         }
         cur = dst;
     }
@@ -401,45 +426,78 @@ int scatter_rows(const float *src, const int64_t *rows, int64_t nr, int e, float
     RQB_LAUNCH_CHECK();
     return 0;
 }
+__global__ void scatter_rows_dev_kernel(const float *__restrict__ src, const int64_t *__restrict__ rows,
+                                        const unsigned long long *__restrict__ nr_dev, int e, float *__restrict__ dst) {
+    const int64_t total = (int64_t)*nr_dev * e;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = p / e;
+        dst[rows[r] * e + (p - r * e)] = src[p];
+    }
+}
 
-// get_indices, fast route: tensor-core encoder → exact-arithmetic quantizer on z~ with a margin gate →
-// exact recomputation of the gated rows.
+// get_indices, fast route.  Three tiers, every one certifying the rows it keeps with the margin gate of the quantizer:
+//   tier 1 (screening, optional): ONE fp16 tensor pass over every row (operands rounded to fp16: |z~ - z| <~ 2^-10 |z|),
+//           rows whose top-2 gap at any level is inside the gate for gamma1 are appended to list1;
+//   tier 2: list1 rows (all rows when screening is off) re-run with split-fp16, three passes (|z~ - z| <~ 2^-16.7 |z|),
+//           gate gamma → list2.  Launched straight behind tier 1: its row count stays on the device;
+//   tier 3: list2 rows re-run by the exact SIMT kernels in the reference's summation order.
+// Codes are therefore identical to the exact route; only the route differs.
 int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes, float *z_out,
                      int64_t *stats_host, cudaStream_t s) {
-    // workspace: z~[n,e] | margin[n] | list[n] | count
-    const size_t zb = sizeof(float) * (size_t)n * m->e;
-    const size_t mb = sizeof(float) * (size_t)n;
-    const size_t lb = sizeof(int64_t) * (size_t)n;
-    const size_t off_m = (zb + 255) & ~(size_t)255;
-    const size_t off_l = (off_m + mb + 255) & ~(size_t)255;
-    const size_t off_c = (off_l + lb + 255) & ~(size_t)255;
-    RQB_TRY(ws_reserve(m->misc, off_c + 256 + sizeof(float) * (size_t)n * m->e / 8 + 4096));
+    // workspace: z~[n,e] | z2[n,e] (compact, tier 2) | list1[n] | list2[n] | count1, count2
+    const size_t zb = (sizeof(float) * (size_t)n * m->e + 255) & ~(size_t)255;
+    const size_t lb = (sizeof(int64_t) * (size_t)n + 255) & ~(size_t)255;
+    const bool screen = m->screen_enabled && quantize_tc_supported(m) && !m->force_simt_quantizer;
+    RQB_TRY(ws_reserve(m->misc, 2 * zb + 2 * lb + 512));
     char *base = (char *)m->misc.ptr;
-    float *z = z_out ? z_out : (float *)base;
-    float *margin = (float *)(base + off_m);
-    int64_t *list = (int64_t *)(base + off_l);
-    unsigned long long *count = (unsigned long long *)(base + off_c);
-    RQB_TRY(mlp_tc(m, 0, x, n, z, s));
-    RQB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), s));
-    if (quantize_tc_supported(m) && !m->force_simt_quantizer) {
-        RQB_TRY(quantize_tc(m, z, n, codes, list, count, s));          // distances on the tensor cores, gate fused
+    float *z1 = z_out ? z_out : (float *)base;
+    float *z2 = (float *)(base + zb);
+    int64_t *list1 = (int64_t *)(base + 2 * zb);
+    int64_t *list2 = (int64_t *)(base + 2 * zb + lb);
+    unsigned long long *counts = (unsigned long long *)(base + 2 * zb + 2 * lb);
+    RQB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), s));
+    unsigned long long h[2] = {0, 0};
+    if (screen) {
+        RQB_TRY(mlp_tc(m, 0, x, n, z1, s, 1, nullptr, nullptr, true));
+        {
+            ProfScope ps(PROF_QUANTIZE, s);
+            RQB_TRY(quantize_tc(m, z1, n, codes, list1, counts, s, m->screen_gamma));
+        }
+        {
+            ProfScope ps(PROF_TIER2, s);
+            RQB_TRY(mlp_tc(m, 0, x, n, z2, s, 3, list1, counts, false));
+            RQB_TRY(quantize_tc(m, z2, n, codes, list2, counts + 1, s, m->gate_gamma, list1, counts));
+            if (z_out) {
+                count_launch();
+                scatter_rows_dev_kernel<<<kNumSMs * 4, 256, 0, s>>>(z2, list1, counts, m->e, z_out);
+                RQB_LAUNCH_CHECK();
+            }
+        }
     } else {
-        RQB_TRY(quantize_exact(m, z, n, codes, nullptr, nullptr, nullptr, nullptr, margin, s));   // margin - threshold
-        count_launch();
-        gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(margin, n, list, count);
-        RQB_LAUNCH_CHECK();
+        RQB_TRY(mlp_tc(m, 0, x, n, z1, s, 3, nullptr, nullptr, true));
+        if (quantize_tc_supported(m) && !m->force_simt_quantizer) {
+            ProfScope ps(PROF_QUANTIZE, s);
+            RQB_TRY(quantize_tc(m, z1, n, codes, list2, counts + 1, s, m->gate_gamma));   // distances on the tensor cores, gate fused
+        } else {
+            float *margin = z2;                                                          // [n] floats, z2 is unused here
+            RQB_TRY(quantize_exact(m, z1, n, codes, nullptr, nullptr, nullptr, nullptr, margin, s));   // margin - threshold
+            count_launch();
+            gate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(margin, n, list2, counts + 1);
+            RQB_LAUNCH_CHECK();
+        }
     }
-    unsigned long long h = 0;
-    RQB_CUDA(cudaMemcpyAsync(&h, count, sizeof(h), cudaMemcpyDeviceToHost, s));
+    RQB_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));
     RQB_CUDA(cudaStreamSynchronize(s));
-    if (stats_host) stats_host[0] = (int64_t)h;
-    if (h > 0) {
+    if (stats_host) stats_host[0] = (int64_t)h[1];
+    m->last_tier_rows[0] = (int64_t)h[0];
+    m->last_tier_rows[1] = (int64_t)h[1];
+    if (h[1] > 0) {
         // exact route for the gated rows: gather → exact MLP → exact quantizer → scatter codes
-        const int64_t nr = (int64_t)h;
+        ProfScope ps(PROF_RESCUE, s);
+        const int64_t nr = (int64_t)h[1];
         Workspace &zw = m->rescue;
         RQB_TRY(ws_reserve(zw, sizeof(float) * (size_t)nr * m->e));
         float *zr = (float *)zw.ptr;
-        // run_mlp equivalent with row gather (exact kernels)
         int maxdim = 0;
         for (int i = 0; i + 1 < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
         RQB_TRY(ws_reserve(m->rescue_act[0], sizeof(float) * (size_t)nr * maxdim));
@@ -448,14 +506,11 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
         for (int i = 0; i < m->n_layers; ++i) {
             const bool last = i == m->n_layers - 1;
             float *dst = last ? zr : (float *)m->rescue_act[i & 1].ptr;
-            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list : nullptr, nr, dst, !last, s));
+            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list2 : nullptr, nr, dst, !last, s));
             cur = dst;
         }
-        RQB_TRY(quantize_exact(m, zr, nr, codes, list, nullptr, nullptr, nullptr, nullptr, s));
-        if (z_out) {
-            // keep the caller's latent exact on rescued rows as well
-            RQB_TRY(scatter_rows(zr, list, nr, m->e, z_out, s));
-        }
+        RQB_TRY(quantize_exact(m, zr, nr, codes, list2, nullptr, nullptr, nullptr, nullptr, s));
+        if (z_out) RQB_TRY(scatter_rows(zr, list2, nr, m->e, z_out, s));      // keep the caller's latent exact on rescued rows
     }
     return 0;
 }

@@ -36,13 +36,17 @@ constexpr int T2_RSTEP = T2_CONV * 32 / 16;                 // rows covered by o
 constexpr int T2_MMA_WARP = T2_EPI + T2_CONV, T2_LOAD_WARP = T2_MMA_WARP + 1;
 constexpr int T2_A_TILE = TM2 * BK2 * 2;   // 16 KB (hi or lo)
 constexpr int T2_W_TILE = NH2 * BK2 * 2;   // 16 KB (hi or lo, this CTA's half)
-constexpr int T2_STAGE = 2 * T2_A_TILE + 2 * T2_W_TILE;     // 64 KB
-constexpr int T2_STAGES = 3;
+// PASSES = 3: split-fp16 (hi+lo) operands, three MMAs per K step;  PASSES = 1: hi halves only (tier-1 screening pass)
+template <int PASSES> struct T2Cfg {
+    static constexpr int NSPLIT = PASSES == 1 ? 1 : 2;                    // tiles per operand (hi [, lo])
+    static constexpr int STAGE = NSPLIT * (T2_A_TILE + T2_W_TILE);        // 64 KB / 32 KB
+    static constexpr int STAGES = PASSES == 1 ? 6 : 3;
+    static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + T2_EPI * 32 * EPI_LD * 4;
+};
 #ifndef T2_PREFETCH_N
 #define T2_PREFETCH_N 2
 #endif
 constexpr int T2_PREFETCH = T2_PREFETCH_N;     // K slabs of X in flight per producer thread (registers)
-constexpr int T2_SMEM = T2_STAGES * T2_STAGE + 1024 + 256 + T2_EPI * 32 * EPI_LD * 4;
 constexpr int T2_TMEM_COLS = 512;          // two 256-column accumulator buffers
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -98,9 +102,15 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
                  : "memory");
 }
 
+// rows (may be NULL): gather — tile row i reads X[rows[i]] (tier-2 re-run of gated rows), Y stays compact.
+// n_dev (may be NULL): the row count lives on the device (written by the previous tier's gate), n is its upper bound.
+template <int PASSES, bool GATHER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
-                  const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y) {
+                  const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y,
+                  const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev) {
+    constexpr int T2_STAGE = T2Cfg<PASSES>::STAGE, T2_STAGES = T2Cfg<PASSES>::STAGES;
+    if (GATHER && n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + T2_STAGES * T2_STAGE);
@@ -164,10 +174,17 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
         auto load_slab = [&](int64_t st, float4 (&dst)[T2_NF4]) {
             const int64_t pt = pair0 + (st / KS) * npairs;
             const int k0 = (int)(st % KS) * BK2 + c4 * 4;
+            int64_t src[T2_NF4];
+#pragma unroll
+            for (int i = 0; i < T2_NF4; ++i) {                   // (the row indices first, as one batch of independent loads)
+                const int64_t row = pt * (2 * TM2) + rank * TM2 + rbase + T2_RSTEP * i;
+                src[i] = row;
+                if (GATHER) src[i] = row < n ? __ldg(rows + row) : 0;
+            }
 #pragma unroll
             for (int i = 0; i < T2_NF4; ++i) {
                 const int64_t row = pt * (2 * TM2) + rank * TM2 + rbase + T2_RSTEP * i;
-                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
+                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + src[i] * (int64_t)K + k0));
                 else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -180,12 +197,17 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
 #pragma unroll
             for (int i = 0; i < T2_NF4; ++i) {
                 const int r = rbase + T2_RSTEP * i;
-                uint2 hi, lo;
-                split2(src[i].x, src[i].y, hi.x, lo.x);
-                split2(src[i].z, src[i].w, hi.y, lo.y);
                 const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
-                *reinterpret_cast<uint2 *>(a_hi + off) = hi;
-                *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                if (PASSES == 1) {
+                    __half2 h0 = __floats2half2_rn(src[i].x, src[i].y), h1 = __floats2half2_rn(src[i].z, src[i].w);
+                    *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                } else {
+                    uint2 hi, lo;
+                    split2(src[i].x, src[i].y, hi.x, lo.x);
+                    split2(src[i].z, src[i].w, hi.y, lo.y);
+                    *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                    *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -226,14 +248,18 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(smem + stage * T2_STAGE);
                         const uint32_t a_lo = a_hi + T2_A_TILE;
-                        const uint32_t w_hi = a_hi + 2 * T2_A_TILE;
+                        const uint32_t w_hi = a_hi + T2Cfg<PASSES>::NSPLIT * T2_A_TILE;
                         const uint32_t w_lo = w_hi + T2_W_TILE;
 #pragma unroll
                         for (int kk = 0; kk < BK2 / 16; ++kk) {
                             const uint32_t ko = kk * 32;
-                            umma_f16_2cta(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
-                            umma_f16_2cta(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
-                            umma_f16_2cta(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                            if (PASSES == 1) {
+                                umma_f16_2cta(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                            } else {
+                                umma_f16_2cta(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                                umma_f16_2cta(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
+                                umma_f16_2cta(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                            }
                         }
                         umma_commit_2cta(&empty[stage]);
                         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
@@ -256,12 +282,13 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            constexpr uint32_t half_bytes = 2 * T2_W_TILE;              // hi | lo of this CTA's 128 features
+            constexpr uint32_t half_bytes = 2 * T2_W_TILE;              // hi | lo of this CTA's 128 features (packed image)
+            constexpr uint32_t copy_bytes = T2Cfg<PASSES>::NSPLIT * T2_W_TILE;   // one pass needs the hi tile only
             for (int64_t pt = pair0; pt < npt; pt += npairs) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&ready[stage], half_bytes);
-                    bulk_g2s(smem + stage * T2_STAGE + 2 * T2_A_TILE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, half_bytes,
+                    mbar_arrive_expect_tx(&ready[stage], copy_bytes);
+                    bulk_g2s(smem + stage * T2_STAGE + T2Cfg<PASSES>::NSPLIT * T2_A_TILE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, copy_bytes,
                              &ready[stage]);
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -305,8 +332,27 @@ __global__ void pack_w2_kernel(const float *__restrict__ W, int K, int KS, float
 
 bool linear_tc2_supported(const Linear &l) { return l.out == N2 && l.in % 8 == 0; }
 
-// requires l.tc_scale_exp to be set (ensure_packed of encode_tc.cu ran)
-int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s) {
+template <int PASSES, bool GATHER>
+static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, const int64_t *rows,
+                      const unsigned long long *n_dev, cudaStream_t s) {
+    auto kern = linear_tc2_kernel<PASSES, GATHER>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg<PASSES>::SMEM));
+        attr_done = true;
+    }
+    const int64_t npt = (n + 2 * TM2 - 1) / (2 * TM2);
+    int64_t pairs = npt < kNumSMs / 2 ? npt : kNumSMs / 2;
+    count_launch();
+    kern<<<(unsigned)(pairs * 2), T2_THREADS, T2Cfg<PASSES>::SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
+                                                                       ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y, rows, n_dev);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+// requires l.tc_scale_exp to be set (ensure_packed of encode_tc.cu ran).  n is an upper bound when n_dev is given.
+int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes,
+               const int64_t *rows, const unsigned long long *n_dev) {
     if (n == 0) return 0;
     const int KS = (l.in + BK2 - 1) / BK2;
     if (!l.W_tc2) {
@@ -317,18 +363,12 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
         RQB_LAUNCH_CHECK();
         l.W_tc2 = p;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        RQB_CUDA(cudaFuncSetAttribute(linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-        attr_done = true;
+    if (rows) {
+        RQB_CHECK(passes == 3, "row gather is only built for the three-pass kernel");
+        return launch_tc2<3, true>(l, x, n, y, relu, rows, n_dev, s);
     }
-    const int64_t npt = (n + 2 * TM2 - 1) / (2 * TM2);
-    int64_t pairs = npt < kNumSMs / 2 ? npt : kNumSMs / 2;
-    count_launch();
-    linear_tc2_kernel<<<(unsigned)(pairs * 2), T2_THREADS, T2_SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
-                                                                        ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y);
-    RQB_LAUNCH_CHECK();
-    return 0;
+    RQB_CHECK(n_dev == nullptr, "a device-side row count needs the gather variant");
+    return passes == 1 ? launch_tc2<1, false>(l, x, n, y, relu, nullptr, nullptr, s) : launch_tc2<3, false>(l, x, n, y, relu, nullptr, nullptr, s);
 }
 
 }  // namespace rqb

@@ -60,8 +60,9 @@ template <int E>
 __global__ void __launch_bounds__(QTC_THREADS, 1)
 quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *__restrict__ codes,
                    int64_t *__restrict__ list, unsigned long long *__restrict__ list_count, float gate_gamma,
-                   float gate_floor) {
+                   float gate_floor, const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev) {
     static_assert(E % 8 == 0 && E <= 64, "tensor-core quantizer supports e_dim <= 64");
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *a_base = smem;                                     // [group][hi|lo] 16 KB each
@@ -113,6 +114,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
             if (!active) { cb_round += nchunks_total; continue; }
             const int64_t row = tile * QTM + rloc;
             const bool live = row < n;
+            const int64_t item = live ? (rows ? __ldg(rows + row) : row) : 0;      // where the codes of this row go
             float r[E];
 #pragma unroll
             for (int k = 0; k < E; k += 4) {
@@ -159,10 +161,8 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     mbar_wait(&d_full[g], round & 1);
                     ++round;
                     tc_fence_after();
-#pragma unroll 1
-                    for (int cc0 = 0; cc0 < ncols; cc0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + (uint32_t)cc0, v);
+                    // two register buffers: the TMEM load of the next 32 columns is in flight while this one is scanned
+                    auto scan32 = [&](const uint32_t (&v)[32], int cc0) {
 #pragma unroll
                         for (int t4 = 0; t4 < 8; ++t4) {
 #pragma unroll
@@ -173,6 +173,19 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                                 sd[u] = fminf(sd[u], fmaxf(d, bd[u]));
                                 if (d < bd[u]) { bd[u] = d; bi[u] = c0 + cc0 + 4 * t4 + u; }
                             }
+                        }
+                    };
+                    uint32_t va[32], vb[32];
+                    tmem_ld32_async(t_addr, va);
+#pragma unroll 1
+                    for (int cc0 = 0; cc0 < ncols; cc0 += 64) {
+                        tmem_ld_wait(va);
+                        if (cc0 + 32 < ncols) tmem_ld32_async(t_addr + (uint32_t)(cc0 + 32), vb);
+                        scan32(va, cc0);
+                        if (cc0 + 32 < ncols) {
+                            tmem_ld_wait(vb);
+                            if (cc0 + 64 < ncols) tmem_ld32_async(t_addr + (uint32_t)(cc0 + 64), va);
+                            scan32(vb, cc0 + 32);
                         }
                     }
                     tc_fence_before();
@@ -192,7 +205,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 if (bad_index) best = 0;
                 second = fmaf(second, inv_s, xx);
                 bestd = fmaf(bestd, inv_s, xx);
-                if (live) codes[row * qa.L + l] = best;
+                if (live) codes[item * qa.L + l] = best;
                 {
                     // Let eps bound |r~ - r| (tensor-core encoder) and rho = |r - c_best|.  A code j can overtake `best`
                     // only if |c_j - c_best| <= 2 rho + 2 eps, and then (d_j - d_best) moves by at most
@@ -224,7 +237,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(list_count, (unsigned long long)__popc(ballot));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = row;
+                if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = item;
             }
         }
     } else if (warp == 8) {
@@ -381,7 +394,8 @@ bool quantize_tc_supported(const rqb200_model *m) { return m->e == 16 || m->e ==
 
 template <int E>
 static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list,
-                      unsigned long long *count, cudaStream_t s) {
+                      unsigned long long *count, cudaStream_t s, float gamma, const int64_t *rows,
+                      const unsigned long long *n_dev) {
     auto kern = quantize_tc_kernel<E>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -403,22 +417,21 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
     const int64_t npairs = ((n + QTM - 1) / QTM + 1) / 2;
     const unsigned grid = (unsigned)(npairs < kNumSMs ? npairs : kNumSMs);
     count_launch();
-    kern<<<grid, QTC_THREADS, Q_SMEM, s>>>(z, n, qa, codes, list, count, m->gate_gamma, m->gate_floor);
+    kern<<<grid, QTC_THREADS, Q_SMEM, s>>>(z, n, qa, codes, list, count, gamma, m->gate_floor, rows, n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
 
 // z~[n,e] → codes[n,L] (approximate route) + list of rows that need the exact route
 int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int64_t *list, unsigned long long *count,
-                cudaStream_t s) {
+                cudaStream_t s, float gamma, const int64_t *rows, const unsigned long long *n_dev) {
     if (n == 0) return 0;
     RQB_TRY(quantize_tc_prepare(m, s));
-    ProfScope ps(PROF_QUANTIZE, s);
     switch (m->e) {
-        case 16: return launch_qtc<16>(m, z, n, codes, list, count, s);
-        case 32: return launch_qtc<32>(m, z, n, codes, list, count, s);
-        case 48: return launch_qtc<48>(m, z, n, codes, list, count, s);
-        case 64: return launch_qtc<64>(m, z, n, codes, list, count, s);
+        case 16: return launch_qtc<16>(m, z, n, codes, list, count, s, gamma, rows, n_dev);
+        case 32: return launch_qtc<32>(m, z, n, codes, list, count, s, gamma, rows, n_dev);
+        case 48: return launch_qtc<48>(m, z, n, codes, list, count, s, gamma, rows, n_dev);
+        case 64: return launch_qtc<64>(m, z, n, codes, list, count, s, gamma, rows, n_dev);
     }
     set_error("tensor-core quantizer: e_dim %d not supported", m->e);
     return RQB200_EINVAL;

@@ -331,6 +331,11 @@ class RQVAE(nn.Module):
         self._ensure_handle()
         check(_cabi.lib().rqb200_model_set_gate(self._handle, float(gamma), float(floor_abs)))
 
+    def set_screen(self, enabled: bool, gamma1: float = 0.0):
+        """Screening tier of the fast route (one fp16 pass over every row; see rqb200_model_set_screen)."""
+        self._ensure_handle()
+        check(_cabi.lib().rqb200_model_set_screen(self._handle, int(bool(enabled)), float(gamma1)))
+
     @torch.no_grad()
     def encode_tc(self, x: torch.Tensor) -> torch.Tensor:
         """Encoder MLP on the tensor cores (fp32-class accuracy, not bit-exact) — diagnostic / building block."""
@@ -444,7 +449,10 @@ class RQVAE(nn.Module):
         stats = (ctypes.c_int64 * 4)()
         check(_cabi.lib().rqb200_get_indices(self._handle, int(self.encode_mode), ptr(x2), n, ptr(codes), 0, stats,
                                              stream_ptr(xs.device)))
-        self.last_stats = {"rescued_rows": int(stats[0])}
+        tiers = (ctypes.c_int64 * 2)()
+        check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
+        self.last_stats = {"rescued_rows": int(stats[0]),
+                           "three_pass_rows": int(tiers[0]) if self.encode_mode == _cabi.ENCODE_FAST else 0}
         return codes.view(*xs.shape[:-1], Lv)
 
     def compute_loss(self, out, quant_loss, xs=None):

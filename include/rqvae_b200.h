@@ -53,7 +53,9 @@ int         rqb200_device_count(void);
  * rqb200_profile_enable(1) makes the library record cudaEvent pairs around its main kernels on the
  * launching stream; rqb200_profile_read waits for them and returns accumulated milliseconds and
  * launch counts per slot: 0 first Linear (exact), 1 other Linears (exact), 2 quantizer, 3 dedup
- * (sort + segmented rank), 4 tensor-core first Linear, 5 Sinkhorn regroup, 6 other tensor-core Linears.                        */
+ * (sort + segmented rank), 4 tensor-core first Linear, 5 Sinkhorn regroup, 6 other tensor-core Linears,
+ * 7 three-pass re-run tier of the fast route (all its kernels), 8 exact rescue tier (all its kernels; its
+ * quantizer launch is also counted in slot 2).                                                          */
 long long rqb200_launch_count(void);
 int rqb200_profile_enable(int on);
 int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
@@ -62,6 +64,10 @@ int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
 int rqb200_debug_tc_trace(long long *buf_dev);
 /* Diagnostics: ablation switches of the tensor-core linear kernel (tools/ablate_tc.py); 0 = production. */
 int rqb200_debug_tc_flags(int flags);
+/* Diagnostics: one tensor-core Linear (+bias, optional ReLU) of the model in isolation; passes = 3 (split-fp16)
+ * or 1 (fp16 screening pass).  Used by tools/ to time and ablate the kernels.                        */
+int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
+                           int passes, int relu, void *stream);
 
 /* ---- model lifetime ---------------------------------------------------------------
  * Replaces the module tree RQVAE.__init__ builds (rqvae.py:45-58): an encoder MLP
@@ -83,6 +89,13 @@ int rqb200_model_set_codebook(rqb200_model *m, int level, const float *E);
  * |z~ - z| <= gamma * (|z| + floor_abs) per row; rows whose top-2 distance gap could be closed by
  * such an error are re-run by the exact kernels.  Defaults: gamma = 2^-15, floor_abs = 1e-3.       */
 int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_abs);
+/* Screening tier of the fast route: when enabled (default), every row first takes ONE fp16 tensor pass and is
+ * certified with the same margin gate at the looser bound gamma1 (default 2^-11; 0 keeps the current value);
+ * only rows inside that gate are re-run with the three-pass split-fp16 kernels, and only rows inside the
+ * tight gate of rqb200_model_set_gate go to the exact kernels.  rqb200_model_last_tier_rows: rows re-run by
+ * the three-pass tier [0] and by the exact tier [1] in the last RQB200_ENCODE_FAST call.                  */
+int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma1);
+int rqb200_model_last_tier_rows(rqb200_model *m, int64_t *out2);
 /* Copy the current codebook of `level` back (host or device destination). */
 int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out);
 

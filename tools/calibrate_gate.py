@@ -29,9 +29,17 @@ for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
            "rel_err_log2_max": float(torch.log2(rel.max())), "best_scale_minus_1": s_opt - 1.0,
            "rel_err_after_scale_max": float(rel2.max()), "rel_err_after_scale_mean": float(rel2.mean())}
     m.encode_mode = _cabi.ENCODE_FAST
+    m.set_screen(False)
     for gamma_log2 in (-30, -19, -17, -16, -15, -14):
         m.set_gate(2.0 ** gamma_log2 if gamma_log2 > -30 else 0.0, 1e-3)
         fast = m.get_indices(x)
         out[f"gamma=2^{gamma_log2}"] = {"rescued": m.last_stats["rescued_rows"],
                                         "mismatching_rows": int((fast != exact).any(1).sum())}
+    # screening tier (one fp16 pass): rows sent on to the three-pass tier, rows mis-coded if the tight gate were off
+    m.set_gate(2.0 ** -15, 1e-3)
+    for g1 in (-14, -13, -12.5, -12, -11.5, -11, -10.5, -10, -9):
+        m.set_screen(True, 2.0 ** g1)
+        fast = m.get_indices(x)
+        out[f"screen=2^{g1}"] = {"three_pass_rows": m.last_stats["three_pass_rows"], "rescued": m.last_stats["rescued_rows"],
+                                 "mismatching_rows": int((fast != exact).any(1).sum())}
     print(json.dumps(out))
