@@ -352,8 +352,11 @@ __global__ void gate_kernel(const float *__restrict__ margin, int64_t n, int64_t
 
 }  // namespace
 
+static int g_tc_debug_host = 0;
+int tc_debug_flags() { return g_tc_debug_host; }
 int tc_set_debug(int flags) {
     RQB_CUDA(cudaMemcpyToSymbol(g_tc_debug, &flags, sizeof(flags)));
+    g_tc_debug_host = flags;
     return 0;
 }
 

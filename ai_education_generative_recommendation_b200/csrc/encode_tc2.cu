@@ -69,6 +69,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank)
         "r"(rank)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
 // wait with cluster-scope acquire (barriers that receive remote arrivals)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
@@ -108,7 +118,9 @@ template <int PASSES, bool GATHER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
                   const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y,
-                  const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev) {
+                  const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev, int dbg) {
+    // dbg: ablation switches of tools/ablate_tc2.py (0 in production) — bit0 no epilogue stores, bit1 no MMA,
+    // bit2 no producer smem stores, bit3 no W bulk loads, bit4 no X loads
     constexpr int T2_STAGE = T2Cfg<PASSES>::STAGE, T2_STAGES = T2Cfg<PASSES>::STAGES;
     if (GATHER && n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
@@ -159,7 +171,7 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             epilogue_rows<N2>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N2), patch, lane, bias, inv_scale, relu,
-                              Y, pt * (2 * TM2) + rank * TM2 + warp * 32, n, true);
+                              Y, pt * (2 * TM2) + rank * TM2 + warp * 32, n, !(dbg & 1));
             tc_fence_before();
             if (rank == 0) mbar_arrive(&tmem_empty[buf]);
             else mbar_arrive_remote(&tmem_empty[buf], 0);
@@ -184,7 +196,7 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
 #pragma unroll
             for (int i = 0; i < T2_NF4; ++i) {
                 const int64_t row = pt * (2 * TM2) + rank * TM2 + rbase + T2_RSTEP * i;
-                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + src[i] * (int64_t)K + k0));
+                if (row < n && k0 < K && !(dbg & 16)) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + src[i] * (int64_t)K + k0));
                 else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -200,16 +212,19 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                 const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
                 if (PASSES == 1) {
                     __half2 h0 = __floats2half2_rn(src[i].x, src[i].y), h1 = __floats2half2_rn(src[i].z, src[i].w);
-                    *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    if (!(dbg & 4))
+                        *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
                 } else {
                     uint2 hi, lo;
                     split2(src[i].x, src[i].y, hi.x, lo.x);
                     split2(src[i].z, src[i].w, hi.y, lo.y);
-                    *reinterpret_cast<uint2 *>(a_hi + off) = hi;
-                    *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                    if (!(dbg & 4)) {
+                        *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                        *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+                    }
                 }
             }
-            fence_proxy_async();
+            if (!(dbg & 32)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[stage]);
             if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
@@ -244,12 +259,14 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N2);
                     for (int slab = 0; slab < KS; ++slab) {
                         mbar_wait(&ready[stage], phase);
-                        mbar_wait_cluster(&peer_ready[stage], phase);
+                        if (dbg & 256) mbar_wait(&peer_ready[stage], phase);
+                        else mbar_wait_cluster(&peer_ready[stage], phase);
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(smem + stage * T2_STAGE);
                         const uint32_t a_lo = a_hi + T2_A_TILE;
                         const uint32_t w_hi = a_hi + T2Cfg<PASSES>::NSPLIT * T2_A_TILE;
                         const uint32_t w_lo = w_hi + T2_W_TILE;
+                        if (!(dbg & 2))
 #pragma unroll
                         for (int kk = 0; kk < BK2 / 16; ++kk) {
                             const uint32_t ko = kk * 32;
@@ -271,7 +288,8 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                 for (int64_t pt = pair0; pt < npt; pt += npairs) {
                     for (int slab = 0; slab < KS; ++slab) {
                         mbar_wait(&ready[stage], phase);
-                        mbar_arrive_remote(&peer_ready[stage], 0);
+                        if (dbg & 128) mbar_arrive_remote_relaxed(&peer_ready[stage], 0);
+                        else mbar_arrive_remote(&peer_ready[stage], 0);
                         if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -287,9 +305,13 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             for (int64_t pt = pair0; pt < npt; pt += npairs) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&ready[stage], copy_bytes);
-                    bulk_g2s(smem + stage * T2_STAGE + T2Cfg<PASSES>::NSPLIT * T2_A_TILE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, copy_bytes,
-                             &ready[stage]);
+                    if (dbg & 8) {
+                        mbar_arrive(&ready[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&ready[stage], copy_bytes);
+                        bulk_g2s(smem + stage * T2_STAGE + T2Cfg<PASSES>::NSPLIT * T2_A_TILE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes,
+                                 copy_bytes, &ready[stage]);
+                    }
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -332,6 +354,8 @@ __global__ void pack_w2_kernel(const float *__restrict__ W, int K, int KS, float
 
 bool linear_tc2_supported(const Linear &l) { return l.out == N2 && l.in % 8 == 0; }
 
+int tc_debug_flags();     // encode_tc.cu
+
 template <int PASSES, bool GATHER>
 static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, const int64_t *rows,
                       const unsigned long long *n_dev, cudaStream_t s) {
@@ -345,7 +369,8 @@ static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu,
     int64_t pairs = npt < kNumSMs / 2 ? npt : kNumSMs / 2;
     count_launch();
     kern<<<(unsigned)(pairs * 2), T2_THREADS, T2Cfg<PASSES>::SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
-                                                                       ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y, rows, n_dev);
+                                                                       ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y, rows, n_dev,
+                                                                       tc_debug_flags());
     RQB_LAUNCH_CHECK();
     return 0;
 }

@@ -32,11 +32,12 @@ constexpr int Q_STAGES = 2;
 constexpr int Q_A_BYTES = QTM * 128;       // one of hi / lo, one 64-wide K slab
 constexpr int Q_CB_TILE = QCH * 128;       // one of hi / lo
 constexpr int Q_STAGE_BYTES = 2 * Q_CB_TILE;               // hi | lo
-constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + 1024 + 256;
+constexpr int Q_CC_MAX = 4096;            // code norms of all levels kept in shared memory when sum(K) fits (16 KB)
+constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + 1024 + 256 + Q_CC_MAX * 4;
 
 struct QtcArgs {
     const unsigned char *cbp[RQB200_MAX_LEVELS];   // packed chunks: [hi tile | lo tile]
-    const float *ccs[RQB200_MAX_LEVELS];           // E == 64 only (no room for the augmented column): |c_j|^2 2^s, +huge on padding
+    const float *ccs[RQB200_MAX_LEVELS];           // |c_j|^2 2^s per code, padded to 256 per chunk with +huge
     uint32_t aug_half[RQB200_MAX_LEVELS];          // fp16 bits of 2^t: value of the augmented A column (see pack_codebook_kernel)
     const float *cb[RQB200_MAX_LEVELS];            // fp32 codebooks for the gather
     const float *cc[RQB200_MAX_LEVELS];
@@ -74,6 +75,18 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     uint64_t *cb_full = bars + 6;       // [Q_STAGES] loader → MMA (tx)
     uint64_t *cb_empty = bars + 8;      // [Q_STAGES] MMA → loader (commit)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
+    float *cc_s = reinterpret_cast<float *>(cb_base + Q_STAGES * Q_STAGE_BYTES + 256);      // per level, padded to 256: |c_j|^2 2^s (+huge on padding)
+    int cc_total = 0;
+    for (int l = 0; l < qa.L; ++l) cc_total += (qa.K[l] + QCH - 1) / QCH * QCH;
+    const bool cc_in_smem = cc_total <= Q_CC_MAX;
+    if (cc_in_smem) {
+        int off = 0;
+        for (int l = 0; l < qa.L; ++l) {
+            const int kp = (qa.K[l] + QCH - 1) / QCH * QCH;
+            for (int i = threadIdx.x; i < kp; i += QTC_THREADS) cc_s[off + i] = qa.ccs[l][i];
+            off += kp;
+        }
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (n + QTM - 1) / QTM;
@@ -123,7 +136,8 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
             }
             float min_margin = __int_as_float(0x7f800000);
             float gate_eps = 0.0f;
-            for (int l = 0; l < qa.L; ++l) {
+            int cc_base = 0;                                                   // offset of this level's norms in cc_s
+            for (int l = 0; l < qa.L; cc_base += (qa.K[l] + QCH - 1) / QCH * QCH, ++l) {
                 const float xx = sumsq_plain<E>(r);
                 if (l == 0) gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
                 // residual tile → split fp16, UMMA K-major SWIZZLE_128B (row = 128 B, chunk c of 8 halves)
@@ -150,7 +164,10 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
                 const float inv_s = qa.inv_scale[l];
-                // four independent (best, second) trackers (column mod 4) keep the compare chains short
+                // Scan of the accumulator (= 2^s (|c_j|^2 - 2 r.c_j), the distance up to the row constant |r|^2).
+                // Four independent (best, second) trackers (column mod 4) keep the compare chains short; inside a 32-column
+                // block the column index is an immediate (no per-element index arithmetic), and two register buffers
+                // keep the TMEM load of the next block in flight while this one is scanned.
                 float bd[4], sd[4];
                 int bi[4];
 #pragma unroll
@@ -161,19 +178,29 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     mbar_wait(&d_full[g], round & 1);
                     ++round;
                     tc_fence_after();
-                    // two register buffers: the TMEM load of the next 32 columns is in flight while this one is scanned
+                    const float *ccs_l = cc_in_smem ? cc_s + cc_base + c0 : qa.ccs[l] + c0;      // scaled norms of this chunk
+                    // per tracker: column inside its 32-column block (an immediate) and the block's first column
+                    int bil[4] = {0, 0, 0, 0}, bcc[4] = {-1, -1, -1, -1};
                     auto scan32 = [&](const uint32_t (&v)[32], int cc0) {
+                        float before[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) before[u] = bd[u];
 #pragma unroll
                         for (int t4 = 0; t4 < 8; ++t4) {
+                            float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!AUG) n4 = *reinterpret_cast<const float4 *>(ccs_l + cc0 + 4 * t4);   // same address in every lane
+                            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                // accumulator = 2^s (|c_j|^2 - 2 r.c_j): the distance up to the row constant |r|^2, scaled
                                 float d = __uint_as_float(v[4 * t4 + u]);
-                                if (!AUG) d += __ldg(qa.ccs[l] + c0 + cc0 + 4 * t4 + u);
+                                if (!AUG) d += nn[u];
                                 sd[u] = fminf(sd[u], fmaxf(d, bd[u]));
-                                if (d < bd[u]) { bd[u] = d; bi[u] = c0 + cc0 + 4 * t4 + u; }
+                                if (d < bd[u]) { bd[u] = d; bil[u] = 4 * t4 + u; }
                             }
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (bd[u] < before[u]) bcc[u] = cc0;
                     };
                     uint32_t va[32], vb[32];
                     tmem_ld32_async(t_addr, va);
@@ -188,6 +215,9 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                             scan32(vb, cc0 + 32);
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (bcc[u] >= 0) bi[u] = c0 + bcc[u] + bil[u];
                     tc_fence_before();
                     mbar_arrive(&d_empty[g]);
                 }
@@ -205,24 +235,27 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 if (bad_index) best = 0;
                 second = fmaf(second, inv_s, xx);
                 bestd = fmaf(bestd, inv_s, xx);
+                // gather of the chosen code: issued first, so the loads fly while the gate is evaluated
+                const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
+                float4 qv4[E / 4];
+#pragma unroll
+                for (int k = 0; k < E / 4; ++k) qv4[k] = __ldg(q4 + k);
+                const float ccb = cc_in_smem ? cc_s[cc_base + best] * inv_s : __ldg(qa.cc[l] + best);
                 if (live) codes[item * qa.L + l] = best;
                 {
                     // Let eps bound |r~ - r| (tensor-core encoder) and rho = |r - c_best|.  A code j can overtake `best`
                     // only if |c_j - c_best| <= 2 rho + 2 eps, and then (d_j - d_best) moves by at most
                     // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM
                     // and of the reference's own fp32 evaluation of d.
-                    const float ccb = __ldg(qa.cc[l] + best);
                     const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
                     const float tau = 4.0f * gate_eps * (rho + gate_eps) + 4.0e-6f * (xx + fabsf(ccb));
                     const float mg = (second - bestd) - tau;
                     min_margin = (mg == mg && min_margin == min_margin && !bad_index) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
                 }
-                // gather + straight-through residual update, same operations as vq.py:95 / rq.py:47
-                const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
+                // straight-through residual update, same operations as vq.py:95 / rq.py:47
 #pragma unroll
                 for (int k = 0; k < E; k += 4) {
-                    const float4 q = __ldg(q4 + k / 4);
-                    const float qv[4] = {q.x, q.y, q.z, q.w};
+                    const float qv[4] = {qv4[k / 4].x, qv4[k / 4].y, qv4[k / 4].z, qv4[k / 4].w};
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const float xres = __fadd_rn(r[k + t], __fsub_rn(qv[t], r[k + t]));
@@ -380,10 +413,10 @@ int quantize_tc_prepare(rqb200_model *m, cudaStream_t s) {
         m->cb_tc_aug_exp[l] = t;
         void *p = nullptr;
         RQB_CUDA(cudaMalloc(&p, (size_t)nchunks * Q_STAGE_BYTES));
-        if (m->e >= 64 && !m->ccs_tc[l]) RQB_CUDA(cudaMalloc(&m->ccs_tc[l], sizeof(float) * (size_t)nchunks * QCH));
+        if (!m->ccs_tc[l]) RQB_CUDA(cudaMalloc(&m->ccs_tc[l], sizeof(float) * (size_t)nchunks * QCH));
         count_launch();
         pack_codebook_kernel<<<64, 256, 0, s>>>(m->cb[l], m->cc[l], m->K[l], m->e, ldexpf(1.0f, ex), ldexpf(1.0f, ex - t),
-                                                (unsigned char *)p, m->e >= 64 ? m->ccs_tc[l] : nullptr);
+                                                (unsigned char *)p, m->ccs_tc[l]);
         RQB_LAUNCH_CHECK();
         m->cb_tc[l] = p;
     }

@@ -31,6 +31,13 @@ UNIT = "items/s"
 WORKLOAD = "BASELINE configs[1]: 1M items x 768-d, 3 levels x 256 codes, e_dim 32, layers [256,128]"
 N_PER_GPU = 1_000_000
 SEED = 2024
+# --config selects the shapes (default c2 = the configuration the metric is quoted on; c3 / c5 are documentation runs)
+CONFIGS = {
+    "c2": ("c2_slice", WORKLOAD),
+    "c3": ("c3_slice", "BASELINE configs[2] shapes: 768-d, 4 levels x 256 codes, e_dim 64, layers [256,128]"),
+    "c5": ("c5_slice", "BASELINE configs[4] shapes: 1024-d, 4 levels x 1024 codes, e_dim 64, layers [256,128]"),
+}
+GOLDEN = "c2_slice"
 
 
 def load_peaks():
@@ -93,8 +100,8 @@ class ClockSampler:
 
 def golden_model(device):
     from conftest import build_model, load_golden
-    g, cfg, cbs = load_golden("c2_slice")
-    cfg = dict(cfg, sk_epsilons=[0.0, 0.0, 0.0])           # bench step = pass 1 + suffix dedup (no Sinkhorn rounds)
+    g, cfg, cbs = load_golden(GOLDEN)
+    cfg = dict(cfg, sk_epsilons=[0.0] * len(cfg["num_emb_list"]))      # bench step = pass 1 + suffix dedup (no Sinkhorn rounds)
     return build_model(cfg, cbs, device=device), cfg, cbs
 
 
@@ -105,10 +112,10 @@ def cpu_reference_leg(sample_rows, threads, x_host=None):
     from oracle import oracle as O
     from ai_education_generative_recommendation_b200 import synth
     O.build()
-    g, cfg, cbs = load_golden("c2_slice")
+    g, cfg, cbs = load_golden(GOLDEN)
     _, (ew, eb), _ = synth_weights(cfg)
     if x_host is None:
-        x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample_rows - r0), 768, N_PER_GPU)
+        x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample_rows - r0), cfg["in_dim"], N_PER_GPU)
                                  for r0 in range(0, sample_rows, 65536)])
     x = np.ascontiguousarray(x_host[:sample_rows])
     O.get_indices(x[:4096], ew, eb, cbs, threads=threads)     # warm-up
@@ -126,8 +133,10 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     sample = 262144
     import numpy as np
+    from conftest import load_golden
     from ai_education_generative_recommendation_b200 import synth
-    x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample - r0), 768, N_PER_GPU)
+    in_dim = json.loads(str(load_golden(GOLDEN)[0]["cfg"]))["in_dim"]
+    x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample - r0), in_dim, N_PER_GPU)
                              for r0 in range(0, sample, 65536)])          # generated once, outside the timed steps
     vals = []
     for i in range(args.warmup + args.steps):
@@ -155,7 +164,10 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RQB200_MODE", "auto"), choices=["auto", "exact", "fast"])
     ap.add_argument("--items", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     args = ap.parse_args()
+    global GOLDEN, WORKLOAD
+    GOLDEN, WORKLOAD = CONFIGS[args.config]
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -182,7 +194,7 @@ def main():
     if args.mode in ("auto", "fast"):
         model.encode_mode = _cabi.ENCODE_FAST
         try:
-            model.get_indices(torch.zeros((256, 768), device=dev))
+            model.get_indices(torch.zeros((256, cfg["in_dim"]), device=dev))
         except _cabi.RQB200Error as exc:
             if args.mode == "fast":
                 raise
@@ -195,8 +207,9 @@ def main():
     n = args.items
     n_total = n * world
     lo = rank * n
-    x = torch.empty((n, 768), dtype=torch.float32, device=dev)
-    _cabi.check(lib.rqb200_synth_items(SEED, lo, n, 768, n_total, x.data_ptr(), _cabi.stream_ptr()))
+    in_dim, n_levels, first_out = cfg["in_dim"], len(cfg["num_emb_list"]), cfg["layers"][0]
+    x = torch.empty((n, in_dim), dtype=torch.float32, device=dev)
+    _cabi.check(lib.rqb200_synth_items(SEED, lo, n, in_dim, n_total, x.data_ptr(), _cabi.stream_ptr()))
     Ks = cfg["num_emb_list"]
     # N > 1: the suffix column is global — keys travel to their owner rank through NVLink peer memory
     # (rqb200_shard_suffix_dedup: the library's own kernels store into the peers' buffers, no NCCL call per step)
@@ -249,9 +262,9 @@ def main():
     barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     launches = lib.rqb200_launch_count() - launches0
-    prof_ms = (ctypes.c_double * 8)()
-    prof_cnt = (ctypes.c_longlong * 8)()
-    lib.rqb200_profile_read(prof_ms, prof_cnt, 8)
+    prof_ms = (ctypes.c_double * 12)()
+    prof_cnt = (ctypes.c_longlong * 12)()
+    lib.rqb200_profile_read(prof_ms, prof_cnt, 12)
     lib.rqb200_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -260,7 +273,7 @@ def main():
     value = n_total / (ms_step * 1e-3)
 
     # ---- e2e through the host-buffer C-ABI call (pinned host in, host out), same workload per rank
-    xh = torch.empty((n, 768), dtype=torch.float32).pin_memory()
+    xh = torch.empty((n, in_dim), dtype=torch.float32).pin_memory()
     xh.copy_(x)
     torch.cuda.synchronize()
     ids_host = torch.empty((n, len(Ks) + 1), dtype=torch.int64).pin_memory()
@@ -291,8 +304,8 @@ def main():
         # Algorithmic work of that kernel per item: 4*in_dim bytes read, 2*in_dim*256 flop.
         slot = 4 if (fast_ok and prof_cnt[4] > 0) else 0
         k_ms = prof_ms[slot] / max(prof_cnt[slot], 1)
-        alg_bytes = 4.0 * 768 * n
-        alg_flops = 2.0 * 768 * 256 * n
+        alg_bytes = 4.0 * in_dim * n
+        alg_flops = 2.0 * in_dim * first_out * n
         kname = ("linear_tc2_kernel (encoder layer 1: tcgen05 cta_group::2, split-fp16, 3 MMA passes)" if slot == 4
                  else "linear_exact_kernel<128,128,8,8> (encoder layer 1, fp32 FMA chains)")
         traffic = None
@@ -305,7 +318,8 @@ def main():
         tc_peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         stage = {"tc_linear0": prof_ms[4] / args.steps, "tc_linear_rest": prof_ms[6] / args.steps,
                  "exact_linear0": prof_ms[0] / args.steps, "exact_linear_rest": prof_ms[1] / args.steps,
-                 "quantize_incl_rescue": prof_ms[2] / args.steps, "dedup": prof_ms[3] / args.steps}
+                 "quantize_incl_rescue_quantizer": prof_ms[2] / args.steps, "dedup": prof_ms[3] / args.steps,
+                 "three_pass_rerun_tier": prof_ms[7] / args.steps, "exact_rescue_tier": prof_ms[8] / args.steps}
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
                     "traffic": traffic, "kernel": kname, "kernel_ms": k_ms,
                     "peak_source": f"{peak_src} hbm_gbs; SURVEY §8d: a bf16-rate pass over this shape is HBM-bound (AI 96 flop/B < ridge 207)",
@@ -313,25 +327,25 @@ def main():
                     "tensor_view": {"achieved_tflops": tfl, "peak_tflops": tc_peak, "frac": tfl / tc_peak if tc_peak else None,
                                     "note": "algorithmic flops of ONE pass; the kernel issues 3 fp16 passes for fp32-class accuracy"},
                     "step_share": (prof_ms[slot] / args.steps) / ms_step if ms_step else None,
-                    "whole_step_hbm_frac": (value / world) * (4 * 768 + 8 * 3) / (hbm_peak * 1e9),
+                    "whole_step_hbm_frac": (value / world) * (4 * in_dim + 8 * n_levels) / (hbm_peak * 1e9),
                     "stage_ms_per_step": stage}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "items_per_gpu": n, "global_items": n_total, "encode_mode": mode_name,
                            "step": "get_indices(use_sk=False) + suffix dedup" + (" (global: keys routed to owner ranks over NVLink peer memory)" if world > 1 else ""),
-                           "l2": "inputs 3.07 GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
+                           "l2": f"inputs {n * in_dim * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
                            "parallelism": f"items sharded x{world}, codebooks replicated",
                            "multi_gpu_ids_equal_single_gpu": multi_check},
                 "roofline": roofline,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 768 * 4),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * in_dim * 4),
                         "d2h_bytes_per_step": int(n * (len(Ks) + 1) * 8), "api": "rqb200_generate_codes_host (pinned host buffers)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = min(n, 1_000_000)
             v, dt, ids = cpu_reference_leg(sample, threads, x_host=xh.numpy())
-            same = bool(np.array_equal(ids[:, :3], ids_host.numpy()[:sample, :3]))
+            same = bool(np.array_equal(ids[:, :n_levels], ids_host.numpy()[:sample, :n_levels]))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{sample} rows of the same catalogue, {dt:.1f} s: oracle C restatement of "
                                               f"get_indices + suffix dedup (pthreads); codes equal to GPU: {same}"}

@@ -142,6 +142,20 @@ def test_suffix_dedup_bit_exact(oracle, n, L, K):
         assert np.array_equal(out2.cpu().numpy(), ref)
 
 
+def test_peer_memory_dedup_single_rank_equals_plain_dedup(oracle):
+    """rqb200_shard_* with world = 1 (no peers): the owner is the rank itself, same ids as rqb200_suffix_dedup."""
+    from ai_education_generative_recommendation_b200 import sharding
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    rng = np.random.default_rng(11)
+    for n, spread in ((0, 4), (1, 4), (5000, 4), (70_001, 40)):
+        codes = rng.integers(0, spread, size=(n, 3)).astype(np.int64)
+        pd = sharding.PeerShardDedup(m, None, max_local_items=max(n, 1))
+        got = pd(torch.from_numpy(codes).to(DEV), [256, 256, 256]).cpu().numpy()
+        pd.close()
+        assert np.array_equal(got, oracle.suffix_dedup(codes))
+
+
 def test_suffix_dedup_shipped_artifact():
     arr = np.load(os.path.join(os.path.dirname(__file__), "golden", "course_semantic_ids.npy")).astype(np.int64)
     out, stats = rq.suffix_dedup(None, torch.from_numpy(arr[:, :3].copy()).to(DEV), [8, 8, 8])

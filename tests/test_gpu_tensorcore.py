@@ -50,6 +50,25 @@ def test_fast_route_codes_equal_exact_route(name):
         assert rescued <= 0.05 * n, rescued
 
 
+@pytest.mark.parametrize("name", ["c2_slice", "c3_slice", "c5_slice"])
+def test_screening_tier_keeps_codes_bit_exact(name):
+    """Opt-in tier 1 (one fp16 pass, looser gate) → three-pass re-run of the gated rows → exact rescue: same codes."""
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n = 200_000 + 13
+    x = gpu_synth(2024, 0, n, cfg["in_dim"], int(g["n_total"]))
+    exact = m.get_indices(x)
+    m.encode_mode = _cabi.ENCODE_FAST
+    m.set_screen(True, 2.0 ** -11)
+    fast = m.get_indices(x)
+    st = dict(m.last_stats)
+    m.set_screen(False)
+    m.encode_mode = _cabi.ENCODE_EXACT
+    assert torch.equal(fast, exact)
+    assert 0 < st["three_pass_rows"] < 0.5 * n, st          # the screening pass certifies most rows by itself
+    assert st["rescued_rows"] <= st["three_pass_rows"]
+
+
 def test_fast_route_handles_overflowing_rows():
     g, cfg, cbs = load_golden("c2_slice")
     m = build_model(cfg, cbs)
