@@ -26,18 +26,23 @@ namespace rqb {
 namespace {
 
 constexpr int QTM = 128;                   // rows per group tile
-constexpr int QCH = 256;                   // codes per MMA (UMMA N)
-constexpr int QTC_THREADS = 320;
+constexpr int QCH = 128;                   // codes per MMA (UMMA N)
+constexpr int QB = 1;                      // TMEM accumulator buffers per group (QG * QB * QCH <= 512 columns).  Measured on C2/C3/C5
+                                           // (ms per 1M rows): 4 groups x 1 x 128 codes 0.43/0.83/2.7 (this), 4 x 2 x 64 0.50/0.95/3.2
+                                           // (N=64 MMAs are shared-memory-bound), 2 x 2 x 128 0.51/0.88/2.8, 2 x 1 x 256 0.47/1.05/3.0
+constexpr int QG = 4;                      // row groups per CTA (one 128-row tile each, thread = row)
+constexpr int Q_MMA_WARP = 4 * QG, Q_LOAD_WARP = 4 * QG + 1;
+constexpr int QTC_THREADS = (4 * QG + 2) * 32;              // 576
 constexpr int Q_STAGES = 2;
-constexpr int Q_A_BYTES = QTM * 128;       // one of hi / lo, one 64-wide K slab
-constexpr int Q_CB_TILE = QCH * 128;       // one of hi / lo
+constexpr int Q_A_BYTES = QTM * 128;       // one of hi / lo, one 64-wide K slab (16 KB)
+constexpr int Q_CB_TILE = QCH * 128;       // one of hi / lo (16 KB)
 constexpr int Q_STAGE_BYTES = 2 * Q_CB_TILE;               // hi | lo
-constexpr int Q_CC_MAX = 4096;            // code norms of all levels kept in shared memory when sum(K) fits (16 KB)
-constexpr int Q_SMEM = 2 * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + 1024 + 256 + Q_CC_MAX * 4;
+constexpr int Q_CC_MAX = 4096;             // scaled code norms of all levels kept in shared memory when they fit (16 KB)
+constexpr int Q_SMEM = QG * 2 * Q_A_BYTES + Q_STAGES * Q_STAGE_BYTES + 1024 + 256 + Q_CC_MAX * 4;
 
 struct QtcArgs {
-    const unsigned char *cbp[RQB200_MAX_LEVELS];   // packed chunks: [hi tile | lo tile]
-    const float *ccs[RQB200_MAX_LEVELS];           // |c_j|^2 2^s per code, padded to 256 per chunk with +huge
+    const unsigned char *cbp[RQB200_MAX_LEVELS];   // packed chunks of QCH codes: [hi tile | lo tile]
+    const float *ccs[RQB200_MAX_LEVELS];           // |c_j|^2 2^s per code, padded to QCH per chunk with +huge
     uint32_t aug_half[RQB200_MAX_LEVELS];          // fp16 bits of 2^t: value of the augmented A column (see pack_codebook_kernel)
     const float *cb[RQB200_MAX_LEVELS];            // fp32 codebooks for the gather
     const float *cc[RQB200_MAX_LEVELS];
@@ -46,36 +51,35 @@ struct QtcArgs {
     int L;
 };
 
-template <int E>
-__device__ __forceinline__ float sumsq_plain(const float (&v)[E]) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < E; k += 4) {
-        s0 = fmaf(v[k], v[k], s0); s1 = fmaf(v[k + 1], v[k + 1], s1);
-        s2 = fmaf(v[k + 2], v[k + 2], s2); s3 = fmaf(v[k + 3], v[k + 3], s3);
-    }
-    return (s0 + s1) + (s2 + s3);
+__device__ __forceinline__ int q_swz(int rloc, int c) {          // byte offset of 16-byte chunk c of row rloc (SW128 K-major tile)
+    return (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
 }
 
+// CTA = 576 threads: warps 0-15 are four independent "row groups" (one 128-row tile each, thread = row), warp 16
+// issues the MMAs for all groups, warp 17 streams codebook chunks.  While a group scans its distances or updates
+// its residual (the next level needs the argmin of this one) the tensor core works for the other groups.  The residual of a row lives ONLY in the group's A tile in shared memory, as the
+// split-fp16 pair the MMA reads (r ~ hi + lo to 2^-22, far inside the gate's error budget): no register copy, so
+// sixteen row warps fit and e_dim 64 does not spill.
 template <int E>
 __global__ void __launch_bounds__(QTC_THREADS, 1)
 quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *__restrict__ codes,
                    int64_t *__restrict__ list, unsigned long long *__restrict__ list_count, float gate_gamma,
                    float gate_floor, const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev) {
     static_assert(E % 8 == 0 && E <= 64, "tensor-core quantizer supports e_dim <= 64");
+    constexpr bool AUG = E < 64;           // the 64-wide K slab has a free column: the MMA itself adds the code norm
     if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *a_base = smem;                                     // [group][hi|lo] 16 KB each
-    unsigned char *cb_base = smem + 4 * Q_A_BYTES;                    // [stage] hi | lo | cc
+    unsigned char *cb_base = smem + QG * 2 * Q_A_BYTES;               // [stage] hi | lo
     uint64_t *bars = reinterpret_cast<uint64_t *>(cb_base + Q_STAGES * Q_STAGE_BYTES);
-    uint64_t *a_full = bars;            // [2]  row warps → MMA   (count 4)
-    uint64_t *d_full = bars + 2;        // [2]  MMA → row warps   (count 1, tcgen05.commit)
-    uint64_t *d_empty = bars + 4;       // [2]  row warps → MMA   (count 128)
-    uint64_t *cb_full = bars + 6;       // [Q_STAGES] loader → MMA (tx)
-    uint64_t *cb_empty = bars + 8;      // [Q_STAGES] MMA → loader (commit)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10);
-    float *cc_s = reinterpret_cast<float *>(cb_base + Q_STAGES * Q_STAGE_BYTES + 256);      // per level, padded to 256: |c_j|^2 2^s (+huge on padding)
+    uint64_t *a_full = bars;                       // [QG]     row warps → MMA   (count 4)
+    uint64_t *d_full = bars + QG;                  // [QG][QB]  MMA → row warps   (count 1, tcgen05.commit)
+    uint64_t *d_empty = bars + (1 + QB) * QG;      // [QG][QB]  row warps → MMA   (count 4: one arrival per warp)
+    uint64_t *cb_full = bars + (1 + 2 * QB) * QG;  // [Q_STAGES] loader → MMA (tx)
+    uint64_t *cb_empty = cb_full + Q_STAGES;       // [Q_STAGES] MMA → loader (commit)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cb_empty + Q_STAGES);
+    float *cc_s = reinterpret_cast<float *>(cb_base + Q_STAGES * Q_STAGE_BYTES + 256);      // per level, padded to QCH: |c_j|^2 2^s
     int cc_total = 0;
     for (int l = 0; l < qa.L; ++l) cc_total += (qa.K[l] + QCH - 1) / QCH * QCH;
     const bool cc_in_smem = cc_total <= Q_CC_MAX;
@@ -90,15 +94,19 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (n + QTM - 1) / QTM;
+    const int64_t nbatches = (ntiles + QG - 1) / QG;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < 2; ++g) { mbar_init(&a_full[g], 4); mbar_init(&d_full[g], 1); mbar_init(&d_empty[g], 128); }
+        for (int g = 0; g < QG; ++g) {
+            mbar_init(&a_full[g], 4);
+            for (int b = 0; b < QB; ++b) { mbar_init(&d_full[QB * g + b], 1); mbar_init(&d_empty[QB * g + b], 4); }
+        }
         for (int s = 0; s < Q_STAGES; ++s) { mbar_init(&cb_full[s], 1); mbar_init(&cb_empty[s], 1); }
         fence_barrier_init();
     }
-    // zero the A tiles once: columns >= E of the 64-wide K slab stay zero for the whole kernel
-    for (int i = threadIdx.x; i < 4 * Q_A_BYTES / 16; i += QTC_THREADS) reinterpret_cast<uint4 *>(a_base)[i] = make_uint4(0, 0, 0, 0);
-    if (warp == 8) {
+    // zero the A tiles once: columns >= E (+ the augmented one) of the 64-wide K slab stay zero for the whole kernel
+    for (int i = threadIdx.x; i < QG * 2 * Q_A_BYTES / 16; i += QTC_THREADS) reinterpret_cast<uint4 *>(a_base)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == Q_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -108,80 +116,72 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < 4 * QG) {
         // ===================== row groups =====================
         const int g = warp >> 2;
         const int rloc = (warp & 3) * 32 + lane;
         unsigned char *a_hi = a_base + g * 2 * Q_A_BYTES;
         unsigned char *a_lo = a_hi + Q_A_BYTES;
-        const uint32_t t_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * QCH);
-        uint32_t round = 0;                       // MMA rounds consumed by this group so far
-        uint32_t cb_round = 0;                    // chunks consumed so far (all groups see the same sequence)
-        for (int64_t pair = blockIdx.x;; pair += gridDim.x) {
-            const int64_t tile = pair * 2 + g;
-            if (pair * 2 >= ntiles) break;
-            const bool active = tile < ntiles;
-            // chunk bookkeeping must advance identically in both groups even if this one is idle
-            int nchunks_total = 0;
-            for (int l = 0; l < qa.L; ++l) nchunks_total += (qa.K[l] + QCH - 1) / QCH;
-            if (!active) { cb_round += nchunks_total; continue; }
+        const uint32_t t_group = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * QB * QCH);
+        uint32_t round = 0;                       // chunks consumed by this group so far: buffer = round % QB
+        for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+            const int64_t tile = batch * QG + g;
+            if (tile >= ntiles) continue;         // idle group in the last batch (the MMA warp skips it too)
             const int64_t row = tile * QTM + rloc;
             const bool live = row < n;
             const int64_t item = live ? (rows ? __ldg(rows + row) : row) : 0;      // where the codes of this row go
-            float r[E];
-#pragma unroll
-            for (int k = 0; k < E; k += 4) {
-                float4 v = live ? *reinterpret_cast<const float4 *>(z + row * E + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
-            }
-            float min_margin = __int_as_float(0x7f800000);
-            float gate_eps = 0.0f;
-            int cc_base = 0;                                                   // offset of this level's norms in cc_s
-            for (int l = 0; l < qa.L; cc_base += (qa.K[l] + QCH - 1) / QCH * QCH, ++l) {
-                const float xx = sumsq_plain<E>(r);
-                if (l == 0) gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
-                // residual tile → split fp16, UMMA K-major SWIZZLE_128B (row = 128 B, chunk c of 8 halves)
+            // latent row → split fp16 → A tile; |z|^2 on the way
+            float xx;
+            {
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < E / 8; ++c) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (live) {
+                        v0 = *reinterpret_cast<const float4 *>(z + row * E + 8 * c);
+                        v1 = *reinterpret_cast<const float4 *>(z + row * E + 8 * c + 4);
+                    }
+                    s0 = fmaf(v0.x, v0.x, s0); s1 = fmaf(v0.y, v0.y, s1); s0 = fmaf(v0.z, v0.z, s0); s1 = fmaf(v0.w, v0.w, s1);
+                    s0 = fmaf(v1.x, v1.x, s0); s1 = fmaf(v1.y, v1.y, s1); s0 = fmaf(v1.z, v1.z, s0); s1 = fmaf(v1.w, v1.w, s1);
                     uint4 hi, lo;
-                    split2(r[8 * c], r[8 * c + 1], hi.x, lo.x);
-                    split2(r[8 * c + 2], r[8 * c + 3], hi.y, lo.y);
-                    split2(r[8 * c + 4], r[8 * c + 5], hi.z, lo.z);
-                    split2(r[8 * c + 6], r[8 * c + 7], hi.w, lo.w);
-                    const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
-                    *reinterpret_cast<uint4 *>(a_hi + off) = hi;
-                    *reinterpret_cast<uint4 *>(a_lo + off) = lo;
+                    split2(v0.x, v0.y, hi.x, lo.x); split2(v0.z, v0.w, hi.y, lo.y);
+                    split2(v1.x, v1.y, hi.z, lo.z); split2(v1.z, v1.w, hi.w, lo.w);
+                    *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = hi;
+                    *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = lo;
                 }
-                constexpr bool AUG = E < 64;          // the 64-wide K slab has a free column for the code norm
-                if (AUG) {
-                    // augmented K column E: A = 2^t, B = |c_j|^2 * 2^(s-t)  ⇒  the MMA itself adds the code norm
-                    const int c = E / 8;
-                    const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
-                    *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(qa.aug_half[l], 0, 0, 0);
-                    *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(0, 0, 0, 0);
-                }
+                xx = s0 + s1;
+            }
+            float min_margin = __int_as_float(0x7f800000);
+            const float gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
+            int cc_base = 0;                                                   // offset of this level's norms in cc_s
+            for (int l = 0; l < qa.L; cc_base += (qa.K[l] + QCH - 1) / QCH * QCH, ++l) {
+                if (AUG)   // augmented K column E: A = 2^t, B = |c_j|^2 * 2^(s-t)  ⇒  the MMA itself adds the code norm
+                    *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, E / 8)) = make_uint4(qa.aug_half[l], 0, 0, 0);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
                 const float inv_s = qa.inv_scale[l];
-                // Scan of the accumulator (= 2^s (|c_j|^2 - 2 r.c_j), the distance up to the row constant |r|^2).
-                // Four independent (best, second) trackers (column mod 4) keep the compare chains short; inside a 32-column
-                // block the column index is an immediate (no per-element index arithmetic), and two register buffers
-                // keep the TMEM load of the next block in flight while this one is scanned.
+                // Scan of the accumulator (= 2^s (|c_j|^2 - 2 r.c_j), the distance up to the row constant |r|^2): four
+                // independent (best, second) trackers (column mod 4) keep the compare chains short; inside a 32-column
+                // block the column index is an immediate (no per-element index arithmetic).
                 float bd[4], sd[4];
                 int bi[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { bd[u] = __int_as_float(0x7f800000); sd[u] = __int_as_float(0x7f800000); bi[u] = 0; }
                 const int K = qa.K[l];
-                for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
+                for (int c0 = 0; c0 < K; c0 += QCH) {
                     const int ncols = min(QCH, ((K - c0) + 31) & ~31);
-                    mbar_wait(&d_full[g], round & 1);
+                    const uint32_t buf = round % QB;
+                    const uint32_t t_addr = t_group + buf * QCH;
+                    mbar_wait(&d_full[QB * g + buf], (round / QB) & 1);
                     ++round;
                     tc_fence_after();
                     const float *ccs_l = cc_in_smem ? cc_s + cc_base + c0 : qa.ccs[l] + c0;      // scaled norms of this chunk
-                    // per tracker: column inside its 32-column block (an immediate) and the block's first column
                     int bil[4] = {0, 0, 0, 0}, bcc[4] = {-1, -1, -1, -1};
-                    auto scan32 = [&](const uint32_t (&v)[32], int cc0) {
+#pragma unroll 1
+                    for (int cc0 = 0; cc0 < ncols; cc0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + (uint32_t)cc0, v);
                         float before[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) before[u] = bd[u];
@@ -201,25 +201,13 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                             if (bd[u] < before[u]) bcc[u] = cc0;
-                    };
-                    uint32_t va[32], vb[32];
-                    tmem_ld32_async(t_addr, va);
-#pragma unroll 1
-                    for (int cc0 = 0; cc0 < ncols; cc0 += 64) {
-                        tmem_ld_wait(va);
-                        if (cc0 + 32 < ncols) tmem_ld32_async(t_addr + (uint32_t)(cc0 + 32), vb);
-                        scan32(va, cc0);
-                        if (cc0 + 32 < ncols) {
-                            tmem_ld_wait(vb);
-                            if (cc0 + 64 < ncols) tmem_ld32_async(t_addr + (uint32_t)(cc0 + 64), va);
-                            scan32(vb, cc0 + 32);
-                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (bcc[u] >= 0) bi[u] = c0 + bcc[u] + bil[u];
                     tc_fence_before();
-                    mbar_arrive(&d_empty[g]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[QB * g + buf]);
                 }
                 // merge the trackers: global best, and second = min(other bests, all seconds)
                 float bestd = bd[0], second = sd[0];
@@ -235,32 +223,49 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 if (bad_index) best = 0;
                 second = fmaf(second, inv_s, xx);
                 bestd = fmaf(bestd, inv_s, xx);
-                // gather of the chosen code: issued first, so the loads fly while the gate is evaluated
-                const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
-                float4 qv4[E / 4];
-#pragma unroll
-                for (int k = 0; k < E / 4; ++k) qv4[k] = __ldg(q4 + k);
                 const float ccb = cc_in_smem ? cc_s[cc_base + best] * inv_s : __ldg(qa.cc[l] + best);
                 if (live) codes[item * qa.L + l] = best;
                 {
                     // Let eps bound |r~ - r| (tensor-core encoder) and rho = |r - c_best|.  A code j can overtake `best`
                     // only if |c_j - c_best| <= 2 rho + 2 eps, and then (d_j - d_best) moves by at most
-                    // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM
-                    // and of the reference's own fp32 evaluation of d.
+                    // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM,
+                    // of the fp16-pair residual and of the reference's own fp32 evaluation of d.
                     const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
                     const float tau = 4.0f * gate_eps * (rho + gate_eps) + 4.0e-6f * (xx + fabsf(ccb));
                     const float mg = (second - bestd) - tau;
                     min_margin = (mg == mg && min_margin == min_margin && !bad_index) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
                 }
-                // straight-through residual update, same operations as vq.py:95 / rq.py:47
+                if (l + 1 < qa.L) {
+                    // gather + straight-through residual update (vq.py:95 / rq.py:47) on the A tile, 8 dims at a time:
+                    // r = hi + lo, xres = r + (q - r), r' = r - xres → split → back into the tile; |r'|^2 for the next level
+                    const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
+                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int k = 0; k < E; k += 4) {
-                    const float qv[4] = {qv4[k / 4].x, qv4[k / 4].y, qv4[k / 4].z, qv4[k / 4].w};
+                    for (int c = 0; c < E / 8; ++c) {
+                        const float4 qa4 = __ldg(q4 + 2 * c), qb4 = __ldg(q4 + 2 * c + 1);
+                        const uint4 hi = *reinterpret_cast<const uint4 *>(a_hi + q_swz(rloc, c));
+                        const uint4 lo = *reinterpret_cast<const uint4 *>(a_lo + q_swz(rloc, c));
+                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                        const float qv[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
+                        float rn[8];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float xres = __fadd_rn(r[k + t], __fsub_rn(qv[t], r[k + t]));
-                        r[k + t] = __fsub_rn(r[k + t], xres);
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&hw[t]));
+                            const float2 l2 = __half22float2(*reinterpret_cast<const __half2 *>(&lw[t]));
+                            const float r0 = h2.x + l2.x, r1 = h2.y + l2.y;
+                            const float x0 = __fadd_rn(r0, __fsub_rn(qv[2 * t], r0)), x1 = __fadd_rn(r1, __fsub_rn(qv[2 * t + 1], r1));
+                            rn[2 * t] = __fsub_rn(r0, x0);
+                            rn[2 * t + 1] = __fsub_rn(r1, x1);
+                            s0 = fmaf(rn[2 * t], rn[2 * t], s0);
+                            s1 = fmaf(rn[2 * t + 1], rn[2 * t + 1], s1);
+                        }
+                        uint4 nh, nl;
+                        split2(rn[0], rn[1], nh.x, nl.x); split2(rn[2], rn[3], nh.y, nl.y);
+                        split2(rn[4], rn[5], nh.z, nl.z); split2(rn[6], rn[7], nh.w, nl.w);
+                        *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = nh;
+                        *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = nl;
                     }
+                    xx = s0 + s1;
                 }
             }
             // rows that cannot be certified → rescue list (warp-aggregated append)
@@ -273,40 +278,45 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 if (flag) list[base + __popc(ballot & ((1u << lane) - 1u))] = item;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == Q_MMA_WARP) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t a_round[2] = {0, 0}, d_round[2] = {0, 0};
+            uint32_t a_round[QG], d_round[QG];
+            uint64_t da_hi[QG], da_lo[QG];            // the A tiles never move: descriptors built once (+2 per 32-byte K step)
+#pragma unroll
+            for (int g = 0; g < QG; ++g) {
+                a_round[g] = 0; d_round[g] = 0;
+                da_hi[g] = umma_desc(smem_u32(a_base + g * 2 * Q_A_BYTES));
+                da_lo[g] = umma_desc(smem_u32(a_base + g * 2 * Q_A_BYTES + Q_A_BYTES));
+            }
             uint32_t cb_round = 0;
-            for (int64_t pair = blockIdx.x; pair * 2 < ntiles; pair += gridDim.x) {
-                const bool act[2] = {true, pair * 2 + 1 < ntiles};
+            for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
                 for (int l = 0; l < qa.L; ++l) {
                     const int K = qa.K[l];
                     for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
                         const int ncols = min(QCH, ((K - c0) + 31) & ~31);
                         const int st = cb_round % Q_STAGES;
                         mbar_wait(&cb_full[st], (cb_round / Q_STAGES) & 1);
-                        const uint32_t w_hi = smem_u32(cb_base + st * Q_STAGE_BYTES);
-                        const uint32_t w_lo = w_hi + Q_CB_TILE;
+                        const uint64_t dw_hi = umma_desc(smem_u32(cb_base + st * Q_STAGE_BYTES));
+                        const uint64_t dw_lo = umma_desc(smem_u32(cb_base + st * Q_STAGE_BYTES + Q_CB_TILE));
                         const uint32_t idesc = umma_idesc(QTM, ncols);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            if (!act[g]) continue;
+                        for (int g = 0; g < QG; ++g) {
+                            if (batch * QG + g >= ntiles) continue;
                             if (c0 == 0) { mbar_wait(&a_full[g], a_round[g] & 1); ++a_round[g]; }
-                            mbar_wait(&d_empty[g], (d_round[g] & 1) ^ 1);
+                            const uint32_t buf = d_round[g] % QB;
+                            mbar_wait(&d_empty[QB * g + buf], ((d_round[g] / QB) & 1) ^ 1);
                             ++d_round[g];
                             tc_fence_after();
-                            const uint32_t a_hi = smem_u32(a_base + g * 2 * Q_A_BYTES);
-                            const uint32_t a_lo = a_hi + Q_A_BYTES;
-                            const uint32_t d_tmem = tmem_base + (uint32_t)(g * QCH);
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((g * QB + buf) * QCH);
 #pragma unroll
-                            for (int kk = 0; kk < (E + (E < 64 ? 1 : 0) + 15) / 16; ++kk) {      // E residual columns (+ the augmented norm column)
-                                const uint32_t ko = kk * 32;
-                                umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc, kk != 0);
-                                umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc, 1);
-                                umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc, 1);
+                            for (int kk = 0; kk < (E + (AUG ? 1 : 0) + 15) / 16; ++kk) {      // E residual columns (+ the augmented norm column)
+                                const uint64_t ko = (uint64_t)(2 * kk);                      // 32 bytes along K = 2 descriptor units
+                                umma_f16(d_tmem, da_lo[g] + ko, dw_hi + ko, idesc, kk != 0);
+                                umma_f16(d_tmem, da_hi[g] + ko, dw_lo + ko, idesc, 1);
+                                umma_f16(d_tmem, da_hi[g] + ko, dw_hi + ko, idesc, 1);
                             }
-                            umma_commit(&d_full[g]);
+                            umma_commit(&d_full[QB * g + buf]);
                         }
                         umma_commit(&cb_empty[st]);
                     }
@@ -317,7 +327,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
         // ===================== codebook loader =====================
         if (lane == 0) {
             uint32_t cb_round = 0;
-            for (int64_t pair = blockIdx.x; pair * 2 < ntiles; pair += gridDim.x) {
+            for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
                 for (int l = 0; l < qa.L; ++l) {
                     const int K = qa.K[l];
                     int chunk = 0;
@@ -334,13 +344,13 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == Q_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
-// codebook [K,e] fp32 → per 256-code chunk: hi tile | lo tile (SW128 K-major, 64-wide K slab).  Column k < e holds
+// codebook [K,e] fp32 → per QCH-code chunk: hi tile | lo tile (SW128 K-major, 64-wide K slab).  Column k < e holds
 // -2 c_jk 2^s, column e holds |c_j|^2 2^(s-t) (the A operand carries 2^t there), padded codes get a huge norm.
 __global__ void pack_codebook_kernel(const float *__restrict__ cb, const float *__restrict__ cc, int K, int e, float scale,
                                      float cc_scale, unsigned char *__restrict__ out, float *__restrict__ ccs) {
@@ -447,8 +457,8 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
         qa.ccs[l] = on ? m->ccs_tc[l] : nullptr;
         qa.aug_half[l] = on ? (uint32_t)__half_as_ushort(__float2half(ldexpf(1.0f, m->cb_tc_aug_exp[l]))) : 0u;
     }
-    const int64_t npairs = ((n + QTM - 1) / QTM + 1) / 2;
-    const unsigned grid = (unsigned)(npairs < kNumSMs ? npairs : kNumSMs);
+    const int64_t nbatches = ((n + QTM - 1) / QTM + QG - 1) / QG;
+    const unsigned grid = (unsigned)(nbatches < kNumSMs ? nbatches : kNumSMs);
     count_launch();
     kern<<<grid, QTC_THREADS, Q_SMEM, s>>>(z, n, qa, codes, list, count, gamma, m->gate_floor, rows, n_dev);
     RQB_LAUNCH_CHECK();
