@@ -270,6 +270,141 @@ int launch_quant(const rqb200_model *m, const float *z, int64_t n, int64_t *code
     return 0;
 }
 
+
+// ---- few rows (the exact rescue tier of the fast route, collision-group re-encodes): with one thread per row a few
+// thousand rows leave most SMs idle and every thread walks L*K*E dependent FMAs.  Here a row is shared by QS
+// consecutive lanes; lane s evaluates the codes j = s (mod QS) in ascending order and the lanes merge their
+// (distance, index) candidates with the same rule as the sequential scan — NaN first, then the smaller distance, then
+// the smaller index — so the chosen code is bit-identical to quantize_kernel's.  Codes only (MODE 0 without the
+// optional outputs).  The codebook chunk is staged with a row pitch of E+4 floats: the QS codes a warp reads at once
+// then fall into different banks.
+constexpr int QS = 8;                      // lanes per row
+constexpr int QS_ROWS = QT / QS;           // rows per CTA
+
+template <int E>
+__global__ void __launch_bounds__(QT)
+quantize_sliced_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
+                       const int64_t *__restrict__ rows_out) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int PITCH = E + 4;
+    constexpr int CH = (CHUNK_FLOATS / PITCH) / QS * QS;    // codes per chunk (multiple of QS)
+    float *s_cb = smem;                     // [CH][PITCH]
+    float *s_cc = smem + CH * PITCH;        // [CH]
+    const int tid = threadIdx.x, sl = tid % QS;
+    const int64_t row = (int64_t)blockIdx.x * QS_ROWS + tid / QS;
+    const bool live = row < n;
+    float r[E];
+#pragma unroll
+    for (int k = 0; k < E; k += 4) {
+        float4 v = live ? *reinterpret_cast<const float4 *>(z + row * E + k) : make_float4(0, 0, 0, 0);
+        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+    }
+    for (int l = 0; l < qa.L; ++l) {
+        const int K = qa.K[l];
+        const float *cb = qa.cb[l];
+        const float *cc = qa.cc[l];
+        const float xx = sumsq_aten<E>(r);
+        int best = 0x7fffffff;              // this lane has not seen a code yet
+        float bestd = 0.0f;
+        for (int c0 = 0; c0 < K; c0 += CH) {
+            const int cn = min(CH, K - c0);
+            __syncthreads();
+            // asynchronous 16-byte copies (LDGSTS): all of them in flight at once instead of one load-store round trip
+            // per iteration — with few rows per CTA the staging would otherwise dominate
+            for (int i = tid; i < cn * (E / 4); i += QT) {
+                const int j = i / (E / 4), k4 = i % (E / 4);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(s_cb + j * PITCH + 4 * k4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(cb + (int64_t)(c0 + j) * E + 4 * k4) : "memory");
+            }
+            for (int i = tid; i < cn; i += QT) s_cc[i] = cc[c0 + i];
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            // four codes (j, j+QS, j+2QS, j+3QS) at a time: four independent FMA chains per lane
+            int j = sl;
+            for (; j + 3 * QS < cn; j += 4 * QS) {
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < E / 4; ++k) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float4 v = *reinterpret_cast<const float4 *>(s_cb + (j + t * QS) * PITCH + 4 * k);
+                        a[t] = __fmaf_rn(r[4 * k], v.x, a[t]);
+                        a[t] = __fmaf_rn(r[4 * k + 1], v.y, a[t]);
+                        a[t] = __fmaf_rn(r[4 * k + 2], v.z, a[t]);
+                        a[t] = __fmaf_rn(r[4 * k + 3], v.w, a[t]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float d = __fsub_rn(__fadd_rn(xx, s_cc[j + t * QS]), __fmul_rn(2.0f, a[t]));
+                    if (best == 0x7fffffff || better(d, bestd)) { bestd = d; best = c0 + j + t * QS; }
+                }
+            }
+            for (; j < cn; j += QS) {
+                float a0 = 0.f;
+                const float4 *c4 = reinterpret_cast<const float4 *>(s_cb + j * PITCH);
+#pragma unroll
+                for (int k = 0; k < E / 4; ++k) {
+                    const float4 v = c4[k];
+                    a0 = __fmaf_rn(r[4 * k], v.x, a0);
+                    a0 = __fmaf_rn(r[4 * k + 1], v.y, a0);
+                    a0 = __fmaf_rn(r[4 * k + 2], v.z, a0);
+                    a0 = __fmaf_rn(r[4 * k + 3], v.w, a0);
+                }
+                const float d = __fsub_rn(__fadd_rn(xx, s_cc[j]), __fmul_rn(2.0f, a0));
+                if (best == 0x7fffffff || better(d, bestd)) { bestd = d; best = c0 + j; }
+            }
+        }
+        // merge the QS lanes of the row (xor butterfly inside the aligned group of QS lanes)
+#pragma unroll
+        for (int o = 1; o < QS; o <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bestd, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+            if (oi != 0x7fffffff) {
+                bool take;
+                if (best == 0x7fffffff) take = true;
+                else {
+                    const bool mn = bestd != bestd, on = od != od;
+                    if (mn || on) take = on && (!mn || oi < best);              // NaN is the minimum; the first NaN wins
+                    else take = od < bestd || (od == bestd && oi < best);      // first index wins ties
+                }
+                if (take) { bestd = od; best = oi; }
+            }
+        }
+        if (live && sl == 0) codes[(rows_out ? rows_out[row] : row) * qa.L + l] = best;
+        const float4 *q4 = reinterpret_cast<const float4 *>(cb + (int64_t)best * E);
+#pragma unroll
+        for (int k = 0; k < E; k += 4) {
+            const float4 q = __ldg(q4 + k / 4);
+            const float qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float xres = __fadd_rn(r[k + t], __fsub_rn(qv[t], r[k + t]));
+                r[k + t] = __fsub_rn(r[k + t], xres);
+            }
+        }
+    }
+}
+
+template <int E>
+int launch_quant_sliced(const rqb200_model *m, const float *z, int64_t n, int64_t *codes, const int64_t *rows_out,
+                        cudaStream_t s) {
+    auto kern = quantize_sliced_kernel<E>;
+    constexpr int PITCH = E + 4;
+    constexpr int CH = (CHUNK_FLOATS / PITCH) / QS * QS;
+    size_t smem = sizeof(float) * (CH * PITCH + CH);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    unsigned grid = (unsigned)((n + QS_ROWS - 1) / QS_ROWS);
+    rqb::count_launch();
+    kern<<<grid, QT, smem, s>>>(z, n, make_args(m), codes, rows_out);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
 #define RQB_DISPATCH_E(e, CALL)                                                     \
     switch (e) {                                                                    \
         case 8:   { constexpr int E = 8;   CALL; } break;                            \
@@ -329,6 +464,12 @@ int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *co
                    float *margin_out, cudaStream_t s) {
     if (n == 0) return 0;
     ProfScope ps(PROF_QUANTIZE, s);
+    // few rows and codes only: share a row between QS lanes so that the whole GPU works on it (measured: faster than a row
+    // per thread up to about half a wave of 128-row CTAs, slower beyond — the row-per-thread kernel then fills the SMs)
+    if (n <= (int64_t)kNumSMs * QT / 2 && !xq && !sumsq && !last_residual && !margin_out && m->e <= 64) {
+        RQB_DISPATCH_E(m->e, return (launch_quant_sliced<E>(m, z, n, codes, rows_out, s)));
+        return 0;
+    }
     RQB_DISPATCH_E(m->e, return (launch_quant<E, 0>(m, z, n, codes, rows_out, xq, sumsq, last_residual,
                                                    margin_out, nullptr, 0, s)));
     return 0;

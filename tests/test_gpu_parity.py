@@ -112,6 +112,32 @@ def test_exact_integer_lane_with_ties(oracle):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("name", ["c2_slice", "c5_slice"])
+def test_sliced_and_row_per_thread_quantizers_agree(oracle, name):
+    """The exact quantizer has two thread mappings (a row per thread; a row shared by 8 lanes when few rows are in
+    flight).  Same codes bit for bit, including NaN rows ("NaN is the minimum", torch.argmin) and exact ties."""
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    m._sync()
+    e, Lv = cfg["e_dim"], len(cbs)
+    rng = np.random.default_rng(21)
+    n = 5000
+    z = (rng.standard_normal((n, e)) * 0.3).astype(np.float32)
+    z[7, 3] = np.nan                                              # a NaN latent: every distance is NaN, code 0 wins
+    z[100:200] = cbs[0][rng.integers(0, cbs[0].shape[0], size=100)]   # rows sitting exactly on codes
+    zt = torch.from_numpy(z).to(DEV)
+    lib = _cabi.lib()
+    sliced = torch.empty((n, Lv), dtype=torch.int64, device=DEV)
+    plain = torch.empty((n, Lv), dtype=torch.int64, device=DEV)
+    xq = torch.empty((n, e), dtype=torch.float32, device=DEV)    # asking for x_q selects the row-per-thread kernel
+    _cabi.check(lib.rqb200_quantize(m._handle, zt.data_ptr(), n, sliced.data_ptr(), 0, 0, 0, 0, _cabi.stream_ptr()))
+    _cabi.check(lib.rqb200_quantize(m._handle, zt.data_ptr(), n, plain.data_ptr(), 0, xq.data_ptr(), 0, 0, _cabi.stream_ptr()))
+    assert torch.equal(sliced, plain)
+    ok = ~np.isnan(z).any(1)
+    ref = oracle.quantize(z[ok], cbs, want_xq=False)[0]
+    assert np.array_equal(sliced.cpu().numpy()[ok], ref)
+
+
 def test_distances_match_oracle(oracle):
     g, cfg, cbs = load_golden("c3_slice")
     m = build_model(cfg, cbs)
