@@ -252,6 +252,278 @@ linear_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned c
     }
 }
 
+
+// ---- layers 2 + 3 fused: H1[n,K2] → relu(H1·W2ᵀ+b2) [128 wide, never leaves the SM] → ·W3ᵀ+b3 → Z[n,N3] --------------
+//
+// Same pipeline as linear_tc_kernel<128,3> for the second Linear; its epilogue does not store H2 but re-splits it into
+// fp16 hi/lo and writes it as the A operand (UMMA K-major SWIZZLE_128B, two 64-wide slabs) of the third Linear, whose
+// pre-packed weights stay resident in shared memory.  The third layer of tile i is issued behind the second layer of
+// tile i+1 (software pipelining), so the tensor pipe never waits for the conversion.  Saves the H2 round trip through
+// HBM (1 GB per million rows) and a launch.
+template <int N3>
+struct Tc23Cfg {
+    static constexpr int N2 = 128;
+    static constexpr int W2_TILE = N2 * BK * 2;                       // 16 KB (hi or lo)
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * W2_TILE;   // 64 KB
+    static constexpr int STAGES = 2;
+    static constexpr int H2_BYTES = 2 * 2 * A_TILE_BYTES;             // two K slabs x (hi | lo) = 64 KB
+    static constexpr int W3_TILE = N3 * BK * 2;                        // hi or lo of one slab
+    static constexpr int W3_BYTES = 2 * 2 * W3_TILE;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + H2_BYTES + W3_BYTES + 1024 + 256;
+    static constexpr int ACC3_COL = 2 * N2;                            // TMEM: two 128-column buffers, then the third layer's accumulator
+};
+
+template <int N3>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
+                const float *__restrict__ bias2, float inv_scale2, const unsigned char *__restrict__ Wp3,
+                const float *__restrict__ bias3, float inv_scale3, float *__restrict__ Z,
+                const unsigned long long *__restrict__ n_dev) {
+    using Cfg = Tc23Cfg<N3>;
+    constexpr int N2 = Cfg::N2;
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *h2 = smem + Cfg::STAGES * Cfg::STAGE_BYTES;        // slab s: hi at s*32 KB, lo at s*32 KB + 16 KB
+    unsigned char *w3 = h2 + Cfg::H2_BYTES;                            // slab s: hi at s*2*W3_TILE, lo behind it
+    uint64_t *bars = reinterpret_cast<uint64_t *>(w3 + Cfg::W3_BYTES);
+    uint64_t *full_a = bars;                       // [STAGES]
+    uint64_t *full_w = bars + Cfg::STAGES;         // [STAGES]
+    uint64_t *empty = bars + 2 * Cfg::STAGES;      // [STAGES]
+    uint64_t *tmem_full = bars + 3 * Cfg::STAGES;  // [2]
+    uint64_t *tmem_empty = tmem_full + 2;          // [2]
+    uint64_t *h2_full = tmem_empty + 2;            // epilogue → MMA: the H2 tile of a row tile is in place (count 4)
+    uint64_t *z_full = h2_full + 1;                // MMA → epilogue: third-layer accumulator complete (commit)
+    uint64_t *w3_full = z_full + 1;                // loader → MMA: W3 resident
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w3_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KS = (K + BK - 1) / BK;
+    const int64_t ntiles = (n + TM - 1) / TM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_a[s], CONV_WARPS); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS * 32); }
+        mbar_init(h2_full, EPI_WARPS);
+        mbar_init(z_full, 1);
+        mbar_init(w3_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < EPI_WARPS) {
+        // ===================== epilogue: thread = row (TMEM lane) =====================
+        const int rloc = warp * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        auto store_z = [&](int64_t tile) {         // third-layer accumulator → *2^-s + bias → Z rows
+            tc_fence_after();
+            const int64_t row = tile * TM + rloc;
+#pragma unroll
+            for (int c = 0; c < N3; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)(Cfg::ACC3_COL + c), v);
+                if (row < n) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias3 + c) + j);
+                        float4 o;
+                        o.x = fmaf(__uint_as_float(v[4 * j]), inv_scale3, b4.x); o.y = fmaf(__uint_as_float(v[4 * j + 1]), inv_scale3, b4.y);
+                        o.z = fmaf(__uint_as_float(v[4 * j + 2]), inv_scale3, b4.z); o.w = fmaf(__uint_as_float(v[4 * j + 3]), inv_scale3, b4.w);
+                        *reinterpret_cast<float4 *>(Z + row * (int64_t)N3 + c + 4 * j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+        };
+        int64_t it = 0, prev_tile = -1;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            if (it > 0) {                           // the third layer of the previous tile: done ⇒ its H2 reads are done too
+                mbar_wait(z_full, (uint32_t)((it - 1) & 1));
+                store_z(prev_tile);
+            }
+            tc_fence_after();
+            // second-layer accumulator → *2^-s + bias → ReLU → fp16 hi/lo → the third layer's A operand
+#pragma unroll 1
+            for (int c = 0; c < N2; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)(buf * N2 + c), v);
+                unsigned char *hi_t = h2 + (c >> 6) * (2 * A_TILE_BYTES);
+                unsigned char *lo_t = hi_t + A_TILE_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {       // 8 columns = one 16-byte chunk of the swizzled row
+                    const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias2 + c) + 2 * j);
+                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias2 + c) + 2 * j + 1);
+                    const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+                    float h[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float y = fmaf(__uint_as_float(v[8 * j + t]), inv_scale2, bv[t]);
+                        h[t] = (y != y) ? y : fmaxf(y, 0.0f);
+                    }
+                    uint4 hi, lo;
+                    split2(h[0], h[1], hi.x, lo.x); split2(h[2], h[3], hi.y, lo.y);
+                    split2(h[4], h[5], hi.z, lo.z); split2(h[6], h[7], hi.w, lo.w);
+                    const int chunk = ((c & 63) >> 3) + j;
+                    const int off = (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((chunk ^ (rloc & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(hi_t + off) = hi;
+                    *reinterpret_cast<uint4 *>(lo_t + off) = lo;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h2_full);
+            prev_tile = tile;
+        }
+        if (it > 0) {
+            mbar_wait(z_full, (uint32_t)((it - 1) & 1));
+            store_z(prev_tile);
+        }
+    } else if (warp < EPI_WARPS + CONV_WARPS) {
+        // ===================== A producers (identical to linear_tc_kernel) =====================
+        const int ct = threadIdx.x - EPI_WARPS * 32;
+        const int c4 = ct & 15;
+        const int rbase = ct >> 4;
+        auto load_slab = [&](int64_t tile, int slab, float4 (&dst)[8]) {
+            const int k0 = slab * BK + c4 * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = tile * TM + rbase + 16 * i;
+                if (row < n && k0 < K) dst[i] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k0));
+                else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        auto convert_slab = [&](const float4 (&src)[8]) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char *a_hi = smem + stage * Cfg::STAGE_BYTES;
+            unsigned char *a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const int off = (r >> 3) * 1024 + (r & 7) * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + ((c4 & 1) << 3);
+                uint2 hi, lo;
+                split2(src[i].x, src[i].y, hi.x, lo.x);
+                split2(src[i].z, src[i].w, hi.y, lo.y);
+                *reinterpret_cast<uint2 *>(a_hi + off) = hi;
+                *reinterpret_cast<uint2 *>(a_lo + off) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[stage]);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        };
+        const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t steps = my_tiles * KS;
+        float4 bufA[8], bufB[8];
+        auto coords = [&](int64_t st, int64_t &tile, int &slab) {
+            tile = blockIdx.x + (st / KS) * (int64_t)gridDim.x;
+            slab = (int)(st % KS);
+        };
+        int64_t t0; int s0;
+        if (steps > 0) { coords(0, t0, s0); load_slab(t0, s0, bufA); }
+        for (int64_t st = 0; st < steps; st += 2) {
+            if (st + 1 < steps) { coords(st + 1, t0, s0); load_slab(t0, s0, bufB); }
+            convert_slab(bufA);
+            if (st + 1 < steps) {
+                if (st + 2 < steps) { coords(st + 2, t0, s0); load_slab(t0, s0, bufA); }
+                convert_slab(bufB);
+            }
+        }
+    } else if (warp == 12) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc2 = umma_idesc(TM, N2);
+            constexpr uint32_t idesc3 = umma_idesc(TM, N3);
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t it = 0;
+            auto issue_third = [&](int64_t j) {     // third layer of the j-th tile of this CTA
+                if (j == 0) mbar_wait(w3_full, 0);
+                mbar_wait(h2_full, (uint32_t)(j & 1));
+                tc_fence_after();
+                const uint32_t d3 = tmem_base + (uint32_t)Cfg::ACC3_COL;
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const uint32_t a_hi = smem_u32(h2 + sl * (2 * A_TILE_BYTES));
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t w_hi = smem_u32(w3 + sl * (2 * Cfg::W3_TILE));
+                    const uint32_t w_lo = w_hi + Cfg::W3_TILE;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        umma_f16(d3, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc3, (sl | kk) != 0);
+                        umma_f16(d3, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc3, 1);
+                        umma_f16(d3, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc3, 1);
+                    }
+                }
+                umma_commit(z_full);
+            };
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int buf = (int)(it & 1);
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N2);
+                for (int slab = 0; slab < KS; ++slab) {
+                    mbar_wait(&full_a[stage], phase);
+                    mbar_wait(&full_w[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t w_hi = a_hi + 2 * A_TILE_BYTES;
+                    const uint32_t w_lo = w_hi + Cfg::W2_TILE;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        umma_f16(d_tmem, umma_desc(a_lo + ko), umma_desc(w_hi + ko), idesc2, (slab | kk) != 0);
+                        umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_lo + ko), idesc2, 1);
+                        umma_f16(d_tmem, umma_desc(a_hi + ko), umma_desc(w_hi + ko), idesc2, 1);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[buf]);
+                if (it > 0) issue_third(it - 1);    // behind this tile's second layer: its H2 was converted meanwhile
+            }
+            if (it > 0) issue_third(it - 1);
+        }
+    } else {
+        // ===================== W loader =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w3_full, (uint32_t)Cfg::W3_BYTES);
+            bulk_g2s(w3, Wp3, (uint32_t)Cfg::W3_BYTES, w3_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            constexpr uint32_t slab_bytes = 2 * Cfg::W2_TILE;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int slab = 0; slab < KS; ++slab) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_w[stage], slab_bytes);
+                    bulk_g2s(smem + stage * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES, Wp2 + (size_t)slab * slab_bytes, slab_bytes, &full_w[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
 // ---- weight packing -----------------------------------------------------------------------------
 
 __global__ void absmax_kernel(const float *__restrict__ w, int64_t count, float *__restrict__ out) {
@@ -374,6 +646,12 @@ static bool env_tc2() {
 
 // passes: 3 (split-fp16, fp32-class) or 1 (fp16 screening pass).  rows: gather of the input rows (first layer of a
 // re-run tier; needs the 2-CTA kernel).  n_dev: device-resident row count, n = upper bound.
+static bool env_unfused() {      // RQB200_UNFUSED=1: keep the last two layers as separate kernels (A/B measurements)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("RQB200_UNFUSED"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes, const int64_t *rows,
               const unsigned long long *n_dev) {
     if (n == 0) return 0;
@@ -394,6 +672,30 @@ int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStr
     return RQB200_EINVAL;
 }
 
+
+template <int N3>
+static int launch_mlp23(Linear &l2, Linear &l3, const float *x, int64_t n, float *z, const unsigned long long *n_dev, cudaStream_t s) {
+    using Cfg = Tc23Cfg<N3>;
+    auto kern = mlp23_tc_kernel<N3>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int64_t ntiles = (n + TM - 1) / TM;
+    const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    count_launch();
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(x, n, l2.in, (const unsigned char *)l2.W_tc, l2.b, ldexpf(1.0f, -l2.tc_scale_exp),
+                                                  (const unsigned char *)l3.W_tc, l3.b, ldexpf(1.0f, -l3.tc_scale_exp), z, n_dev);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+// layers i and i+1 of a three-pass MLP can run as one kernel when the middle width is 128 and the output 32 or 64
+static bool mlp23_supported(const Linear &l2, const Linear &l3) {
+    return l2.out == 128 && l3.in == 128 && (l3.out == 32 || l3.out == 64) && l2.in % 8 == 0;
+}
+
 int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s, int passes,
            const int64_t *rows, const unsigned long long *n_dev, bool profile) {
     Linear *ls = which == 0 ? m->enc : m->dec;
@@ -407,10 +709,16 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
     for (int i = 0; i < m->n_layers; ++i) {
         const bool last = i == m->n_layers - 1;
         float *dst = last ? y : (float *)m->act[i & 1].ptr;
-        {
-            ProfScope ps(!profile ? -1 : (i == 0 ? PROF_TC_ENCODER : PROF_TC_REST), s);      // slot 4 = the wide first layer alone
-            RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev));
+        ProfScope ps(!profile ? -1 : (i == 0 ? PROF_TC_ENCODER : PROF_TC_REST), s);      // slot 4 = the wide first layer alone
+        if (i > 0 && i + 2 == m->n_layers && passes == 3 && mlp23_supported(ls[i], ls[i + 1]) && !env_unfused()) {
+            // the last two layers as one kernel: the 128-wide activation between them never leaves the SM
+            RQB_TRY(ensure_packed(ls[i], s));
+            RQB_TRY(ensure_packed(ls[i + 1], s));
+            if (ls[i + 1].out == 32) RQB_TRY(launch_mlp23<32>(ls[i], ls[i + 1], cur, n, y, n_dev, s));
+            else RQB_TRY(launch_mlp23<64>(ls[i], ls[i + 1], cur, n, y, n_dev, s));
+            return 0;
         }
+        RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev));
         cur = dst;
     }
     return 0;
