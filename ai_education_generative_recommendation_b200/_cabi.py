@@ -12,7 +12,7 @@ import re
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librqvae_b200.so")
+LIB_PATH = os.environ.get("RQB200_LIB") or os.path.join(_PKG, "librqvae_b200.so")   # RQB200_LIB: A/B builds (tools/)
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "rqvae_b200.h")
 
 ENCODE_EXACT = 0

@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--items", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--e2e-items", type=int, default=0,
+                    help="rows per rank of the host-buffer (e2e) leg; 0 = the same rows as the device leg, capped at 2M "
+                         "(catalogue-scale runs would otherwise pin tens of GB of host memory per rank)")
     args = ap.parse_args()
     global GOLDEN, WORKLOAD
     GOLDEN, WORKLOAD = CONFIGS[args.config]
@@ -273,15 +276,17 @@ def main():
     value = n_total / (ms_step * 1e-3)
 
     # ---- e2e through the host-buffer C-ABI call (pinned host in, host out), same workload per rank
-    xh = torch.empty((n, in_dim), dtype=torch.float32).pin_memory()
-    xh.copy_(x)
+    ne = args.e2e_items if args.e2e_items > 0 else min(n, 2_000_000)
+    ne = min(ne, n)
+    xh = torch.empty((ne, in_dim), dtype=torch.float32).pin_memory()
+    xh.copy_(x[:ne])
     torch.cuda.synchronize()
-    ids_host = torch.empty((n, len(Ks) + 1), dtype=torch.int64).pin_memory()
+    ids_host = torch.empty((ne, len(Ks) + 1), dtype=torch.int64).pin_memory()
     stats = (ctypes.c_int64 * 4)()
     mode_id = _cabi.ENCODE_FAST if fast_ok else _cabi.ENCODE_EXACT
 
     def e2e_step():
-        _cabi.check(lib.rqb200_generate_codes_host(model._handle, mode_id, xh.data_ptr(), n, 131072, ids_host.data_ptr(), stats))
+        _cabi.check(lib.rqb200_generate_codes_host(model._handle, mode_id, xh.data_ptr(), ne, 131072, ids_host.data_ptr(), stats))
 
     for _ in range(2):
         e2e_step()
@@ -294,8 +299,8 @@ def main():
     e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = n_total / float(e2e_s.item())
-    if world == 1:
+    e2e_value = ne * world / float(e2e_s.item())
+    if world == 1 and ne == n:
         assert np.array_equal(ids_host.numpy(), out.cpu().numpy()), "host-buffer path and device path disagree"
 
     if rank == 0:
@@ -338,12 +343,13 @@ def main():
                            "parallelism": f"items sharded x{world}, codebooks replicated",
                            "multi_gpu_ids_equal_single_gpu": multi_check},
                 "roofline": roofline,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * in_dim * 4),
-                        "d2h_bytes_per_step": int(n * (len(Ks) + 1) * 8), "api": "rqb200_generate_codes_host (pinned host buffers)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ne * in_dim * 4),
+                        "d2h_bytes_per_step": int(ne * (len(Ks) + 1) * 8), "items_per_gpu": ne,
+                        "api": "rqb200_generate_codes_host (pinned host buffers)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = min(n, 1_000_000)
+            sample = min(ne, 1_000_000)
             v, dt, ids = cpu_reference_leg(sample, threads, x_host=xh.numpy())
             same = bool(np.array_equal(ids[:, :n_levels], ids_host.numpy()[:sample, :n_levels]))
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
