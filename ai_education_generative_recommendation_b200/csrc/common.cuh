@@ -115,10 +115,10 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
 // encode_tc2.cu
 bool linear_tc2_supported(const Linear &l);
 int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
-               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr);
+               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
-              const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr);
+              const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
 int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s, int passes = 3,
            const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool profile = true);
 // quantize_tc.cu

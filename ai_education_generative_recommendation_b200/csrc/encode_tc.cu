@@ -273,7 +273,9 @@ struct Tc23Cfg {
     static constexpr int ACC3_COL = 2 * N2;                            // TMEM: two 128-column buffers, then the third layer's accumulator
 };
 
-template <int N3>
+// TILED_A: X is the previous layer's activation as split-fp16 UMMA tiles (epilogue_rows_split): the loader lane stages a
+// whole A slab (hi | lo, 32 KB) with one bulk copy next to the W2 slab and the converter warps have nothing to do.
+template <int N3, bool TILED_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
                 const float *__restrict__ bias2, float inv_scale2, const unsigned char *__restrict__ Wp3,
@@ -302,7 +304,7 @@ mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned ch
     const int64_t ntiles = (n + TM - 1) / TM;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_a[s], CONV_WARPS); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_a[s], TILED_A ? 1 : CONV_WARPS); mbar_init(&full_w[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS * 32); }
         mbar_init(h2_full, EPI_WARPS);
         mbar_init(z_full, 1);
@@ -390,7 +392,8 @@ mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned ch
             store_z(prev_tile);
         }
     } else if (warp < EPI_WARPS + CONV_WARPS) {
-        // ===================== A producers (identical to linear_tc_kernel) =====================
+        // ===================== A producers (identical to linear_tc_kernel; idle when the input arrives as tiles) =====================
+        if (TILED_A) goto teardown;
         const int ct = threadIdx.x - EPI_WARPS * 32;
         const int c4 = ct & 15;
         const int rbase = ct >> 4;
@@ -506,9 +509,15 @@ mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned ch
             int stage = 0;
             uint32_t phase = 0;
             constexpr uint32_t slab_bytes = 2 * Cfg::W2_TILE;
+            const unsigned char *Xt = reinterpret_cast<const unsigned char *>(X);
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
+                    if (TILED_A) {
+                        mbar_arrive_expect_tx(&full_a[stage], 2 * A_TILE_BYTES);
+                        bulk_g2s(smem + stage * Cfg::STAGE_BYTES, Xt + ((size_t)tile * KS + slab) * (2 * A_TILE_BYTES), 2 * A_TILE_BYTES,
+                                 &full_a[stage]);
+                    }
                     mbar_arrive_expect_tx(&full_w[stage], slab_bytes);
                     bulk_g2s(smem + stage * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES, Wp2 + (size_t)slab * slab_bytes, slab_bytes, &full_w[stage]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -516,6 +525,7 @@ mlp23_tc_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned ch
             }
         }
     }
+teardown:
     tc_fence_before();
     __syncthreads();
     if (warp == 12) {
@@ -646,6 +656,11 @@ static bool env_tc2() {
 
 // passes: 3 (split-fp16, fp32-class) or 1 (fp16 screening pass).  rows: gather of the input rows (first layer of a
 // re-run tier; needs the 2-CTA kernel).  n_dev: device-resident row count, n = upper bound.
+static bool env_untiled() {      // RQB200_UNTILED=1: fp32 rows between the first layer and the fused kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("RQB200_UNTILED"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 static bool env_unfused() {      // RQB200_UNFUSED=1: keep the last two layers as separate kernels (A/B measurements)
     static int v = -1;
     if (v < 0) { const char *e = getenv("RQB200_UNFUSED"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -653,12 +668,12 @@ static bool env_unfused() {      // RQB200_UNFUSED=1: keep the last two layers a
 }
 
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes, const int64_t *rows,
-              const unsigned long long *n_dev) {
+              const unsigned long long *n_dev, bool tiled_out) {
     if (n == 0) return 0;
     RQB_CHECK(passes == 1 || passes == 3, "passes must be 1 or 3");
     RQB_TRY(ensure_packed(l, s));
-    if (linear_tc2_supported(l) && (env_tc2() || rows)) return linear_tc2(l, x, n, y, relu, s, passes, rows, n_dev);
-    RQB_CHECK(rows == nullptr, "row gather needs the 2-CTA kernel (out_features 256)");
+    if (linear_tc2_supported(l) && (env_tc2() || rows || tiled_out)) return linear_tc2(l, x, n, y, relu, s, passes, rows, n_dev, tiled_out);
+    RQB_CHECK(rows == nullptr && !tiled_out, "row gather / tiled output need the 2-CTA kernel (out_features 256)");
 #define RQB_TC_CASE(NN)                                                                              \
     case NN: return passes == 1 ? launch_tc<NN, 1>(l, x, n, y, relu, n_dev, s) : launch_tc<NN, 3>(l, x, n, y, relu, n_dev, s);
     switch (l.out) {
@@ -673,10 +688,10 @@ int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStr
 }
 
 
-template <int N3>
+template <int N3, bool TILED_A>
 static int launch_mlp23(Linear &l2, Linear &l3, const float *x, int64_t n, float *z, const unsigned long long *n_dev, cudaStream_t s) {
     using Cfg = Tc23Cfg<N3>;
-    auto kern = mlp23_tc_kernel<N3>;
+    auto kern = mlp23_tc_kernel<N3, TILED_A>;
     static bool attr_done = false;
     if (!attr_done) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -701,11 +716,13 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
     Linear *ls = which == 0 ? m->enc : m->dec;
     int maxdim = 0;
     for (int i = 0; i + 1 < m->n_layers; ++i) maxdim = ls[i].out > maxdim ? ls[i].out : maxdim;
+    const size_t n_pad = (size_t)((n + 255) / 256) * 256;      // the tiled hand-off is written in whole 256-row pair tiles
     if (m->n_layers > 1) {
-        RQB_TRY(ws_reserve(m->act[0], sizeof(float) * (size_t)n * maxdim));
-        if (m->n_layers > 2) RQB_TRY(ws_reserve(m->act[1], sizeof(float) * (size_t)n * maxdim));
+        RQB_TRY(ws_reserve(m->act[0], sizeof(float) * n_pad * maxdim));
+        if (m->n_layers > 2) RQB_TRY(ws_reserve(m->act[1], sizeof(float) * n_pad * maxdim));
     }
     const float *cur = x;
+    bool cur_tiled = false;             // `cur` holds split-fp16 UMMA tiles (written by the 2-CTA kernel for the fused kernel)
     for (int i = 0; i < m->n_layers; ++i) {
         const bool last = i == m->n_layers - 1;
         float *dst = last ? y : (float *)m->act[i & 1].ptr;
@@ -714,12 +731,21 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
             // the last two layers as one kernel: the 128-wide activation between them never leaves the SM
             RQB_TRY(ensure_packed(ls[i], s));
             RQB_TRY(ensure_packed(ls[i + 1], s));
-            if (ls[i + 1].out == 32) RQB_TRY(launch_mlp23<32>(ls[i], ls[i + 1], cur, n, y, n_dev, s));
-            else RQB_TRY(launch_mlp23<64>(ls[i], ls[i + 1], cur, n, y, n_dev, s));
+            if (ls[i + 1].out == 32) {
+                if (cur_tiled) RQB_TRY((launch_mlp23<32, true>(ls[i], ls[i + 1], cur, n, y, n_dev, s)));
+                else RQB_TRY((launch_mlp23<32, false>(ls[i], ls[i + 1], cur, n, y, n_dev, s)));
+            } else {
+                if (cur_tiled) RQB_TRY((launch_mlp23<64, true>(ls[i], ls[i + 1], cur, n, y, n_dev, s)));
+                else RQB_TRY((launch_mlp23<64, false>(ls[i], ls[i + 1], cur, n, y, n_dev, s)));
+            }
             return 0;
         }
-        RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev));
+        // first layer of a 3-layer three-pass MLP whose tail is fused: emit the tiles the fused kernel bulk-loads
+        const bool tiled = i == 0 && m->n_layers == 3 && passes == 3 && linear_tc2_supported(ls[0]) && ls[0].out == 256 &&
+                           mlp23_supported(ls[1], ls[2]) && !env_unfused() && !env_untiled();
+        RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev, tiled));
         cur = dst;
+        cur_tiled = tiled;
     }
     return 0;
 }

@@ -118,7 +118,8 @@ template <int PASSES, bool GATHER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
                   const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y,
-                  const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev, int dbg) {
+                  const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev, int dbg, int tiled_out) {
+    // tiled_out: Y receives the activation as split-fp16 UMMA tiles (epilogue_rows_split) instead of fp32 rows
     // dbg: ablation switches of tools/ablate_tc2.py (0 in production) — bit0 no epilogue stores, bit1 no MMA,
     // bit2 no producer smem stores, bit3 no W bulk loads, bit4 no X loads
     constexpr int T2_STAGE = T2Cfg<PASSES>::STAGE, T2_STAGES = T2Cfg<PASSES>::STAGES;
@@ -170,8 +171,12 @@ linear_tc2_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             const int buf = (int)(it & 1);
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            epilogue_rows<N2>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N2), patch, lane, bias, inv_scale, relu,
-                              Y, pt * (2 * TM2) + rank * TM2 + warp * 32, n, !(dbg & 1));
+            if (tiled_out)
+                epilogue_rows_split<N2>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N2), patch, lane, bias, inv_scale,
+                                        relu, reinterpret_cast<unsigned char *>(Y), pt * 2 + rank, warp * 32);
+            else
+                epilogue_rows<N2>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * N2), patch, lane, bias, inv_scale, relu,
+                                  Y, pt * (2 * TM2) + rank * TM2 + warp * 32, n, !(dbg & 1));
             tc_fence_before();
             if (rank == 0) mbar_arrive(&tmem_empty[buf]);
             else mbar_arrive_remote(&tmem_empty[buf], 0);
@@ -358,7 +363,7 @@ int tc_debug_flags();     // encode_tc.cu
 
 template <int PASSES, bool GATHER>
 static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, const int64_t *rows,
-                      const unsigned long long *n_dev, cudaStream_t s) {
+                      const unsigned long long *n_dev, cudaStream_t s, bool tiled_out) {
     auto kern = linear_tc2_kernel<PASSES, GATHER>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -370,14 +375,14 @@ static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu,
     count_launch();
     kern<<<(unsigned)(pairs * 2), T2_THREADS, T2Cfg<PASSES>::SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
                                                                        ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y, rows, n_dev,
-                                                                       tc_debug_flags());
+                                                                       tc_debug_flags(), tiled_out ? 1 : 0);
     RQB_LAUNCH_CHECK();
     return 0;
 }
 
 // requires l.tc_scale_exp to be set (ensure_packed of encode_tc.cu ran).  n is an upper bound when n_dev is given.
 int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes,
-               const int64_t *rows, const unsigned long long *n_dev) {
+               const int64_t *rows, const unsigned long long *n_dev, bool tiled_out) {
     if (n == 0) return 0;
     const int KS = (l.in + BK2 - 1) / BK2;
     if (!l.W_tc2) {
@@ -390,10 +395,11 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
     }
     if (rows) {
         RQB_CHECK(passes == 3, "row gather is only built for the three-pass kernel");
-        return launch_tc2<3, true>(l, x, n, y, relu, rows, n_dev, s);
+        return launch_tc2<3, true>(l, x, n, y, relu, rows, n_dev, s, tiled_out);
     }
     RQB_CHECK(n_dev == nullptr, "a device-side row count needs the gather variant");
-    return passes == 1 ? launch_tc2<1, false>(l, x, n, y, relu, nullptr, nullptr, s) : launch_tc2<3, false>(l, x, n, y, relu, nullptr, nullptr, s);
+    return passes == 1 ? launch_tc2<1, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out)
+                       : launch_tc2<3, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out);
 }
 
 }  // namespace rqb

@@ -158,5 +158,54 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, float *patch, int 
     }
 }
 
+
+// Epilogue variant that hands the activation to the next tensor-core kernel in the form it consumes: per 128-row tile
+// and 64-column slab one [hi tile | lo tile] pair (16 KB each) of fp16 in the UMMA K-major SWIZZLE_128B layout, so the
+// consumer stages its A operand with ONE bulk copy per slab and needs no converter warps.  Same bytes as fp32.
+// Tile (t, s) lives at tiled + ((t * (N/64) + s) * 2) * 16384.  The 32x32 chunk still goes through the per-warp smem
+// patch: afterwards lane (row = 8i + lane/4, chunk = lane%4) holds 8 consecutive columns = one 16-byte piece of hi and
+// of lo, and the four lanes of a row store 64 contiguous bytes.
+template <int N>
+__device__ __forceinline__ void epilogue_rows_split(uint32_t taddr, float *patch, int lane, const float *__restrict__ bias,
+                                                    float inv_scale, int relu, unsigned char *__restrict__ tiled, int64_t tile,
+                                                    int row_in_tile0) {
+    const int rsub = lane >> 2, ch = lane & 3;
+#pragma unroll 1
+    for (int c = 0; c < N; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4 *>(patch + lane * EPI_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * ch));
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * ch + 4));
+        const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+        unsigned char *hi_t = tiled + ((size_t)tile * (N / 64) + (c >> 6)) * 32768;
+        const int chunk = ((c & 63) >> 3) + ch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + rsub;
+            const float4 a0 = *reinterpret_cast<const float4 *>(patch + rr * EPI_LD + 8 * ch);
+            const float4 a1 = *reinterpret_cast<const float4 *>(patch + rr * EPI_LD + 8 * ch + 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float h[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float y = fmaf(av[t], inv_scale, bv[t]);
+                h[t] = (relu && !(y != y)) ? fmaxf(y, 0.0f) : y;
+            }
+            uint4 hi, lo;
+            split2(h[0], h[1], hi.x, lo.x); split2(h[2], h[3], hi.y, lo.y);
+            split2(h[4], h[5], hi.z, lo.z); split2(h[6], h[7], hi.w, lo.w);
+            const int r = row_in_tile0 + rr;
+            const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4 *>(hi_t + off) = hi;
+            *reinterpret_cast<uint4 *>(hi_t + 16384 + off) = lo;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 }  // namespace rqb
