@@ -57,7 +57,7 @@ struct Linear {
     int kblocks[16];
     int nblk = 0;
     bool set = false;
-    // tensor-core path: split-bf16 images of W, packed per K-slab in UMMA SW128 layout
+    // tensor-core path: split-fp16 (hi | lo) images of W, packed per K-slab in UMMA SW128 layout
     void *W_tc = nullptr;
     size_t W_tc_bytes = 0;
     float *absW_rowmax = nullptr;

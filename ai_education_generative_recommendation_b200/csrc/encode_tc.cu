@@ -19,6 +19,12 @@
 //   warp 13     W loader (one lane): cp.async.bulk of the pre-packed, pre-swizzled W slab (hi|lo)
 // mbarrier rings: full_a / full_w / empty per smem stage, tmem_full / tmem_empty per accumulator buffer
 // (two buffers, so the epilogue of tile i overlaps the MMAs of tile i+1).
+//
+// In the shipped fast route this generic kernel only serves layer shapes the specialised ones do not cover:
+//   * the wide first layer (out = 256) runs in the 2-CTA kernel of encode_tc2.cu, which hands its output on as
+//     split-fp16 UMMA tiles (tc_common.cuh: epilogue_rows_split);
+//   * the last two layers run fused in mlp23_tc_kernel below (the 128-wide activation never leaves the SM, the
+//     tiles are staged by bulk copies).
 #include <cuda_fp16.h>
 
 #include <stdlib.h>

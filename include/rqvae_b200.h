@@ -121,7 +121,7 @@ int rqb200_quantize(rqb200_model *m, const float *z_dev, int64_t n, int64_t *cod
 
 /* ---- RQVAE.get_indices(xs, use_sk=False) (rqvae.py:67-71) ---------------------------
  * mode: RQB200_ENCODE_EXACT — SIMT fp32 in the reference's summation order;
- *       RQB200_ENCODE_FAST  — tcgen05 split-bf16 tensor-core encoder + margin gate, rows
+ *       RQB200_ENCODE_FAST  — tcgen05 split-fp16 tensor-core encoder + quantizer with a margin gate, rows
  *                             inside the gate re-run by the exact kernels (same codes).
  * z_out (may be NULL) receives the latent.  stats (host, may be NULL): [0]=rows rescued. */
 #define RQB200_ENCODE_EXACT 0
