@@ -169,14 +169,17 @@ __device__ void center_and_exp(double *Q, int count, double epsilon, float *s_mm
 __global__ void __launch_bounds__(SK_THREADS)
 sinkhorn_regroup_kernel(const float *__restrict__ residual, const int64_t *__restrict__ items,
                         const int64_t *__restrict__ offsets, int e, const float *__restrict__ cb,
-                        const float *__restrict__ cc, int K, int L, int cap_rows, double epsilon, int iters,
+                        const float *__restrict__ cc, int K, int L, int min_rows, int cap_rows, double epsilon, int iters,
                         int64_t *__restrict__ codes) {
     extern __shared__ __align__(16) unsigned char sk_smem[];
     __shared__ double s_red[SK_THREADS / 32];
     __shared__ float s_mm[64];
     const int64_t g0 = offsets[blockIdx.x], g1 = offsets[blockIdx.x + 1];
-    const int B = (int)(g1 - g0);
-    if (B < 2 || B > cap_rows) return;     // oversized groups are re-encoded by the host-driven path
+    const int64_t B64 = g1 - g0;
+    // this launch serves one size class (its shared memory is sized for cap_rows); larger groups are taken by the
+    // next class or by sinkhorn_regroup_large_kernel
+    if (B64 < 2 || B64 < min_rows || B64 > cap_rows) return;
+    const int B = (int)B64;
     double *Q = reinterpret_cast<double *>(sk_smem);                    // [B][K]
     float *s_r = reinterpret_cast<float *>(Q + (size_t)cap_rows * K);   // [B][e]
     float *s_xx = s_r + (size_t)cap_rows * e;                           // [B]
@@ -194,6 +197,40 @@ sinkhorn_regroup_kernel(const float *__restrict__ residual, const int64_t *__res
         float acc = 0.0f;
         for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
         Q[p] = (double)__fsub_rn(__fadd_rn(s_xx[i], cc[j]), __fmul_rn(2.0f, acc));
+    }
+    __syncthreads();
+    center_and_exp(Q, B * K, epsilon, s_mm);
+    sinkhorn_cta(Q, B, K, iters, s_red);
+    argmax_rows(Q, B, K, gi, codes, L, nullptr);
+}
+
+
+// collision groups too large for shared memory: same computation, the fp64 matrix and the row norms live in a global
+// scratch slice (offset given per listed group).  One CTA per listed group.
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_regroup_large_kernel(const float *__restrict__ residual, const int64_t *__restrict__ items,
+                              const int64_t *__restrict__ offsets, const int64_t *__restrict__ group_ids,
+                              const int64_t *__restrict__ scratch_off, double *__restrict__ scratch, int e,
+                              const float *__restrict__ cb, const float *__restrict__ cc, int K, int L, double epsilon,
+                              int iters, int64_t *__restrict__ codes) {
+    __shared__ double s_red[SK_THREADS / 32];
+    __shared__ float s_mm[64];
+    const int64_t g = group_ids[blockIdx.x];
+    const int64_t g0 = offsets[g], g1 = offsets[g + 1];
+    const int B = (int)(g1 - g0);
+    double *Q = scratch + scratch_off[blockIdx.x];              // [B][K]
+    float *xx = reinterpret_cast<float *>(Q + (size_t)B * K);    // [B]
+    const int64_t *gi = items + g0;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < B; i += SK_THREADS) xx[i] = sumsq_aten_rt(residual + gi[i] * e, e);
+    __syncthreads();
+    for (int64_t p = tid; p < (int64_t)B * K; p += SK_THREADS) {
+        const int i = (int)(p / K), j = (int)(p % K);
+        const float *r = residual + gi[i] * e;
+        const float *c = cb + (size_t)j * e;
+        float acc = 0.0f;
+        for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
+        Q[p] = (double)__fsub_rn(__fadd_rn(xx[i], cc[j]), __fmul_rn(2.0f, acc));
     }
     __syncthreads();
     center_and_exp(Q, B * K, epsilon, s_mm);
@@ -242,20 +279,51 @@ extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_de
     // rows that fit in shared memory next to the fp64 matrix
     const size_t budget = 200 * 1024;
     const size_t per_row = sizeof(double) * K + sizeof(float) * (e + 1);
-    int cap = (int)(budget / per_row);
-    RQB_CHECK(cap >= 2, "K=%d too large for the shared-memory Sinkhorn kernel", K);
-    if (max_group > 0 && max_group < cap) cap = max_group < 2 ? 2 : max_group;
-    size_t smem = per_row * cap + 16;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    const int cap_max = (int)(budget / per_row);
+    RQB_CHECK(cap_max >= 2, "K=%d too large for the shared-memory Sinkhorn kernel", K);
+    int top = cap_max;
+    if (max_group > 0 && max_group < top) top = max_group < 2 ? 2 : max_group;
+    static bool attr_done = false;
+    if (!attr_done) {
         RQB_CUDA(cudaFuncSetAttribute(sinkhorn_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(budget + 1024)));
-        smem_set = budget + 1024;
+        attr_done = true;
     }
+    // Most groups have a handful of members: one launch per size class, shared memory sized for the class, so that many
+    // small groups share an SM instead of every CTA reserving room for the largest group.
+    ProfScope ps(PROF_SINKHORN, (cudaStream_t)stream);
+    const int bounds[4] = {8, 24, 48, top};
+    int lo = 2;
+    for (int c = 0; c < 4 && lo <= top; ++c) {
+        const int hi = bounds[c] < top ? bounds[c] : top;
+        if (hi < lo) continue;
+        const size_t smem = per_row * hi + 16;
+        rqb::count_launch();
+        sinkhorn_regroup_kernel<<<(unsigned)n_groups, SK_THREADS, smem, (cudaStream_t)stream>>>(
+            residual_dev, items_dev, offsets_dev, e, m->cb[L - 1], m->cc[L - 1], K, L, lo, hi, epsilon, iters, codes_dev);
+        lo = hi + 1;
+    }
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rqb200_sinkhorn_regroup_large(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
+                                             const int64_t *offsets_dev, const int64_t *group_ids_dev,
+                                             const int64_t *scratch_off_dev, int64_t n_listed, double *scratch_dev,
+                                             double epsilon, int iters, int64_t *codes_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    if (n_listed == 0) return 0;
+    RQB_CHECK(residual_dev && items_dev && offsets_dev && group_ids_dev && scratch_off_dev && scratch_dev && codes_dev, "NULL buffer");
+    RQB_CHECK(epsilon > 0.0, "epsilon must be > 0");
+    RQB_CHECK(m->e < 512, "e_dim >= 512 not supported");
+    RQB_CUDA(cudaSetDevice(m->device));
+    const int L = m->L, K = m->K[L - 1], e = m->e;
+    RQB_CHECK(m->cb_set[L - 1], "codebook %d not loaded", L - 1);
     rqb::count_launch();
     ProfScope ps(PROF_SINKHORN, (cudaStream_t)stream);
-    sinkhorn_regroup_kernel<<<(unsigned)n_groups, SK_THREADS, smem, (cudaStream_t)stream>>>(
-        residual_dev, items_dev, offsets_dev, e, m->cb[L - 1], m->cc[L - 1], K, L, cap, epsilon, iters, codes_dev);
+    sinkhorn_regroup_large_kernel<<<(unsigned)n_listed, SK_THREADS, 0, (cudaStream_t)stream>>>(
+        residual_dev, items_dev, offsets_dev, group_ids_dev, scratch_off_dev, scratch_dev, e, m->cb[L - 1], m->cc[L - 1], K, L,
+        epsilon, iters, codes_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }

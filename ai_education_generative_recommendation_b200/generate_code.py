@@ -97,24 +97,91 @@ def _scratch_handle(device):
 
 
 @torch.no_grad()
-def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 262144, verbose: bool = False
-                   ) -> Tuple[torch.Tensor, dict]:
-    """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats)."""
+def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Tensor:
+    """Pass 1 on the tensor-core route: codes[N, L] (bit-identical to the exact route)."""
+    data = _as_rows(data)
+    dev = model._device()
+    n, Lv = data.shape[0], len(model.num_emb_list)
+    codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
+    model._sync()
+    L = _cabi.lib()
+    stats = (ctypes.c_int64 * 4)()
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        chunk = data[r0:r1]
+        if not chunk.is_cuda:
+            chunk = chunk.contiguous().to(dev, non_blocking=True)
+        chunk = chunk.contiguous()
+        check(L.rqb200_get_indices(model._handle, _cabi.ENCODE_FAST, ptr(chunk), r1 - r0, ptr(codes[r0:r1]), 0, stats,
+                                   stream_ptr(dev)))
+    return codes
+
+
+class _LazyResidual:
+    """Residual entering the LAST level, per item, for the Sinkhorn re-encode rounds — computed (exact route) only
+    for the items that ever land in a collision group, the first time they do.  It is a pure function of the item
+    (levels < L-1 never change), so it is cached."""
+
+    def __init__(self, model: RQVAE, data, n: int):
+        self.model, self.data, self.n = model, _as_rows(data), n
+        dev = model._device()
+        self.buf = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
+        self.have = torch.zeros((n,), dtype=torch.bool, device=dev)
+
+    def ensure(self, items: torch.Tensor, codes: torch.Tensor):
+        missing = items[~self.have[items]]
+        if missing.numel() == 0:
+            return
+        m, dev = self.model, self.model._device()
+        if self.data.is_cuda:
+            rows = self.data[missing].contiguous()
+        else:
+            rows = self.data[missing.cpu()].contiguous().to(dev)
+        k, Lv = rows.shape[0], len(m.num_emb_list)
+        lib = _cabi.lib()
+        z = torch.empty((k, m.e_dim), dtype=torch.float32, device=dev)
+        check(lib.rqb200_mlp_exact(m._handle, 0, ptr(rows), 0, k, ptr(z), stream_ptr(dev)))
+        sub_codes = torch.empty((k, Lv), dtype=torch.int64, device=dev)
+        res = torch.empty((k, m.e_dim), dtype=torch.float32, device=dev)
+        check(lib.rqb200_quantize(m._handle, ptr(z), k, ptr(sub_codes), 0, 0, 0, ptr(res), stream_ptr(dev)))
+        if Lv > 1 and not torch.equal(sub_codes[:, :Lv - 1], codes[missing, :Lv - 1]):
+            raise RuntimeError("tensor-core route and exact route disagree on a code (this is a bug: please report)")
+        self.buf[missing] = res
+        self.have[missing] = True
+
+
+@torch.no_grad()
+def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 262144, verbose: bool = False,
+                   fast: Optional[bool] = None) -> Tuple[torch.Tensor, dict]:
+    """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats).
+
+    fast (default: whenever the model's shapes allow it): pass 1 runs on the tensor-core route and the last-level
+    residuals the re-encode rounds need are computed on the exact route only for the items that collide.  The result
+    is identical either way."""
     Lv = len(model.num_emb_list)
     if Lv > MAX_LEVELS_OF_REFERENCE_DRIVER:
         raise IndexError("list index out of range")        # what prefix[i] raises in the reference
+    if fast is None:
+        fast = model.fast_route_supported()
     was_training = model.training
     model.eval()
     try:
         dev = model._device()
         lib = _cabi.lib()
-        z = encode_latents(model, data, chunk_rows)
-        n = z.shape[0]
-        codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
-        residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
-        model._sync()
-        check(lib.rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
-        del z
+        if fast:
+            codes = encode_codes_fast(model, data, chunk_rows)
+            n = codes.shape[0]
+            lazy = _LazyResidual(model, data, n)
+            residual = lazy.buf
+        else:
+            z = encode_latents(model, data, chunk_rows)
+            n = z.shape[0]
+            codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
+            residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
+            model._sync()
+            check(lib.rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
+            del z
+            lazy = None
         # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
         for vq in model.rq.vq_layers[:-1]:
             vq.sk_epsilon = 0.0
@@ -129,6 +196,8 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
                     break
                 if verbose:
                     print(f"Iteration {rounds}: Found {n_groups} collision groups")
+                if lazy is not None:
+                    lazy.ensure(items, codes)
                 new_codes = codes.clone()      # a round reads the codes of the previous round only
                 check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
                                                   min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters),
@@ -139,24 +208,50 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
                 rounds += 1
         out, stats = suffix_dedup(model, codes)
         stats["rounds"] = rounds
+        stats["pass1_route"] = "tensor-core" if fast else "exact"
+        if lazy is not None:
+            stats["items_needing_exact_residual"] = int(lazy.have.sum().item())
         return out, stats
     finally:
         if was_training:
             model.train()
 
 
-def _regroup_oversized(model, residual, items, offsets, cap, codes):
-    """Groups too large for the shared-memory kernel: per group, distance matrix + global-memory Sinkhorn."""
-    off = offsets.cpu().tolist()
+def _regroup_oversized(model, residual, items, offsets, cap, codes, scratch_doubles: int = 1 << 27):
+    """Groups too large for the shared-memory kernel: one batched launch per wave of groups whose fp64 matrices fit in
+    a bounded global scratch (1 GiB by default); a single group beyond that budget gets a scratch of its own."""
     last = model.rq.vq_layers[-1]
-    Lv = len(model.num_emb_list)
-    for g in range(len(off) - 1):
-        if off[g + 1] - off[g] <= cap:
-            continue
-        idx = items[off[g]:off[g + 1]]
-        r = residual[idx].contiguous()
-        d = model._distances(Lv - 1, r)
-        codes[idx, Lv - 1] = model._sinkhorn_assign(d, last.sk_epsilon, last.sk_iters)
+    K = model.num_emb_list[-1]
+    dev = codes.device
+    sizes = (offsets[1:] - offsets[:-1])
+    big = torch.nonzero(sizes > cap).flatten()
+    if big.numel() == 0:
+        return
+    big_sizes = sizes[big].cpu().tolist()
+    big_ids = big.cpu().tolist()
+    lib = _cabi.lib()
+    wave_ids, wave_off, used = [], [], 0
+
+    def flush():
+        nonlocal wave_ids, wave_off, used
+        if not wave_ids:
+            return
+        scratch = torch.empty((used,), dtype=torch.float64, device=dev)
+        gid = torch.tensor(wave_ids, dtype=torch.int64, device=dev)
+        off = torch.tensor(wave_off, dtype=torch.int64, device=dev)
+        check(lib.rqb200_sinkhorn_regroup_large(model._handle, ptr(residual), ptr(items), ptr(offsets), ptr(gid), ptr(off),
+                                                len(wave_ids), ptr(scratch), float(last.sk_epsilon), int(last.sk_iters),
+                                                ptr(codes), stream_ptr(dev)))
+        wave_ids, wave_off, used = [], [], 0
+
+    for g, b in zip(big_ids, big_sizes):
+        need = b * K + (b + 1) // 2 + 1
+        if used and used + need > scratch_doubles:
+            flush()
+        wave_ids.append(g)
+        wave_off.append(used)
+        used += need
+    flush()
 
 
 def infer(params):

@@ -331,6 +331,12 @@ class RQVAE(nn.Module):
         self._ensure_handle()
         check(_cabi.lib().rqb200_model_set_gate(self._handle, float(gamma), float(floor_abs)))
 
+    def fast_route_supported(self) -> bool:
+        """Shapes the tensor-core route is built for (everything else runs the exact SIMT route)."""
+        dims = list(self.encode_layer_dims)
+        return (not self.bn and dims[0] % 8 == 0 and all(d in (32, 64, 128, 256) for d in dims[1:])
+                and self.e_dim in (16, 32, 48, 64))
+
     def set_screen(self, enabled: bool, gamma1: float = 0.0):
         """Screening tier of the fast route (one fp16 pass over every row; see rqb200_model_set_screen)."""
         self._ensure_handle()

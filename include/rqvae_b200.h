@@ -147,6 +147,13 @@ int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const in
 /* Largest group (rows) rqb200_sinkhorn_regroup handles in shared memory for this model; larger
  * groups are skipped by it and must go through rqb200_distances + rqb200_sinkhorn_assign.   */
 int rqb200_sinkhorn_group_cap(rqb200_model *m);
+/* Groups with more members than rqb200_sinkhorn_group_cap: same re-encode with the fp64 matrix in a caller-provided
+ * global scratch.  group_ids_dev[n_listed] = indices into offsets_dev, scratch_off_dev[n_listed] = offset (in doubles)
+ * of each listed group's slice, which needs B*K + (B+1)/2 doubles for a group of B members.  One launch for all.   */
+int rqb200_sinkhorn_regroup_large(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
+                                  const int64_t *offsets_dev, const int64_t *group_ids_dev,
+                                  const int64_t *scratch_off_dev, int64_t n_listed, double *scratch_dev,
+                                  double epsilon, int iters, int64_t *codes_dev, void *stream);
 /* sinkhorn_algorithm(distances, epsilon, iters) (layers.py:85-108): D[B,K] fp64 distances are
  * replaced in place by Q.                                                               */
 int rqb200_sinkhorn(double *D_dev, int64_t B, int K, double epsilon, int iters, void *stream);

@@ -273,6 +273,26 @@ def test_generate_codes_matches_oracle_driver_at_scale(oracle):
     assert len(np.unique(ref, axis=0)) == n
 
 
+def test_generate_codes_fast_and_exact_pass1_agree():
+    """The driver's default (tensor-core pass 1 + exact residuals only for colliding items) gives the same ids as the
+    all-exact driver, Sinkhorn rounds included."""
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    n = 40_000
+    x = synth.synth_items(2024, 0, n, 768, 1_000_000)
+    x[20_000:20_300] = x[500:800]                                              # exact duplicates → collision groups
+    xt = torch.from_numpy(x).to(DEV)
+    fast, fs = rq.generate_codes(m, xt, fast=True)
+    m2 = build_model(cfg, cbs)
+    exact, es = rq.generate_codes(m2, xt, fast=False)
+    assert fs["pass1_route"] == "tensor-core" and es["pass1_route"] == "exact"
+    assert fs["rounds"] == es["rounds"] and fs["rounds"] >= 1
+    assert torch.equal(fast, exact)
+    assert 600 <= fs["items_needing_exact_residual"] <= n                      # only items that ever collided took the exact route
+    host, _ = rq.generate_codes(build_model(cfg, cbs), x, fast=True)           # host (numpy) catalogue: same result
+    assert torch.equal(host, exact)
+
+
 def test_kmeans_lloyd_matches_oracle(oracle):
     rng = np.random.default_rng(3)
     centres = rng.standard_normal((16, 32)).astype(np.float32)
