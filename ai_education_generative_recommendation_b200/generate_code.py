@@ -151,6 +151,54 @@ class _LazyResidual:
 
 
 @torch.no_grad()
+def resolve_rounds(model: RQVAE, codes: torch.Tensor, residual: torch.Tensor, lazy=None, max_rounds: int = 30,
+                   verbose: bool = False) -> Tuple[torch.Tensor, int]:
+    """Pass 2 (infer.py:109-130): ≤ max_rounds rounds, every group of items sharing a full code is re-encoded with
+    Sinkhorn on the LAST level from `residual[item]` (the residual entering that level).  Returns (codes, rounds)."""
+    lib = _cabi.lib()
+    dev = codes.device
+    # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
+    for vq in model.rq.vq_layers[:-1]:
+        vq.sk_epsilon = 0.0
+    last = model.rq.vq_layers[-1]
+    rounds = 0
+    if last.sk_epsilon is not None and last.sk_epsilon > 0:
+        model._sync()
+        cap = lib.rqb200_sinkhorn_group_cap(model._handle)
+        while rounds < max_rounds:
+            items, offsets, max_group = collision_groups(model, codes)
+            n_groups = offsets.numel() - 1
+            if n_groups <= 0:
+                break
+            if verbose:
+                print(f"Iteration {rounds}: Found {n_groups} collision groups")
+            if lazy is not None:
+                lazy.ensure(items, codes)
+            new_codes = codes.clone()      # a round reads the codes of the previous round only
+            check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
+                                              min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters),
+                                              ptr(new_codes), stream_ptr(dev)))
+            if max_group > cap:
+                _regroup_oversized(model, residual, items, offsets, cap, new_codes)
+            codes = new_codes
+            rounds += 1
+    return codes, rounds
+
+
+@torch.no_grad()
+def encode_codes_and_residual(model: RQVAE, data, chunk_rows: int = 262144) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pass 1 on the exact route: (codes[N, L], residual entering the last level [N, e])."""
+    dev = model._device()
+    z = encode_latents(model, data, chunk_rows)
+    n, Lv = z.shape[0], len(model.num_emb_list)
+    codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
+    residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
+    model._sync()
+    check(_cabi.lib().rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
+    return codes, residual
+
+
+@torch.no_grad()
 def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 262144, verbose: bool = False,
                    fast: Optional[bool] = None) -> Tuple[torch.Tensor, dict]:
     """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats).
@@ -174,38 +222,10 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
             lazy = _LazyResidual(model, data, n)
             residual = lazy.buf
         else:
-            z = encode_latents(model, data, chunk_rows)
-            n = z.shape[0]
-            codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
-            residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
-            model._sync()
-            check(lib.rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
-            del z
+            codes, residual = encode_codes_and_residual(model, data, chunk_rows)
+            n = codes.shape[0]
             lazy = None
-        # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
-        for vq in model.rq.vq_layers[:-1]:
-            vq.sk_epsilon = 0.0
-        last = model.rq.vq_layers[-1]
-        rounds = 0
-        if last.sk_epsilon is not None and last.sk_epsilon > 0:
-            cap = lib.rqb200_sinkhorn_group_cap(model._handle)
-            while rounds < max_rounds:
-                items, offsets, max_group = collision_groups(model, codes)
-                n_groups = offsets.numel() - 1
-                if n_groups <= 0:
-                    break
-                if verbose:
-                    print(f"Iteration {rounds}: Found {n_groups} collision groups")
-                if lazy is not None:
-                    lazy.ensure(items, codes)
-                new_codes = codes.clone()      # a round reads the codes of the previous round only
-                check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
-                                                  min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters),
-                                                  ptr(new_codes), stream_ptr(dev)))
-                if max_group > cap:
-                    _regroup_oversized(model, residual, items, offsets, cap, new_codes)
-                codes = new_codes
-                rounds += 1
+        codes, rounds = resolve_rounds(model, codes, residual, lazy=lazy, max_rounds=max_rounds, verbose=verbose)
         out, stats = suffix_dedup(model, codes)
         stats["rounds"] = rounds
         stats["pass1_route"] = "tensor-core" if fast else "exact"

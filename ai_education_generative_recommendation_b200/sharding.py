@@ -5,8 +5,9 @@ The reference is single-process; this is new design for BASELIN
   * global collision handling needs ONE exchange step: every item's packed code is routed to the rank
     that owns the key (all-to-all), the owner ranks equal keys in ascending GLOBAL item order, and the
     ranks travel back (all-to-all).  The result is bit-identical to the single-GPU suffix column;
-  * the Sinkhorn re-encode rounds (reference infer.py:109-130) co-locate each collision group on the
-    key's owner together with the residual rows it needs.
+  * the Sinkhorn re-encode rounds (reference infer.py:109-130) only ever touch the last level, so items are
+    routed once by the hash of their PREFIX codes together with the residual entering the last level; the
+    owner runs all rounds and the suffix ranking locally (`generate_codes_sharded`).
 Collectives go through torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests); the
 per-rank work is behind a small `ops` object — `CudaShardOps` (C-ABI kernels) in production, an
 oracle-backed numpy twin only inside tests/.
@@ -73,6 +74,22 @@ class CudaShardOps:
         check(lib.rqb200_segment_rank(self.model._handle, ptr(sk), n, ptr(rk), s))
         out[pos] = rk
         return out
+
+
+    # ---- the complete sharded driver (generate_codes_sharded) ----
+    def encode_shard(self, data):
+        """Pass 1 on this rank's shard: (codes[n, L], residual entering the last level [n, e])."""
+        from .generate_code import encode_codes_and_residual
+        return encode_codes_and_residual(self.model, data)
+
+    def resolve_owned(self, codes: torch.Tensor, residual: torch.Tensor, max_rounds: int):
+        """Passes 2-3 over the items this rank owns (they arrive in ascending global item order)."""
+        from .generate_code import resolve_rounds, suffix_dedup
+        if codes.shape[0] == 0:
+            return torch.empty((0, codes.shape[1] + 1), dtype=torch.int64, device=codes.device), 0
+        codes, rounds = resolve_rounds(self.model, codes.contiguous(), residual.contiguous(), max_rounds=max_rounds)
+        out, _ = suffix_dedup(self.model, codes)
+        return out, rounds
 
 
 class PeerShardDedup:
@@ -177,6 +194,47 @@ def global_suffix(codes: torch.Tensor, num_emb_list, ops, group=None) -> torch.T
     out[:, :-1] = codes
     out[order, -1] = back
     return out
+
+
+def generate_codes_sharded(model, data_shard, group=None, max_rounds: int = 30, ops=None) -> Tuple[torch.Tensor, dict]:
+    """The whole encode driver (reference infer.py:88-177) over a catalogue sharded by contiguous item ranges:
+    `data_shard` = this rank's rows; returns this rank's [n_local, L+1] semantic ids, identical to the rows a
+    single-GPU `generate_codes` of the concatenated catalogue produces.
+
+    Levels < L-1 never change during the Sinkhorn rounds (infer.py:109-110), so every collision group — in any
+    round — lives inside one PREFIX (first L-1 codes) class.  Items are therefore routed ONCE to
+    owner = hash(prefix) mod G together with the residual entering the last level (all-to-all: 8(L+1) + 4e bytes
+    per item); the owner holds them in ascending global item order, runs the ≤30 re-encode rounds and the suffix
+    ranking locally with the single-GPU kernels, and the finished rows travel back (all-to-all, 8(L+1) bytes per
+    item).  Two exchanges in total, none per round."""
+    ops = ops if ops is not None else CudaShardOps(model)
+    Ks = list(model.num_emb_list)
+    Lv = len(Ks)
+    codes, residual = ops.encode_shard(data_shard)
+    world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
+    if world == 1:
+        out, rounds = ops.resolve_owned(codes, residual, max_rounds)
+        stats = global_stats(out, None)
+        stats["rounds"] = rounds
+        return out, stats
+    if Lv > 1:
+        prefix = ops.pack_keys(codes[:, :Lv - 1].contiguous(), Ks[:Lv - 1])
+    else:
+        prefix = torch.zeros((codes.shape[0],), dtype=torch.int64, device=codes.device)   # one class: a single owner
+    owner = owner_of(prefix, world)
+    order, send_counts = ops.bucket_by_owner(owner, world)        # stable: ascending item index inside a bucket
+    sc, rc = _exchange_counts(send_counts, group)
+    recv_codes = _all_to_all(codes[order], sc, rc, group)         # arrival order = (source rank, local index)
+    recv_res = _all_to_all(residual[order], sc, rc, group)        #               = ascending global item index
+    owned, rounds = ops.resolve_owned(recv_codes, recv_res, max_rounds)
+    back = _all_to_all(owned, rc, sc, group)
+    out = torch.empty((codes.shape[0], Lv + 1), dtype=torch.int64, device=codes.device)
+    out[order] = back
+    r = torch.tensor([rounds], dtype=torch.int64, device=codes.device)
+    dist.all_reduce(r, op=dist.ReduceOp.MAX, group=group)
+    stats = global_stats(out, group)
+    stats["rounds"] = int(r.item())
+    return out, stats
 
 
 def global_stats(codes_with_suffix: torch.Tensor, group=None) -> dict:

@@ -34,6 +34,73 @@ class NumpyShardOps:
         return torch.from_numpy(O.suffix_dedup(keys.numpy()[:, None])[:, 1].copy())
 
 
+class NumpyDriverOps(NumpyShardOps):
+    """Oracle-backed twin of CudaShardOps.encode_shard / resolve_owned (tests only)."""
+
+    def __init__(self, enc_w, enc_b, cbs, eps, iters):
+        self.enc_w, self.enc_b, self.cbs, self.eps, self.iters = enc_w, enc_b, cbs, eps, iters
+
+    def encode_shard(self, data):
+        from oracle import oracle as O
+        z = O.mlp(data.numpy(), self.enc_w, self.enc_b, threads=1)
+        codes = O.quantize(z, self.cbs, want_xq=False, threads=1)[0]
+        r = z.copy()
+        for l in range(len(self.cbs) - 1):                    # vq.py:95, rq.py:47
+            q = self.cbs[l][codes[:, l]]
+            r = r - (r + (q - r))
+        return torch.from_numpy(codes), torch.from_numpy(r)
+
+    def resolve_owned(self, codes, residual, max_rounds):
+        from oracle import oracle as O
+        codes, residual = codes.numpy().copy(), residual.numpy()
+        if codes.shape[0] == 0:
+            return torch.zeros((0, codes.shape[1] + 1), dtype=torch.int64), 0
+        rounds = 0
+        while rounds < max_rounds:
+            groups = O.collision_groups(codes)
+            if not groups:
+                break
+            new = codes.copy()
+            for g in groups:
+                d = O.quantize(residual[g], [self.cbs[-1]], want_xq=False, dist_level=0, threads=1)[3]
+                new[g, -1] = O.sinkhorn_assign(d, self.eps, self.iters)
+            codes = new
+            rounds += 1
+        return torch.from_numpy(O.suffix_dedup(codes)), rounds
+
+
+class _Cfg:
+    def __init__(self, Ks):
+        self.num_emb_list = Ks
+
+
+def _driver_job(rank, world, x_all, enc_w, enc_b, cbs, eps, iters):
+    lo, hi = sharding.shard_range(x_all.shape[0], rank, world)
+    ops = NumpyDriverOps(enc_w, enc_b, cbs, eps, iters)
+    return sharding.generate_codes_sharded(_Cfg([c.shape[0] for c in cbs]), x_all[lo:hi], dist.group.WORLD, ops=ops)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_driver_matches_single_process_driver(tmp_path, oracle, world):
+    """Sinkhorn re-encode rounds + suffix over a sharded catalogue == the single-process driver (infer.py:88-177)."""
+    from conftest import load_golden, synth_weights
+    from ai_education_generative_recommendation_b200 import synth
+    g, cfg, cbs = load_golden("c1_slice")
+    _, (ew, eb), _ = synth_weights(cfg)
+    n = 600
+    x = synth.synth_items(2024, 0, n, cfg["in_dim"], 1_000_000)
+    x[300:340] = x[10:50]                                   # exact duplicates across the shard boundary
+    ref, rstats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"])
+    assert rstats["rounds"] >= 1
+    res = run_world(_driver_job, (torch.from_numpy(x), ew, eb, cbs, float(cfg["sk_epsilons"][-1]), cfg["sk_iters"]),
+                    tmp_path, world=world)
+    got = torch.cat([r[0] for r in res]).numpy()
+    assert np.array_equal(got, ref)
+    assert all(r[1] == res[0][1] for r in res)
+    assert res[0][1]["rounds"] == rstats["rounds"]
+    assert res[0][1]["distinct"] == len(np.unique(ref[:, :-1], axis=0))
+
+
 class NumpyKMeansOps:
     def assign(self, x, centers):
         d = ((x[:, None, :].double() - centers[None].double()) ** 2).sum(-1)
