@@ -72,6 +72,17 @@ _PROTOS = {
     "rqb200_kmeans_distances": (c_int, [_P, c_int64, c_int, _P, c_int, _P, _P, _P]),
     "rqb200_kmeans_accumulate": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P]),
     "rqb200_kmeans_update": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
+    "rqb200_dropout": (c_int, [_P, c_int64, c_float, c_uint64, _P, _P]),
+    "rqb200_linear_forward": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "rqb200_linear_backward_scratch_floats": (c_int64, [c_int64, c_int, c_int]),
+    "rqb200_linear_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),
+    "rqb200_rq_level_apply": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P]),
+    "rqb200_vq_codebook_grad": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_float, _P, _P, _P]),
+    "rqb200_rq_latent_grad": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, _P, _P, _P]),
+    "rqb200_recon_loss": (c_int, [_P, _P, c_int64, _P, _P]),
+    "rqb200_recon_grad": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
+    "rqb200_adamw_clip_step": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float,
+                                       c_float, c_int64, _P]),
     "rqb200_synth_items": (c_int, [c_uint64, c_int64, c_int64, c_int, c_int64, _P, _P]),
     "rqb200_generate_codes_host": (c_int, [c_void_p, c_int, _P, c_int64, c_int64, _P, POINTER(c_int64)]),
 }

@@ -107,6 +107,8 @@ static int default_kblocks(int K, int *out) {
     return K > 0 ? -1 : n;
 }
 
+int default_kblocks_public(int K, int *out) { return default_kblocks(K, out); }
+
 static void free_linear(Linear &l) {
     if (l.W) cudaFree(l.W);
     if (l.b) cudaFree(l.b);

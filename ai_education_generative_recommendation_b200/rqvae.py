@@ -7,8 +7,9 @@ loads with ``load_state_dict`` and the reference's driver code (``model.get_indi
 PyTorch: every forward / get_indices call goes through ``librqvae_b200.so``; tensors must live on a
 CUDA device (RuntimeError otherwise — there is no CPU fallback).
 
-Scope note: this round implements inference-mode forward (no autograd graph); the training step
-(``Trainer._train_epoch``) is a "next" row of SURVEY.md §8f.
+With gradients enabled, ``forward`` / ``compute_loss`` build an autograd graph out of ``train_ops`` Functions
+(forward and backward both in the CUDA library), so the reference's training loop (train.py:97-124) runs
+unchanged on this class; ``trainer.py`` is the B200-side Trainer (fused clip + AdamW, data-parallel all-reduce).
 """
 from __future__ import annotations
 
@@ -157,7 +158,9 @@ class VectorQuantizer(nn.Module):
         return z_q
 
     def init_emb(self, data):
-        centers = kmeans(data, self.n_e, self.kmeans_iters)
+        # `_kmeans_group` (set by the data-parallel Trainer): every rank contributes its rows of the first batch and all
+        # ranks end up with the same centres
+        centers = kmeans(data, self.n_e, self.kmeans_iters, group=getattr(self, "_kmeans_group", None))
         self.embedding.weight.data.copy_(centers)
         self.initted = True
 
@@ -431,13 +434,55 @@ class RQVAE(nn.Module):
         return xq.view(x.shape), mean_loss, codes.view(*x.shape[:-1], Lv)
 
     # ---- reference API -------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, x, use_sk=True):
-        """rqvae.py:60-65 (inference semantics: no autograd graph is built)."""
+        """rqvae.py:60-65.  In training mode with gradients enabled this builds the autograd graph of the training
+        step (train.py:113); in eval mode or under no_grad it is the inference forward (no graph is kept — the one
+        deviation from the reference, where an eval-mode forward outside no_grad still records one)."""
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(x, use_sk)
+        return self._forward_inference(x, use_sk)
+
+    @torch.no_grad()
+    def _forward_inference(self, x, use_sk=True):
         x_e = self.encoder(x)
         x_q, rq_loss, indices = self.rq(x_e, use_sk=use_sk)
         out = self.decoder(x_q)
         return out, rq_loss, indices
+
+    def _mlp_params(self, mlp):
+        if self.bn:
+            raise NotImplementedError("BatchNorm training is not part of the reference's default path (bn=False)")
+        out = []
+        for lin, _ in mlp.linears():
+            out += [lin.weight, lin.bias]
+        return out
+
+    def _forward_train(self, x, use_sk=True):
+        """Differentiable forward: Dropout (training mode) → encoder → residual quantizer with Sinkhorn where
+        ``use_sk`` and ε > 0 (k-means codebook init on the first training batch, vq.py:67-68) → decoder."""
+        from .train_ops import MLPFunction, RQFunction
+        _require_cuda_tensor(x, "input")
+        x2 = x.reshape(-1, self.in_dim)
+        p = float(self.dropout_prob) if self.training else 0.0
+        self._train_calls = getattr(self, "_train_calls", 0) + 1
+        seed = (int(getattr(self, "dropout_seed", 2024)) << 32) ^ self._train_calls
+        z = MLPFunction.apply(x2, p, seed * 2, *self._mlp_params(self.encoder))
+        layers = self.rq.vq_layers
+        if self.training and any(not q.initted for q in layers):
+            with torch.no_grad():                         # rq.py:43-48 level by level on this first batch
+                r = z.detach()
+                for q in layers:
+                    if not q.initted:
+                        q.init_emb(r)
+                    e_l = float(q.sk_epsilon) if (use_sk and q.sk_epsilon is not None and q.sk_epsilon > 0) else 0.0
+                    _, _, idx = RQFunction.apply(r, [q.beta], [e_l], q.sk_iters, q.embedding.weight.detach())
+                    qv = q.embedding.weight.detach()[idx[:, 0]]
+                    r = r - (r + (qv - r))
+        eps = [float(q.sk_epsilon) if (use_sk and q.sk_epsilon is not None and q.sk_epsilon > 0) else 0.0 for q in layers]
+        x_q, rq_loss, indices = RQFunction.apply(z, [q.beta for q in layers], eps, int(layers[0].sk_iters),
+                                                 *[q.embedding.weight for q in layers])
+        out = MLPFunction.apply(x_q, p, seed * 2 + 1, *self._mlp_params(self.decoder))
+        return out.view(*x.shape[:-1], self.in_dim), rq_loss, indices.view(*x.shape[:-1], len(layers))
 
     @torch.no_grad()
     def get_indices(self, xs, use_sk=False):
@@ -462,13 +507,12 @@ class RQVAE(nn.Module):
         return codes.view(*xs.shape[:-1], Lv)
 
     def compute_loss(self, out, quant_loss, xs=None):
-        """rqvae.py:73-84."""
-        if self.loss_type == "mse":
-            loss_recon = torch.mean((out - xs) ** 2)
-        elif self.loss_type == "l1":
-            loss_recon = torch.mean(torch.abs(out - xs))
-        else:
+        """rqvae.py:73-84 (the reconstruction term and its gradient run in the CUDA library)."""
+        if self.loss_type not in ("mse", "l1"):
             raise ValueError("incompatible loss type")
+        from .train_ops import ReconFunction
+        _require_cuda_tensor(out, "out")
+        loss_recon = ReconFunction.apply(out, xs, self.loss_type == "l1")
         loss_total = loss_recon + self.quant_loss_weight * quant_loss
         return loss_total, loss_recon
 

@@ -234,6 +234,46 @@ int rqb200_kmeans_accumulate(const float *x_dev, int64_t n, int e, const int64_t
 int rqb200_kmeans_update(float *centers_dev, int K, int e, const double *sums_dev,
                          const int64_t *counts_dev, double *shift_dev, void *stream);
 
+/* ---- training step (reference RQ-VAE/train.py:97-124) ----------
+ * The Python RQVAE mirror calls these from torch.autograd.Functions when gradients are enabled, so the
+ * reference's own loop (model(data) → compute_loss → backward → clip → optimizer.step) runs unchanged.
+ * All pointers are device pointers; nothing synchronises.                                  */
+/* nn.Dropout in training mode (layers.py:21): y = x * keep / (1 - p), keep a pure function of (seed, index);
+ * calling it again on a gradient with the same seed applies the same mask (backward).     */
+int rqb200_dropout(const float *x_dev, int64_t count, float p, uint64_t seed, float *y_dev, void *stream);
+/* nn.Linear (+ReLU) with caller-owned parameters, the reference's fp32 summation order (layers.py:23).      */
+int rqb200_linear_forward(const float *x_dev, const float *W_dev, const float *b_dev, int64_t n, int in_dim,
+                          int out_dim, int relu, float *y_dev, void *stream);
+int64_t rqb200_linear_backward_scratch_floats(int64_t n, int in_dim, int out_dim);
+/* Backward of y = relu?(x Wᵀ + b): dy_dev is masked in place by (y > 0) when relu, then dW[out,in] = dyᵀ x,
+ * db[out] = Σ_rows dy, dx[n,in] = dy W (dx_dev may be NULL for the first layer).  Deterministic.             */
+int rqb200_linear_backward(const float *x_dev, const float *W_dev, const float *y_dev, float *dy_dev, int64_t n,
+                           int in_dim, int out_dim, int relu, float *dx_dev, float *dW_dev, float *db_dev,
+                           float *scratch_dev, int64_t scratch_floats, void *stream);
+/* One residual level once its codes are chosen (vq.py:87-95, rq.py:47-48): sumsq += Σ (E[idx] - r)²,
+ * x_res = r + (E[idx] - r), r_next = r - x_res, x_q = (first ? 0 : x_q) + x_res.           */
+int rqb200_rq_level_apply(const float *r_dev, const int64_t *idx_dev, const float *cb_dev, int64_t n, int e,
+                          int first, float *xq_dev, float *r_next_dev, double *sumsq_dev, void *stream);
+/* Gradient of the codebook loss mse(E[idx], r.detach()) (vq.py:91): dE[k] = coef * g[0] * Σ_{idx[i]=k} (E[k] - r[i]). */
+int rqb200_vq_codebook_grad(const float *r_dev, const int64_t *idx_dev, const float *cb_dev, int64_t n, int e, int K,
+                            float coef, const float *g_dev, float *dE_dev, void *stream);
+/* Gradient reaching the latent through the straight-through estimator (vq.py:95) and the commitment loss of
+ * level 0 (vq.py:90): dz = g_xq + coef * g[0] * (z - E0[idx0]); g_xq may be NULL.          */
+int rqb200_rq_latent_grad(const float *z_dev, const int64_t *idx0_dev, const float *cb0_dev, const float *gxq_dev,
+                          int64_t n, int e, float coef, const float *g_dev, float *dz_dev, void *stream);
+/* compute_loss (rqvae.py:73-84): sums2[0] += Σ (out - x)², sums2[1] += Σ |out - x|; and its gradient
+ * d_out = g[0] * 2 (out - x) / count (mse) or g[0] * sign(out - x) / count (l1).           */
+int rqb200_recon_loss(const float *out_dev, const float *x_dev, int64_t count, double *sums2_dev, void *stream);
+int rqb200_recon_grad(const float *out_dev, const float *x_dev, int64_t count, int l1, const float *g_dev,
+                      float *d_out_dev, void *stream);
+/* clip_grad_norm_(params, max_norm) + AdamW.step() (train.py:116-117) over every parameter in three launches.
+ * chunks_dev[n_chunks][5] = {param, grad, exp_avg, exp_avg_sq (device addresses), element count}; gradients
+ * are read as grad * grad_scale (data-parallel averaging); stats_dev[0] = total norm, [1] = clip coefficient;
+ * step counts from 1; max_norm <= 0 disables clipping.                                     */
+int rqb200_adamw_clip_step(const int64_t *chunks_dev, int n_chunks, double *partial_dev, float *stats_dev,
+                           float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, int64_t step, void *stream);
+
 /* ---- synthetic catalogue (bench / tests) --------------------------------------------
  * Integer-hash generator of clustered BERT-like item embeddings; the same function exists in
  * numpy (package `synth.py`) so CPU and GPU produce identical bytes for any row range.    */

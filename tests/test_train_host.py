@@ -1,0 +1,53 @@
+"""Host-side pieces of the training driver that need no GPU: the schedule restated from transformers
+(train.py:80-91), the golden fixture's integrity, and the no-CPU-fallback rule of the training path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, train_case_state
+
+
+def test_warmup_lambda_equals_transformers_schedules():
+    transformers = pytest.importorskip("transformers")
+    from ai_education_generative_recommendation_b200.trainer import warmup_lambda
+    for kind, make in (("linear", lambda o, w, t: transformers.get_linear_schedule_with_warmup(o, w, t)),
+                       ("constant", lambda o, w, t: transformers.get_constant_schedule_with_warmup(o, w))):
+        for warm, total in ((0, 10), (5, 40), (7, 7), (3, 100)):
+            p = torch.nn.Parameter(torch.zeros(1))
+            opt = torch.optim.SGD([p], lr=0.25)
+            sched = make(opt, warm, total)
+            lam = warmup_lambda(kind, warm, total)
+            for step in range(total + 3):
+                assert abs(sched.get_last_lr()[0] - 0.25 * lam(step)) < 1e-15, (kind, warm, total, step)
+                opt.step()
+                sched.step()
+
+
+def test_training_fixture_is_consistent_with_its_generator_inputs():
+    g = np.load(os.path.join(GOLD, "train_steps.npz"))
+    cases = json.loads(str(g["cases"]))
+    assert set(cases) == {"sk_mse", "argmin_l1", "c1_shape"}
+    for name, cfg in cases.items():
+        x, sd = train_case_state(cfg)
+        assert x.shape == (cfg["batch"], cfg["in_dim"]) and x.dtype == np.float32
+        names = [str(s) for s in g[f"{name}/names"]]
+        assert names == list(sd.keys()) or set(names) == set(sd.keys())
+        assert g[f"{name}/loss"].shape == (cfg["steps"],)
+        assert g[f"{name}/lr"][0] == 0.0                       # LambdaLR starts the warmup at factor 0 (train.py:84-86)
+        assert abs(g[f"{name}/loss"][0] - g[f"{name}/loss"][1]) < 1e-12    # … so the first step changes nothing
+        assert g[f"{name}/codes"].shape == (cfg["steps"], cfg["batch"], len(cfg["num_emb_list"]))
+        tot = g[f"{name}/recon"] + cfg["quant_loss_weight"] * g[f"{name}/rq"]        # rqvae.py:82
+        assert np.allclose(tot, g[f"{name}/loss"], rtol=1e-6)
+
+
+def test_training_forward_refuses_cpu_tensors():
+    import ai_education_generative_recommendation_b200 as rq
+    m = rq.RQVAE(in_dim=16, num_emb_list=[4, 4], e_dim=4, layers=[8], sk_epsilons=[0.0, 0.0]).train()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(3, 16))
+    with pytest.raises(ValueError, match="incompatible loss type"):
+        m.loss_type = "huber"
+        m.compute_loss(torch.zeros(1), torch.zeros(()), xs=torch.zeros(1))
