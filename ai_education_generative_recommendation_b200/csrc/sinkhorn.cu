@@ -13,6 +13,8 @@
 // residual entering the last level, and every division of the reference is kept as a separate
 // fp64 division so the iteration follows the same trajectory.  Latency/fp64-ALU bound by nature;
 // reported as time, not against a roofline.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rqb {
@@ -260,6 +262,135 @@ sinkhorn_assign_kernel(const float *__restrict__ d, double *__restrict__ Q, int 
     argmax_rows(Q, B, K, nullptr, nullptr, 0, idx);
 }
 
+
+// ---- training-size batches on the whole GPU ------------------------------------------------------
+// vq.py:77-83 on one [B,K] batch: the rows are split over up to 148 co-resident CTAs (cooperative launch), each CTA keeps
+// its rows as fp64 in shared memory for all iterations.  Row normalisation is local; column sums are the only global
+// quantity: per iteration every CTA publishes its partial column sums, one grid barrier, then every CTA adds the
+// partials in CTA order (deterministic).
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_assign_grid_kernel(const float *__restrict__ d, double *__restrict__ ws, int B, int K, int rows_per_cta, double epsilon,
+                            int iters, int64_t *__restrict__ idx_out) {
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    __shared__ double s_red[SK_THREADS / 32];
+    __shared__ float s_mm[64];
+    double *Q = reinterpret_cast<double *>(sk_smem);                 // [rows][K]
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = SK_THREADS / 32;
+    const int row0 = cta * rows_per_cta;
+    const int rows = max(0, min(B, row0 + rows_per_cta) - row0);
+    unsigned long long *counter = reinterpret_cast<unsigned long long *>(ws);
+    double *scal = ws + 8;                                           // [G][4]: max, min, total
+    double *colp = ws + 8 + (size_t)4 * G;                           // [2][G][K] partial column sums
+    double *vglob = colp + (size_t)2 * G * K;                        // [2][K] column factors of the iteration
+    const int cpc = (K + G - 1) / G;                                 // columns whose sum this CTA owns
+    unsigned long long epoch = 0;
+    const int count = rows * K;
+    // centre (fp32, over the WHOLE matrix) …
+    float mx = -__int_as_float(0x7f800000), mn = __int_as_float(0x7f800000);
+    for (int i = tid; i < count; i += SK_THREADS) {
+        const float v = d[(size_t)row0 * K + i];
+        Q[i] = (double)v;
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) { s_mm[wid] = mx; s_mm[32 + wid] = mn; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NW; ++w) { mx = fmaxf(mx, s_mm[w]); mn = fminf(mn, s_mm[32 + w]); }
+        scal[cta * 4 + 0] = (double)mx;
+        scal[cta * 4 + 1] = (double)mn;
+    }
+    grid_barrier(counter, (++epoch) * G);
+    mx = -__int_as_float(0x7f800000); mn = __int_as_float(0x7f800000);
+    for (int c = 0; c < G; ++c) {
+        mx = fmaxf(mx, (float)__ldcg(&scal[c * 4 + 0]));
+        mn = fminf(mn, (float)__ldcg(&scal[c * 4 + 1]));
+    }
+    const float middle = __fdiv_rn(__fadd_rn(mx, mn), 2.0f);
+    const float amplitude = __fadd_rn(__fsub_rn(mx, middle), 1e-5f);
+    // … exp (fp64), total sum
+    double part = 0.0;
+    for (int i = tid; i < count; i += SK_THREADS) {
+        const float c = __fdiv_rn(__fsub_rn((float)Q[i], middle), amplitude);
+        const double q = exp(-((double)c) / epsilon);
+        Q[i] = q;
+        part += q;
+    }
+    double tot = block_sum(part, s_red);
+    if (tid == 0) scal[cta * 4 + 2] = tot;
+    grid_barrier(counter, (++epoch) * G);
+    double total = 0.0;
+    for (int c = 0; c < G; ++c) total += __ldcg(&scal[c * 4 + 2]);
+    for (int i = tid; i < count; i += SK_THREADS) Q[i] = Q[i] / total;
+    __syncthreads();
+    // The iteration only ever rescales rows and columns, so Q_t = diag(u) Q_0 diag(v): keep Q_0 in shared memory and
+    // iterate on the two vectors (2 fp64 FMAs per element and iteration instead of 4 divisions).  Same fixed point and
+    // the same arg-max as the element-wise form of layers.py:96-104 up to fp64 rounding.
+    double *u = Q + (size_t)rows_per_cta * K;                        // [rows]  this CTA's row factors
+    double *v = u + rows_per_cta;                                    // [K]     column factors (identical in every CTA)
+    for (int j = tid; j < K; j += SK_THREADS) v[j] = 1.0;
+    for (int i = tid; i < rows; i += SK_THREADS) u[i] = 1.0;
+    __syncthreads();
+    const double dB = (double)B, dK = (double)K;
+    for (int it = 0; it < iters; ++it) {
+        // Q /= rowsum; Q /= B      →  u_i = 1 / (B * Σ_j Q0_ij v_j)
+        for (int i = wid; i < rows; i += NW) {
+            double rs = 0.0;
+            for (int j = lane; j < K; j += 32) rs = fma(Q[(size_t)i * K + j], v[j], rs);
+            rs = warp_sum(rs);
+            if (lane == 0) u[i] = (1.0 / rs) / dB;
+        }
+        __syncthreads();
+        // Q /= colsum; Q /= K      →  v_j = 1 / (K * Σ_i u_i Q0_ij), the sum taken over all CTAs
+        double *mine = colp + ((size_t)(it & 1) * G + cta) * K;
+        for (int j = tid; j < K; j += SK_THREADS) {
+            double cs = 0.0;
+            for (int i = 0; i < rows; ++i) cs = fma(u[i], Q[(size_t)i * K + j], cs);
+            mine[j] = cs;
+        }
+        grid_barrier(counter, (++epoch) * G);
+        // two-level sum: this CTA adds the G partials of the few columns it owns (a warp per column, fixed order) and
+        // publishes the new factor; after the second barrier everybody reads the K factors (2 KB instead of G x K)
+        const double *all = colp + (size_t)(it & 1) * G * K;
+        double *vnew = vglob + (size_t)(it & 1) * K;
+        for (int jj = wid; jj < cpc; jj += NW) {
+            const int j = cta * cpc + jj;
+            if (j < K) {
+                double cs = 0.0;
+                for (int c = lane; c < G; c += 32) cs += __ldcg(&all[(size_t)c * K + j]);
+                cs = warp_sum(cs);
+                if (lane == 0) vnew[j] = (1.0 / cs) / dK;
+            }
+        }
+        grid_barrier(counter, (++epoch) * G);
+        for (int j = tid; j < K; j += SK_THREADS) v[j] = __ldcg(&vnew[j]);
+        __syncthreads();
+    }
+    for (int i = tid; i < count; i += SK_THREADS) Q[i] = ((u[i / K] * Q[i]) * v[i % K]) * dB;      // Q *= B
+    __syncthreads();
+    argmax_rows(Q, rows, K, nullptr, nullptr, 0, idx_out + row0);
+}
+
 }  // namespace
 }  // namespace rqb
 
@@ -351,9 +482,38 @@ extern "C" int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, doub
     RQB_CHECK(d_dev && idx_dev && scratch_dev, "NULL buffer");
     RQB_CHECK(epsilon > 0.0, "epsilon must be > 0");
     RQB_CHECK(B * (int64_t)K < ((int64_t)1 << 31), "matrix too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    // whole-GPU variant when the rows fit in the shared memory of <= 148 CTAs and the caller's [B,K] scratch holds the
+    // exchange area; tiny or huge batches keep the one-CTA kernel
+    const size_t row_bytes = sizeof(double) * (size_t)K;
+    const int cap_rows = (int)((200 * 1024 - sizeof(double) * (size_t)K) / (row_bytes + sizeof(double)));
+    int G = (int)((B + 7) / 8);
+    if (G > kNumSMs) G = kNumSMs;
+    const int rows_per_cta = (int)((B + G - 1) / G);
+    G = (int)((B + rows_per_cta - 1) / rows_per_cta);
+    const size_t ws_doubles = 8 + (size_t)4 * G + (size_t)2 * G * K + (size_t)2 * K;
+    static int use_grid = -1;
+    if (use_grid < 0) {
+        const char *e = getenv("RQB200_SINKHORN_GRID");
+        use_grid = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_grid && G >= 2 && rows_per_cta <= cap_rows && ws_doubles <= (size_t)B * K) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            RQB_CUDA(cudaFuncSetAttribute(sinkhorn_assign_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+            attr_done = true;
+        }
+        RQB_CUDA(cudaMemsetAsync(scratch_dev, 0, 64, s));
+        int Bi = (int)B, rpc = rows_per_cta;
+        void *args[] = {(void *)&d_dev, (void *)&scratch_dev, (void *)&Bi, (void *)&K, (void *)&rpc, (void *)&epsilon,
+                        (void *)&iters, (void *)&idx_dev};
+        rqb::count_launch();
+        RQB_CUDA(cudaLaunchCooperativeKernel((void *)sinkhorn_assign_grid_kernel, dim3((unsigned)G), dim3(SK_THREADS), args,
+                                             (row_bytes + sizeof(double)) * rows_per_cta + sizeof(double) * (size_t)K + 16, s));
+        return 0;
+    }
     rqb::count_launch();
-    sinkhorn_assign_kernel<<<1, SK_THREADS, 0, (cudaStream_t)stream>>>(d_dev, scratch_dev, (int)B, K, epsilon,
-                                                                      iters, idx_dev);
+    sinkhorn_assign_kernel<<<1, SK_THREADS, 0, s>>>(d_dev, scratch_dev, (int)B, K, epsilon, iters, idx_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }

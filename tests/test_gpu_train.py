@@ -254,3 +254,26 @@ def test_training_forward_bits_equal_inference_forward():
     assert out_t.requires_grad and not out_i.requires_grad
     assert torch.equal(idx_t, idx_i) and torch.equal(out_t.detach(), out_i)
     assert abs(float(loss_t) - float(loss_i)) <= 1e-6 * abs(float(loss_i))
+
+
+@pytest.mark.parametrize("B,K", [(2048, 256), (5000, 256), (300, 64), (1111, 1024), (17, 8)])
+def test_batch_sinkhorn_on_the_whole_gpu_matches_oracle(oracle, B, K):
+    """vq.py:74-83 on a training-size batch: the cooperative multi-CTA kernel (rows split over the SMs) picks the same
+    code as the oracle's restatement of layers.py:85-108 for every row."""
+    import ai_education_generative_recommendation_b200 as rq
+    rng = np.random.default_rng(B + K)
+    e = 32
+    centres = rng.standard_normal((K, e)).astype(np.float32) * 0.3
+    z = (centres[rng.integers(0, K, size=B)] + 0.25 * rng.standard_normal((B, e))).astype(np.float32)
+    _, _, _, d = oracle.quantize(z, [centres], want_xq=False, dist_level=0, threads=1)
+    ref = oracle.sinkhorn_assign(d, 0.01, 50)
+    dt = torch.from_numpy(d).to(DEV)
+    scratch = torch.empty((B, K), dtype=torch.float64, device=DEV)
+    idx = torch.empty((B,), dtype=torch.int64, device=DEV)
+    from ai_education_generative_recommendation_b200._cabi import check, lib, ptr, stream_ptr
+    check(lib().rqb200_sinkhorn_assign(ptr(dt), B, K, 0.01, 50, ptr(scratch), ptr(idx), stream_ptr(dt.device)))
+    got = idx.cpu().numpy()
+    assert np.array_equal(got, ref), f"{int((got != ref).sum())} of {B} rows differ"
+    # balanced assignment: no code is starved or flooded beyond what the arg-max of a doubly-normalised Q allows
+    counts = np.bincount(got, minlength=K)
+    assert counts.max() <= max(4 * B // K, 8)
