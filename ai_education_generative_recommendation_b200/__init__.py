@@ -11,9 +11,10 @@ from .rqvae import (MLPLayers, RQVAE, ResidualVectorQuantizer, VectorQuantizer, 
                     sinkhorn_algorithm)
 from .generate_code import collision_groups, encode_latents, generate_codes, infer, suffix_dedup
 from .dataset import EmbDataset
+from .consumers import build_tiger_splits, gather_item_tokens, offset_codes
 from .trainer import DeviceBatches, Trainer, train, warmup_lambda
 from .train_ops import FusedAdamW
 
 __all__ = ["RQVAE", "MLPLayers", "ResidualVectorQuantizer", "VectorQuantizer", "activation_layer", "kmeans",
            "sinkhorn_algorithm", "generate_codes", "infer", "suffix_dedup", "collision_groups", "encode_latents",
-           "EmbDataset", "Trainer", "train", "DeviceBatches", "FusedAdamW", "warmup_lambda", "ENCODE_EXACT", "ENCODE_FAST", "RQB200Error"]
+           "EmbDataset", "offset_codes", "gather_item_tokens", "build_tiger_splits", "Trainer", "train", "DeviceBatches", "FusedAdamW", "warmup_lambda", "ENCODE_EXACT", "ENCODE_FAST", "RQB200Error"]

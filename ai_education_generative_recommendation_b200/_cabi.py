@@ -83,6 +83,8 @@ _PROTOS = {
     "rqb200_recon_grad": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P]),
     "rqb200_adamw_clip_step": (c_int, [_P, c_int, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float,
                                        c_float, c_int64, _P]),
+    "rqb200_offset_tokens": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "rqb200_gather_item_tokens": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
     "rqb200_synth_items": (c_int, [c_uint64, c_int64, c_int64, c_int, c_int64, _P, _P]),
     "rqb200_generate_codes_host": (c_int, [c_void_p, c_int, _P, c_int64, c_int64, _P, POINTER(c_int64)]),
 }

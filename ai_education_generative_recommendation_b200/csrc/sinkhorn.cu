@@ -497,7 +497,10 @@ extern "C" int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, doub
         const char *e = getenv("RQB200_SINKHORN_GRID");
         use_grid = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use_grid && G >= 2 && rows_per_cta <= cap_rows && ws_doubles <= (size_t)B * K) {
+    // Below 1024 rows (collision groups, the reference's batch of 64) the one-CTA kernel stays: it keeps every division of
+    // layers.py:96-104 and reproduces all of the reference's golden use_sk cases; the scaling-vector form picked another
+    // code in 1 of their 840 rows (a 1e-13 near-tie), which is inside the training tolerance but not index parity.
+    if (use_grid && B >= 1024 && G >= 2 && rows_per_cta <= cap_rows && ws_doubles <= (size_t)B * K) {
         static bool attr_done = false;
         if (!attr_done) {
             RQB_CUDA(cudaFuncSetAttribute(sinkhorn_assign_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));

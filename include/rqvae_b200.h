@@ -274,6 +274,16 @@ int rqb200_adamw_clip_step(const int64_t *chunks_dev, int n_chunks, double *part
                            float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
                            float weight_decay, int64_t step, void *stream);
 
+/* ---- consumers of the semantic ids -------------------------------
+ * token = id + column * codebook_size + 1 for every column of the [n, n_cols] id array (item_to_offset_code,
+ * RQVAE-T5/data_read.ipynb cell 2; ranges per position: check_data_alignment.py:105-121), int32 like the TIGER files. */
+int rqb200_offset_tokens(const int64_t *ids_dev, int64_t n, int n_cols, int codebook_size, int32_t *tokens_dev,
+                         void *stream);
+/* out[j, :] = tokens[item_ids[j] - 1, :] for 1-indexed item ids (same cell: data[item_id - 1]); an id outside
+ * [1, n] sets *bad_flag_dev to 1 and yields a zero row.                                     */
+int rqb200_gather_item_tokens(const int32_t *tokens_dev, int64_t n, int n_cols, const int64_t *item_ids_dev,
+                              int64_t count, int32_t *out_dev, int *bad_flag_dev, void *stream);
+
 /* ---- synthetic catalogue (bench / tests) --------------------------------------------
  * Integer-hash generator of clustered BERT-like item embeddings; the same function exists in
  * numpy (package `synth.py`) so CPU and GPU produce identical bytes for any row range.    */

@@ -301,3 +301,30 @@ def kmeans_lloyd(x: np.ndarray, init: np.ndarray, iters: int, tol: float = 1e-4)
         if tol > 0 and shift <= tol * xv:
             break
     return c
+
+
+# --------------------------------------------------------------------------- consumers (tokens, TIGER splits)
+
+def item_to_offset_code(data: np.ndarray, item_id: int, codebook_size: int) -> List[int]:
+    """RQVAE-T5/data_read.ipynb cell 2, verbatim semantics: 1-indexed item id, token = c + i * K + 1."""
+    raw_code = data[item_id - 1]
+    return [int(c + i * codebook_size + 1) for i, c in enumerate(raw_code)]
+
+
+def tiger_splits(user_ids, item_lists, data: np.ndarray, codebook_size: int):
+    """The leave-one-out / teacher-forcing split of the same cell → (train_list, test_list) of dicts."""
+    f = lambda iid: item_to_offset_code(data, int(iid), codebook_size)
+    train_list, test_list = [], []
+    for uid, user_seq in zip(user_ids, item_lists):
+        seq_len = len(user_seq)
+        if seq_len < 2:
+            continue
+        if seq_len == 2:
+            train_list.append({"user_id": int(uid), "history": [f(i) for i in user_seq[:1]],
+                               "target": [f(i) for i in user_seq[1:]]})
+        else:
+            test_list.append({"user_id": int(uid), "history": [f(i) for i in user_seq[:-1]],
+                              "target": [f(i) for i in user_seq[-1:]]})
+            train_list.append({"user_id": int(uid), "history": [f(i) for i in user_seq[:-2]],
+                               "target": [f(i) for i in user_seq[1:-1]]})
+    return train_list, test_list

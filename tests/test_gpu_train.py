@@ -256,10 +256,11 @@ def test_training_forward_bits_equal_inference_forward():
     assert abs(float(loss_t) - float(loss_i)) <= 1e-6 * abs(float(loss_i))
 
 
-@pytest.mark.parametrize("B,K", [(2048, 256), (5000, 256), (300, 64), (1111, 1024), (17, 8)])
+@pytest.mark.parametrize("B,K", [(2048, 256), (5000, 256), (1024, 64), (1111, 1024), (300, 64), (17, 8)])
 def test_batch_sinkhorn_on_the_whole_gpu_matches_oracle(oracle, B, K):
-    """vq.py:74-83 on a training-size batch: the cooperative multi-CTA kernel (rows split over the SMs) picks the same
-    code as the oracle's restatement of layers.py:85-108 for every row."""
+    """vq.py:74-83 on a training-size batch: the cooperative multi-CTA kernel (rows split over the SMs; used from 1024
+    rows up, smaller batches keep the one-CTA kernel) picks the same code as the oracle's restatement of
+    layers.py:85-108 for every row of these batches."""
     import ai_education_generative_recommendation_b200 as rq
     rng = np.random.default_rng(B + K)
     e = 32
