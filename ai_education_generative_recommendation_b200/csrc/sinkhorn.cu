@@ -22,6 +22,7 @@ namespace rqb {
 namespace {
 
 constexpr int SK_THREADS = 256;
+constexpr int SK_ONE_LEVEL_MAX = 64;    // grid Sinkhorn: up to this many CTAs every CTA sums all column partials itself
 
 // torch.sum(v*v) for a runtime length e < 512 (ATen order; see oracle/rqvae_oracle.c)
 __device__ float sumsq_aten_rt(const float *v, int e) {
@@ -369,9 +370,27 @@ sinkhorn_assign_grid_kernel(const float *__restrict__ d, double *__restrict__ ws
             mine[j] = cs;
         }
         grid_barrier(counter, (++epoch) * G);
+        const double *all = colp + (size_t)(it & 1) * G * K;
+        if (G <= SK_ONE_LEVEL_MAX) {
+            // few CTAs: every CTA adds all partials itself (G loads per column, 4 independent chains) — one barrier per
+            // iteration
+            for (int j = tid; j < K; j += SK_THREADS) {
+                double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                int c = 0;
+                for (; c + 3 < G; c += 4) {
+                    c0 += __ldcg(&all[(size_t)c * K + j]);
+                    c1 += __ldcg(&all[(size_t)(c + 1) * K + j]);
+                    c2 += __ldcg(&all[(size_t)(c + 2) * K + j]);
+                    c3 += __ldcg(&all[(size_t)(c + 3) * K + j]);
+                }
+                for (; c < G; ++c) c0 += __ldcg(&all[(size_t)c * K + j]);
+                v[j] = (1.0 / ((c0 + c1) + (c2 + c3))) / dK;
+            }
+            __syncthreads();
+            continue;
+        }
         // two-level sum: this CTA adds the G partials of the few columns it owns (a warp per column, fixed order) and
         // publishes the new factor; after the second barrier everybody reads the K factors (2 KB instead of G x K)
-        const double *all = colp + (size_t)(it & 1) * G * K;
         double *vnew = vglob + (size_t)(it & 1) * K;
         for (int jj = wid; jj < cpc; jj += NW) {
             const int j = cta * cpc + jj;
@@ -489,6 +508,17 @@ extern "C" int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, doub
     const int cap_rows = (int)((200 * 1024 - sizeof(double) * (size_t)K) / (row_bytes + sizeof(double)));
     int G = (int)((B + 7) / 8);
     if (G > kNumSMs) G = kNumSMs;
+    static int max_ctas = -1;              // RQB200_SINKHORN_CTAS: cap on the CTAs (A/B of barrier cost vs rows per CTA)
+    if (max_ctas < 0) {
+        const char *e = getenv("RQB200_SINKHORN_CTAS");
+        max_ctas = e ? atoi(e) : 0;
+    }
+    if (max_ctas > 0 && G > max_ctas) {
+        G = max_ctas;
+        const int need = (int)((B + cap_rows - 1) / cap_rows);
+        if (G < need) G = need;
+        if (G > kNumSMs) G = kNumSMs;
+    }
     const int rows_per_cta = (int)((B + G - 1) / G);
     G = (int)((B + rows_per_cta - 1) / rows_per_cta);
     const size_t ws_doubles = 8 + (size_t)4 * G + (size_t)2 * G * K + (size_t)2 * K;

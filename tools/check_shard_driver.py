@@ -3,7 +3,7 @@ Sinkhorn re-encode rounds and global suffix included — equal the single-GPU ge
 catalogue, and how long both take.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
-        tools/check_shard_driver.py [items_total]
+        tools/check_shard_driver.py [items_total] [c2_slice,c1_slice]
 """
 import os
 import sys
@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device(dev))
     n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
     ok_all = True
-    for name in ("c2_slice", "c1_slice"):
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["c2_slice", "c1_slice"]
+    for name in names:
         g, cfg, cbs = load_golden(name)
         model = build_model(cfg, cbs, device=dev)
         lo, hi = sharding.shard_range(n_total, rank, world)
