@@ -16,6 +16,8 @@
 // Mapping: one row per thread (E values in registers), codebook chunk + its norms staged in shared
 // memory and read as warp-wide broadcasts (conflict free), four independent chains in flight per
 // thread.  Bound: fp32 FMA pipe (L*K*E FMA per row); HBM traffic is 4E+8L bytes per row.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rqb {
@@ -405,6 +407,176 @@ int launch_quant_sliced(const rqb200_model *m, const float *z, int64_t n, int64_
     return 0;
 }
 
+
+// ---- many rows, codes only (the exact rescue tier at catalogue scale: tens of thousands of gated rows, K = 1024):
+// one row per thread walks L*K*E dependent FMAs with a handful of warps per SM, and the sliced kernel re-stages the
+// whole codebook for every 16 rows.  Here a CTA owns 64 rows as a register-tiled contraction: thread (ty, tx) holds
+// 4 rows x 4 codes = 16 independent chains, each the same sequential FMA chain over k as the scan kernels, so every
+// distance has the same bits; the 16 code lanes of a row merge their candidates with the sequential rule (NaN first,
+// smaller distance, smaller index).  Codebook chunks are double-buffered with cp.async; the residual tile lives in
+// shared memory between levels.
+constexpr int QTL_ROWS = 64, QTL_THREADS = 256, QTL_CODES = 128;     // rows per CTA, threads, codes per staged chunk
+
+template <int E>
+__global__ void __launch_bounds__(QTL_THREADS, 2)
+quantize_tiled_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
+                      const int64_t *__restrict__ rows_out) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int PITCH = E + 4;
+    float *s_r = smem;                                   // [64][PITCH]  residual tile
+    float *s_cb = s_r + QTL_ROWS * PITCH;                // [2][QTL_CODES][PITCH]
+    float *s_cc = s_cb + 2 * QTL_CODES * PITCH;          // [2][QTL_CODES]
+    float *s_xx = s_cc + 2 * QTL_CODES;                  // [64]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t row0 = (int64_t)blockIdx.x * QTL_ROWS;
+    for (int i = tid; i < QTL_ROWS * (E / 4); i += QTL_THREADS) {
+        const int rr = i / (E / 4), k4 = i % (E / 4);
+        const float4 v = row0 + rr < n ? *reinterpret_cast<const float4 *>(z + (row0 + rr) * E + 4 * k4) : make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4 *>(s_r + rr * PITCH + 4 * k4) = v;
+    }
+    auto stage = [&](const float *cb, const float *cc, int c0, int cn, int buf) {
+        float *dst = s_cb + buf * QTL_CODES * PITCH;
+        for (int i = tid; i < cn * (E / 4); i += QTL_THREADS) {
+            const int j = i / (E / 4), k4 = i % (E / 4);
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + j * PITCH + 4 * k4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(cb + (int64_t)(c0 + j) * E + 4 * k4) : "memory");
+        }
+        for (int i = tid; i < cn; i += QTL_THREADS) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(s_cc + buf * QTL_CODES + i);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(cc + c0 + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int l = 0; l < qa.L; ++l) {
+        const int K = qa.K[l];
+        const float *cb = qa.cb[l];
+        const float *cc = qa.cc[l];
+        __syncthreads();                                 // residual tile complete (initial load / previous level's update)
+        if (tx < 4) {                                    // row norms in the reference's order, one lane per row
+            float rv[E];
+            const int rr = ty * 4 + tx;
+#pragma unroll
+            for (int k = 0; k < E; ++k) rv[k] = s_r[rr * PITCH + k];
+            s_xx[rr] = sumsq_aten<E>(rv);
+        }
+        const int nchunks = (K + QTL_CODES - 1) / QTL_CODES;
+        stage(cb, cc, 0, min(QTL_CODES, K), 0);
+        int best[4];
+        float bestd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { best[i] = 0x7fffffff; bestd[i] = 0.0f; }
+        float xx[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int c0 = ch * QTL_CODES, cn = min(QTL_CODES, K - c0), buf = ch & 1;
+            if (ch + 1 < nchunks) {
+                stage(cb, cc, c0 + QTL_CODES, min(QTL_CODES, K - c0 - QTL_CODES), buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();                             // chunk `buf` (and, the first time, s_xx) visible to everybody
+            if (ch == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xx[i] = s_xx[ty * 4 + i];
+            }
+            const float *cbuf = s_cb + buf * QTL_CODES * PITCH;
+            const float *ccbuf = s_cc + buf * QTL_CODES;
+            for (int j0 = 0; j0 < cn; j0 += 64) {        // 64 codes per step: this lane takes j0 + tx + 16 t
+                float a[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) a[i][t] = 0.0f;
+#pragma unroll 4
+                for (int k4 = 0; k4 < E / 4; ++k4) {
+                    float4 rv[4], cv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = *reinterpret_cast<const float4 *>(s_r + (ty * 4 + i) * PITCH + 4 * k4);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = min(j0 + tx + 16 * t, cn - 1);         // clamped lanes are ignored below
+                        cv[t] = *reinterpret_cast<const float4 *>(cbuf + j * PITCH + 4 * k4);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            a[i][t] = __fmaf_rn(rv[i].x, cv[t].x, a[i][t]);
+                            a[i][t] = __fmaf_rn(rv[i].y, cv[t].y, a[i][t]);
+                            a[i][t] = __fmaf_rn(rv[i].z, cv[t].z, a[i][t]);
+                            a[i][t] = __fmaf_rn(rv[i].w, cv[t].w, a[i][t]);
+                        }
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int j = j0 + tx + 16 * t;
+                    if (j < cn) {
+                        const float ccj = ccbuf[j];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float d = __fsub_rn(__fadd_rn(xx[i], ccj), __fmul_rn(2.0f, a[i][t]));
+                            if (best[i] == 0x7fffffff || better(d, bestd[i])) { bestd[i] = d; best[i] = c0 + j; }
+                        }
+                    }
+                }
+            }
+            __syncthreads();                             // everybody is done with `buf` before it is staged again
+        }
+        // merge the 16 code lanes of every row (xor butterfly inside the aligned half warp)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bestd[i], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best[i], o);
+                if (oi != 0x7fffffff) {
+                    bool take;
+                    if (best[i] == 0x7fffffff) take = true;
+                    else {
+                        const bool mn = bestd[i] != bestd[i], on = od != od;
+                        if (mn || on) take = on && (!mn || oi < best[i]);
+                        else take = od < bestd[i] || (od == bestd[i] && oi < best[i]);
+                    }
+                    if (take) { bestd[i] = od; best[i] = oi; }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t row = row0 + ty * 4 + i;
+            if (tx == 0 && row < n) codes[(rows_out ? rows_out[row] : row) * qa.L + l] = best[i];
+            // straight-through residual update (vq.py:95, rq.py:47): lane tx owns dims 4tx.. (+64, ...) of the row
+            for (int k = 4 * tx; k < E; k += 64) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(cb + (int64_t)best[i] * E + k));
+                float4 rv = *reinterpret_cast<float4 *>(s_r + (ty * 4 + i) * PITCH + k);
+                rv.x = __fsub_rn(rv.x, __fadd_rn(rv.x, __fsub_rn(q.x, rv.x)));
+                rv.y = __fsub_rn(rv.y, __fadd_rn(rv.y, __fsub_rn(q.y, rv.y)));
+                rv.z = __fsub_rn(rv.z, __fadd_rn(rv.z, __fsub_rn(q.z, rv.z)));
+                rv.w = __fsub_rn(rv.w, __fadd_rn(rv.w, __fsub_rn(q.w, rv.w)));
+                *reinterpret_cast<float4 *>(s_r + (ty * 4 + i) * PITCH + k) = rv;
+            }
+        }
+    }
+}
+
+template <int E>
+int launch_quant_tiled(const rqb200_model *m, const float *z, int64_t n, int64_t *codes, const int64_t *rows_out,
+                       cudaStream_t s) {
+    auto kern = quantize_tiled_kernel<E>;
+    constexpr int PITCH = E + 4;
+    size_t smem = sizeof(float) * (QTL_ROWS * PITCH + 2 * QTL_CODES * PITCH + 2 * QTL_CODES + QTL_ROWS);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    unsigned grid = (unsigned)((n + QTL_ROWS - 1) / QTL_ROWS);
+    rqb::count_launch();
+    kern<<<grid, QTL_THREADS, smem, s>>>(z, n, make_args(m), codes, rows_out);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
 #define RQB_DISPATCH_E(e, CALL)                                                     \
     switch (e) {                                                                    \
         case 8:   { constexpr int E = 8;   CALL; } break;                            \
@@ -468,6 +640,16 @@ int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *co
     // per thread up to about half a wave of 128-row CTAs, slower beyond — the row-per-thread kernel then fills the SMs)
     if (n <= (int64_t)kNumSMs * QT / 2 && !xq && !sumsq && !last_residual && !margin_out && m->e <= 64) {
         RQB_DISPATCH_E(m->e, return (launch_quant_sliced<E>(m, z, n, codes, rows_out, s)));
+        return 0;
+    }
+    // many rows, codes only (rescue tier at catalogue scale): register-tiled kernel, same bits
+    static int tiled_mode = -1;            // RQB200_QUANT_TILED=0 keeps the row-per-thread kernel (A/B, tests)
+    if (tiled_mode < 0) {
+        const char *ev = getenv("RQB200_QUANT_TILED");
+        tiled_mode = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    if (tiled_mode && !xq && !sumsq && !last_residual && !margin_out && m->e <= 128) {
+        RQB_DISPATCH_E(m->e, return (launch_quant_tiled<E>(m, z, n, codes, rows_out, s)));
         return 0;
     }
     RQB_DISPATCH_E(m->e, return (launch_quant<E, 0>(m, z, n, codes, rows_out, xq, sumsq, last_residual,

@@ -112,19 +112,23 @@ def test_exact_integer_lane_with_ties(oracle):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("name", ["c2_slice", "c5_slice"])
-def test_sliced_and_row_per_thread_quantizers_agree(oracle, name):
-    """The exact quantizer has two thread mappings (a row per thread; a row shared by 8 lanes when few rows are in
-    flight).  Same codes bit for bit, including NaN rows ("NaN is the minimum", torch.argmin) and exact ties."""
+@pytest.mark.parametrize("n", [5000, 20011])
+@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c5_slice"])
+def test_sliced_tiled_and_row_per_thread_quantizers_agree(oracle, name, n):
+    """The exact quantizer has three thread mappings: a row per thread (any outputs); codes only — a row shared by
+    8 lanes when few rows are in flight (n = 5000) and a register-tiled 64-row CTA beyond that (n = 20011).  Same codes
+    bit for bit, including NaN rows ("NaN is the minimum", torch.argmin) and exact ties."""
     g, cfg, cbs = load_golden(name)
     m = build_model(cfg, cbs)
     m._sync()
     e, Lv = cfg["e_dim"], len(cbs)
     rng = np.random.default_rng(21)
-    n = 5000
     z = (rng.standard_normal((n, e)) * 0.3).astype(np.float32)
     z[7, 3] = np.nan                                              # a NaN latent: every distance is NaN, code 0 wins
+    z[n - 1, 0] = np.inf
     z[100:200] = cbs[0][rng.integers(0, cbs[0].shape[0], size=100)]   # rows sitting exactly on codes
+    km = min(100, cbs[0].shape[0] - 1)
+    z[300:300 + km] = 0.5 * (cbs[0][:km] + cbs[0][1:km + 1])      # midpoints between neighbouring codes
     zt = torch.from_numpy(z).to(DEV)
     lib = _cabi.lib()
     sliced = torch.empty((n, Lv), dtype=torch.int64, device=DEV)
@@ -133,7 +137,7 @@ def test_sliced_and_row_per_thread_quantizers_agree(oracle, name):
     _cabi.check(lib.rqb200_quantize(m._handle, zt.data_ptr(), n, sliced.data_ptr(), 0, 0, 0, 0, _cabi.stream_ptr()))
     _cabi.check(lib.rqb200_quantize(m._handle, zt.data_ptr(), n, plain.data_ptr(), 0, xq.data_ptr(), 0, 0, _cabi.stream_ptr()))
     assert torch.equal(sliced, plain)
-    ok = ~np.isnan(z).any(1)
+    ok = np.isfinite(z).all(1)
     ref = oracle.quantize(z[ok], cbs, want_xq=False)[0]
     assert np.array_equal(sliced.cpu().numpy()[ok], ref)
 
