@@ -34,6 +34,13 @@ class EmbDataset(data.Dataset):
             meta = json.loads(f["meta"][()].decode("utf-8")) if "meta" in f else {}
         return np.ascontiguousarray(emb, dtype=np.float32), meta
 
+    def shard(self, rank: int, world: int) -> np.ndarray:
+        """This rank's contiguous row range [r*N/G, (r+1)*N/G) of the catalogue — what a torchrun worker
+        feeds to `sharding.generate_codes_sharded` / `rqb200_generate_codes_host`."""
+        n = len(self.embeddings)
+        lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+        return self.embeddings[lo:hi]
+
     def __getitem__(self, index):
         return torch.from_numpy(np.asarray(self.embeddings[index], dtype=np.float32))
 

@@ -325,6 +325,24 @@ def main():
                  "exact_linear0": prof_ms[0] / args.steps, "exact_linear_rest": prof_ms[1] / args.steps,
                  "quantize_incl_rescue_quantizer": prof_ms[2] / args.steps, "dedup": prof_ms[3] / args.steps,
                  "three_pass_rerun_tier": prof_ms[7] / args.steps, "exact_rescue_tier": prof_ms[8] / args.steps}
+        def _st(name, bound, ms, work, peak, unit, note):
+            ach = work / (ms * 1e-3) / (1e9 if unit == "GB/s" else 1e12) if ms > 0 else 0.0
+            return {"stage": name, "bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak if peak else None, "algorithmic_work_per_item": work / n, "note": note}
+        e_dim = int(model.e_dim)
+        stages = []
+        if slot == 4:           # per-stage view of the fast route (algorithmic work only, per item)
+            stages = [
+                _st("encoder layer 1 (linear_tc2_kernel)", "hbm", stage["tc_linear0"], 4.0 * in_dim * n, hbm_peak, "GB/s",
+                    "reads X once: 4*in_dim B"),
+                _st("encoder layers 2+3 fused (mlp23_tc_kernel)", "hbm", stage["tc_linear_rest"],
+                    (4.0 * first_out + 4.0 * e_dim) * n, hbm_peak, "GB/s", "reads H1 (4 B per feature as fp16 hi+lo), writes z"),
+                _st("residual quantizer (quantize_tc_kernel + the rescue tier's exact quantizer)", "tensor",
+                    stage["quantize_incl_rescue_quantizer"], 2.0 * sum(Ks) * e_dim * n, tc_peak, "TFLOP/s",
+                    "2*sum(K)*e flop of ONE pass; the kernel issues 3 fp16 passes and is bound by its per-level latency chain"),
+                _st("suffix dedup (radix sort + segmented rank)", "hbm", stage["dedup"], (8.0 * n_levels + 8.0 * (n_levels + 1)) * n,
+                    hbm_peak, "GB/s", "reads codes, writes ids; launch-bound at 1M items"),
+            ]
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
                     "traffic": traffic, "kernel": kname, "kernel_ms": k_ms,
                     "peak_source": f"{peak_src} hbm_gbs; SURVEY §8d: a bf16-rate pass over this shape is HBM-bound (AI 96 flop/B < ridge 207)",
@@ -333,7 +351,7 @@ def main():
                                     "note": "algorithmic flops of ONE pass; the kernel issues 3 fp16 passes for fp32-class accuracy"},
                     "step_share": (prof_ms[slot] / args.steps) / ms_step if ms_step else None,
                     "whole_step_hbm_frac": (value / world) * (4 * in_dim + 8 * n_levels) / (hbm_peak * 1e9),
-                    "stage_ms_per_step": stage}
+                    "stage_ms_per_step": stage, "stages": stages}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -51,3 +51,16 @@ def test_training_forward_refuses_cpu_tensors():
     with pytest.raises(ValueError, match="incompatible loss type"):
         m.loss_type = "huber"
         m.compute_loss(torch.zeros(1), torch.zeros(()), xs=torch.zeros(1))
+
+
+def test_emb_dataset_npy_and_shards(tmp_path):
+    """vision_data.py:9-30 contract on the .npy stand-in: float32 rows, dim, meta side file, contiguous shards."""
+    from ai_education_generative_recommendation_b200 import EmbDataset
+    x = np.arange(35 * 6, dtype=np.float64).reshape(35, 6)
+    np.save(tmp_path / "embs.npy", x)
+    (tmp_path / "embs_meta.json").write_text('{"num_items": 35}')
+    ds = EmbDataset(str(tmp_path / "embs.npy"))
+    assert len(ds) == 35 and ds.dim == 6 and ds.meta == {"num_items": 35}
+    assert ds[3].dtype == torch.float32 and torch.equal(ds[3], torch.from_numpy(x[3].astype(np.float32)))
+    parts = [ds.shard(r, 4) for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), x.astype(np.float32)) and parts[0].dtype == np.float32
