@@ -73,6 +73,9 @@ _PROTOS = {
     "rqb200_kmeans_accumulate": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, _P]),
     "rqb200_kmeans_update": (c_int, [_P, c_int, c_int, _P, _P, _P, _P]),
     "rqb200_dropout": (c_int, [_P, c_int64, c_float, c_uint64, _P, _P]),
+    "rqb200_dropout_dev": (c_int, [_P, c_int64, c_float, c_uint64, _P, _P, _P]),
+    "rqb200_set_floats": (c_int, [_P, c_int, POINTER(c_float), _P]),
+    "rqb200_adamw_clip_step_dev": (c_int, [_P, c_int, _P, _P, c_float, c_float, _P, _P]),
     "rqb200_linear_forward": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "rqb200_linear_backward_scratch_floats": (c_int64, [c_int64, c_int, c_int]),
     "rqb200_linear_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int64, _P]),

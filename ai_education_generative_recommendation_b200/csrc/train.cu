@@ -24,7 +24,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 // y = x * keep / (1 - p); keep(i) is a pure function of (seed, i) so the backward pass regenerates the mask instead
 // of storing it.  One hash yields four 16-bit uniforms → four neighbouring elements.
 __global__ void dropout_kernel(const float *__restrict__ x, int64_t count, uint32_t thresh16, float scale, uint64_t seed,
-                               float *__restrict__ y) {
+                               const uint64_t *__restrict__ seed_dev, float *__restrict__ y) {
+    if (seed_dev) seed ^= mix64(*seed_dev);      // replayed CUDA graphs: the per-step part of the seed lives on the device
     const int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = q0; q * 4 < count; q += stride) {
@@ -116,20 +117,20 @@ __global__ void reduce_slices_kernel(const float *__restrict__ part, int S, int6
     out[i] = s;
 }
 
-// db[j] = sum_r dy[r, j]; 32 columns per CTA, 8 row lanes per column, fixed combination order
-__global__ void __launch_bounds__(256) colsum_kernel(const float *__restrict__ dy, int64_t n, int out, float *__restrict__ db) {
-    __shared__ float part[8][33];
+// db[j] = sum_r dy[r, j]; 32 columns per CTA, 32 row lanes per column (1024 threads), fixed combination order
+__global__ void __launch_bounds__(1024) colsum_kernel(const float *__restrict__ dy, int64_t n, int out, float *__restrict__ db) {
+    __shared__ float part[32][33];
     const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + c;
     float s = 0.0f;
     if (j < out)
-        for (int64_t r = rl; r < n; r += 8) s += dy[r * out + j];
+        for (int64_t r = rl; r < n; r += 32) s += dy[r * out + j];
     part[rl][c] = s;
     __syncthreads();
     if (rl == 0 && j < out) {
         float t = part[0][c];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) t += part[q][c];
+        for (int q = 1; q < 32; ++q) t += part[q][c];
         db[j] = t;
     }
 }
@@ -308,6 +309,35 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_chunks_kernel(const int64_t
     }
 }
 
+// the same update with the per-step scalars read from device memory: hyper = {decay, step_size, sqrt(bc2), b1, b2, eps}
+// (a captured CUDA graph replays the launch; the host refreshes the six floats before every replay)
+__global__ void __launch_bounds__(OPT_THREADS) adamw_chunks_dev_kernel(const int64_t *__restrict__ chunks, const float *__restrict__ stats,
+                                                                       float grad_scale, const float *__restrict__ hyper) {
+    const int64_t *c = chunks + (int64_t)blockIdx.x * 5;
+    float *p = reinterpret_cast<float *>(c[0]);
+    const float *g = reinterpret_cast<const float *>(c[1]);
+    float *m = reinterpret_cast<float *>(c[2]);
+    float *v = reinterpret_cast<float *>(c[3]);
+    const int64_t n = c[4];
+    const float coef = stats[1] * grad_scale;
+    const float decay = hyper[0], step_size = hyper[1], bc2_sqrt = hyper[2], b1 = hyper[3], b2 = hyper[4], eps = hyper[5];
+    for (int64_t i = threadIdx.x; i < n; i += OPT_THREADS) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * decay;
+        const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+        const float vi = v[i] * b2 + gi * gi * (1.0f - b2);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+
+struct Floats8 { float v[8]; };
+// the values travel as launch arguments (copied at launch time), so the host may run many steps ahead of the device
+__global__ void set_floats_kernel(float *__restrict__ dst, int n, Floats8 vals) {
+    if (threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
 int grid_for(int64_t count) {
     int64_t b = (count + 255) / 256;
     if (b > kNumSMs * 8) b = kNumSMs * 8;
@@ -323,12 +353,17 @@ int default_kblocks_public(int K, int *out);       // api.cu
 using namespace rqb;
 
 extern "C" int rqb200_dropout(const float *x_dev, int64_t count, float p, uint64_t seed, float *y_dev, void *stream) {
+    return rqb200_dropout_dev(x_dev, count, p, seed, nullptr, y_dev, stream);
+}
+
+extern "C" int rqb200_dropout_dev(const float *x_dev, int64_t count, float p, uint64_t seed, const uint64_t *seed_dev,
+                                  float *y_dev, void *stream) {
     if (count == 0) return 0;
     RQB_CHECK(x_dev && y_dev, "NULL buffer");
     RQB_CHECK(p >= 0.0f && p < 1.0f, "dropout probability must be in [0, 1)");
     const uint32_t thresh = (uint32_t)lrintf(p * 65536.0f);
     count_launch();
-    dropout_kernel<<<grid_for((count + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x_dev, count, thresh, 1.0f / (1.0f - p), seed, y_dev);
+    dropout_kernel<<<grid_for((count + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x_dev, count, thresh, 1.0f / (1.0f - p), seed, seed_dev, y_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -368,7 +403,7 @@ extern "C" int rqb200_linear_backward(const float *x_dev, const float *W_dev, co
     RQB_TRY(sgemm(dy_dev, 1, out_dim, x_dev, in_dim, 1, dW_dev, out_dim, in_dim, (int)n, scratch_dev,
                   scratch_dev ? (size_t)scratch_floats : 0, s));
     count_launch();
-    colsum_kernel<<<(out_dim + 31) / 32, 256, 0, s>>>(dy_dev, n, out_dim, db_dev);
+    colsum_kernel<<<(out_dim + 31) / 32, 1024, 0, s>>>(dy_dev, n, out_dim, db_dev);
     RQB_LAUNCH_CHECK();
     // dx[n, in] = dy · W : A(m = r, k = o) = dy[r * out + o], B(k = o, n = i) = W[o * in + i]
     if (dx_dev)
@@ -442,6 +477,31 @@ extern "C" int rqb200_adamw_clip_step(const int64_t *chunks_dev, int n_chunks, d
     adamw_chunks_kernel<<<n_chunks, OPT_THREADS, 0, s>>>(chunks_dev, stats_dev, grad_scale,
                                                         (float)(1.0 - (double)lr * (double)weight_decay), beta1, beta2, eps,
                                                         (float)((double)lr / bc1), (float)sqrt(bc2));
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rqb200_adamw_clip_step_dev(const int64_t *chunks_dev, int n_chunks, double *partial_dev, float *stats_dev,
+                                          float grad_scale, float max_norm, const float *hyper_dev, void *stream) {
+    if (n_chunks == 0) return 0;
+    RQB_CHECK(chunks_dev && partial_dev && stats_dev && hyper_dev, "NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    count_launch();
+    gradnorm_chunks_kernel<<<n_chunks, OPT_THREADS, 0, s>>>(chunks_dev, grad_scale, partial_dev);
+    count_launch();
+    gradnorm_finish_kernel<<<1, 32, 0, s>>>(partial_dev, n_chunks, max_norm, stats_dev);
+    count_launch();
+    adamw_chunks_dev_kernel<<<n_chunks, OPT_THREADS, 0, s>>>(chunks_dev, stats_dev, grad_scale, hyper_dev);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int rqb200_set_floats(float *dst_dev, int n, const float *values_host, void *stream) {
+    RQB_CHECK(dst_dev && values_host && n >= 1 && n <= 8, "1..8 floats");
+    Floats8 f;
+    for (int i = 0; i < 8; ++i) f.v[i] = i < n ? values_host[i] : 0.0f;
+    count_launch();
+    set_floats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(dst_dev, n, f);
     RQB_LAUNCH_CHECK();
     return 0;
 }

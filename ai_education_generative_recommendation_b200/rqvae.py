@@ -466,7 +466,8 @@ class RQVAE(nn.Module):
         p = float(self.dropout_prob) if self.training else 0.0
         self._train_calls = getattr(self, "_train_calls", 0) + 1
         seed = (int(getattr(self, "dropout_seed", 2024)) << 32) ^ self._train_calls
-        z = MLPFunction.apply(x2, p, seed * 2, *self._mlp_params(self.encoder))
+        seed_dev = getattr(self, "_dropout_seed_dev", None)      # set by the Trainer when the step is a replayed CUDA graph
+        z = MLPFunction.apply(x2, p, seed * 2, seed_dev, *self._mlp_params(self.encoder))
         layers = self.rq.vq_layers
         if self.training and any(not q.initted for q in layers):
             with torch.no_grad():                         # rq.py:43-48 level by level on this first batch
@@ -481,7 +482,7 @@ class RQVAE(nn.Module):
         eps = [float(q.sk_epsilon) if (use_sk and q.sk_epsilon is not None and q.sk_epsilon > 0) else 0.0 for q in layers]
         x_q, rq_loss, indices = RQFunction.apply(z, [q.beta for q in layers], eps, int(layers[0].sk_iters),
                                                  *[q.embedding.weight for q in layers])
-        out = MLPFunction.apply(x_q, p, seed * 2 + 1, *self._mlp_params(self.decoder))
+        out = MLPFunction.apply(x_q, p, seed * 2 + 1, seed_dev, *self._mlp_params(self.decoder))
         return out.view(*x.shape[:-1], self.in_dim), rq_loss, indices.view(*x.shape[:-1], len(layers))
 
     @torch.no_grad()

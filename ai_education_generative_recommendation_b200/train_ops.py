@@ -32,10 +32,26 @@ def _mix(seed: int, a: int) -> int:
     return x ^ (x >> 31)
 
 
-def _dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+def _dropout(x: torch.Tensor, p: float, seed: int, seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """seed_dev: optional int64[1] device tensor mixed into the seed on the device (CUDA-graph replays, see Trainer)."""
     y = torch.empty_like(x)
-    check(_cabi.lib().rqb200_dropout(ptr(x), x.numel(), float(p), ctypes.c_uint64(seed), ptr(y), stream_ptr(x.device)))
+    check(_cabi.lib().rqb200_dropout_dev(ptr(x), x.numel(), float(p), ctypes.c_uint64(seed), ptr(seed_dev), ptr(y),
+                                         stream_ptr(x.device)))
     return y
+
+
+_CONST_CACHE = {}
+
+
+def _const_tensor(values, dtype, device) -> torch.Tensor:
+    """Small constant device tensors (betas …) are created once: a host→device copy is not allowed while a CUDA graph
+    is being captured."""
+    key = (tuple(float(v) for v in values), dtype, str(device))
+    t = _CONST_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(list(values), dtype=dtype, device=device)
+        _CONST_CACHE[key] = t
+    return t
 
 
 class MLPFunction(torch.autograd.Function):
@@ -43,7 +59,7 @@ class MLPFunction(torch.autograd.Function):
     every Linear when p > 0 (masks are regenerated from `seed` in backward, never stored)."""
 
     @staticmethod
-    def forward(ctx, x, p_drop, seed, *params):
+    def forward(ctx, x, p_drop, seed, seed_dev, *params):
         lib = _cabi.lib()
         n_layers = len(params) // 2
         h = x.contiguous()
@@ -52,13 +68,13 @@ class MLPFunction(torch.autograd.Function):
         saved = []
         for i in range(n_layers):
             W, b = params[2 * i].contiguous(), params[2 * i + 1].contiguous()
-            hd = _dropout(h, p_drop, _mix(seed, i)) if p_drop > 0 else h
+            hd = _dropout(h, p_drop, _mix(seed, i), seed_dev) if p_drop > 0 else h
             y = torch.empty((n, W.shape[0]), dtype=torch.float32, device=h.device)
             check(lib.rqb200_linear_forward(ptr(hd), ptr(W), ptr(b), n, W.shape[1], W.shape[0],
                                             1 if i < n_layers - 1 else 0, ptr(y), s))
             saved += [hd, y]
             h = y
-        ctx.p_drop, ctx.seed, ctx.n_layers = p_drop, seed, n_layers
+        ctx.p_drop, ctx.seed, ctx.n_layers, ctx.seed_dev = p_drop, seed, n_layers, seed_dev
         ctx.save_for_backward(*saved, *params)
         return h
 
@@ -88,9 +104,9 @@ class MLPFunction(torch.autograd.Function):
                                              1 if i < nl - 1 else 0, ptr(dx), ptr(dW), ptr(db), ptr(scratch), nscr, s))
             grads[2 * i], grads[2 * i + 1] = dW, db
             if need_dx and ctx.p_drop > 0:
-                dx = _dropout(dx, ctx.p_drop, _mix(ctx.seed, i))
+                dx = _dropout(dx, ctx.p_drop, _mix(ctx.seed, i), ctx.seed_dev)
             dy = dx
-        return (dx if ctx.needs_input_grad[0] else None, None, None, *grads)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
 
 
 class RQFunction(torch.autograd.Function):
@@ -127,7 +143,7 @@ class RQFunction(torch.autograd.Function):
             residuals.append(r)
             r = r_next
         mse = sumsq / float(max(n * e, 1))
-        bt = torch.tensor(list(betas), dtype=torch.float64, device=dev)
+        bt = _const_tensor(betas, torch.float64, dev)
         loss = (mse + bt * mse).mean().to(torch.float32)
         ctx.betas, ctx.Lv = list(betas), Lv
         ctx.save_for_backward(idx_all, *residuals, *codebooks)
@@ -246,6 +262,42 @@ class FusedAdamW(torch.optim.Optimizer):
         self._stats = torch.zeros((2,), dtype=torch.float32, device=dev)
         self._sig = [(p.data_ptr(), p.numel()) for p in ps]
         self._steps = int(max([float(self.state[p]["step"]) for p in ps] + [0.0]))
+
+    # ---- CUDA-graph replay support: per-step scalars in device memory --------------------------------
+    def refresh_hyper(self):
+        """Host side of one graph-replayed step: advances the step count and refreshes the six scalars the captured
+        `step_from_device` launch reads (decay, lr / bc1, sqrt(bc2), beta1, beta2, eps).  Call right before replay."""
+        if self._flat is None:
+            self._build()
+        g = self.param_groups[0]
+        self._steps += 1
+        b1, b2 = float(g["betas"][0]), float(g["betas"][1])
+        lr, wd = float(g["lr"]), float(g["weight_decay"])
+        bc1, bc2 = 1.0 - b1 ** self._steps, 1.0 - b2 ** self._steps
+        if getattr(self, "_hyper", None) is None:
+            self._hyper = torch.zeros((6,), dtype=torch.float32, device=self._flat.device)
+        vals = (ctypes.c_float * 6)(1.0 - lr * wd, lr / bc1, bc2 ** 0.5, b1, b2, float(g["eps"]))
+        check(_cabi.lib().rqb200_set_floats(ptr(self._hyper), 6, vals, stream_ptr(self._flat.device)))
+
+    def step_from_device(self):
+        """The launch a CUDA graph captures: clip + AdamW with the scalars of `refresh_hyper` (nothing else — no host
+        bookkeeping, no pointer checks)."""
+        if getattr(self, "_hyper", None) is None:
+            raise RuntimeError("call refresh_hyper() once before capturing step_from_device()")
+        check(_cabi.lib().rqb200_adamw_clip_step_dev(ptr(self._table), self._table.shape[0], ptr(self._partial), ptr(self._stats),
+                                                     float(self.grad_scale), self.max_norm, ptr(self._hyper),
+                                                     stream_ptr(self._flat.device)))
+        self.last_stats = self._stats
+
+    def after_replay(self):
+        """Host bookkeeping after a replayed step (parameter version counters)."""
+        _bump_versions(self._params())
+
+    def state_dict(self):
+        for p in self._params():
+            if p in self.state:
+                self.state[p]["step"] = torch.tensor(float(getattr(self, "_steps", 0)))
+        return super().state_dict()
 
     @property
     def flat_grad(self) -> torch.Tensor:

@@ -241,6 +241,10 @@ int rqb200_kmeans_update(float *centers_dev, int K, int e, const double *sums_de
 /* nn.Dropout in training mode (layers.py:21): y = x * keep / (1 - p), keep a pure function of (seed, index);
  * calling it again on a gradient with the same seed applies the same mask (backward).     */
 int rqb200_dropout(const float *x_dev, int64_t count, float p, uint64_t seed, float *y_dev, void *stream);
+/* Same with a second, device-resident seed word mixed in (may be NULL): a captured CUDA graph replays identical launch
+ * arguments, so the per-step part of the seed has to live in device memory.                */
+int rqb200_dropout_dev(const float *x_dev, int64_t count, float p, uint64_t seed, const uint64_t *seed_dev, float *y_dev,
+                       void *stream);
 /* nn.Linear (+ReLU) with caller-owned parameters, the reference's fp32 summation order (layers.py:23).      */
 int rqb200_linear_forward(const float *x_dev, const float *W_dev, const float *b_dev, int64_t n, int in_dim,
                           int out_dim, int relu, float *y_dev, void *stream);
@@ -273,6 +277,14 @@ int rqb200_recon_grad(const float *out_dev, const float *x_dev, int64_t count, i
 int rqb200_adamw_clip_step(const int64_t *chunks_dev, int n_chunks, double *partial_dev, float *stats_dev,
                            float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
                            float weight_decay, int64_t step, void *stream);
+
+/* Graph-replayable variant: the per-step scalars come from device memory, hyper_dev[6] = {1 - lr*wd, lr / (1 - beta1^t),
+ * sqrt(1 - beta2^t), beta1, beta2, eps} — the host refreshes them before each replay.                 */
+/* dst_dev[0..n) = values_host[0..n), n <= 8, as one tiny launch whose arguments carry the values (safe however far the host
+ * runs ahead of the stream) — how the per-step scalars above reach the device.            */
+int rqb200_set_floats(float *dst_dev, int n, const float *values_host, void *stream);
+int rqb200_adamw_clip_step_dev(const int64_t *chunks_dev, int n_chunks, double *partial_dev, float *stats_dev,
+                               float grad_scale, float max_norm, const float *hyper_dev, void *stream);
 
 /* ---- consumers of the semantic ids -------------------------------
  * token = id + column * codebook_size + 1 for every column of the [n, n_cols] id array (item_to_offset_code,

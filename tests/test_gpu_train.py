@@ -104,7 +104,7 @@ def test_mlp_backward_matches_torch_autograd():
             ps += [(torch.randn(b, a, device=DEV) / a ** 0.5).requires_grad_(), (0.1 * torch.randn(b, device=DEV)).requires_grad_()]
         x = torch.randn(n, dims[0], device=DEV, requires_grad=True)
         gy = torch.randn(n, dims[-1], device=DEV)
-        y = MLPFunction.apply(x, 0.0, 0, *ps)
+        y = MLPFunction.apply(x, 0.0, 0, None, *ps)
         got = torch.autograd.grad(y, [x] + ps, gy)
         h = x
         for i in range(len(ps) // 2):
@@ -129,7 +129,7 @@ def test_dropout_mask_statistics_and_backward():
     W = torch.eye(64, device=DEV).requires_grad_()
     b = torch.zeros(64, device=DEV).requires_grad_()
     xin = torch.randn(512, 64, device=DEV, requires_grad=True)
-    out = MLPFunction.apply(xin, 0.5, 77, W, b)
+    out = MLPFunction.apply(xin, 0.5, 77, None, W, b)
     out.sum().backward()
     mask = (out.detach() != 0)
     assert torch.allclose(xin.grad[mask], torch.full((1,), 2.0, device=DEV))
@@ -278,3 +278,48 @@ def test_batch_sinkhorn_on_the_whole_gpu_matches_oracle(oracle, B, K):
     # balanced assignment: no code is starved or flooded beyond what the arg-max of a doubly-normalised Q allows
     counts = np.bincount(got, minlength=K)
     assert counts.max() <= max(4 * B // K, 8)
+
+
+def test_graph_replayed_steps_equal_eager_steps(tmp_path):
+    """The Trainer captures the step as a CUDA graph after three eager steps; with dropout off the replayed steps give the
+    losses and weights of the eager loop (same kernels, per-step scalars read from device memory)."""
+    import ai_education_generative_recommendation_b200 as rq
+    from ai_education_generative_recommendation_b200 import synth
+    x = torch.from_numpy(synth.synth_items(2024, 0, 12 * 1024, 768, 1_000_000)).to(DEV)
+    results = []
+    for use_graph in (True, False):
+        torch.manual_seed(11)
+        m = rq.RQVAE(in_dim=768, num_emb_list=[64, 64, 64], e_dim=32, layers=[256, 128], dropout_prob=0.0, kmeans_init=True,
+                     kmeans_iters=5, quant_loss_weight=0.1, sk_epsilons=[0.01, 0.01, 0.0], sk_iters=50)
+        params = dict(lr=5e-4, learner="AdamW", lr_scheduler_type="linear", weight_decay=1e-4, epochs=2, warmup_epochs=1,
+                      save_limit=1, eval_step=5, device=DEV, ckpt_dir=str(tmp_path / f"ck{int(use_graph)}"), cuda_graph=use_graph)
+        loader = rq.DeviceBatches(x, 1024, shuffle=False)
+        tr = rq.Trainer(params, m, len(loader))
+        l0 = tr._train_epoch(loader, 0)
+        l1 = tr._train_epoch(loader, 1)
+        results.append((l0, l1, [p.detach().clone() for p in m.parameters()], tr.graph_replays, tr.optimizer._steps))
+    (a0, a1, pa, ra, sa), (b0, b1, pb, rb, sb) = results
+    assert ra >= 20 and rb == 0 and sa == sb == 24
+    assert np.allclose(a0, b0, rtol=1e-4) and np.allclose(a1, b1, rtol=1e-3), (a0, b0, a1, b1)
+    for p, q in zip(pa, pb):
+        assert float((p - q).norm()) <= 2e-2 * float((q - q.mean()).norm() + 1e-12)
+
+
+def test_graph_replay_changes_the_dropout_mask_every_step():
+    import ai_education_generative_recommendation_b200 as rq
+    from ai_education_generative_recommendation_b200.train_ops import _dropout
+    x = torch.ones(1 << 16, device=DEV)
+    seed_dev = torch.zeros((1,), dtype=torch.int64, device=DEV)
+    y0 = _dropout(x, 0.5, 99, seed_dev)
+    g = torch.cuda.CUDAGraph()
+    static = torch.empty_like(x)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        seed_dev.add_(1)
+        static.copy_(_dropout(x, 0.5, 99, seed_dev))
+    g.replay()
+    y1 = static.clone()
+    g.replay()
+    y2 = static.clone()
+    assert not torch.equal(y1, y2) and not torch.equal(y0, y1)
+    assert abs((y1 != 0).float().mean().item() - 0.5) < 0.02
