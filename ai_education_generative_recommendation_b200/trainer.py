@@ -14,8 +14,8 @@ What changes underneath:
     epoch over millions of items is not bounded by a host DataLoader;
   * the whole step (zero_grad → forward → losses → backward → [all-reduce] → clip + AdamW) is ≈ 70 of our launches plus
     torch's graph glue, ≈ 3 ms of GPU time at batch 4096 but 4–6 ms of Python: after three eager steps it is captured
-    once as a CUDA graph and replayed per batch (`params["cuda_graph"]`, default on; batches of another size and any
-    capture failure fall back to the eager step).  Per-step scalars (learning rate, bias corrections, dropout seed)
+    once as a CUDA graph and replayed per batch (`params["cuda_graph"]`, default on, single-GPU runs only; batches of
+    another size and any capture failure fall back to the eager step).  Per-step scalars (learning rate, bias corrections, dropout seed)
     live in device memory so the replay is exact.
 """
 from __future__ import annotations
@@ -109,7 +109,9 @@ class Trainer(object):
         self.optimizer = self._build_optimizer()
         self.scheduler = self._get_scheduler()
         self.last_epoch_steps = 0
-        self.use_cuda_graph = bool(params.get("cuda_graph", True))
+        # single-GPU only: with the NCCL all-reduce inside the captured graph the step got slower (6.8 vs 4.0 ms at N = 2)
+        # and process-group teardown hung (measured once, round 1) — data-parallel runs keep the eager step
+        self.use_cuda_graph = bool(params.get("cuda_graph", True)) and self.world == 1
         self._graph = None               # (CUDAGraph, static input, static [loss, recon]) once captured
         self._graph_failed = False
         self._eager_steps = 0
