@@ -65,6 +65,20 @@ struct Linear {
     void *W_tc2 = nullptr;   // image for the 2-CTA kernel (each CTA of a pair stages half of the output features)
 };
 
+// "Do this once per device": cudaFuncSetAttribute is a per-device setting, and one process may drive several devices
+// through the C ABI (rqb200_model_create takes a device index).  first() is true the first time it is called while
+// a given device is current.
+struct DeviceOnce {
+    unsigned long long mask = 0;
+    bool first() {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
+        return !(old & bit);
+    }
+};
+
 struct Workspace {
     void *ptr = nullptr;
     size_t bytes = 0;

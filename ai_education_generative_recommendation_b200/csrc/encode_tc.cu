@@ -610,10 +610,9 @@ template <int N, int PASSES>
 int launch_tc(const Linear &l, const float *x, int64_t n, float *y, bool relu, const unsigned long long *n_dev, cudaStream_t s) {
     using Cfg = TcCfg<N, PASSES>;
     auto kern = linear_tc_kernel<N, PASSES>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
     }
     const int64_t ntiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -698,10 +697,9 @@ template <int N3, bool TILED_A>
 static int launch_mlp23(Linear &l2, Linear &l3, const float *x, int64_t n, float *z, const unsigned long long *n_dev, cudaStream_t s) {
     using Cfg = Tc23Cfg<N3>;
     auto kern = mlp23_tc_kernel<N3, TILED_A>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
     }
     const int64_t ntiles = (n + TM - 1) / TM;
     const unsigned grid = (unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs);

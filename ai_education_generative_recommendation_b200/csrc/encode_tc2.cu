@@ -365,10 +365,9 @@ template <int PASSES, bool GATHER>
 static int launch_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, const int64_t *rows,
                       const unsigned long long *n_dev, cudaStream_t s, bool tiled_out) {
     auto kern = linear_tc2_kernel<PASSES, GATHER>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Cfg<PASSES>::SMEM));
-        attr_done = true;
     }
     const int64_t npt = (n + 2 * TM2 - 1) / (2 * TM2);
     int64_t pairs = npt < kNumSMs / 2 ? npt : kNumSMs / 2;

@@ -118,11 +118,10 @@ extern "C" int rqb200_kmeans_accumulate(const float *x_dev, int64_t n, int e, co
     RQB_CHECK(x_dev && assign_dev && centers_dev && sums_dev && counts_dev, "NULL buffer");
     const size_t smem = sizeof(double) * (size_t)K * e;
     const int use_smem = smem <= 160 * 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kmeans_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       160 * 1024));
-        attr_done = true;
     }
     int64_t grid = (n + 1023) / 1024;
     if (grid > kNumSMs) grid = kNumSMs;

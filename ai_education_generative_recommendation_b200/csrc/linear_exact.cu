@@ -228,11 +228,10 @@ int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, fl
            cudaStream_t s) {
     auto kern = linear_exact_kernel<BM, BN, TM, TN>;
     size_t stash = lin.nblk > 1 ? sizeof(float) * TM * TN * NTHREADS : 0;
-    static bool attr_done = false;   // per template instantiation
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;   // per template instantiation
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(float) * TM * TN * NTHREADS)));
-        attr_done = true;
     }
     int kb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < lin.nblk; ++i) kb[i] = lin.kblocks[i];

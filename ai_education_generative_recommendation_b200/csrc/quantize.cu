@@ -259,10 +259,9 @@ int launch_quant(const rqb200_model *m, const float *z, int64_t n, int64_t *code
     auto kern = quantize_kernel<E, MODE>;
     constexpr int CH = CHUNK_FLOATS / E;
     size_t smem = sizeof(float) * (CH * E + CH);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     unsigned grid = (unsigned)((n + QT - 1) / QT);
     rqb::count_launch();
@@ -395,10 +394,9 @@ int launch_quant_sliced(const rqb200_model *m, const float *z, int64_t n, int64_
     constexpr int PITCH = E + 4;
     constexpr int CH = (CHUNK_FLOATS / PITCH) / QS * QS;
     size_t smem = sizeof(float) * (CH * PITCH + CH);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     unsigned grid = (unsigned)((n + QS_ROWS - 1) / QS_ROWS);
     rqb::count_launch();
@@ -565,10 +563,9 @@ int launch_quant_tiled(const rqb200_model *m, const float *z, int64_t n, int64_t
     auto kern = quantize_tiled_kernel<E>;
     constexpr int PITCH = E + 4;
     size_t smem = sizeof(float) * (QTL_ROWS * PITCH + 2 * QTL_CODES * PITCH + 2 * QTL_CODES + QTL_ROWS);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
     }
     unsigned grid = (unsigned)((n + QTL_ROWS - 1) / QTL_ROWS);
     rqb::count_launch();

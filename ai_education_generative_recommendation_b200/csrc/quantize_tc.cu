@@ -440,10 +440,9 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
                       unsigned long long *count, cudaStream_t s, float gamma, const int64_t *rows,
                       const unsigned long long *n_dev) {
     auto kern = quantize_tc_kernel<E>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
-        attr_done = true;
     }
     QtcArgs qa;
     qa.L = m->L;

@@ -433,11 +433,10 @@ extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_de
     RQB_CHECK(cap_max >= 2, "K=%d too large for the shared-memory Sinkhorn kernel", K);
     int top = cap_max;
     if (max_group > 0 && max_group < top) top = max_group < 2 ? 2 : max_group;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(sinkhorn_regroup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(budget + 1024)));
-        attr_done = true;
     }
     // Most groups have a handful of members: one launch per size class, shared memory sized for the class, so that many
     // small groups share an SM instead of every CTA reserving room for the largest group.
@@ -531,10 +530,9 @@ extern "C" int rqb200_sinkhorn_assign(const float *d_dev, int64_t B, int K, doub
     // layers.py:96-104 and reproduces all of the reference's golden use_sk cases; the scaling-vector form picked another
     // code in 1 of their 840 rows (a 1e-13 near-tie), which is inside the training tolerance but not index parity.
     if (use_grid && B >= 1024 && G >= 2 && rows_per_cta <= cap_rows && ws_doubles <= (size_t)B * K) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static rqb::DeviceOnce attr_once;
+        if (attr_once.first()) {
             RQB_CUDA(cudaFuncSetAttribute(sinkhorn_assign_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
-            attr_done = true;
         }
         RQB_CUDA(cudaMemsetAsync(scratch_dev, 0, 64, s));
         int Bi = (int)B, rpc = rows_per_cta;
