@@ -64,7 +64,7 @@ def main():
                     yield b
         loader = _Head()
     params = dict(lr=1e-3, learner="AdamW", lr_scheduler_type="linear", weight_decay=1e-4, epochs=1, warmup_epochs=0,
-                  save_limit=1, eval_step=1, device=dev, ckpt_dir="/tmp/rqb200_bench_ckpt")
+                  save_limit=1, eval_step=1, device=dev, ckpt_dir=os.path.join(ROOT, "gpurun_out", "bench_ckpt"))
     trainer = rq.Trainer(params, model, len(loader), group=group)
     trainer.slice_batches = False                      # every rank iterates over its own shard
     # first batch: k-means init of every level (timed separately), then the epoch
