@@ -1,6 +1,7 @@
 """Item-embedding input contract of the encode driver (reference RQ-VAE/vision_data.py:9-30):
-float32 [N, dim] `item_embs` (+ JSON `meta`).  Reads the reference's HDF5 file when h5py is
-importable, otherwise a `.npy` with the same array (h5py is not part of this image)."""
+float32 [N, dim] `item_embs` (+ JSON `meta`).  Reads the reference's HDF5 file with h5py when it is
+importable, otherwise with the package's own reader for that layout (`h5lite`; h5py is not part of this image),
+or a `.npy` with the same array."""
 from __future__ import annotations
 
 import json
@@ -27,8 +28,8 @@ class EmbDataset(data.Dataset):
             return np.ascontiguousarray(emb, dtype=np.float32), meta
         try:
             import h5py
-        except ImportError as exc:   # pragma: no cover
-            raise ImportError("h5py is required to read .h5 inputs; convert to .npy or install h5py") from exc
+        except ImportError:
+            from . import h5lite as h5py          # same two accesses (vision_data.py:18-21), read-only subset of HDF5
         with h5py.File(path, "r") as f:
             emb = f["item_embs"][:]
             meta = json.loads(f["meta"][()].decode("utf-8")) if "meta" in f else {}
