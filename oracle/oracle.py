@@ -328,3 +328,100 @@ def tiger_splits(user_ids, item_lists, data: np.ndarray, codebook_size: int):
             train_list.append({"user_id": int(uid), "history": [f(i) for i in user_seq[:-2]],
                                "target": [f(i) for i in user_seq[1:-1]]})
     return train_list, test_list
+
+
+# --------------------------------------------------------------------------- training step (tolerance parity)
+
+def train_step_grads(x, sd, cfg):
+    """One forward + backward of the reference training step (train.py:112-115) in numpy, dropout off:
+    returns (losses dict, indices [B, L], grads dict keyed like the state_dict).  Restates rqvae.py:60-84, rq.py:39-56,
+    vq.py:63-99 and their autograd: straight-through estimator (identity to the latent through level 0 only — deeper
+    levels cancel because r_{l+1} = r_l − (r_l + (q_l − r_l).detach())), commitment gradient β·2(z − q_0)/(B·e·L),
+    codebook gradient 2(q − r)/(B·e·L) scattered by code.  TEST INFRASTRUCTURE; pinned against
+    tests/golden/train_steps.npz (the unmodified reference loop) in tests/test_train_host.py."""
+    f32 = np.float32
+    nl = len(cfg["layers"]) + 1
+    Ks, e, beta, w = cfg["num_emb_list"], cfg["e_dim"], f32(cfg["beta"]), f32(cfg["quant_loss_weight"])
+    L = len(Ks)
+    x = np.asarray(x, dtype=f32)
+    B = x.shape[0]
+
+    def mlp_fwd(h, name):
+        acts = [h]
+        for i in range(nl):
+            W, b = sd[f"{name}.mlp_layers.{1 + 3 * i}.weight"], sd[f"{name}.mlp_layers.{1 + 3 * i}.bias"]
+            h = (h @ W.T + b).astype(f32)
+            if i < nl - 1:
+                h = np.maximum(h, f32(0))
+            acts.append(h)
+        return acts
+
+    def mlp_bwd(acts, name, dy, grads):
+        for i in range(nl - 1, -1, -1):
+            W = sd[f"{name}.mlp_layers.{1 + 3 * i}.weight"]
+            if i < nl - 1:
+                dy = dy * (acts[i + 1] > 0)
+            grads[f"{name}.mlp_layers.{1 + 3 * i}.weight"] = (dy.T @ acts[i]).astype(f32)
+            grads[f"{name}.mlp_layers.{1 + 3 * i}.bias"] = dy.sum(0).astype(f32)
+            dy = (dy @ W).astype(f32)
+        return dy
+
+    enc = mlp_fwd(x, "encoder")
+    z = enc[-1]
+    r = z.copy()
+    xq = np.zeros_like(z)
+    idxs, resid, level_loss = [], [], []
+    for l in range(L):
+        cb = np.ascontiguousarray(sd[f"rq.vq_layers.{l}.embedding.weight"], dtype=f32)
+        idx, _, _, d = quantize(r, [cb], want_xq=False, dist_level=0, threads=1)
+        ind = idx[:, 0]
+        if cfg["sk_epsilons"][l] > 0:
+            ind = sinkhorn_assign(d, cfg["sk_epsilons"][l], cfg["sk_iters"])
+        q = cb[ind]
+        mse = np.mean((q - r).astype(np.float64) ** 2)
+        level_loss.append(mse + float(beta) * mse)
+        resid.append(r)
+        idxs.append(ind)
+        xres = r + (q - r)
+        r = r - xres
+        xq = xq + xres
+    rq_loss = float(np.mean(level_loss))
+    dec = mlp_fwd(xq.astype(f32), "decoder")
+    out = dec[-1]
+    diff = (out - x).astype(np.float64)
+    recon = float(np.mean(diff ** 2)) if cfg["loss_type"] == "mse" else float(np.mean(np.abs(diff)))
+    total = recon + float(w) * rq_loss
+    grads = {}
+    d_out = (2.0 * diff / diff.size if cfg["loss_type"] == "mse" else np.sign(diff) / diff.size).astype(f32)
+    g_xq = mlp_bwd(dec, "decoder", d_out, grads)
+    base = 2.0 / (B * e) / L * float(w)
+    for l in range(L):
+        cb = sd[f"rq.vq_layers.{l}.embedding.weight"]
+        dE = np.zeros_like(cb, dtype=np.float64)
+        np.add.at(dE, idxs[l], (cb[idxs[l]] - resid[l]).astype(np.float64))
+        grads[f"rq.vq_layers.{l}.embedding.weight"] = (base * dE).astype(f32)
+    cb0 = sd["rq.vq_layers.0.embedding.weight"]
+    dz = (g_xq + base * float(beta) * (z - cb0[idxs[0]])).astype(f32)
+    mlp_bwd(enc, "encoder", dz, grads)
+    return {"loss": total, "recon": recon, "rq": rq_loss}, np.stack(idxs, -1).astype(np.int64), grads
+
+
+def adamw_clip_update(sd, grads, state, lr, weight_decay, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8):
+    """clip_grad_norm_(…, max_norm) + torch.optim.AdamW.step() (train.py:116-117) in numpy, in place on `sd`;
+    `state` = {"step": int, "m": {}, "v": {}}.  Returns the gradient norm before clipping."""
+    gn = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads.values())))
+    coef = min(1.0, max_norm / (gn + 1e-6)) if max_norm > 0 else 1.0
+    state["step"] += 1
+    t = state["step"]
+    b1, b2 = betas
+    for k, g in grads.items():
+        g = g.astype(np.float64) * coef
+        m = state["m"].get(k, np.zeros_like(g))
+        v = state["v"].get(k, np.zeros_like(g))
+        m = m + (g - m) * (1 - b1)
+        v = v * b2 + g * g * (1 - b2)
+        state["m"][k], state["v"][k] = m, v
+        p = sd[k].astype(np.float64) * (1 - lr * weight_decay)
+        p -= (lr / (1 - b1 ** t)) * (m / (np.sqrt(v) / np.sqrt(1 - b2 ** t) + eps))
+        sd[k] = p.astype(np.float32)
+    return gn

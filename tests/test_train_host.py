@@ -64,3 +64,40 @@ def test_emb_dataset_npy_and_shards(tmp_path):
     assert ds[3].dtype == torch.float32 and torch.equal(ds[3], torch.from_numpy(x[3].astype(np.float32)))
     parts = [ds.shard(r, 4) for r in range(4)]
     assert np.array_equal(np.concatenate(parts), x.astype(np.float32)) and parts[0].dtype == np.float32
+
+
+@pytest.mark.parametrize("name", ["sk_mse", "argmin_l1", "c1_shape"])
+def test_oracle_training_step_matches_reference_golden(oracle, name):
+    """The numpy restatement of the training step (forward, autograd algebra of the straight-through quantizer, clip +
+    AdamW, warmup schedule) reproduces the unmodified reference loop recorded in train_steps.npz."""
+    from ai_education_generative_recommendation_b200.trainer import warmup_lambda
+    g = np.load(os.path.join(GOLD, "train_steps.npz"))
+    cfg = json.loads(str(g["cases"]))[name]
+    x, sd = train_case_state(cfg)
+    init = {k: v.copy() for k, v in sd.items()}
+    lam = warmup_lambda("linear", cfg["warmup_steps"], cfg["max_steps"])
+    state = {"step": 0, "m": {}, "v": {}}
+    names = [str(s) for s in g[f"{name}/names"]]
+    for step in range(cfg["steps"]):
+        losses, idx, grads = oracle.train_step_grads(x, sd, cfg)
+        assert np.array_equal(idx, g[f"{name}/codes"][step].astype(np.int64)), step
+        for key in ("loss", "recon", "rq"):
+            assert abs(losses[key] - g[f"{name}/{key}"][step]) <= 1e-4 * abs(g[f"{name}/{key}"][step]), (key, step)
+        if step == 0:
+            for i, n in enumerate(names):
+                if f"{name}/grad0/{n}" in g:
+                    ref = g[f"{name}/grad0/{n}"]
+                    assert np.abs(grads[n] - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-30), n
+                else:
+                    ref = g[f"{name}/grad0_norms"][i]
+                    assert abs(np.linalg.norm(grads[n].astype(np.float64)) - ref) <= 1e-4 * max(ref, 1e-12), n
+        gn = oracle.adamw_clip_update(sd, grads, state, cfg["lr"] * lam(step), cfg["weight_decay"])
+        assert abs(gn - g[f"{name}/gnorm"][step]) <= (1e-4 if step <= 1 else 2e-3) * g[f"{name}/gnorm"][step]
+    for i, n in enumerate(names):
+        if f"{name}/final/{n}" in g:
+            ref = g[f"{name}/final/{n}"].astype(np.float64)
+            upd = np.linalg.norm(ref - init[n])
+            assert np.linalg.norm(sd[n] - ref) <= 2e-3 * max(upd, 1e-12), n
+        else:
+            ref = g[f"{name}/delta_norms"][i]
+            assert abs(np.linalg.norm(sd[n].astype(np.float64) - init[n]) - ref) <= 2e-3 * max(ref, 1e-12), n
