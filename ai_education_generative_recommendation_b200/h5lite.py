@@ -7,11 +7,15 @@ and `RQ-VAE/vision_data.py:17-22` reads `f['item_embs'][:]` and `f['meta'][()]`.
 image, so `EmbDataset` falls back to this module when h5py is missing.  It implements exactly what those files use, from
 the HDF5 File Format Specification (version 0/1 superblock, version 1 object headers with continuation blocks, old-style
 groups: version 1 B-tree + local heap + symbol nodes, dataspace v1/v2, fixed-point / floating-point / string datatypes,
-layout v3 compact / contiguous / chunked with a version 1 chunk B-tree, filter pipeline v1/v2 with deflate and shuffle).
+layout v1/v2/v3 compact / contiguous / chunked with a version 1 chunk B-tree, filter pipeline v1/v2 with deflate and
+shuffle).
 Anything else raises `H5LiteError` naming the feature, so the caller knows to use h5py.
 
 Validation status: written from the specification and tested against files produced by `tests/h5_writer.py` (an
-independent writer for the same subset); NOT yet checked against a file written by libhdf5 — there is none in the image.
+independent writer for the same subset), and against the one libhdf5-written file this image holds (scipy's MATLAB v7.3
+test fixture `testhdf5_7.4_GLNX86.mat`: 512-byte user block, version 0 superblock, old-style root group, version 1 object
+header, IEEE float64, contiguous layout v2 — `tests/test_h5lite.py::test_reads_a_libhdf5_written_file`).  A libhdf5-written
+chunked + deflate file has not been seen here: that part rests on the specification and the independent writer.
 """
 from __future__ import annotations
 
@@ -128,11 +132,31 @@ class _Dataset:
 
     def read(self) -> np.ndarray:
         b = self._one(0x0008, "data layout")
-        version, cls = b[0], b[1]
-        if version != 3:
-            raise H5LiteError(f"data layout message version {version} (files written with libver='latest' need h5py)")
+        version = b[0]
         O, Lz = self.f.off_size, self.f.len_size
         count = int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+        if version in (1, 2):
+            # libhdf5 <= 1.6 writers: [version, ndims, class, 5 reserved] [address unless compact] ndims x u32
+            # (for chunked storage ndims = rank + 1, the last entry being the element size) [compact: u32 size + data].
+            # Re-packed here into the version 3 body the code below reads.
+            nd, cls = b[1], b[2]
+            pos = 8
+            addr_b = b""
+            if cls != 0:
+                addr_b = b[pos:pos + O]
+                pos += O
+            dims_b = b[pos:pos + 4 * nd]
+            pos += 4 * nd
+            if cls == 0:
+                size = struct.unpack_from("<I", b, pos)[0]
+                b = bytes([3, 0]) + struct.pack("<H", size) + b[pos + 4:pos + 4 + size]
+            elif cls == 1:
+                b = bytes([3, 1]) + addr_b + (count * self.dtype.itemsize).to_bytes(Lz, "little")
+            else:
+                b = bytes([3, 2, nd]) + addr_b + dims_b
+        elif version != 3:
+            raise H5LiteError(f"data layout message version {version} (files written with libver='latest' need h5py)")
+        cls = b[1]
         if cls == 0:                                            # compact
             size = struct.unpack_from("<H", b, 2)[0]
             raw = b[4:4 + size]

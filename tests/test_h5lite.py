@@ -55,3 +55,23 @@ def test_unsupported_files_fail_loudly(tmp_path):
         h5lite.File(str(p))
     with pytest.raises(h5lite.H5LiteError, match="read-only"):
         h5lite.File(str(p), "w")
+
+
+def test_reads_a_libhdf5_written_file():
+    """The only file in the image that libhdf5 itself wrote: scipy's MATLAB v7.3 fixture (an HDF5 file behind a 512-byte
+    user block; MATLAB stores `testdouble = 0:pi/4:2*pi`).  Pins the superblock / group / object-header / datatype parse
+    against the real library rather than against tests/h5_writer.py."""
+    import importlib.util
+    import os
+    from ai_education_generative_recommendation_b200 import h5lite
+    spec = importlib.util.find_spec("scipy")
+    if spec is None:
+        pytest.skip("scipy is not installed")
+    path = os.path.join(os.path.dirname(spec.origin), "io", "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("scipy's MATLAB v7.3 fixture is not shipped with this scipy")
+    with h5lite.File(path) as f:
+        assert f.keys() == ["testdouble"]
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.float64
+        np.testing.assert_array_equal(d[:].ravel(), np.arange(9) * (np.pi / 4))
