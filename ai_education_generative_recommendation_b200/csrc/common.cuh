@@ -130,6 +130,9 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
 bool linear_tc2_supported(const Linear &l);
 int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
                const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
+// encode_tc3.cu (experimental, off unless RQB200_TC3=1 or debug flag 4096): same contract as the plain three-pass linear_tc2
+bool linear_tc3_enabled();
+int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out);
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_pair.cuh"
 
 namespace rqb {
 
@@ -48,69 +49,6 @@ template <int PASSES> struct T2Cfg {
 #endif
 constexpr int T2_PREFETCH = T2_PREFETCH_N;     // K slabs of X in flight per producer thread (registers)
 constexpr int T2_TMEM_COLS = 512;          // two 256-column accumulator buffers
-
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(rank)
-        : "memory");
-}
-// wait with cluster-scope acquire (barriers that receive remote arrivals)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
 
 // rows (may be NULL): gather — tile row i reads X[rows[i]] (tier-2 re-run of gated rows), Y stays compact.
 // n_dev (may be NULL): the row count lives on the device (written by the previous tier's gate), n is its upper bound.
@@ -397,6 +335,7 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
         return launch_tc2<3, true>(l, x, n, y, relu, rows, n_dev, s, tiled_out);
     }
     RQB_CHECK(n_dev == nullptr, "a device-side row count needs the gather variant");
+    if (passes == 3 && linear_tc3_enabled()) return linear_tc3(l, x, n, y, relu, s, tiled_out);
     return passes == 1 ? launch_tc2<1, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out)
                        : launch_tc2<3, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out);
 }

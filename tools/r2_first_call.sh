@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of round 2 (run as:  gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh').
+# Order: the regression gate first, then the experiments written blind at the end of round 1 (each under its own
+# timeout: an untested tcgen05 pipeline can hang), then the bench lines with and without them.
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r2_pytest_gpu.log
+# 1. does tcgen05.mma take A from tensor memory in the layouts linear_tc3_kernel assumes, and at what rate?
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I ai_education_generative_recommendation_b200/csrc \
+     tools/tmem_a_probe.cu -o tools/tmem_a_probe > gpurun_out/r2_tmem_a_probe.txt 2>&1
+timeout 60 tools/tmem_a_probe >> gpurun_out/r2_tmem_a_probe.txt 2>&1; echo "probe exit $?" >> gpurun_out/r2_tmem_a_probe.txt
+# 2. linear_tc3_kernel: bit-identical to linear_tc2_kernel?  faster?
+for cfg in c2_slice c5_slice; do
+    timeout 240 python tools/check_tc3.py $cfg > gpurun_out/r2_check_tc3_$cfg.txt 2>&1; echo "check_tc3 exit $?" >> gpurun_out/r2_check_tc3_$cfg.txt
+done
+# 3. bench lines: production kernels, then with linear_tc3_kernel in the step (only meaningful if step 2 said bit-identical)
+python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2_n1.json 2> gpurun_out/r2_bench_c2_n1.err
+RQB200_TC3=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_tc3.json 2> gpurun_out/r2_bench_c2_n1_tc3.err
+tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_check_tc3_c2_slice.txt

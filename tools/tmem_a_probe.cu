@@ -3,13 +3,16 @@
 //
 //   D[128 x 64] (fp32, TMEM) = A[128 x 64] (fp16) * B[64 x 64]^T (fp16, shared memory, K-major SWIZZLE_128B)
 //   TS form: A written to TMEM by its own row's thread with tcgen05.st (lane = row, one 32-bit column = two K elements)
+//   TS 16x256b: A written with the 16-lane fragment form (lane t: rows t/4 and t/4+8 of a 16-row block, columns 2(t%4),
+//            2(t%4)+1 of every 8-column group) — the mapping linear_tc3_kernel (csrc/encode_tc3.cu) relies on
 //   SS form: A staged in shared memory like B (what the kernels do today)
 // Both results are compared with a host reference; then each form is issued REPS times back to back for a rate.
 //
 // build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I ai_education_generative_recommendation_b200/csrc \
 //              tools/tmem_a_probe.cu -o tools/tmem_a_probe
 // run (GPU box):  timeout 60 tools/tmem_a_probe
-// STATUS: compiles (ptxas accepts the TS operand form); NOT yet run on a B200 — first thing to do in round 2.
+// STATUS: compiles (ptxas accepts the TS operand form and both store shapes); NOT yet run on a B200 — first thing to do
+// in round 2 (tools/r2_first_call.sh).
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -47,10 +50,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 16 lanes x 32 columns: v[4b + 0/1] = (row lane/4, columns 8b + 2(lane%4) + 0/1), v[4b + 2/3] = same columns of row lane/4 + 8
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // row r, 16-byte chunk c8 (8 fp16) of a K-major SWIZZLE_128B tile with 64 fp16 per row
 __device__ __forceinline__ int sw128_off(int r, int c8) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4); }
 
-// mode 0: TS (A from TMEM), mode 1: SS (A from shared memory); out[M][N] fp32; cycles[0] = clocks for REPS x 4 MMAs
+// mode 0: TS (A from TMEM, 32x32b stores), mode 1: SS (A from shared memory), mode 2: TS with 16x256b stores; out[M][N] fp32; cycles[0] = clocks for REPS x 4 MMAs
 __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, float *__restrict__ out,
                                                     long long *__restrict__ cycles, int mode) {
     extern __shared__ unsigned char smem_raw[];
@@ -81,6 +95,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t d_tmem = tmem_base;                       // columns 0..63: accumulator
     const uint32_t a_tmem = tmem_base + 64;                  // columns 64..95: A (64 fp16 per row = 32 columns)
+    {
+        // tensor memory keeps its contents between launches: poison the A block (fp16 NaNs) so that a store that lands in the
+        // wrong place cannot pass on the previous mode's data
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0x7E007E00u;
+        tmem_st32(a_tmem + ((uint32_t)(warp * 32) << 16), v);
+    }
     if (mode == 0) {
         // thread = row = TMEM lane; column j of the A block holds K elements 2j, 2j+1
         uint32_t v[32];
@@ -88,6 +110,23 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = src[j];
         tmem_st32(a_tmem + ((uint32_t)(warp * 32) << 16), v);
+    }
+    if (mode == 2) {
+        const int lane = tid & 31;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {                  // the warp's two 16-row blocks
+            const int r0 = warp * 32 + blk * 16 + (lane >> 2);
+            uint32_t v[16];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {                    // 8-column group b = K elements 16b .. 16b+15
+                const int k = 16 * b + 4 * (lane & 3);
+                const uint32_t *lo_row = reinterpret_cast<const uint32_t *>(A + r0 * K + k);
+                const uint32_t *hi_row = reinterpret_cast<const uint32_t *>(A + (r0 + 8) * K + k);
+                v[4 * b + 0] = lo_row[0]; v[4 * b + 1] = lo_row[1];
+                v[4 * b + 2] = hi_row[0]; v[4 * b + 3] = hi_row[1];
+            }
+            tmem_st_16x256b_x4(a_tmem + ((uint32_t)(warp * 32 + blk * 16) << 16), v);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -100,7 +139,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
 #pragma unroll
             for (int kk = 0; kk < K / 16; ++kk) {
                 const uint64_t db = umma_desc(smem_u32(sB) + kk * 32);
-                if (mode == 0) umma_f16_ts(d_tmem, a_tmem + kk * 8, db, idesc, kk != 0);
+                if (mode != 1) umma_f16_ts(d_tmem, a_tmem + kk * 8, db, idesc, kk != 0);
                 else umma_f16(d_tmem, umma_desc(smem_u32(sA) + kk * 32), db, idesc, kk != 0);
             }
         }
@@ -142,7 +181,7 @@ int main() {
     cudaMemcpy(dB, hB, N * K * sizeof(__half), cudaMemcpyHostToDevice);
     const int smem = 8192 + 16384 + 64 + 1024;
     int rc = 0;
-    for (int mode = 0; mode < 2; ++mode) {
+    for (int mode = 0; mode < 3; ++mode) {
         cudaMemset(dO, 0, M * N * sizeof(float));
         probe_kernel<<<1, 128, smem>>>(dA, dB, dO, dC, mode);
         cudaError_t e = cudaDeviceSynchronize();
@@ -153,7 +192,7 @@ int main() {
         int bad = 0;
         for (int i = 0; i < M * N; ++i) bad += got[i] != ref[i];
         printf("%s: %d of %d outputs differ from the host reference; %lld clocks for %d x %d MMAs (%.1f clk per 128x64x16 MMA)\n",
-               mode == 0 ? "A from TMEM  (TS)" : "A from shared (SS)", bad, M * N, cyc, REPS, K / 16, (double)cyc / (REPS * (K / 16)));
+               mode == 0 ? "A from TMEM  (TS, 32x32b stores) " : mode == 1 ? "A from shared (SS)               " : "A from TMEM  (TS, 16x256b stores)", bad, M * N, cyc, REPS, K / 16, (double)cyc / (REPS * (K / 16)));
         rc |= bad != 0;
     }
     return rc;
