@@ -133,6 +133,11 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
 // encode_tc3.cu (experimental, off unless RQB200_TC3=1 or debug flag 4096): same contract as the plain three-pass linear_tc2
 bool linear_tc3_enabled();
 int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out);
+// dedup_list.cu (experimental, off unless RQB200_DEDUP_LIST=1 or debug flag 8192): suffix column from a hash table with
+// per-code item lists instead of a sort; *done = 0 ⇒ the caller runs the sort path
+bool dedup_list_enabled();
+int suffix_dedup_list(rqb200_model *m, const int64_t *codes, int64_t n, int L, const int *K_host, int64_t *out,
+                      int64_t *n_distinct_host, int64_t *max_group_host, cudaStream_t s, int *done);
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);

@@ -12,7 +12,10 @@ timeout 60 tools/tmem_a_probe >> gpurun_out/r2_tmem_a_probe.txt 2>&1; echo "prob
 for cfg in c2_slice c5_slice; do
     timeout 240 python tools/check_tc3.py $cfg > gpurun_out/r2_check_tc3_$cfg.txt 2>&1; echo "check_tc3 exit $?" >> gpurun_out/r2_check_tc3_$cfg.txt
 done
+# 2b. sort-free suffix dedup: identical ids / statistics?  faster?
+timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.txt 2>&1; echo "check_dedup_list exit $?" >> gpurun_out/r2_check_dedup_list.txt
 # 3. bench lines: production kernels, then with linear_tc3_kernel in the step (only meaningful if step 2 said bit-identical)
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2_n1.json 2> gpurun_out/r2_bench_c2_n1.err
 RQB200_TC3=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_tc3.json 2> gpurun_out/r2_bench_c2_n1_tc3.err
-tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_check_tc3_c2_slice.txt
+RQB200_DEDUP_LIST=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_dedup_list.json 2> gpurun_out/r2_bench_c2_n1_dedup_list.err
+tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_check_tc3_c2_slice.txt gpurun_out/r2_check_dedup_list.txt
