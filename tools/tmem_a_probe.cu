@@ -160,6 +160,70 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
 }
 
+// Layout dump: every (thread, register) of a tcgen05.st.16x256b.x4 writes its own tag into a 32-column block, the block is
+// read back with the 32x32b load (lane = row, register j = column j).  tags[lane][col] = (thread << 8) | register.
+__global__ void __launch_bounds__(128) layout_kernel(uint32_t *__restrict__ tags) {
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(32u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = tmem_slot;
+    {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0xFFFFFFFFu;
+        tmem_st32(base + ((uint32_t)(warp * 32) << 16), v);
+    }
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+        uint32_t v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = ((uint32_t)lane << 8) | (uint32_t)r;
+        tmem_st_16x256b_x4(base + ((uint32_t)(warp * 32 + blk * 16) << 16), v);
+    }
+    {
+        uint32_t v[32];
+        tmem_ld32(base + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tags[tid * 32 + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(32u));
+}
+
+static int check_layout() {
+    uint32_t *d = nullptr, *h = (uint32_t *)malloc(128 * 32 * sizeof(uint32_t));
+    cudaMalloc(&d, 128 * 32 * sizeof(uint32_t));
+    layout_kernel<<<1, 128>>>(d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("layout dump: %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(h, d, 128 * 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    // assumed by linear_tc3_kernel: register 4b + 2h + p of thread t → lane 16*blk + t/4 + 8h (within the warp's 32), column 8b + 2(t%4) + p
+    int bad = 0;
+    for (int row = 0; row < 128; ++row)
+        for (int col = 0; col < 32; ++col) {
+            const int rl = row & 15, t = (rl & 7) * 4 + ((col & 7) >> 1), reg = 4 * (col >> 3) + 2 * (rl >> 3) + (col & 1);
+            bad += h[row * 32 + col] != (((uint32_t)t << 8) | (uint32_t)reg);
+        }
+    printf("tcgen05.st.16x256b.x4 layout: %d of 4096 cells differ from the mapping linear_tc3_kernel assumes\n", bad);
+    if (bad) {
+        printf("observed (thread:register) per column, rows 0..17 of warp 0:\n");
+        for (int row = 0; row < 18; ++row) {
+            printf("row %2d:", row);
+            for (int col = 0; col < 32; ++col) printf(" %2u:%-2u", (h[row * 32 + col] >> 8) & 0xFFFFFF, h[row * 32 + col] & 0xFF);
+            printf("\n");
+        }
+    }
+    cudaFree(d); free(h);
+    return bad != 0;
+}
+
 int main() {
     __half *hA = (__half *)malloc(M * K * sizeof(__half)), *hB = (__half *)malloc(N * K * sizeof(__half));
     float *ref = (float *)malloc(M * N * sizeof(float)), *got = (float *)malloc(M * N * sizeof(float));
@@ -195,5 +259,6 @@ int main() {
                mode == 0 ? "A from TMEM  (TS, 32x32b stores) " : mode == 1 ? "A from shared (SS)               " : "A from TMEM  (TS, 16x256b stores)", bad, M * N, cyc, REPS, K / 16, (double)cyc / (REPS * (K / 16)));
         rc |= bad != 0;
     }
+    rc |= check_layout();
     return rc;
 }
