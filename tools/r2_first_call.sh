@@ -18,4 +18,9 @@ timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.tx
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2_n1.json 2> gpurun_out/r2_bench_c2_n1.err
 RQB200_TC3=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_tc3.json 2> gpurun_out/r2_bench_c2_n1_tc3.err
 RQB200_DEDUP_LIST=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_dedup_list.json 2> gpurun_out/r2_bench_c2_n1_dedup_list.err
+# 4. one full ncu capture of the new first-layer kernel, only if it is correct (the run above exited 0 without ncu)
+if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
+    RQB200_TC3=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_tc3_kernel -c 1 \
+        -o gpurun_out/r2_ncu_full_linear_tc3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_tc3.log 2>&1
+fi
 tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_check_tc3_c2_slice.txt gpurun_out/r2_check_dedup_list.txt
