@@ -158,7 +158,10 @@ __device__ __forceinline__ void store_split_from_drain(const unsigned char *drai
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
-                  const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y, int tiled_out) {
+                  const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y, int tiled_out, int dbg) {
+    // dbg: ablation switches of tools/ablate_tc3.py (0 in production; same meaning as in linear_tc2_kernel) — bit0 no
+    // epilogue conversion / global stores (the accumulator is still drained), bit1 no MMA, bit2 no tensor-memory stores by
+    // the producers, bit3 no W bulk loads, bit4 no X loads
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *drain_all = smem + T3_STAGES * T3_STAGE;
@@ -209,6 +212,7 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             if (rank == 0) mbar_arrive(tmem_empty);
             else mbar_arrive_remote(tmem_empty, 0);
             __syncwarp();                                // the warp's rows are all in its drain buffer
+            if (dbg & 1) continue;
             if (tiled_out)
                 store_split_from_drain(drain, lane, bias, inv_scale, relu, reinterpret_cast<unsigned char *>(Y), pt * 2 + rank, warp * 32);
             else
@@ -236,7 +240,7 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                 for (int h = 0; h < 2; ++h) {
                     const int64_t row = row0 + 8 * h;
                     const int k = k0 + 16 * g;
-                    if (row < n && k < K) dst[2 * g + h] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k));
+                    if (row < n && k < K && !(dbg & 16)) dst[2 * g + h] = __ldg(reinterpret_cast<const float4 *>(X + row * (int64_t)K + k));
                     else dst[2 * g + h] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         };
@@ -254,9 +258,11 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             mbar_wait(&empty[stage], phase ^ 1);
             tc_fence_after();
             const uint32_t a_hi = tmem_base + a_lane + (uint32_t)(T3_A_COL0 + stage * T3_A_STAGE_COLS + 16 * khalf);
-            tmem_st_16x256b_x2(a_hi, hi);
-            tmem_st_16x256b_x2(a_hi + T3_A_COLS, lo);
-            tmem_st_wait();
+            if (!(dbg & 4)) {
+                tmem_st_16x256b_x2(a_hi, hi);
+                tmem_st_16x256b_x2(a_hi + T3_A_COLS, lo);
+                tmem_st_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[stage]);
@@ -295,6 +301,7 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                         const uint32_t w_lo = w_hi + T3_W_TILE;
                         const uint32_t a_hi = tmem_base + (uint32_t)(T3_A_COL0 + stage * T3_A_STAGE_COLS);
                         const uint32_t a_lo = a_hi + T3_A_COLS;
+                        if (!(dbg & 2))
 #pragma unroll
                         for (int kk = 0; kk < BK3 / 16; ++kk) {
                             const uint32_t ko = kk * 32;             // bytes along K in the SWIZZLE_128B W tile
@@ -330,8 +337,12 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             for (int64_t pt = pair0; pt < npt; pt += npairs) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&ready[stage], half_bytes);
-                    bulk_g2s(smem + stage * T3_STAGE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, half_bytes, &ready[stage]);
+                    if (dbg & 8) {
+                        mbar_arrive(&ready[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&ready[stage], half_bytes);
+                        bulk_g2s(smem + stage * T3_STAGE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, half_bytes, &ready[stage]);
+                    }
                     if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -373,7 +384,7 @@ int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
     count_launch();
     linear_tc3_kernel<<<(unsigned)(pairs * 2), T3_THREADS, T3_SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
                                                                         ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y,
-                                                                        tiled_out ? 1 : 0);
+                                                                        tiled_out ? 1 : 0, tc_debug_flags() & 31);
     RQB_LAUNCH_CHECK();
     return 0;
 }

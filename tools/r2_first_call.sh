@@ -12,6 +12,9 @@ timeout 60 tools/tmem_a_probe >> gpurun_out/r2_tmem_a_probe.txt 2>&1; echo "prob
 for cfg in c2_slice c5_slice; do
     timeout 240 python tools/check_tc3.py $cfg > gpurun_out/r2_check_tc3_$cfg.txt 2>&1; echo "check_tc3 exit $?" >> gpurun_out/r2_check_tc3_$cfg.txt
 done
+if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
+    timeout 300 python tools/ablate_tc3.py > gpurun_out/r2_ablation_linear_tc3.txt 2>&1
+fi
 # 2b. sort-free suffix dedup: identical ids / statistics?  faster?
 timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.txt 2>&1; echo "check_dedup_list exit $?" >> gpurun_out/r2_check_dedup_list.txt
 # 3. bench lines: production kernels, then with linear_tc3_kernel in the step (only meaningful if step 2 said bit-identical)
