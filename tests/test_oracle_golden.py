@@ -114,3 +114,17 @@ def test_kblock_rule(oracle):
     assert oracle.mkl_kblocks(256) == [256]
     assert oracle.mkl_kblocks(1024) == [384, 384, 256]
     assert oracle.mkl_kblocks(400) == [200, 200]
+
+
+def test_oracle_sinkhorn_real_collision_groups(oracle):
+    """300 real collision groups of the C2 catalogue re-encoded by the reference's own Sinkhorn branch
+    (oracle/make_golden_sk_groups.py): rows with exact and last-bit ties in Q, where only the reference's sequence of fp64
+    divisions gives the reference's arg-max."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sinkhorn_groups_c2.npz"))
+    off, cb = g["offsets"], g["codebook"]
+    eps, iters = float(g["eps"]), int(g["iters"])
+    for a, b in zip(off[:-1], off[1:]):
+        r = np.ascontiguousarray(g["residual"][a:b])
+        d = oracle.quantize(r, [cb], want_xq=False, dist_level=0, threads=1)[3]
+        assert np.array_equal(oracle.sinkhorn_assign(d, eps, iters), g["idx"][a:b].astype(np.int64)), int(a)
