@@ -58,7 +58,11 @@ constexpr int T3_A_COL0 = N3;              // first tensor-memory column of the 
 constexpr int T3_A_COLS = BK3 / 2;         // 32 columns = 64 fp16 per row (hi or lo)
 constexpr int T3_A_STAGE_COLS = 2 * T3_A_COLS;
 static_assert(T3_A_COL0 + T3_STAGES * T3_A_STAGE_COLS <= T3_TMEM_COLS, "A ring does not fit in tensor memory");
-constexpr int T3_PREFETCH = 2;             // K slabs of X in flight per producer thread (registers)
+#ifndef T3_PREFETCH_N
+#define T3_PREFETCH_N 2
+#endif
+constexpr int T3_PREFETCH = T3_PREFETCH_N; // K slabs of X in flight per producer thread (registers); -DT3_PREFETCH_N=3 for an
+                                           // A/B build loaded through RQB200_LIB (tools/r2_first_call.sh)
 constexpr int T3_NF4 = 4;                  // float4 per producer thread per slab: 2 rows x 2 K groups
 
 // D[tmem] (+)= A[tmem] * B[smem desc]^T, issued for the CTA pair

@@ -14,6 +14,10 @@ for cfg in c2_slice c5_slice; do
 done
 if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
     timeout 300 python tools/ablate_tc3.py > gpurun_out/r2_ablation_linear_tc3.txt 2>&1
+    # A/B: three K slabs of X in flight per producer thread instead of two
+    bash tools/build_variant.sh p3 encode_tc3.cu -DT3_PREFETCH_N=3 > gpurun_out/r2_build_p3.log 2>&1 && \
+        RQB200_LIB=$PWD/ai_education_generative_recommendation_b200/librqvae_b200_p3.so timeout 240 python tools/check_tc3.py c2_slice \
+        > gpurun_out/r2_check_tc3_c2_slice_p3.txt 2>&1
 fi
 # 2b. sort-free suffix dedup: identical ids / statistics?  faster?
 timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.txt 2>&1; echo "check_dedup_list exit $?" >> gpurun_out/r2_check_dedup_list.txt
