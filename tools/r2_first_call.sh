@@ -8,6 +8,9 @@ python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo "p
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I ai_education_generative_recommendation_b200/csrc \
      tools/tmem_a_probe.cu -o tools/tmem_a_probe > gpurun_out/r2_tmem_a_probe.txt 2>&1
 timeout 60 tools/tmem_a_probe >> gpurun_out/r2_tmem_a_probe.txt 2>&1; echo "probe exit $?" >> gpurun_out/r2_tmem_a_probe.txt
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I ai_education_generative_recommendation_b200/csrc \
+     tools/tmem_a_probe2.cu -o tools/tmem_a_probe2 > gpurun_out/r2_tmem_a_probe2.txt 2>&1
+timeout 60 tools/tmem_a_probe2 >> gpurun_out/r2_tmem_a_probe2.txt 2>&1; echo "probe2 exit $?" >> gpurun_out/r2_tmem_a_probe2.txt
 # 2. linear_tc3_kernel: bit-identical to linear_tc2_kernel?  faster?
 for cfg in c2_slice c5_slice; do
     timeout 240 python tools/check_tc3.py $cfg > gpurun_out/r2_check_tc3_$cfg.txt 2>&1; echo "check_tc3 exit $?" >> gpurun_out/r2_check_tc3_$cfg.txt
@@ -30,4 +33,4 @@ if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
     RQB200_TC3=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_tc3_kernel -c 1 \
         -o gpurun_out/r2_ncu_full_linear_tc3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_tc3.log 2>&1
 fi
-tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_check_tc3_c2_slice.txt gpurun_out/r2_check_dedup_list.txt
+tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_tmem_a_probe2.txt gpurun_out/r2_check_tc3_c2_slice.txt gpurun_out/r2_check_dedup_list.txt
