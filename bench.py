@@ -311,12 +311,15 @@ def main():
         k_ms = prof_ms[slot] / max(prof_cnt[slot], 1)
         alg_bytes = 4.0 * in_dim * n
         alg_flops = 2.0 * in_dim * first_out * n
-        kname = ("linear_tc2_kernel (encoder layer 1: tcgen05 cta_group::2, split-fp16, 3 MMA passes)" if slot == 4
+        tc3 = os.environ.get("RQB200_TC3", "0")[:1] == "1"      # experimental first-layer kernel (csrc/encode_tc3.cu)
+        l1_kernel = "linear_tc3_kernel" if tc3 else "linear_tc2_kernel"
+        kname = ((l1_kernel + " (encoder layer 1: tcgen05 cta_group::2, split-fp16, 3 MMA passes"
+                  + (", A operand in tensor memory)" if tc3 else ")")) if slot == 4
                  else "linear_exact_kernel<128,128,8,8> (encoder layer 1, fp32 FMA chains)")
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("linear_tc2_kernel" if slot == 4 else "linear_exact_kernel")
+        if os.path.exists(tpath):           # dram bytes per launch from the committed ncu --set full capture (null if not captured)
+            traffic = json.load(open(tpath)).get(l1_kernel if slot == 4 else "linear_exact_kernel")
         gbs = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         tfl = alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         hbm_peak = float(peaks["hbm_gbs"])
@@ -333,7 +336,7 @@ def main():
         stages = []
         if slot == 4:           # per-stage view of the fast route (algorithmic work only, per item)
             stages = [
-                _st("encoder layer 1 (linear_tc2_kernel)", "hbm", stage["tc_linear0"], 4.0 * in_dim * n, hbm_peak, "GB/s",
+                _st(f"encoder layer 1 ({l1_kernel})", "hbm", stage["tc_linear0"], 4.0 * in_dim * n, hbm_peak, "GB/s",
                     "reads X once: 4*in_dim B"),
                 _st("encoder layers 2+3 fused (mlp23_tc_kernel)", "hbm", stage["tc_linear_rest"],
                     (4.0 * first_out + 4.0 * e_dim) * n, hbm_peak, "GB/s", "reads H1 (4 B per feature as fp16 hi+lo), writes z"),
