@@ -42,7 +42,14 @@ constexpr int TM3 = 128;                   // rows per CTA (256 per pair)
 constexpr int BK3 = 64;
 constexpr int N3 = 256;                    // output features of the pair tile
 constexpr int NH3 = N3 / 2;                // W rows staged per CTA
-constexpr int T3_EPI = 4, T3_CONV = 16;
+#ifndef T3_EPI_WARPS
+#define T3_EPI_WARPS 4
+#endif
+// Epilogue warps: 4 (one per tensor-memory lane quarter, all 256 columns) or 8 (two per quarter, 128 columns each; A/B build
+// -DT3_EPI_WARPS=8: 832 threads leave 72 registers per thread).  The producers follow, so their warp id % 4 stays pw % 4.
+constexpr int T3_EPI = T3_EPI_WARPS, T3_CONV = 16;
+static_assert(T3_EPI == 4 || T3_EPI == 8, "4 or 8 epilogue warps");
+constexpr int T3_EPI_COLS = 256 / (T3_EPI / 4);          // accumulator columns per epilogue warp
 constexpr int T3_THREADS = (T3_EPI + T3_CONV + 2) * 32;
 constexpr int T3_MMA_WARP = T3_EPI + T3_CONV;
 constexpr int T3_W_TILE = NH3 * BK3 * 2;   // 16 KB (hi or lo, this CTA's half of the features)
@@ -51,7 +58,7 @@ constexpr int T3_STAGES = 3;
 constexpr int T3_DRAIN_ROW = N3 * 4;       // bytes per accumulator row in the drain buffer (no padding: 16-byte chunks
                                            // are XOR-swizzled with the row number instead)
 constexpr int T3_DRAIN_WARP = 32 * T3_DRAIN_ROW;      // 32 KB per epilogue warp (its 32 rows)
-constexpr int T3_SMEM = T3_STAGES * T3_STAGE + T3_EPI * T3_DRAIN_WARP + 256 + 1024;
+constexpr int T3_SMEM = T3_STAGES * T3_STAGE + 4 * T3_DRAIN_WARP + 256 + 1024;
 static_assert(T3_SMEM <= 227 * 1024, "linear_tc3_kernel: shared memory over the per-CTA limit");
 constexpr int T3_TMEM_COLS = 512;
 constexpr int T3_A_COL0 = N3;              // first tensor-memory column of the A ring
@@ -90,10 +97,10 @@ __device__ __forceinline__ unsigned char *drain_at(unsigned char *drain, int r, 
     return drain + r * T3_DRAIN_ROW + ((chunk ^ (r & 7)) << 4);
 }
 
-// Accumulator rows of this warp (tensor-memory lanes 32w .. 32w+31) → its drain buffer; lane = row.
-__device__ __forceinline__ void drain_accumulator(uint32_t taddr, unsigned char *drain, int lane) {
+// Accumulator rows of this warp's lane quarter, columns c0 .. c0 + T3_EPI_COLS - 1 → the quarter's drain buffer; lane = row.
+__device__ __forceinline__ void drain_accumulator(uint32_t taddr, unsigned char *drain, int lane, int c0) {
 #pragma unroll 1
-    for (int c = 0; c < N3; c += 32) {
+    for (int c = c0; c < c0 + T3_EPI_COLS; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
 #pragma unroll
@@ -104,10 +111,11 @@ __device__ __forceinline__ void drain_accumulator(uint32_t taddr, unsigned char 
 
 // Second half of epilogue_rows (tc_common.cuh) reading the drained accumulator: fp32 rows, 128 contiguous bytes per row.
 __device__ __forceinline__ void store_rows_from_drain(const unsigned char *drain, int lane, const float *__restrict__ bias,
-                                                      float inv_scale, int relu, float *__restrict__ Y, int64_t row0, int64_t n) {
+                                                      float inv_scale, int relu, float *__restrict__ Y, int64_t row0, int64_t n,
+                                                      int c0) {
     const int sub = lane >> 3, q = lane & 7;
 #pragma unroll 1
-    for (int c = 0; c < N3; c += 32) {
+    for (int c = c0; c < c0 + T3_EPI_COLS; c += 32) {
         const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + c) + q);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -128,10 +136,10 @@ __device__ __forceinline__ void store_rows_from_drain(const unsigned char *drain
 // Second half of epilogue_rows_split (tc_common.cuh): the activation as split-fp16 UMMA tiles for mlp23_tc_kernel.
 __device__ __forceinline__ void store_split_from_drain(const unsigned char *drain, int lane, const float *__restrict__ bias,
                                                        float inv_scale, int relu, unsigned char *__restrict__ tiled, int64_t tile,
-                                                       int row_in_tile0) {
+                                                       int row_in_tile0, int c0) {
     const int rsub = lane >> 2, ch = lane & 3;
 #pragma unroll 1
-    for (int c = 0; c < N3; c += 32) {
+    for (int c = c0; c < c0 + T3_EPI_COLS; c += 32) {
         const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * ch));
         const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + c + 8 * ch + 4));
         const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
@@ -169,7 +177,7 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *drain_all = smem + T3_STAGES * T3_STAGE;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(drain_all + T3_EPI * T3_DRAIN_WARP);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(drain_all + 4 * T3_DRAIN_WARP);
     uint64_t *ready = bars;                              // [STAGES] 16 producer warps + the W bulk copy (tx) of this CTA
     uint64_t *peer_ready = bars + T3_STAGES;             // [STAGES] (used in the leader)
     uint64_t *empty = bars + 2 * T3_STAGES;              // [STAGES] commit multicast: W stage and A ring stage are free
@@ -206,21 +214,23 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
 
     if (warp < T3_EPI) {
         // ===================== epilogue (each CTA drains its own 128 rows) =====================
-        unsigned char *drain = drain_all + warp * T3_DRAIN_WARP;
+        const int quarter = warp & 3, c0 = (warp >> 2) * T3_EPI_COLS;      // lane quarter, first accumulator column
+        unsigned char *drain = drain_all + quarter * T3_DRAIN_WARP;      // (two warps of a quarter use disjoint columns of it)
         int64_t it = 0;
         for (int64_t pt = pair0; pt < npt; pt += npairs, ++it) {
             mbar_wait(tmem_full, (uint32_t)(it & 1));
             tc_fence_after();
-            drain_accumulator(tmem_base + ((uint32_t)(warp * 32) << 16), drain, lane);
+            drain_accumulator(tmem_base + ((uint32_t)(quarter * 32) << 16), drain, lane, c0);
             tc_fence_before();
             if (rank == 0) mbar_arrive(tmem_empty);
             else mbar_arrive_remote(tmem_empty, 0);
             __syncwarp();                                // the warp's rows are all in its drain buffer
             if (dbg & 1) continue;
             if (tiled_out)
-                store_split_from_drain(drain, lane, bias, inv_scale, relu, reinterpret_cast<unsigned char *>(Y), pt * 2 + rank, warp * 32);
+                store_split_from_drain(drain, lane, bias, inv_scale, relu, reinterpret_cast<unsigned char *>(Y), pt * 2 + rank,
+                                       quarter * 32, c0);
             else
-                store_rows_from_drain(drain, lane, bias, inv_scale, relu, Y, pt * (2 * TM3) + rank * TM3 + warp * 32, n);
+                store_rows_from_drain(drain, lane, bias, inv_scale, relu, Y, pt * (2 * TM3) + rank * TM3 + quarter * 32, n, c0);
             __syncwarp();                                // before the next tile overwrites the buffer
         }
     } else if (warp < T3_EPI + T3_CONV) {

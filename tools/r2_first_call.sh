@@ -21,6 +21,10 @@ if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
     bash tools/build_variant.sh p3 encode_tc3.cu -DT3_PREFETCH_N=3 > gpurun_out/r2_build_p3.log 2>&1 && \
         RQB200_LIB=$PWD/ai_education_generative_recommendation_b200/librqvae_b200_p3.so timeout 240 python tools/check_tc3.py c2_slice \
         > gpurun_out/r2_check_tc3_c2_slice_p3.txt 2>&1
+    # A/B: eight epilogue warps (two per tensor-memory lane quarter) instead of four
+    bash tools/build_variant.sh e8 encode_tc3.cu -DT3_EPI_WARPS=8 > gpurun_out/r2_build_e8.log 2>&1 && \
+        RQB200_LIB=$PWD/ai_education_generative_recommendation_b200/librqvae_b200_e8.so timeout 240 python tools/check_tc3.py c2_slice \
+        > gpurun_out/r2_check_tc3_c2_slice_e8.txt 2>&1
 fi
 # 2b. sort-free suffix dedup: identical ids / statistics?  faster?
 timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.txt 2>&1; echo "check_dedup_list exit $?" >> gpurun_out/r2_check_dedup_list.txt
