@@ -132,7 +132,7 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
                const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
 // encode_tc3.cu (experimental, off unless RQB200_TC3=1 or debug flag 4096): same contract as the plain three-pass linear_tc2
 bool linear_tc3_enabled();
-int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out);
+int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out, int passes = 3);
 // dedup_list.cu (experimental, off unless RQB200_DEDUP_LIST=1 or debug flag 8192): suffix column from a hash table with
 // per-code item lists instead of a sort; *done = 0 ⇒ the caller runs the sort path
 bool dedup_list_enabled();

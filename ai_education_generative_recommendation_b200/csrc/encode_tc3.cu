@@ -27,6 +27,10 @@
 //     block and 4 consecutive K elements per 16-wide K group, so one LDG.128 feeds one fragment pair (hi, lo) and the
 //     four lanes of a row read 64 contiguous bytes.
 //
+// PASSES = 1 (hi halves only, six stages of half the size) is the screening-tier instantiation: with shared memory out of the
+// way a one-pass first layer may become HBM-bound, which is what would make the screening tier of the fast route pay
+// (DESIGN.md §4 "Screening tier": the one-pass linear_tc2_kernel was not faster because it was not tensor-bound).
+//
 // Pair protocol: as in encode_tc2.cu (ready / peer_ready / empty per stage, tmem_full / tmem_empty per accumulator).
 #include <cuda_fp16.h>
 
@@ -53,18 +57,25 @@ constexpr int T3_EPI_COLS = 256 / (T3_EPI / 4);          // accumulator columns 
 constexpr int T3_THREADS = (T3_EPI + T3_CONV + 2) * 32;
 constexpr int T3_MMA_WARP = T3_EPI + T3_CONV;
 constexpr int T3_W_TILE = NH3 * BK3 * 2;   // 16 KB (hi or lo, this CTA's half of the features)
-constexpr int T3_STAGE = 2 * T3_W_TILE;    // shared memory per stage: W hi | W lo
-constexpr int T3_STAGES = 3;
+constexpr int T3_RING_BYTES = 6 * T3_W_TILE;             // shared memory of the W ring (96 KB), whatever the stage size
 constexpr int T3_DRAIN_ROW = N3 * 4;       // bytes per accumulator row in the drain buffer (no padding: 16-byte chunks
                                            // are XOR-swizzled with the row number instead)
 constexpr int T3_DRAIN_WARP = 32 * T3_DRAIN_ROW;      // 32 KB per epilogue warp (its 32 rows)
-constexpr int T3_SMEM = T3_STAGES * T3_STAGE + 4 * T3_DRAIN_WARP + 256 + 1024;
+constexpr int T3_SMEM = T3_RING_BYTES + 4 * T3_DRAIN_WARP + 256 + 1024;
 static_assert(T3_SMEM <= 227 * 1024, "linear_tc3_kernel: shared memory over the per-CTA limit");
 constexpr int T3_TMEM_COLS = 512;
 constexpr int T3_A_COL0 = N3;              // first tensor-memory column of the A ring
 constexpr int T3_A_COLS = BK3 / 2;         // 32 columns = 64 fp16 per row (hi or lo)
-constexpr int T3_A_STAGE_COLS = 2 * T3_A_COLS;
-static_assert(T3_A_COL0 + T3_STAGES * T3_A_STAGE_COLS <= T3_TMEM_COLS, "A ring does not fit in tensor memory");
+// PASSES = 3: split-fp16 (hi + lo) operands, three MMAs per K step, three stages of [W hi | W lo] / [A hi | A lo];
+// PASSES = 1: hi halves only (screening tier of the fast route), six stages of half the size
+template <int PASSES> struct T3Cfg {
+    static constexpr int NSPLIT = PASSES == 1 ? 1 : 2;
+    static constexpr int STAGE = NSPLIT * T3_W_TILE;                 // shared memory per stage
+    static constexpr int STAGES = T3_RING_BYTES / STAGE;             // 3 / 6
+    static constexpr int A_STAGE_COLS = NSPLIT * T3_A_COLS;          // tensor-memory columns per stage of the A ring
+    static_assert(T3_A_COL0 + STAGES * A_STAGE_COLS <= T3_TMEM_COLS, "A ring does not fit in tensor memory");
+    static_assert(4 * STAGES * 8 + 16 + 4 <= 256, "barrier block");
+};
 #ifndef T3_PREFETCH_N
 #define T3_PREFETCH_N 2
 #endif
@@ -168,15 +179,17 @@ __device__ __forceinline__ void store_split_from_drain(const unsigned char *drai
     }
 }
 
+template <int PASSES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T3_THREADS, 1)
 linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned char *__restrict__ Wp2,
                   const float *__restrict__ bias, float inv_scale, int relu, float *__restrict__ Y, int tiled_out, int dbg) {
     // dbg: ablation switches of tools/ablate_tc3.py (0 in production; same meaning as in linear_tc2_kernel) — bit0 no
     // epilogue conversion / global stores (the accumulator is still drained), bit1 no MMA, bit2 no tensor-memory stores by
     // the producers, bit3 no W bulk loads, bit4 no X loads
+    constexpr int T3_STAGE = T3Cfg<PASSES>::STAGE, T3_STAGES = T3Cfg<PASSES>::STAGES, T3_A_STAGE_COLS = T3Cfg<PASSES>::A_STAGE_COLS;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *drain_all = smem + T3_STAGES * T3_STAGE;
+    unsigned char *drain_all = smem + T3_RING_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(drain_all + 4 * T3_DRAIN_WARP);
     uint64_t *ready = bars;                              // [STAGES] 16 producer warps + the W bulk copy (tx) of this CTA
     uint64_t *peer_ready = bars + T3_STAGES;             // [STAGES] (used in the leader)
@@ -264,17 +277,26 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                split2(src[2 * g].x, src[2 * g].y, hi[4 * g + 0], lo[4 * g + 0]);             // row r_lo,     k .. k+1
-                split2(src[2 * g].z, src[2 * g].w, hi[4 * g + 1], lo[4 * g + 1]);             // row r_lo,     k+2 .. k+3
-                split2(src[2 * g + 1].x, src[2 * g + 1].y, hi[4 * g + 2], lo[4 * g + 2]);     // row r_lo + 8, k .. k+1
-                split2(src[2 * g + 1].z, src[2 * g + 1].w, hi[4 * g + 3], lo[4 * g + 3]);     // row r_lo + 8, k+2 .. k+3
+                if (PASSES == 1) {                  // hi halves only: plain round-to-nearest fp16 pairs (as linear_tc2_kernel<1>)
+                    const __half2 p0 = __floats2half2_rn(src[2 * g].x, src[2 * g].y), p1 = __floats2half2_rn(src[2 * g].z, src[2 * g].w);
+                    const __half2 p2 = __floats2half2_rn(src[2 * g + 1].x, src[2 * g + 1].y),
+                                  p3 = __floats2half2_rn(src[2 * g + 1].z, src[2 * g + 1].w);
+                    hi[4 * g + 0] = *reinterpret_cast<const uint32_t *>(&p0); hi[4 * g + 1] = *reinterpret_cast<const uint32_t *>(&p1);
+                    hi[4 * g + 2] = *reinterpret_cast<const uint32_t *>(&p2); hi[4 * g + 3] = *reinterpret_cast<const uint32_t *>(&p3);
+                    lo[4 * g + 0] = lo[4 * g + 1] = lo[4 * g + 2] = lo[4 * g + 3] = 0u;
+                } else {
+                    split2(src[2 * g].x, src[2 * g].y, hi[4 * g + 0], lo[4 * g + 0]);             // row r_lo,     k .. k+1
+                    split2(src[2 * g].z, src[2 * g].w, hi[4 * g + 1], lo[4 * g + 1]);             // row r_lo,     k+2 .. k+3
+                    split2(src[2 * g + 1].x, src[2 * g + 1].y, hi[4 * g + 2], lo[4 * g + 2]);     // row r_lo + 8, k .. k+1
+                    split2(src[2 * g + 1].z, src[2 * g + 1].w, hi[4 * g + 3], lo[4 * g + 3]);     // row r_lo + 8, k+2 .. k+3
+                }
             }
             mbar_wait(&empty[stage], phase ^ 1);
             tc_fence_after();
             const uint32_t a_hi = tmem_base + a_lane + (uint32_t)(T3_A_COL0 + stage * T3_A_STAGE_COLS + 16 * khalf);
             if (!(dbg & 4)) {
                 tmem_st_16x256b_x2(a_hi, hi);
-                tmem_st_16x256b_x2(a_hi + T3_A_COLS, lo);
+                if (PASSES != 1) tmem_st_16x256b_x2(a_hi + T3_A_COLS, lo);
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -320,9 +342,13 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
                         for (int kk = 0; kk < BK3 / 16; ++kk) {
                             const uint32_t ko = kk * 32;             // bytes along K in the SWIZZLE_128B W tile
                             const uint32_t ac = kk * 8;              // tensor-memory columns along K (two fp16 each)
-                            umma_f16_2cta_ts(d_tmem, a_lo + ac, umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
-                            umma_f16_2cta_ts(d_tmem, a_hi + ac, umma_desc(w_lo + ko), idesc, 1);
-                            umma_f16_2cta_ts(d_tmem, a_hi + ac, umma_desc(w_hi + ko), idesc, 1);
+                            if (PASSES == 1) {
+                                umma_f16_2cta_ts(d_tmem, a_hi + ac, umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                            } else {
+                                umma_f16_2cta_ts(d_tmem, a_lo + ac, umma_desc(w_hi + ko), idesc, (slab | kk) != 0);
+                                umma_f16_2cta_ts(d_tmem, a_hi + ac, umma_desc(w_lo + ko), idesc, 1);
+                                umma_f16_2cta_ts(d_tmem, a_hi + ac, umma_desc(w_hi + ko), idesc, 1);
+                            }
                         }
                         umma_commit_2cta(&empty[stage]);
                         if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
@@ -348,14 +374,15 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
             int stage = 0;
             uint32_t phase = 0;
             constexpr uint32_t half_bytes = 2 * T3_W_TILE;              // hi | lo of this CTA's 128 features (packed image)
+            constexpr uint32_t copy_bytes = T3Cfg<PASSES>::NSPLIT * T3_W_TILE;   // one pass needs the hi tile only
             for (int64_t pt = pair0; pt < npt; pt += npairs) {
                 for (int slab = 0; slab < KS; ++slab) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (dbg & 8) {
                         mbar_arrive(&ready[stage]);
                     } else {
-                        mbar_arrive_expect_tx(&ready[stage], half_bytes);
-                        bulk_g2s(smem + stage * T3_STAGE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, half_bytes, &ready[stage]);
+                        mbar_arrive_expect_tx(&ready[stage], copy_bytes);
+                        bulk_g2s(smem + stage * T3_STAGE, Wp2 + ((size_t)slab * 2 + rank) * half_bytes, copy_bytes, &ready[stage]);
                     }
                     if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -374,7 +401,7 @@ linear_tc3_kernel(const float *__restrict__ X, int64_t n, int K, const unsigned 
 
 }  // namespace
 
-// RQB200_TC3=1 routes the plain (no gather, three passes) first-layer launch of linear_tc2 through this kernel.
+// RQB200_TC3=1 routes the plain (no gather) first-layer launches of linear_tc2 through this kernel.
 // rqb200_debug_tc_flags(4096) does the same inside a running process (tools/check_tc3.py compares the two kernels).
 int tc_debug_flags();     // encode_tc.cu
 
@@ -384,23 +411,29 @@ bool linear_tc3_enabled() {
     return v == 1 || (tc_debug_flags() & 4096) != 0;
 }
 
-// Same contract as linear_tc2(l, x, n, y, relu, s, 3, nullptr, nullptr, tiled_out); l.W_tc2 (the packed W image of
-// encode_tc2.cu) must exist.
-int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out) {
-    if (n == 0) return 0;
-    RQB_CHECK(l.W_tc2 != nullptr && l.out == N3 && l.in % 8 == 0, "linear_tc3: layer not packed for the CTA-pair kernel");
-    static rqb::DeviceOnce attr_once;
+template <int PASSES>
+static int launch_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out) {
+    auto kern = linear_tc3_kernel<PASSES>;
+    static rqb::DeviceOnce attr_once;          // per template instantiation
     if (attr_once.first()) {
-        RQB_CUDA(cudaFuncSetAttribute(linear_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
+        RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM));
     }
     const int64_t npt = (n + 2 * TM3 - 1) / (2 * TM3);
     const int64_t pairs = npt < kNumSMs / 2 ? npt : kNumSMs / 2;
     count_launch();
-    linear_tc3_kernel<<<(unsigned)(pairs * 2), T3_THREADS, T3_SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
-                                                                        ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y,
-                                                                        tiled_out ? 1 : 0, tc_debug_flags() & 31);
+    kern<<<(unsigned)(pairs * 2), T3_THREADS, T3_SMEM, s>>>(x, n, l.in, (const unsigned char *)l.W_tc2, l.b,
+                                                           ldexpf(1.0f, -l.tc_scale_exp), relu ? 1 : 0, y, tiled_out ? 1 : 0,
+                                                           tc_debug_flags() & 31);
     RQB_LAUNCH_CHECK();
     return 0;
+}
+
+// Same contract as linear_tc2(l, x, n, y, relu, s, passes, nullptr, nullptr, tiled_out) with passes = 3 (split-fp16) or 1
+// (hi halves only: the screening tier); l.W_tc2 (the packed W image of encode_tc2.cu) must exist.
+int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out, int passes) {
+    if (n == 0) return 0;
+    RQB_CHECK(l.W_tc2 != nullptr && l.out == N3 && l.in % 8 == 0, "linear_tc3: layer not packed for the CTA-pair kernel");
+    return passes == 1 ? launch_tc3<1>(l, x, n, y, relu, s, tiled_out) : launch_tc3<3>(l, x, n, y, relu, s, tiled_out);
 }
 
 }  // namespace rqb
