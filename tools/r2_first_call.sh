@@ -28,6 +28,17 @@ if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
 fi
 # 2b. sort-free suffix dedup: identical ids / statistics?  faster?
 timeout 300 python tools/check_dedup_list.py > gpurun_out/r2_check_dedup_list.txt 2>&1; echo "check_dedup_list exit $?" >> gpurun_out/r2_check_dedup_list.txt
+# 2c. quantizer A/B: hi half of the residual tile from tensor memory, three row groups (quantize_tc.cu, -DQTC_A_HI_TMEM=1)
+bash tools/build_variant.sh qts quantize_tc.cu -DQTC_A_HI_TMEM=1 -DQTC_GROUPS=3 > gpurun_out/r2_build_qts.log 2>&1 && {
+    QLIB=$PWD/ai_education_generative_recommendation_b200/librqvae_b200_qts.so
+    RQB200_LIB=$QLIB timeout 600 python -m pytest tests/test_gpu_tensorcore.py -x -q > gpurun_out/r2_qts_pytest.log 2>&1; echo "qts pytest exit $?" >> gpurun_out/r2_qts_pytest.log
+    if grep -q "qts pytest exit 0" gpurun_out/r2_qts_pytest.log; then
+        for cfg in c2 c5; do
+            timeout 600 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_${cfg}_n1_base.json 2>/dev/null
+            RQB200_LIB=$QLIB timeout 600 python bench.py --config $cfg --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_${cfg}_n1_qts.json 2>/dev/null
+        done
+    fi
+}
 # 3. bench lines: production kernels, then with linear_tc3_kernel in the step (only meaningful if step 2 said bit-identical)
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_c2_n1.json 2> gpurun_out/r2_bench_c2_n1.err
 RQB200_TC3=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2_n1_tc3.json 2> gpurun_out/r2_bench_c2_n1_tc3.err
