@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of round 2 (run as:  gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh').
+# First GPU call of round 2 (run as:  gpurun --timeout 2700 -- 'bash tools/r2_first_call.sh').
 # Order: the regression gate first, then the experiments written blind at the end of round 1 (each under its own
 # timeout: an untested tcgen05 pipeline can hang), then the bench lines with and without them.
 mkdir -p gpurun_out
