@@ -48,4 +48,11 @@ if grep -q "check_tc3 exit 0" gpurun_out/r2_check_tc3_c2_slice.txt; then
     RQB200_TC3=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_tc3_kernel -c 1 \
         -o gpurun_out/r2_ncu_full_linear_tc3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_tc3.log 2>&1
 fi
+# 5. ncu evidence still missing from round 1: achieved DRAM throughput of the dedup kernels (sort path and list path)
+timeout 600 ncu --set full --clock-control none -k "regex:radix_scatter_kernel|seg_rank_kernel|pack_keys_kernel" -c 5 \
+    -o gpurun_out/r2_ncu_full_dedup_sort python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_dedup_sort.log 2>&1
+if grep -q "check_dedup_list exit 0" gpurun_out/r2_check_dedup_list.txt; then
+    RQB200_DEDUP_LIST=1 timeout 600 ncu --set full --clock-control none -k "regex:list_insert_kernel|list_rank_kernel" -c 2 \
+        -o gpurun_out/r2_ncu_full_dedup_list python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ncu_dedup_list.log 2>&1
+fi
 tail -n 3 gpurun_out/r2_pytest_gpu.log gpurun_out/r2_tmem_a_probe.txt gpurun_out/r2_tmem_a_probe2.txt gpurun_out/r2_check_tc3_c2_slice.txt gpurun_out/r2_check_dedup_list.txt
