@@ -4,7 +4,12 @@
 // measurements; it compiles for sm_100a but has NOT run on a B200 yet.  tools/check_tc3.py is the first thing to run:
 // the kernel issues the same MMAs in the same order as linear_tc2_kernel, so its output must be BIT-IDENTICAL.
 // The tensor-memory layout it relies on (tcgen05.st.16x256b fragments forming the MMA's A operand) is checked on its own
-// by tools/tmem_a_probe.cu (mode "TS 16x256b").
+// by tools/tmem_a_probe.cu (mode "TS 16x256b") and tools/tmem_a_probe2.cu (CTA pair).  Both layout assumptions were cross-read
+// against the CuTe headers vendored in the image (read only, nothing included): the (thread, register) → (lane, column) map of
+// tcgen05.st.16x256b.x2 is Copy_Traits<SM100_TMEM_LOAD_16dp256b2x>::DstLayout (cute/atom/copy_traits_sm100.hpp: thread =
+// (t%4 → 64-bit chunk of the row, t/4 → row), values = (64 bits, row + 8, next 8-column block)), and the A operand of a 2-SM
+// M = 256 TS-form MMA is tmem_frg_2sm's "4x1" atom (cute/atom/mma_traits_sm100.hpp: lane = row of the CTA's 128, 16-bit
+// elements packed along K in consecutive columns, same lane addresses as the accumulator).
 //
 // Same math as linear_tc2_kernel (encode_tc2.cu; replaces reference RQ-VAE/models/layers.py:23 for the 768→256 / 1024→256
 // layer): split-fp16 operands, three MMAs per 16-wide K step into one fp32 accumulator, cta_group::2 (256-row pair tile,
