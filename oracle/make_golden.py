@@ -246,10 +246,24 @@ def kblock_probe():
         print(f"  linear {K:5d}->{N:4d} blocks {O.mkl_kblocks(K, N)}: bit-equal {np.array_equal(ref.view(np.int32), mine.view(np.int32))}")
 
 
+def make_odd_slices():
+    """Shapes outside the BASELINE configs (the reference accepts any): ragged codebook sizes with L = 5 (the maximum,
+    infer.py:90) and e_dim 16 behind a narrow MLP; one level with e_dim 48; a five-Linear encoder."""
+    make_slice("odd1_slice", dict(in_dim=104, num_emb_list=[100, 7, 300, 5, 64], e_dim=16, layers=[48, 24], kmeans_iters=5,
+                                  sk_epsilons=[0.0] * 5, sk_iters=50), 2048, 100_000, 2048)
+    make_slice("odd2_slice", dict(in_dim=768, num_emb_list=[256], e_dim=48, layers=[256, 128], kmeans_iters=5,
+                                  sk_epsilons=[0.0], sk_iters=50), 2048, 100_000, 2048)
+    make_slice("odd3_slice", dict(in_dim=512, num_emb_list=[64, 64], e_dim=16, layers=[512, 256, 128, 64], kmeans_iters=5,
+                                  sk_epsilons=[0.0, 0.0], sk_iters=50), 2048, 100_000, 2048)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     print("torch", torch.__version__, "| sklearn", __import__("sklearn").__version__, "| numpy", np.__version__)
+    if sys.argv[1:] == ["odd"]:          # only the odd-shape slices (added later; the other fixtures stay as committed)
+        make_odd_slices()
+        sys.exit(0)
     kblock_probe()
     make_csv_fixture()
     make_sinkhorn_cases()
@@ -262,3 +276,4 @@ if __name__ == "__main__":
     make_slice("c1_slice", dict(in_dim=768, num_emb_list=[8, 8, 8], e_dim=32, layers=[256, 128], kmeans_iters=50,
                                 sk_epsilons=[0.01, 0.01, 0.01], sk_iters=50), 707, 707, 64)
     make_infer_c1()
+    make_odd_slices()

@@ -7,7 +7,7 @@ from conftest import load_golden, synth_weights
 from ai_education_generative_recommendation_b200 import synth
 
 
-@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice"])
+@pytest.mark.parametrize("name", ["c1_slice", "c2_slice", "c3_slice", "c5_slice", "odd1_slice", "odd2_slice", "odd3_slice"])
 def test_oracle_matches_reference_slices(oracle, name):
     g, cfg, cbs = load_golden(name)
     _, (ew, eb), (dw, db) = synth_weights(cfg)
