@@ -88,3 +88,18 @@ def test_list_dedup_twin_matches_oracle(oracle, n, L, K, seed):
     assert np.array_equal(got, ref)
     uniq, counts = np.unique(codes, axis=0, return_counts=True)
     assert distinct == len(uniq) and max_group == counts.max()
+
+
+from hypothesis import given, settings, strategies as st       # noqa: E402
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.integers(1, 80), st.integers(1, 5), st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+def test_list_dedup_twin_property(n, L, K, seed):
+    """Any codes, any completion order of the inserts: suffix[i] = #{j < i : codes[j] == codes[i]} (infer.py:152-163)."""
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, K, size=(n, L), dtype=np.int64)
+    got, distinct, max_group = list_dedup_twin(codes, [K] * L, rng.permutation(n))
+    want = np.array([sum(1 for j in range(i) if (codes[j] == codes[i]).all()) for i in range(n)], dtype=np.int64)
+    assert np.array_equal(got[:, :L], codes) and np.array_equal(got[:, L], want)
+    assert distinct == len({tuple(r) for r in codes.tolist()})
