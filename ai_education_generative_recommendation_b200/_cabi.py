@@ -50,6 +50,7 @@ _PROTOS = {
     "rqb200_get_indices": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P, POINTER(c_int64), _P]),
     "rqb200_forward": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P]),
     "rqb200_sinkhorn_regroup": (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, c_double, c_int, _P, _P]),
+    "rqb200_reencode_groups": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "rqb200_sinkhorn_group_cap": (c_int, [c_void_p]),
     "rqb200_sinkhorn_regroup_large": (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int64, _P, c_double, c_int, _P, _P]),
     "rqb200_sinkhorn": (c_int, [_P, c_int64, c_int, c_double, c_int, _P]),

@@ -209,7 +209,7 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
         if (m->ccs_tc[l]) cudaFree(m->ccs_tc[l]);
     }
     Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1],
-                       &m->rescue, &m->rescue_act[0], &m->rescue_act[1]};
+                       &m->rescue, &m->rescue_act[0], &m->rescue_act[1], &m->groupws};
     for (Workspace *w : ws)
         if (w->ptr) cudaFree(w->ptr);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);

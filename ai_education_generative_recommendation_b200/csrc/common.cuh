@@ -16,7 +16,7 @@ void count_launch();          // bumps the process-wide kernel-launch counter (r
 
 // per-kernel device timing (cudaEvent pairs on the launching stream), enabled by rqb200_profile_enable
 enum ProfSlot { PROF_LINEAR0 = 0, PROF_LINEAR_REST = 1, PROF_QUANTIZE = 2, PROF_DEDUP = 3, PROF_TC_ENCODER = 4,
-                PROF_SINKHORN = 5, PROF_TC_REST = 6, PROF_TIER2 = 7, PROF_RESCUE = 8, PROF_NSLOTS = 12 };
+                PROF_SINKHORN = 5, PROF_TC_REST = 6, PROF_TIER2 = 7, PROF_RESCUE = 8, PROF_REENCODE = 9, PROF_NSLOTS = 12 };
 void prof_begin(int slot, cudaStream_t s);
 void prof_end(int slot, cudaStream_t s);
 struct ProfScope {
@@ -49,6 +49,11 @@ struct ProfScope {
     } while (0)
 
 #define RQB_LAUNCH_CHECK() RQB_CUDA(cudaGetLastError())
+
+// Which [M,K]·[K,N] products the reference's CPU GEMM computes in its small-batch ("lane16") order — see small_batch.cu.
+__host__ __device__ __forceinline__ bool small_batch_lane16(long long M, int K) {
+    return M >= 2 && M <= 15 && 24 * M <= (long long)K;
+}
 
 struct Linear {
     int in = 0, out = 0;
@@ -107,6 +112,7 @@ struct rqb200_model {
     rqb::Workspace misc;            // rescue lists, counters
     rqb::Workspace hostpipe[2];     // device chunks of the host-buffer pipeline
     rqb::Workspace rescue;          // exact latent of gated rows
+    rqb::Workspace groupws;         // per-group re-encode: group sizes + activations of the colliding items
     rqb::Workspace rescue_act[2];
     float gate_gamma = 3.0517578125e-05f;   // 2^-15: bound on |z~ - z| / |z| of the tensor-core encoder
     int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced
@@ -126,6 +132,11 @@ int ws_reserve(Workspace &w, size_t bytes);
 // linear_exact.cu
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
                  bool relu, cudaStream_t s);
+// small_batch.cu: the reference's order for batches of 2..15 rows (and per-row batch sizes for the group re-encode)
+int linear_small(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu, cudaStream_t s);
+int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, const int *msize, int m_uniform, int64_t n,
+                   int levels_run, int64_t *codes, float *residual_out, float *xq_out, double *sumsq_out, float *dist_out,
+                   int dist_level, cudaStream_t s);
 // encode_tc2.cu
 bool linear_tc2_supported(const Linear &l);
 int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,

@@ -633,6 +633,9 @@ int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *co
                    float *margin_out, cudaStream_t s) {
     if (n == 0) return 0;
     ProfScope ps(PROF_QUANTIZE, s);
+    // a batch of 2..15 rows with 24·n <= e: matmul(latent, E.t()) runs in the reference's small-batch order (small_batch.cu)
+    if (small_batch_lane16(n, m->e) && !last_residual && !margin_out)
+        return quantize_small(m, z, rows_out, nullptr, (int)n, n, m->L, codes, nullptr, xq, sumsq, nullptr, 0, s);
     // few rows and codes only: share a row between QS lanes so that the whole GPU works on it (measured: faster than a row
     // per thread up to about half a wave of 128-row CTAs, slower beyond — the row-per-thread kernel then fills the SMs)
     if (n <= (int64_t)kNumSMs * QT / 2 && !xq && !sumsq && !last_residual && !margin_out && m->e <= 64) {
@@ -658,6 +661,8 @@ int distances_exact(const rqb200_model *m, int level, const float *r, int64_t n,
                     cudaStream_t s) {
     if (n == 0) return 0;
     RQB_CHECK(level >= 0 && level < m->L, "level %d out of range", level);
+    if (small_batch_lane16(n, m->e))
+        return quantize_small(m, r, nullptr, nullptr, (int)n, n, 1, nullptr, nullptr, nullptr, nullptr, d, level, s);
     RQB_DISPATCH_E(m->e, return (launch_quant<E, 1>(m, r, n, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                    nullptr, d, level, s)));
     return 0;

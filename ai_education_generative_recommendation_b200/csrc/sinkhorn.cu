@@ -57,6 +57,30 @@ __device__ float sumsq_aten_rt(const float *v, int e) {
     return fin;
 }
 
+// <r, c> in the order the reference's matmul(latent, E.t()) (vq.py:73) uses for a batch of B rows: one sequential fma
+// chain, or for 2 <= B <= 15 with 24·B <= e the small-batch order of small_batch.cu (16 interleaved chains, folded)
+__device__ __forceinline__ float dot_for_batch(const float *r, const float *c, int e, int B) {
+    if (!small_batch_lane16(B, e)) {
+        float acc = 0.0f;
+        for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
+        return acc;
+    }
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
+    int k = 0;
+    for (; k + 16 <= e; k += 16)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+        if (k + q < e) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
+    float s4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s4[q] = __fadd_rn(__fadd_rn(__fadd_rn(acc[q], acc[q + 4]), acc[q + 8]), acc[q + 12]);
+    return __fadd_rn(__fadd_rn(s4[0], s4[1]), __fadd_rn(s4[2], s4[3]));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -197,8 +221,7 @@ sinkhorn_regroup_kernel(const float *__restrict__ residual, const int64_t *__res
         const int i = p / K, j = p % K;
         const float *r = s_r + (size_t)i * e;
         const float *c = cb + (size_t)j * e;
-        float acc = 0.0f;
-        for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
+        const float acc = dot_for_batch(r, c, e, B);
         Q[p] = (double)__fsub_rn(__fadd_rn(s_xx[i], cc[j]), __fmul_rn(2.0f, acc));
     }
     __syncthreads();
@@ -231,8 +254,7 @@ sinkhorn_regroup_large_kernel(const float *__restrict__ residual, const int64_t 
         const int i = (int)(p / K), j = (int)(p % K);
         const float *r = residual + gi[i] * e;
         const float *c = cb + (size_t)j * e;
-        float acc = 0.0f;
-        for (int k = 0; k < e; ++k) acc = __fmaf_rn(r[k], c[k], acc);
+        const float acc = dot_for_batch(r, c, e, B);
         Q[p] = (double)__fsub_rn(__fadd_rn(xx[i], cc[j]), __fmul_rn(2.0f, acc));
     }
     __syncthreads();

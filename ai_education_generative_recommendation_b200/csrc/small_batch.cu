@@ -1,0 +1,363 @@
+// small_batch.cu — the reference's arithmetic on SMALL batches, and the per-group re-encode built on it.
+//
+// The reference resolves collisions by calling `model.get_indices(data[collision_items], use_sk=True)` once per
+// collision group (reference RQ-VAE/infer.py:120-129 ≡ RQ-VAE/generate_code.py:115-124): the encoder
+// (RQ-VAE/models/layers.py:42-43) and every quantizer level (RQ-VAE/models/vq.py:71-75) run again on the 2 … few dozen
+// rows of the group alone.  Its CPU GEMM (MKL sgemm behind ATen addmm / matmul) uses another kernel for such batches
+// than for the catalogue pass, with another summation order, so the latent of an item inside a small group differs in
+// the last bit from its latent in the catalogue pass — enough to flip a Sinkhorn arg-max between near-identical items.
+// Restated here (derived and verified bit for bit on the live reference stack by oracle/probe_sum_order.py):
+//
+//   an [M,K]·[K,N] product with 2 <= M <= 15 and 24·M <= K ("lane16"):
+//       16 fp32 lanes, lane l = sequential fma chain over k ≡ l (mod 16), k ascending;
+//       folded ((p0 + p1) + p2) + p3 with p_q = lanes 4q … 4q+3, then (s0 + s1) + (s2 + s3), bias added last;
+//   everything else: the catalogue order of linear_exact.cu / quantize.cu.
+//
+// Kernels: linear_small_kernel (one Linear over a row list whose rows carry their own batch size M),
+// quantize_small_kernel (levels with the arg-min rule; one warp per row), group_sizes_kernel.  SIMT fp32 by necessity
+// (bit parity with an fp32 fma chain); the volume is the colliding items only.
+#include "common.cuh"
+
+namespace rqb {
+
+namespace {
+
+constexpr int LS_THREADS = 128;
+constexpr int LS_ROWS = 4;
+
+// slot -> size of the group it belongs to (items are stored group by group, offsets[g] .. offsets[g+1])
+__global__ void group_sizes_kernel(const int64_t *__restrict__ offsets, int64_t n_groups, int64_t n_items,
+                                   int *__restrict__ msize) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    int64_t lo = 0, hi = n_groups;              // largest g with offsets[g] <= i
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int64_t sz = offsets[lo + 1] - offsets[lo];
+    msize[i] = sz > 2147483647 ? 2147483647 : (int)sz;
+}
+
+__device__ __forceinline__ float fold_lane16(const float (&acc)[16]) {
+    float s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        s[q] = __fadd_rn(__fadd_rn(__fadd_rn(acc[q], acc[q + 4]), acc[q + 8]), acc[q + 12]);
+    return __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3]));
+}
+
+// Y[slot, :] = act(X[row(slot), :] · Wᵀ + b) where every slot uses the order of ITS batch size (msize[slot], or m_uniform).
+// CTA = LS_ROWS consecutive slots (rows staged in shared memory), thread = output feature(s).
+__global__ void __launch_bounds__(LS_THREADS)
+linear_small_kernel(const float *__restrict__ X, const int64_t *__restrict__ rows, const int *__restrict__ msize,
+                    int m_uniform, int64_t n, const float *__restrict__ W, const float *__restrict__ bias,
+                    float *__restrict__ Y, int K, int N, int relu, int nblk, const int kb0, const int kb1, const int kb2,
+                    const int kb3, const int kb4, const int kb5, const int kb6, const int kb7) {
+    extern __shared__ __align__(16) float xs[];           // [LS_ROWS][K]
+    __shared__ int s_kind[LS_ROWS];
+    const int64_t slot0 = (int64_t)blockIdx.x * LS_ROWS;
+    const int nr = (int)((n - slot0) < LS_ROWS ? (n - slot0) : LS_ROWS);
+    for (int i = threadIdx.x; i < LS_ROWS * (K / 4); i += LS_THREADS) {
+        const int r = i / (K / 4), c = i % (K / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nr) {
+            const int64_t src = rows ? rows[slot0 + r] : slot0 + r;
+            v = *reinterpret_cast<const float4 *>(X + src * K + 4 * c);
+        }
+        *reinterpret_cast<float4 *>(xs + (size_t)r * K + 4 * c) = v;
+    }
+    if (threadIdx.x < LS_ROWS) {
+        const int r = threadIdx.x;
+        const int M = r < nr ? (msize ? msize[slot0 + r] : m_uniform) : 0;
+        s_kind[r] = r < nr ? (small_batch_lane16(M, K) ? 1 : 0) : -1;
+    }
+    __syncthreads();
+    bool any_lane = false, any_blk = false;
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r) { any_lane |= s_kind[r] == 1; any_blk |= s_kind[r] == 0; }
+    const int kb[8] = {kb0, kb1, kb2, kb3, kb4, kb5, kb6, kb7};
+
+    for (int j = threadIdx.x; j < N; j += LS_THREADS) {
+        const float *w = W + (size_t)j * K;
+        const float bj = bias ? bias[j] : 0.0f;
+        float out[LS_ROWS];
+        if (any_lane) {
+            float acc[LS_ROWS][16];
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+                for (int l = 0; l < 16; ++l) acc[r][l] = 0.0f;
+            int k = 0;
+            for (; k + 16 <= K; k += 16) {
+                float wv[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(w + k + 4 * q);
+                    wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+                }
+#pragma unroll
+                for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+                    for (int l = 0; l < 16; ++l) acc[r][l] = __fmaf_rn(xs[(size_t)r * K + k + l], wv[l], acc[r][l]);
+            }
+            // masked tail (K not a multiple of 16): lane l takes element k + l if it exists
+#pragma unroll
+            for (int l = 0; l < 16; ++l)
+                if (k + l < K) {
+#pragma unroll
+                    for (int r = 0; r < LS_ROWS; ++r) acc[r][l] = __fmaf_rn(xs[(size_t)r * K + k + l], w[k + l], acc[r][l]);
+                }
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r)
+                if (s_kind[r] == 1) out[r] = __fadd_rn(fold_lane16(acc[r]), bj);
+        }
+        if (any_blk) {
+            float o[LS_ROWS];
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r) o[r] = bj;
+            int k0 = 0;
+            for (int blk = 0; blk < nblk; ++blk) {
+                const int k1 = k0 + kb[blk];
+                float acc[LS_ROWS];
+#pragma unroll
+                for (int r = 0; r < LS_ROWS; ++r) acc[r] = 0.0f;
+                for (int k = k0; k < k1; k += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(w + k);
+                    const float wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < LS_ROWS; ++r) acc[r] = __fmaf_rn(xs[(size_t)r * K + k + q], wv[q], acc[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < LS_ROWS; ++r) o[r] = __fadd_rn(o[r], acc[r]);
+                k0 = k1;
+            }
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r)
+                if (s_kind[r] == 0) out[r] = o[r];
+        }
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r)
+            if (r < nr) {
+                float v = out[r];
+                if (relu) v = (v != v) ? v : (v > 0.0f ? v : 0.0f);
+                Y[(slot0 + r) * N + j] = v;
+            }
+    }
+}
+
+// torch.sum(v*v) for a runtime length (ATen order; twin of sinkhorn.cu's helper, kept local to this unit)
+__device__ float sumsq_aten_small(const float *v, int e) {
+    const int vec = e / 8, size_ilp = vec / 4;
+    float part[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[k][l] = 0.0f;
+    for (int i = 0; i < size_ilp; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const float x = v[i * 32 + k * 8 + l];
+                part[k][l] = __fadd_rn(part[k][l], __fmul_rn(x, x));
+            }
+    for (int i = size_ilp * 4; i < vec; ++i)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const float x = v[i * 8 + l];
+            part[0][l] = __fadd_rn(part[0][l], __fmul_rn(x, x));
+        }
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+#pragma unroll
+        for (int l = 0; l < 8; ++l) part[0][l] = __fadd_rn(part[0][l], part[k][l]);
+    float fin = 0.0f;
+    for (int k = vec * 8; k < e; ++k) fin = __fadd_rn(fin, __fmul_rn(v[k], v[k]));
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, part[0][l]);
+    return fin;
+}
+
+constexpr int QS_WARPS = 4;
+
+struct SmallQuantArgs {
+    const float *cb[RQB200_MAX_LEVELS];
+    const float *cc[RQB200_MAX_LEVELS];
+    int K[RQB200_MAX_LEVELS];
+    int L;
+};
+
+// ResidualVectorQuantizer.forward with the arg-min rule on levels [0, levels_run) for rows that carry their own batch
+// size (rq.py:39-56, vq.py:63-99).  One warp per slot; the row's residual lives in shared memory.
+//   codes[item(slot), l] for l < levels_run; residual_out[item(slot), :] = residual entering level `levels_run`
+//   (or, with levels_run == L, after the last level); xq_out[slot, :] (optional, levels_run == L);
+//   sumsq_out[l] += Σ (q - r)² (optional, fp64 atomics).
+__global__ void __launch_bounds__(QS_WARPS * 32)
+quantize_small_kernel(const float *__restrict__ z, const int64_t *__restrict__ items, const int *__restrict__ msize,
+                      int m_uniform, int64_t n, int e, SmallQuantArgs qa, int levels_run, int64_t *__restrict__ codes,
+                      float *__restrict__ residual_out, float *__restrict__ xq_out, double *__restrict__ sumsq_out,
+                      float *__restrict__ dist_out, int dist_level) {
+    extern __shared__ __align__(16) float sm[];      // [QS_WARPS][2][e]: residual, x_q
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t slot = (int64_t)blockIdx.x * QS_WARPS + wid;
+    if (slot >= n) return;
+    float *r = sm + (size_t)wid * 2 * e, *xq = r + e;
+    for (int k = lane; k < e; k += 32) { r[k] = z[slot * e + k]; xq[k] = 0.0f; }
+    __syncwarp();
+    const int64_t item = items ? items[slot] : slot;
+    const int M = msize ? msize[slot] : m_uniform;
+    const bool lane16 = small_batch_lane16(M, e);
+    for (int l0 = 0; l0 < levels_run; ++l0) {
+        const int l = dist_out ? dist_level : l0;      // dist_out: distances of ONE level for the rows as given (vq.py:71-73)
+        const int K = qa.K[l];
+        const float *cb = qa.cb[l], *cc = qa.cc[l];
+        const float xx = sumsq_aten_small(r, e);
+        int best = -1;
+        float bestd = 0.0f;
+        for (int j = lane; j < K; j += 32) {
+            const float *c = cb + (size_t)j * e;
+            float dot;
+            if (lane16) {
+                float acc[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
+                int k = 0;
+                for (; k + 16 <= e; k += 16)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (k + q < e) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
+                dot = fold_lane16(acc);
+            } else {
+                dot = 0.0f;
+                for (int k = 0; k < e; ++k) dot = __fmaf_rn(r[k], c[k], dot);
+            }
+            const float d = __fsub_rn(__fadd_rn(xx, cc[j]), __fmul_rn(2.0f, dot));
+            if (dist_out) dist_out[slot * K + j] = d;
+            // torch.argmin: NaN is the minimum, the first index wins
+            if (best < 0 || (!(bestd != bestd) && ((d != d) || d < bestd))) { best = j; bestd = d; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bestd, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, best, o);
+            if (oj >= 0) {
+                const bool onan = od != od, bnan = bestd != bestd;
+                const bool take = best < 0 || (onan && (!bnan || oj < best)) ||
+                                  (!onan && !bnan && (od < bestd || (od == bestd && oj < best)));
+                if (take) { bestd = od; best = oj; }
+            }
+        }
+        if (dist_out) return;
+        if (lane == 0) codes[item * qa.L + l] = best;
+        const float *q = cb + (size_t)best * e;
+        double loss = 0.0;
+        for (int k = lane; k < e; k += 32) {
+            const float diff = __fsub_rn(q[k], r[k]);
+            loss += (double)diff * (double)diff;
+            const float xres = __fadd_rn(r[k], diff);          // x + (x_q - x)   (vq.py:95)
+            r[k] = __fsub_rn(r[k], xres);                       // rq.py:47
+            xq[k] = (l == 0) ? __fadd_rn(0.0f, xres) : __fadd_rn(xq[k], xres);   // rq.py:48
+        }
+        if (sumsq_out) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+            if (lane == 0) atomicAdd(&sumsq_out[l], loss);
+        }
+        __syncwarp();
+    }
+    if (residual_out)
+        for (int k = lane; k < e; k += 32) residual_out[item * e + k] = r[k];
+    if (xq_out)
+        for (int k = lane; k < e; k += 32) xq_out[slot * e + k] = xq[k];
+}
+
+int launch_linear_small(const Linear &lin, const float *x, const int64_t *rows, const int *msize, int m_uniform,
+                        int64_t n, float *y, bool relu, cudaStream_t s) {
+    RQB_CHECK(lin.set, "linear layer not loaded");
+    RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
+    RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);
+    for (int i = 0; i < lin.nblk; ++i) RQB_CHECK(lin.kblocks[i] % 4 == 0, "K-block %d not a multiple of 4", lin.kblocks[i]);
+    const size_t smem = sizeof(float) * LS_ROWS * (size_t)lin.in;
+    RQB_CHECK(smem <= 200 * 1024, "in_features %d too large for the small-batch kernel", lin.in);
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first())
+        RQB_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int kb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < lin.nblk; ++i) kb[i] = lin.kblocks[i];
+    rqb::count_launch();
+    linear_small_kernel<<<(unsigned)((n + LS_ROWS - 1) / LS_ROWS), LS_THREADS, smem, s>>>(
+        x, rows, msize, m_uniform, n, lin.W, lin.b, y, lin.in, lin.out, relu ? 1 : 0, lin.nblk, kb[0], kb[1], kb[2], kb[3],
+        kb[4], kb[5], kb[6], kb[7]);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+// one uniform small batch (module-level get_indices / forward with 2..15 rows)
+int linear_small(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu, cudaStream_t s) {
+    return launch_linear_small(lin, x, rows, nullptr, (int)n, n, y, relu, s);
+}
+
+int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, const int *msize, int m_uniform, int64_t n,
+                   int levels_run, int64_t *codes, float *residual_out, float *xq_out, double *sumsq_out, float *dist_out,
+                   int dist_level, cudaStream_t s) {
+    if (n == 0) return 0;
+    SmallQuantArgs qa;
+    qa.L = m->L;
+    for (int l = 0; l < m->L; ++l) { qa.cb[l] = m->cb[l]; qa.cc[l] = m->cc[l]; qa.K[l] = m->K[l]; }
+    const size_t smem = sizeof(float) * QS_WARPS * 2 * (size_t)m->e;
+    RQB_CHECK(smem <= 48 * 1024, "e_dim %d too large for the small-batch quantizer", m->e);
+    rqb::count_launch();
+    quantize_small_kernel<<<(unsigned)((n + QS_WARPS - 1) / QS_WARPS), QS_WARPS * 32, smem, s>>>(
+        z, items, msize, m_uniform, n, m->e, qa, dist_out ? 1 : levels_run, codes, residual_out, xq_out, sumsq_out, dist_out,
+        dist_level);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rqb
+
+using namespace rqb;
+
+// infer.py:120-122 for ALL collision groups of one round, up to (not including) the last level:
+//   for every group g and every member i:  z = encoder(x_i) in the order of a batch of |g| rows,
+//   codes[i, 0..L-2] = arg-min codes of the first L-1 levels (distance product in the order of that batch size),
+//   residual[i, :]   = residual entering the last level.
+// The last level (Sinkhorn over the group's distance matrix) is rqb200_sinkhorn_regroup on `residual`.
+extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
+                                      const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
+                                      int64_t *codes_dev, float *residual_dev, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_CHECK(m != nullptr, "model is NULL");
+    if (n_groups == 0 || n_items == 0) return 0;
+    RQB_CHECK(x_dev && items_dev && offsets_dev && codes_dev && residual_dev, "NULL buffer");
+    for (int i = 0; i < m->n_layers; ++i) RQB_CHECK(m->enc[i].set, "encoder layer %d not loaded", i);
+    for (int l = 0; l < m->L; ++l) RQB_CHECK(m->cb_set[l], "codebook %d not loaded", l);
+    RQB_CUDA(cudaSetDevice(m->device));
+    int maxdim = m->e;
+    for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
+    const size_t act = sizeof(float) * (size_t)n_items * maxdim;
+    const size_t msz = ((sizeof(int) * (size_t)n_items + 255) / 256) * 256;
+    RQB_TRY(ws_reserve(m->groupws, msz + 2 * act));
+    int *msize = (int *)m->groupws.ptr;
+    float *buf[2] = {(float *)((char *)m->groupws.ptr + msz), (float *)((char *)m->groupws.ptr + msz + act)};
+    ProfScope ps(PROF_REENCODE, s);
+    rqb::count_launch();
+    group_sizes_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(offsets_dev, n_groups, n_items, msize);
+    RQB_LAUNCH_CHECK();
+    const float *cur = x_dev;
+    for (int i = 0; i < m->n_layers; ++i) {
+        const bool last = i == m->n_layers - 1;
+        float *dst = buf[i & 1];
+        RQB_TRY(launch_linear_small(m->enc[i], cur, (i == 0 && !x_is_gathered) ? items_dev : nullptr, msize, 0, n_items, dst,
+                                    !last, s));
+        cur = dst;
+    }
+    return quantize_small(m, cur, items_dev, msize, 0, n_items, m->L - 1, codes_dev, residual_dev, nullptr, nullptr, nullptr, 0, s);
+}

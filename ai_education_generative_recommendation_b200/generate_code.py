@@ -3,9 +3,9 @@
 Same three passes, all on the device:
   pass 1  every item → codes with use_sk=False                      (infer.py:93-103)
   pass 2  ≤30 rounds: items sharing a full code are re-encoded group by group with Sinkhorn on the
-          LAST level only (infer.py:109-130).  Levels < L-1 are a pure function of the item, so only
-          the last-level code of colliding items is recomputed — from the residual the quantizer
-          kernel saved.
+          LAST level only (infer.py:109-130).  As in the reference, the whole model runs again on each
+          group's rows ALONE — in the summation order the reference's CPU GEMM uses for a batch of that
+          size (csrc/small_batch.cu), which differs from the catalogue pass for groups of 2..15 rows.
   pass 3  suffix column: out[i, L] = #{j < i : codes[j] == codes[i]} (infer.py:152-163), np.save of the
           [N, L+1] int64 array (infer.py:174-177) and the `_mapping.json` side file (infer.py:180-184).
 The reference's per-item string building / dict grouping is replaced by integer sort kernels.
@@ -117,85 +117,75 @@ def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Ten
     return codes
 
 
-class _LazyResidual:
-    """Residual entering the LAST level, per item, for the Sinkhorn re-encode rounds — computed (exact route) only
-    for the items that ever land in a collision group, the first time they do.  It is a pure function of the item
-    (levels < L-1 never change), so it is cached."""
-
-    def __init__(self, model: RQVAE, data, n: int):
-        self.model, self.data, self.n = model, _as_rows(data), n
-        dev = model._device()
-        self.buf = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
-        self.have = torch.zeros((n,), dtype=torch.bool, device=dev)
-
-    def ensure(self, items: torch.Tensor, codes: torch.Tensor):
-        missing = items[~self.have[items]]
-        if missing.numel() == 0:
-            return
-        m, dev = self.model, self.model._device()
-        if self.data.is_cuda:
-            rows = self.data[missing].contiguous()
-        else:
-            rows = self.data[missing.cpu()].contiguous().to(dev)
-        k, Lv = rows.shape[0], len(m.num_emb_list)
-        lib = _cabi.lib()
-        z = torch.empty((k, m.e_dim), dtype=torch.float32, device=dev)
-        check(lib.rqb200_mlp_exact(m._handle, 0, ptr(rows), 0, k, ptr(z), stream_ptr(dev)))
-        sub_codes = torch.empty((k, Lv), dtype=torch.int64, device=dev)
-        res = torch.empty((k, m.e_dim), dtype=torch.float32, device=dev)
-        check(lib.rqb200_quantize(m._handle, ptr(z), k, ptr(sub_codes), 0, 0, 0, ptr(res), stream_ptr(dev)))
-        if Lv > 1 and not torch.equal(sub_codes[:, :Lv - 1], codes[missing, :Lv - 1]):
-            raise RuntimeError("tensor-core route and exact route disagree on a code (this is a bug: please report)")
-        self.buf[missing] = res
-        self.have[missing] = True
+@torch.no_grad()
+def reencode_round(model: RQVAE, codes: torch.Tensor, data, residual: Optional[torch.Tensor] = None,
+                   verbose_round: Optional[int] = None) -> int:
+    """ONE round of the loop at infer.py:116-129, in place on `codes`: every group of items sharing a full code goes
+    through `model.get_indices(data[group], use_sk=True)` — as in the reference the WHOLE model runs again on the group's
+    rows alone (encoder, arg-min levels, Sinkhorn on the last level), in the arithmetic the reference uses for a batch of
+    that size (csrc/small_batch.cu), and all L codes of the members are overwritten.  Groups of one round are disjoint
+    and are all found before anything is rewritten, so the round is a pure function of the codes it starts from.
+    Returns the number of groups (0: nothing to do)."""
+    lib = _cabi.lib()
+    dev = codes.device
+    data = _as_rows(data)
+    last = model.rq.vq_layers[-1]
+    if last.sk_epsilon is None or last.sk_epsilon <= 0:
+        return 0
+    model._sync()
+    items, offsets, max_group = collision_groups(model, codes)
+    n_groups = offsets.numel() - 1
+    if n_groups <= 0:
+        return 0
+    if verbose_round is not None:
+        print(f"Iteration {verbose_round}: Found {n_groups} collision groups")
+    if residual is None:
+        residual = torch.empty((codes.shape[0], model.e_dim), dtype=torch.float32, device=dev)
+    if data.is_cuda:
+        x, gathered = data, 0
+    else:
+        x, gathered = data[items.cpu()].contiguous().to(dev), 1
+    cap = lib.rqb200_sinkhorn_group_cap(model._handle)
+    check(lib.rqb200_reencode_groups(model._handle, ptr(x), gathered, ptr(items), ptr(offsets), n_groups, items.numel(),
+                                     ptr(codes), ptr(residual), stream_ptr(dev)))
+    check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
+                                      min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters), ptr(codes),
+                                      stream_ptr(dev)))
+    if max_group > cap:
+        _regroup_oversized(model, residual, items, offsets, cap, codes)
+    return n_groups
 
 
 @torch.no_grad()
-def resolve_rounds(model: RQVAE, codes: torch.Tensor, residual: torch.Tensor, lazy=None, max_rounds: int = 30,
-                   verbose: bool = False) -> Tuple[torch.Tensor, int]:
-    """Pass 2 (infer.py:109-130): ≤ max_rounds rounds, every group of items sharing a full code is re-encoded with
-    Sinkhorn on the LAST level from `residual[item]` (the residual entering that level).  Returns (codes, rounds)."""
-    lib = _cabi.lib()
-    dev = codes.device
+def resolve_rounds(model: RQVAE, codes: torch.Tensor, data, max_rounds: int = 30, verbose: bool = False
+                   ) -> Tuple[torch.Tensor, int]:
+    """Pass 2 (infer.py:109-130): ≤ max_rounds rounds of `reencode_round`, until no two items share a full code.
+    `codes` is updated in place.  `data`: the catalogue rows — a CUDA tensor (members gathered on the device) or a host
+    tensor / array (members gathered on the host and uploaded per round).  Returns (codes, rounds)."""
     # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
     for vq in model.rq.vq_layers[:-1]:
         vq.sk_epsilon = 0.0
     last = model.rq.vq_layers[-1]
     rounds = 0
     if last.sk_epsilon is not None and last.sk_epsilon > 0:
-        model._sync()
-        cap = lib.rqb200_sinkhorn_group_cap(model._handle)
+        residual = torch.empty((codes.shape[0], model.e_dim), dtype=torch.float32, device=codes.device)
         while rounds < max_rounds:
-            items, offsets, max_group = collision_groups(model, codes)
-            n_groups = offsets.numel() - 1
-            if n_groups <= 0:
+            if reencode_round(model, codes, data, residual, rounds if verbose else None) == 0:
                 break
-            if verbose:
-                print(f"Iteration {rounds}: Found {n_groups} collision groups")
-            if lazy is not None:
-                lazy.ensure(items, codes)
-            new_codes = codes.clone()      # a round reads the codes of the previous round only
-            check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
-                                              min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters),
-                                              ptr(new_codes), stream_ptr(dev)))
-            if max_group > cap:
-                _regroup_oversized(model, residual, items, offsets, cap, new_codes)
-            codes = new_codes
             rounds += 1
     return codes, rounds
 
 
 @torch.no_grad()
-def encode_codes_and_residual(model: RQVAE, data, chunk_rows: int = 262144) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Pass 1 on the exact route: (codes[N, L], residual entering the last level [N, e])."""
+def encode_codes_exact(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Tensor:
+    """Pass 1 on the exact route: codes[N, L]."""
     dev = model._device()
     z = encode_latents(model, data, chunk_rows)
     n, Lv = z.shape[0], len(model.num_emb_list)
     codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
-    residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
     model._sync()
-    check(_cabi.lib().rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, ptr(residual), stream_ptr(dev)))
-    return codes, residual
+    check(_cabi.lib().rqb200_quantize(model._handle, ptr(z), n, ptr(codes), 0, 0, 0, 0, stream_ptr(dev)))
+    return codes
 
 
 @torch.no_grad()
@@ -203,9 +193,8 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
                    fast: Optional[bool] = None) -> Tuple[torch.Tensor, dict]:
     """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats).
 
-    fast (default: whenever the model's shapes allow it): pass 1 runs on the tensor-core route and the last-level
-    residuals the re-encode rounds need are computed on the exact route only for the items that collide.  The result
-    is identical either way."""
+    fast (default: whenever the model's shapes allow it): pass 1 runs on the tensor-core route (every row certified by
+    the margin gate or recomputed by the exact kernels); the re-encode rounds always run on the exact kernels."""
     Lv = len(model.num_emb_list)
     if Lv > MAX_LEVELS_OF_REFERENCE_DRIVER:
         raise IndexError("list index out of range")        # what prefix[i] raises in the reference
@@ -214,23 +203,11 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
     was_training = model.training
     model.eval()
     try:
-        dev = model._device()
-        lib = _cabi.lib()
-        if fast:
-            codes = encode_codes_fast(model, data, chunk_rows)
-            n = codes.shape[0]
-            lazy = _LazyResidual(model, data, n)
-            residual = lazy.buf
-        else:
-            codes, residual = encode_codes_and_residual(model, data, chunk_rows)
-            n = codes.shape[0]
-            lazy = None
-        codes, rounds = resolve_rounds(model, codes, residual, lazy=lazy, max_rounds=max_rounds, verbose=verbose)
+        codes = encode_codes_fast(model, data, chunk_rows) if fast else encode_codes_exact(model, data, chunk_rows)
+        codes, rounds = resolve_rounds(model, codes, data, max_rounds=max_rounds, verbose=verbose)
         out, stats = suffix_dedup(model, codes)
         stats["rounds"] = rounds
         stats["pass1_route"] = "tensor-core" if fast else "exact"
-        if lazy is not None:
-            stats["items_needing_exact_residual"] = int(lazy.have.sum().item())
         return out, stats
     finally:
         if was_training:

@@ -144,6 +144,17 @@ int rqb200_forward(rqb200_model *m, const float *x_dev, int64_t n, float *out_de
 int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
                             const int64_t *offsets_dev, int64_t n_groups, int max_group,
                             double epsilon, int iters, int64_t *codes_dev, void *stream);
+/* The part of `model.get_indices(data[collision_items], use_sk=True)` (infer.py:120-122 ≡ generate_code.py:115-117)
+ * that precedes the last level, for ALL collision groups of one round in one call: the reference runs its encoder and
+ * its quantizer levels again on the rows of each group ALONE, and its CPU GEMM sums in another order for such small
+ * batches (2 <= rows <= 15 and 24·rows <= inner dimension; csrc/small_batch.cu) — so every member is re-encoded in the
+ * order of ITS group's size.  Writes codes[item, 0..L-2] and residual[item, :] (the residual entering the last
+ * level; [N,e], indexed by item like codes) for the members only; rqb200_sinkhorn_regroup on that residual finishes
+ * the round.  x_dev: the catalogue [N,in] (x_is_gathered = 0: row of member i is items[i]) or the members' rows in
+ * list order [n_items,in] (x_is_gathered = 1).  Nothing synchronises.                                            */
+int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
+                           const int64_t *offsets_dev, int64_t n_groups, int64_t n_items, int64_t *codes_dev,
+                           float *residual_dev, void *stream);
 /* Largest group (rows) rqb200_sinkhorn_regroup handles in shared memory for this model; larger
  * groups are skipped by it and must go through rqb200_distances + rqb200_sinkhorn_assign.   */
 int rqb200_sinkhorn_group_cap(rqb200_model *m);

@@ -51,6 +51,11 @@ def lib() -> ctypes.CDLL:
         L.rq_oracle_quantize.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, c_f, c_i, ctypes.c_int,
                                          c_l, c_f, c_d, c_f, ctypes.c_int, ctypes.c_int]
         L.rq_oracle_quantize.restype = ctypes.c_int
+        L.rq_oracle_quantize_ex.argtypes = L.rq_oracle_quantize.argtypes + [ctypes.c_int]
+        L.rq_oracle_quantize_ex.restype = ctypes.c_int
+        L.rq_oracle_linear_small.argtypes = [c_f, ctypes.c_int64, ctypes.c_int, c_f, c_f, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, c_f]
+        L.rq_oracle_linear_small.restype = ctypes.c_int
         L.rq_oracle_suffix.argtypes = [c_l, ctypes.c_int64, ctypes.c_int, c_l]
         L.rq_oracle_suffix.restype = ctypes.c_int
         _lib = L
@@ -102,6 +107,61 @@ def linear(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool,
     return y
 
 
+# Small batches.  The reference re-runs the whole model on every collision group (infer.py:120-122), i.e. with
+# 2 … a few dozen rows, and its CPU GEMM switches kernels there.  Measured on the live reference stack with
+# oracle/probe_sum_order.py (torch 2.11 + MKL, 1 and 8 threads give the same table): for M rows, K inputs
+#   M <= small_batch_limit(K)  → "lane16": 16 interleaved fma chains folded ((p0+p1)+p2)+p3, (s0+s1)+(s2+s3), bias last
+#   otherwise                  → the catalogue order (mkl_kblocks), except K = 1024 → 256 with 16 ≤ M < 176, where the
+#                                8-thread build container folds four 256-blocks pairwise (1 thread does not: that one
+#                                range is thread-count dependent in the reference itself).
+_SMALL_BATCH_LIMIT = {1024: 15, 768: 15, 512: 15, 256: 10, 128: 5, 64: 2, 32: 1, 16: 1}
+LANE16, PAIR4 = 1, 2
+
+
+def small_batch_limit(K: int) -> int:
+    """Largest M for which the reference's CPU GEMM with inner dimension K uses the lane16 order (probed values only)."""
+    if K not in _SMALL_BATCH_LIMIT:
+        raise KeyError(f"summation order of the reference for inner dimension {K} at small batch sizes has not been "
+                       f"probed (oracle/probe_sum_order.py)")
+    return _SMALL_BATCH_LIMIT[K]
+
+
+def small_batch_plan(M: int, K: int, N: int) -> int:
+    """0 = catalogue order, LANE16, PAIR4 — the order the reference uses for an [M,K]·[K,N] product."""
+    if M <= small_batch_limit(K):
+        return LANE16
+    if K == 1024 and N == 256 and 16 <= M < 176:
+        if M > 128:
+            raise KeyError("1024 -> 256 with 129..175 rows: a third, thread-count-dependent order of the reference's GEMM; not restated")
+        return PAIR4
+    return 0
+
+
+def linear_group(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool) -> np.ndarray:
+    """``nn.Linear`` (+ReLU) on ONE small batch, in the order the reference's CPU GEMM uses for that batch size."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    W = np.ascontiguousarray(W, dtype=np.float32)
+    n, k = x.shape
+    kind = small_batch_plan(n, k, W.shape[0])
+    if kind == 0:
+        return linear(x, W, b, relu, threads=1)
+    y = np.empty((n, W.shape[0]), dtype=np.float32)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+    rc = lib().rq_oracle_linear_small(_fp(x), n, k, _fp(W), _fp(bb) if bb is not None else None, W.shape[0],
+                                      int(bool(relu)), kind, _fp(y))
+    if rc != 0:
+        raise ValueError(f"rq_oracle_linear_small failed rc={rc}")
+    return y
+
+
+def mlp_group(x: np.ndarray, weights, biases) -> np.ndarray:
+    """``MLPLayers.forward`` on one small batch (a collision group), layer by layer in the batch-size-dependent order."""
+    h = x
+    for i, (W, b) in enumerate(zip(weights, biases)):
+        h = linear_group(h, W, b, relu=(i != len(weights) - 1))
+    return h
+
+
 def mlp(x: np.ndarray, weights: Sequence[np.ndarray], biases: Sequence[np.ndarray],
         kblocks: Optional[Dict[int, Sequence[int]]] = None, threads: Optional[int] = None) -> np.ndarray:
     """``MLPLayers.forward`` in eval mode (layers.py:18-32,42-43): Dropout is the identity, ReLU
@@ -124,7 +184,7 @@ def sumsq(v: np.ndarray) -> np.ndarray:
 
 
 def quantize(z: np.ndarray, codebooks: Sequence[np.ndarray], want_xq: bool = True,
-             dist_level: int = -1, threads: Optional[int] = None
+             dist_level: int = -1, threads: Optional[int] = None, dot_kind: int = 0
              ) -> Tuple[np.ndarray, Optional[np.ndarray], np.ndarray, Optional[np.ndarray]]:
     """``ResidualVectorQuantizer.forward`` with ``use_sk=False`` (rq.py:39-56, vq.py:63-99).
 
@@ -139,12 +199,12 @@ def quantize(z: np.ndarray, codebooks: Sequence[np.ndarray], want_xq: bool = Tru
     xq = np.empty((n, e), dtype=np.float32) if want_xq else None
     loss = np.zeros(L, dtype=np.float64)
     dist = np.empty((n, int(K[dist_level])), dtype=np.float32) if dist_level >= 0 else None
-    rc = lib().rq_oracle_quantize(
+    rc = lib().rq_oracle_quantize_ex(
         _fp(z), n, e, _fp(cat), K.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), L,
         idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
         _fp(xq) if xq is not None else None,
         loss.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-        _fp(dist) if dist is not None else None, dist_level, _threads(threads))
+        _fp(dist) if dist is not None else None, dist_level, _threads(threads), int(dot_kind))
     if rc != 0:
         raise ValueError(f"rq_oracle_quantize failed rc={rc}")
     return idx, xq, loss, dist
@@ -204,17 +264,32 @@ def sinkhorn_assign(d: np.ndarray, epsilon: float, iters: int) -> np.ndarray:
     return np.argmax(Q, axis=-1).astype(np.int64)
 
 
-def quantize_sk(z: np.ndarray, codebooks, sk_epsilons, sk_iters: int) -> np.ndarray:
+def top2_gap(Q: np.ndarray) -> np.ndarray:
+    """Relative gap between the two largest entries of every row of Q — 0 where the arg-max is an exact tie."""
+    if Q.shape[1] < 2:
+        return np.ones(Q.shape[0])
+    top = np.partition(Q, Q.shape[1] - 2, axis=1)[:, -2:]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(top[:, 1] > 0, (top[:, 1] - top[:, 0]) / top[:, 1], 0.0)
+
+
+def quantize_sk(z: np.ndarray, codebooks, sk_epsilons, sk_iters: int, group_order: bool = False,
+                gaps: Optional[list] = None) -> np.ndarray:
     """``ResidualVectorQuantizer.forward(use_sk=True)`` indices for one batch (rq.py:39-56, vq.py:63-99):
-    levels with ε>0 take the Sinkhorn argmax, the rest the plain argmin."""
+    levels with ε>0 take the Sinkhorn argmax, the rest the plain argmin.  group_order: the batch is one small
+    collision group — ``matmul(latent, E.t())`` (vq.py:73) then runs in the reference's small-batch order."""
     r = np.ascontiguousarray(z, dtype=np.float32).copy()
     out = []
     for cb, eps in zip(codebooks, sk_epsilons):
         cb = np.ascontiguousarray(cb, dtype=np.float32)
-        idx, _, _, dist = quantize(r, [cb], want_xq=False, dist_level=0, threads=1)
+        dk = small_batch_plan(r.shape[0], r.shape[1], cb.shape[0]) if group_order else 0
+        idx, _, _, dist = quantize(r, [cb], want_xq=False, dist_level=0, threads=1, dot_kind=dk)
         ind = idx[:, 0]
         if eps > 0:
-            ind = sinkhorn_assign(dist, eps, sk_iters)
+            Q = sinkhorn(center_distance(dist).astype(np.float64), eps, sk_iters)
+            ind = np.argmax(Q, axis=-1).astype(np.int64)
+            if gaps is not None:
+                gaps.append(top2_gap(Q))
         q = cb[ind]
         xres = r + (q - r)
         r = r - xres
@@ -250,11 +325,24 @@ def collision_groups(codes: np.ndarray) -> List[np.ndarray]:
     return groups
 
 
+def reencode_group(xg: np.ndarray, enc_w, enc_b, codebooks, eps, sk_iters: int, gaps: Optional[list] = None) -> np.ndarray:
+    """``model.get_indices(data[collision_items], use_sk=True)`` (infer.py:120-122) on ONE collision group, exactly as
+    the reference computes it: the encoder and every level run again on the group's rows alone, in the summation
+    order its CPU GEMM uses for that batch size (small_batch_plan)."""
+    zg = mlp_group(np.ascontiguousarray(xg, dtype=np.float32), enc_w, enc_b)
+    return quantize_sk(zg, codebooks, eps, sk_iters, group_order=True, gaps=gaps)
+
+
 def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters: int,
-                   max_rounds: int = 30, threads: Optional[int] = None) -> Tuple[np.ndarray, dict]:
+                   max_rounds: int = 30, threads: Optional[int] = None, group_order: bool = False,
+                   trace: Optional[list] = None) -> Tuple[np.ndarray, dict]:
     """The encode driver of infer.py:88-177 / generate_code.py:82-178: pass 1 (argmin codes),
     ≤30 rounds of per-group re-encoding with Sinkhorn on the last level only (infer.py:109-130),
-    then the suffix column.  Returns ([N, L+1] int64, stats)."""
+    then the suffix column.  Returns ([N, L+1] int64, stats).
+
+    group_order=False: every group is re-quantized from the catalogue-pass latents (a pure function of the item);
+    group_order=True: the reference's literal computation — each group goes through the encoder again as its own
+    small batch (reencode_group), which can differ from the former in the last bit of z."""
     L = len(codebooks)
     if L > 5:
         raise IndexError("list index out of range")      # prefix list has 5 entries (infer.py:90)
@@ -262,15 +350,20 @@ def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters
     codes = quantize(z, codebooks, want_xq=False, threads=threads)[0]
     eps = [0.0] * (L - 1) + [float(sk_epsilons[-1])]
     rounds = 0
+    if trace is not None:
+        trace.append(codes.copy())
     while rounds < max_rounds:
         groups = collision_groups(codes)
         if not groups:
             break
         new = codes.copy()
         for g in groups:
-            new[g] = quantize_sk(z[g], codebooks, eps, sk_iters)
+            new[g] = (reencode_group(x[g], enc_w, enc_b, codebooks, eps, sk_iters) if group_order
+                      else quantize_sk(z[g], codebooks, eps, sk_iters))
         codes = new
         rounds += 1
+        if trace is not None:
+            trace.append(codes.copy())
     uniq, counts = np.unique(codes, axis=0, return_counts=True)
     stats = {"rounds": rounds, "max_conflicts": int(counts.max()),
              "collision_rate": (len(codes) - len(uniq)) / len(codes)}

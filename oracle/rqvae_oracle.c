@@ -141,6 +141,55 @@ int rq_oracle_linear(const float *x, int64_t n, int in_dim, const float *W, cons
     return 0;
 }
 
+/* ------------------------------------------------------------------ Linear, small batches
+ *
+ * The reference re-runs its whole model on every collision group (reference RQ-VAE/infer.py:120-122 →
+ * rqvae.py:67-71 → layers.py:42-43), i.e. on batches of 2 … a few dozen rows, and its CPU GEMM (MKL sgemm
+ * behind ATen addmm / matmul) picks another kernel for such small M: a dot-product kernel that keeps 16 fp32
+ * lanes (one AVX-512 register), lane l accumulating k ≡ l (mod 16) as a sequential fma chain, then folds the
+ * register 512 → 128 bits as ((p0 + p1) + p2) + p3 (p_q = lanes 4q … 4q+3), the four survivors as
+ * (s0 + s1) + (s2 + s3), and adds the bias (beta = 1) last.  Derived with oracle/probe_sum_order.py (mask
+ * probe of the summation tree on the live reference stack) and verified bit for bit on random data there.
+ * Which M use it depends on the layer shape; the table lives in oracle.py (small_batch_plan). */
+static float dot_lane16(const float *a, const float *b, int K) {
+    float acc[16];
+    for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+    int k = 0;
+    for (; k + 16 <= K; k += 16)
+        for (int l = 0; l < 16; ++l) acc[l] = __builtin_fmaf(a[k + l], b[k + l], acc[l]);
+    for (int l = 0; k + l < K; ++l) acc[l] = __builtin_fmaf(a[k + l], b[k + l], acc[l]);   /* masked tail (unprobed) */
+    float s[4];
+    for (int m = 0; m < 4; ++m) s[m] = ((acc[m] + acc[m + 4]) + acc[m + 8]) + acc[m + 12];
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+
+/* kind 1: lane16 (above);  kind 2: four K-blocks folded pairwise, ((c0 + b) + c1) + (c2 + c3) — what the
+ * reference stack does for 1024 → 256 with 16 ≤ M < 176 on the 8-thread build container. */
+int rq_oracle_linear_small(const float *x, int64_t n, int in_dim, const float *W, const float *b,
+                           int out_dim, int relu, int kind, float *y) {
+    if (kind != 1 && kind != 2) return -1;
+    if (kind == 2 && (in_dim % 4)) return -1;
+    for (int64_t r = 0; r < n; ++r)
+        for (int j = 0; j < out_dim; ++j) {
+            const float *xr = x + r * in_dim, *wj = W + (int64_t)j * in_dim;
+            float v;
+            if (kind == 1) {
+                v = dot_lane16(xr, wj, in_dim) + (b ? b[j] : 0.0f);
+            } else {
+                int q = in_dim / 4; float c[4];
+                for (int blk = 0; blk < 4; ++blk) {
+                    float acc = 0.0f;
+                    for (int k = blk * q; k < (blk + 1) * q; ++k) acc = __builtin_fmaf(xr[k], wj[k], acc);
+                    c[blk] = acc;
+                }
+                v = ((c[0] + (b ? b[j] : 0.0f)) + c[1]) + (c[2] + c[3]);
+            }
+            if (relu) v = (v != v) ? v : (v > 0.0f ? v : 0.0f);
+            y[r * out_dim + j] = v;
+        }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ sum of squares */
 
 #define LANES 8
@@ -221,7 +270,7 @@ void rq_oracle_sumsq(const float *v, int64_t n, int e, float *out) {
 typedef struct {
     const float *z; int e; int L; const int *K; const float *const *cb; const float *const *cc;
     int64_t *idx; float *xq; double *loss_sq; /* per level, per thread slot */ float *dist0; int dist_level;
-    double *loss_slots; int nslots;
+    double *loss_slots; int nslots; int dot_kind;
 } quant_ctx;
 
 static float dot_chain(const float *a, const float *b, int e) {
@@ -240,7 +289,7 @@ static void quant_rows_impl(quant_ctx *c, int64_t lo, int64_t hi, double *loss /
             const float xx = rq_oracle_sumsq_row(r, e);
             int best = 0; float bestd = 0.0f; int have = 0;
             for (int j = 0; j < c->K[l]; ++j) {
-                float dot = dot_chain(r, cb + (int64_t)j * e, e);
+                float dot = c->dot_kind == 1 ? dot_lane16(r, cb + (int64_t)j * e, e) : dot_chain(r, cb + (int64_t)j * e, e);
                 float d = (xx + c->cc[l][j]) - (2.0f * dot);
                 if (c->dist0 && l == c->dist_level) c->dist0[i * c->K[l] + j] = d;
                 if (!have) { best = j; bestd = d; have = 1; }
@@ -276,9 +325,9 @@ static void quant_rows(void *p, int64_t lo, int64_t hi) {
 /* z[n,e] → idx[n,L] (int64), xq[n,e] (may be NULL), loss_sq[L] = Σ (q-r)^2 per level in fp64
  * (may be NULL), dist_out[n,K[dist_level]] optional full distance matrix of one level.
  * codebooks: concatenated [ΣK, e]; K[l] rows per level.  e ≤ 1024, L ≤ 16. */
-int rq_oracle_quantize(const float *z, int64_t n, int e, const float *codebooks, const int *K, int L,
-                       int64_t *idx, float *xq, double *loss_sq, float *dist_out, int dist_level,
-                       int threads) {
+int rq_oracle_quantize_ex(const float *z, int64_t n, int e, const float *codebooks, const int *K, int L,
+                          int64_t *idx, float *xq, double *loss_sq, float *dist_out, int dist_level,
+                          int threads, int dot_kind) {
     if (e > 1024 || L > 16) return -1;
     const float *cb[16]; float *cc[16];
     int64_t off = 0;
@@ -292,11 +341,17 @@ int rq_oracle_quantize(const float *z, int64_t n, int e, const float *codebooks,
     quant_ctx c;
     memset(&c, 0, sizeof(c));
     c.z = z; c.e = e; c.L = L; c.K = K; c.cb = cb; c.cc = (const float *const *)cc;
-    c.idx = idx; c.xq = xq; c.loss_sq = lsum; c.dist0 = dist_out; c.dist_level = dist_level;
+    c.idx = idx; c.xq = xq; c.loss_sq = lsum; c.dist0 = dist_out; c.dist_level = dist_level; c.dot_kind = dot_kind;
     parallel_rows(quant_rows, &c, n, dist_out ? 1 : threads);
     if (loss_sq) for (int l = 0; l < L; ++l) loss_sq[l] = lsum[l];
     for (int l = 0; l < L; ++l) free(cc[l]);
     return 0;
+}
+
+int rq_oracle_quantize(const float *z, int64_t n, int e, const float *codebooks, const int *K, int L,
+                       int64_t *idx, float *xq, double *loss_sq, float *dist_out, int dist_level,
+                       int threads) {
+    return rq_oracle_quantize_ex(z, n, e, codebooks, K, L, idx, xq, loss_sq, dist_out, dist_level, threads, 0);
 }
 
 /* ------------------------------------------------------------------ suffix dedup */
