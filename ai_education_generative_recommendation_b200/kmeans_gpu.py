@@ -116,6 +116,48 @@ def kmeans_pp_seed(x: torch.Tensor, K: int, gen: torch.Generator, ops, group=Non
     return centers
 
 
+def _relocate_empty(x, assign, centers, sums, counts, group):
+    """scikit-learn's `_relocate_empty_clusters_dense` (what `KMeans.fit` at layers.py:77 does when a cluster loses all
+    its samples): the n_empty samples farthest from their current centre become the centres of the empty clusters and
+    leave their old cluster.  Rare path (host logic over the statistics; the far samples of all shards meet through an
+    all-gather).  Farthest sample → lowest empty cluster id; scikit-learn hands them out in argpartition order, so the
+    SET of centres is the same, their order among the relocated ids may differ."""
+    empty = torch.nonzero(counts == 0).flatten()
+    n_empty, (n, e) = int(empty.numel()), x.shape
+    k = min(n_empty, n)
+    dist = ((x - centers[assign]) ** 2).sum(1) if n else x.new_zeros((0,))
+    vals = torch.full((n_empty,), -1.0, dtype=torch.float32, device=x.device)
+    rows = torch.zeros((n_empty, e), dtype=torch.float32, device=x.device)
+    labs = torch.zeros((n_empty,), dtype=torch.int64, device=x.device)
+    if k:
+        v, i = torch.topk(dist, k)
+        vals[:k], rows[:k], labs[:k] = v, x[i], assign[i]
+    if group is not None:
+        import torch.distributed as dist_
+        world = dist_.get_world_size(group)
+        gv = [torch.empty_like(vals) for _ in range(world)]
+        gr = [torch.empty_like(rows) for _ in range(world)]
+        gl = [torch.empty_like(labs) for _ in range(world)]
+        dist_.all_gather(gv, vals, group=group)
+        dist_.all_gather(gr, rows, group=group)
+        dist_.all_gather(gl, labs, group=group)
+        vals, rows, labs = torch.cat(gv), torch.cat(gr), torch.cat(gl)
+    order = torch.argsort(vals, descending=True, stable=True)[:n_empty]
+    if not bool(vals[order[0]] > 0):
+        return sums, counts                     # more clusters than distinct samples: relocating is pointless
+    sums, counts = sums.clone(), counts.clone()
+    for new_id, j in zip(empty.tolist(), order.tolist()):
+        if float(vals[j]) < 0:
+            break
+        old_id = int(labs[j])
+        row = rows[j].to(torch.float64)
+        sums[old_id] -= row
+        sums[new_id] = row
+        counts[new_id] = 1
+        counts[old_id] -= 1
+    return sums, counts
+
+
 def kmeans_fit(samples: torch.Tensor, num_clusters: int, num_iters: int = 10, seed: Optional[int] = None,
                init: Optional[torch.Tensor] = None, group=None, tol: float = 1e-4, ops=None,
                return_info: bool = False):
@@ -150,6 +192,8 @@ def kmeans_fit(samples: torch.Tensor, num_clusters: int, num_iters: int = 10, se
         sums = packed[:K * e].reshape(K, e).contiguous()
         counts = packed[K * e:K * e + K].round().to(torch.int64).contiguous()
         info["inertia"] = float(packed[-1].item())
+        if bool((counts == 0).any()):
+            sums, counts = _relocate_empty(x, a, centers, sums, counts, group)
         shift = ops.update(centers, sums, counts)
         info["iters"] = it + 1
         if tol > 0 and float(shift.item()) <= tol * var:

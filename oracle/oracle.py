@@ -109,31 +109,22 @@ def linear(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool,
 
 # Small batches.  The reference re-runs the whole model on every collision group (infer.py:120-122), i.e. with
 # 2 … a few dozen rows, and its CPU GEMM switches kernels there.  Measured on the live reference stack with
-# oracle/probe_sum_order.py (torch 2.11 + MKL, 1 and 8 threads give the same table): for M rows, K inputs
-#   M <= small_batch_limit(K)  → "lane16": 16 interleaved fma chains folded ((p0+p1)+p2)+p3, (s0+s1)+(s2+s3), bias last
-#   otherwise                  → the catalogue order (mkl_kblocks), except K = 1024 → 256 with 16 ≤ M < 176, where the
-#                                8-thread build container folds four 256-blocks pairwise (1 thread does not: that one
-#                                range is thread-count dependent in the reference itself).
-_SMALL_BATCH_LIMIT = {1024: 15, 768: 15, 512: 15, 256: 10, 128: 5, 64: 2, 32: 1, 16: 1}
+# oracle/probe_sum_order.py (torch 2.11 + MKL; 1 and 8 threads agree): an [M,K]·[K,N] product uses
+#   2 <= M <= 15 and 24·M <= K  → "lane16": 16 interleaved fma chains folded ((p0+p1)+p2)+p3, (s0+s1)+(s2+s3), bias last
+#   otherwise                    → the catalogue order (mkl_kblocks).
+# Not restated (see the probe's docstring): 1024 → 256 with 16 ≤ M < 176, where the reference's own result depends on
+# its thread count, and N ≤ 128 with K in {384, 640}.
 LANE16, PAIR4 = 1, 2
 
 
-def small_batch_limit(K: int) -> int:
-    """Largest M for which the reference's CPU GEMM with inner dimension K uses the lane16 order (probed values only)."""
-    if K not in _SMALL_BATCH_LIMIT:
-        raise KeyError(f"summation order of the reference for inner dimension {K} at small batch sizes has not been "
-                       f"probed (oracle/probe_sum_order.py)")
-    return _SMALL_BATCH_LIMIT[K]
-
-
 def small_batch_plan(M: int, K: int, N: int) -> int:
-    """0 = catalogue order, LANE16, PAIR4 — the order the reference uses for an [M,K]·[K,N] product."""
-    if M <= small_batch_limit(K):
+    """0 = catalogue order, LANE16 — the order the reference uses for an [M,K]·[K,N] product."""
+    if 2 <= M <= 15 and 24 * M <= K:
+        if N <= 128 and K in (384, 640):
+            raise KeyError(f"[{M},{K}]·[{K},{N}]: an exception of the reference's GEMM dispatch that is not restated")
         return LANE16
     if K == 1024 and N == 256 and 16 <= M < 176:
-        if M > 128:
-            raise KeyError("1024 -> 256 with 129..175 rows: a third, thread-count-dependent order of the reference's GEMM; not restated")
-        return PAIR4
+        raise KeyError("1024 -> 256 with 16..175 rows: the reference's result depends on its thread count; not restated")
     return 0
 
 
@@ -375,21 +366,39 @@ def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters
 def kmeans_lloyd(x: np.ndarray, init: np.ndarray, iters: int, tol: float = 1e-4) -> np.ndarray:
     """Lloyd iterations from given initial centres — the algorithm scikit-learn's ``KMeans``
     (third-party, pinned scikit-learn==1.7.1 in the reference's requirements.txt:7; call site
-    layers.py:77) runs after seeding.  PARITY UNPINNED for seeding: sklearn's k-means++ consumes
-    numpy's global RNG, so only 'same init ⇒ same centres' is checked.  fp64 accumulation."""
+    layers.py:77) runs after seeding, including its relocation of empty clusters (sklearn
+    ``_relocate_empty_clusters_dense``: the n_empty samples farthest from their centre become the new
+    centres and leave their old cluster).  Pinned against scikit-learn itself on given ``init`` arrays
+    (oracle/make_golden_kmeans.py → tests/golden/kmeans_sklearn.npz).  The SEEDING stays unpinned: sklearn's
+    k-means++ consumes numpy's global RNG.  fp64 accumulation (scikit-learn: fp32 on centred data)."""
     x = np.asarray(x, dtype=np.float32)
     c = np.asarray(init, dtype=np.float32).copy()
     xv = float(np.mean(np.var(x.astype(np.float64), axis=0)))
+    x64 = x.astype(np.float64)
+    xx = (x64 ** 2).sum(1)
     for _ in range(iters):
-        d = (x.astype(np.float64) ** 2).sum(1)[:, None] + (c.astype(np.float64) ** 2).sum(1)[None] \
-            - 2.0 * x.astype(np.float64) @ c.astype(np.float64).T
+        c64 = c.astype(np.float64)
+        d = xx[:, None] + (c64 ** 2).sum(1)[None] - 2.0 * x64 @ c64.T
         a = d.argmin(1)
+        K = c.shape[0]
+        sums = np.zeros((K, x.shape[1]), dtype=np.float64)
+        np.add.at(sums, a, x64)
+        counts = np.bincount(a, minlength=K).astype(np.float64)
+        empty = np.nonzero(counts == 0)[0]
+        if len(empty):
+            dist = ((x - c[a]) ** 2).sum(axis=1)
+            if dist.max() > 0:
+                far = np.argpartition(dist, -len(empty))[:-len(empty) - 1:-1]
+                for new_id, far_idx in zip(empty, far):
+                    old_id = a[far_idx]
+                    sums[old_id] -= x64[far_idx]
+                    sums[new_id] = x64[far_idx]
+                    counts[new_id] = 1
+                    counts[old_id] -= 1
         new = c.copy()
-        for k in range(c.shape[0]):
-            m = a == k
-            if m.any():
-                new[k] = x[m].astype(np.float64).mean(0).astype(np.float32)
-        shift = float(((new.astype(np.float64) - c.astype(np.float64)) ** 2).sum())
+        nz = counts > 0
+        new[nz] = (sums[nz] / counts[nz, None]).astype(np.float32)
+        shift = float(((new.astype(np.float64) - c64) ** 2).sum())
         c = new
         if tol > 0 and shift <= tol * xv:
             break

@@ -335,6 +335,24 @@ def test_kmeans_lloyd_matches_oracle(oracle):
         rq.kmeans(torch.from_numpy(x[:10]).to(DEV), 16, 5)
 
 
+def test_gpu_lloyd_matches_scikit_learn_golden():
+    """The GPU Lloyd loop from a given init against scikit-learn's own centres (tests/golden/kmeans_sklearn.npz,
+    oracle/make_golden_kmeans.py): codebook shapes of BASELINE configs 2, 3, 1 and 5; case 3 exercises the relocation of
+    empty clusters.  Centres compared as sets, tolerance = fp32 rounding."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kmeans_sklearn.npz"))
+    srt = lambda a: a[np.lexsort(a.T[::-1])]
+    for i in range(int(g["n_cases"])):
+        n, e, K, iters, n_total = (int(v) for v in g[f"meta{i}"])
+        x = synth.synth_items(2024, 1, n, e, n_total)
+        init = np.ascontiguousarray(x[(np.arange(K) * (n // K)) % n])
+        if n == 3000:
+            init[1::32] = init[0::32]      # duplicated initial centres → empty clusters (as in make_golden_kmeans.py)
+        got = rq.kmeans(torch.from_numpy(x).to(DEV), K, iters, init=torch.from_numpy(init)).cpu().numpy()
+        want = g[f"centers{i}"]
+        rel = np.abs(srt(got) - srt(want)).max() / np.abs(want).max()
+        assert rel <= 1e-5, (i, rel)
+
+
 def test_kmeans_init_path_of_the_model():
     cfg = dict(in_dim=768, num_emb_list=[64, 64], e_dim=32, layers=[256, 128], sk_epsilons=[0.0, 0.0], sk_iters=5)
     m = rq.RQVAE(in_dim=768, num_emb_list=[64, 64], e_dim=32, layers=[256, 128], kmeans_init=True, kmeans_iters=5,
