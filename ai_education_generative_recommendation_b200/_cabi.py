@@ -60,6 +60,8 @@ _PROTOS = {
                                     POINTER(c_int64), _P]),
     "rqb200_collision_groups": (c_int, [c_void_p, _P, c_int64, c_int, POINTER(c_int), _P, _P, POINTER(c_int64),
                                         POINTER(c_int64), POINTER(c_int64), _P]),
+    "rqb200_collision_groups_changed": (c_int, [c_void_p, _P, c_int64, c_int, POINTER(c_int), _P, _P, c_int, _P, _P,
+                                                POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), _P]),
     "rqb200_pack_keys": (c_int, [_P, c_int64, c_int, POINTER(c_int), _P, _P]),
     "rqb200_sort_pairs": (c_int, [c_void_p, _P, _P, c_int64, c_int, _P]),
     "rqb200_segment_rank": (c_int, [c_void_p, _P, c_int64, _P, _P]),

@@ -361,6 +361,42 @@ __global__ void group_flags_kernel(const uint64_t *__restrict__ ks, int64_t n, u
     flags[i] = f;
 }
 
+// Rounds of the collision loop after the first: a group whose member set is EXACTLY a group that was re-encoded in the
+// previous round is a fixed point — its members' codes are the output of re-encoding that very set, and the re-encode is
+// a pure function of the member rows, so running it again changes nothing (typical: exact duplicates that no Sinkhorn
+// pass can separate keep colliding for all 30 rounds of infer.py:112-130).  Such groups are dropped from the work list.
+// Record per item: prev_first = smallest member of the group it was last re-encoded in, prev_meta = (round << 32) | size.
+// Groups partition the items, so "every member carries (first, size, round - 1) of this group" ⇔ same member set.
+// One thread per run head walks its run (sorted positions); runs longer than GROUP_WALK_CAP are always kept (and not
+// recorded, which makes them count as changed next round as well).
+constexpr int GROUP_WALK_CAP = 4096;
+__global__ void group_unchanged_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ perm, int64_t n,
+                                       uint64_t *__restrict__ flags, int64_t *__restrict__ prev_first,
+                                       int64_t *__restrict__ prev_meta, int round, unsigned long long *__restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !(flags[i] >> 32)) return;
+    atomicAdd(&counts[0], 1ull);                               // every multi-member group
+    const uint64_t key = ks[i];
+    int64_t len = 1;
+    while (i + len < n && len <= GROUP_WALK_CAP && ks[i + len] == key) ++len;
+    if (len > GROUP_WALK_CAP) return;
+    const int64_t first = (int64_t)perm[i];                    // stable sort: ascending item index inside a run
+    const int64_t want = ((int64_t)(round - 1) << 32) | len;
+    bool same = round > 0;
+    for (int64_t t = 0; t < len && same; ++t) {
+        const int64_t it = (int64_t)perm[i + t];
+        same = prev_first[it] == first && prev_meta[it] == want;
+    }
+    const int64_t now = ((int64_t)round << 32) | len;
+    for (int64_t t = 0; t < len; ++t) {
+        const int64_t it = (int64_t)perm[i + t];
+        prev_first[it] = first;
+        prev_meta[it] = now;
+        if (same) flags[i + t] = 0;                             // dropped from the compaction below
+    }
+    if (same) atomicAdd(&counts[1], 1ull);
+}
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -864,15 +900,15 @@ extern "C" int rqb200_suffix_dedup(rqb200_model *m, const int64_t *codes_dev, in
     return 0;
 }
 
-extern "C" int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L,
-                                       const int *K_host, int64_t *items_dev, int64_t *offsets_dev,
-                                       int64_t *n_groups_host, int64_t *n_items_host,
-                                       int64_t *max_group_host, void *stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+static int collision_groups_impl(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L, const int *K_host,
+                                 int64_t *items_dev, int64_t *offsets_dev, int64_t *n_groups_host, int64_t *n_items_host,
+                                 int64_t *max_group_host, int64_t *prev_first_dev, int64_t *prev_meta_dev, int round,
+                                 int64_t *n_groups_total_host, cudaStream_t s) {
     RQB_CHECK(m != nullptr, "model is NULL");
     RQB_CHECK(n_groups_host && n_items_host, "count outputs are required");
     *n_groups_host = 0; *n_items_host = 0;
     if (max_group_host) *max_group_host = 0;
+    if (n_groups_total_host) *n_groups_total_host = 0;
     if (n == 0) return 0;
     RQB_CUDA(cudaSetDevice(m->device));
     SortScratch sc;
@@ -883,6 +919,13 @@ extern "C" int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev
     uint64_t *tile_sums = (uint64_t *)sc.tile_last;
     rqb::count_launch();
     group_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc.keys[buf], n, sc.flags);
+    unsigned long long *gcounts = sc.stats + 24;      // stats: [0]=runs [1]=max run [4..19]=column min/max [24..25]=these
+    if (prev_first_dev) {
+        RQB_CUDA(cudaMemsetAsync(gcounts, 0, 2 * sizeof(unsigned long long), s));
+        rqb::count_launch();
+        group_unchanged_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc.keys[buf], sc.vals[buf], n, sc.flags, prev_first_dev,
+                                                                           prev_meta_dev, round, gcounts);
+    }
     rqb::count_launch();
     scan64_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(sc.flags, n, tile_sums);
     rqb::count_launch();
@@ -893,14 +936,35 @@ extern "C" int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev
     write_total_offset_kernel<<<1, 1, 0, s>>>(tile_sums + ntiles, offsets_dev);
     RQB_LAUNCH_CHECK();
     uint64_t total = 0;
-    unsigned long long h[2] = {0, 0};
+    unsigned long long h[2] = {0, 0}, gc[2] = {0, 0};
     RQB_CUDA(cudaMemcpyAsync(&total, tile_sums + ntiles, sizeof(total), cudaMemcpyDeviceToHost, s));
     if (max_group_host) RQB_CUDA(cudaMemcpyAsync(h, sc.stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+    if (prev_first_dev) RQB_CUDA(cudaMemcpyAsync(gc, gcounts, sizeof(gc), cudaMemcpyDeviceToHost, s));
     RQB_CUDA(cudaStreamSynchronize(s));
     *n_items_host = (int64_t)(total & 0xffffffffull);
     *n_groups_host = (int64_t)(total >> 32);
     if (max_group_host) *max_group_host = (int64_t)h[1];
+    if (n_groups_total_host) *n_groups_total_host = prev_first_dev ? (int64_t)gc[0] : *n_groups_host;
     return 0;
+}
+
+extern "C" int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L,
+                                       const int *K_host, int64_t *items_dev, int64_t *offsets_dev,
+                                       int64_t *n_groups_host, int64_t *n_items_host,
+                                       int64_t *max_group_host, void *stream) {
+    return collision_groups_impl(m, codes_dev, n, L, K_host, items_dev, offsets_dev, n_groups_host, n_items_host, max_group_host,
+                                 nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rqb200_collision_groups_changed(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L, const int *K_host,
+                                               int64_t *prev_first_dev, int64_t *prev_meta_dev, int round,
+                                               int64_t *items_dev, int64_t *offsets_dev, int64_t *n_groups_host,
+                                               int64_t *n_items_host, int64_t *max_group_host, int64_t *n_groups_total_host,
+                                               void *stream) {
+    RQB_CHECK(prev_first_dev && prev_meta_dev, "the per-item group records are required");
+    RQB_CHECK(round >= 0, "round < 0");
+    return collision_groups_impl(m, codes_dev, n, L, K_host, items_dev, offsets_dev, n_groups_host, n_items_host, max_group_host,
+                                 prev_first_dev, prev_meta_dev, round, n_groups_total_host, (cudaStream_t)stream);
 }
 
 extern "C" int rqb200_pack_keys(const int64_t *codes_dev, int64_t n, int L, const int *K_host,

@@ -117,30 +117,54 @@ def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Ten
     return codes
 
 
+class _GroupRecords:
+    """Per-item record of the group an item was last re-encoded in (csrc/dedup.cu: group_unchanged_kernel): lets the
+    rounds after the first skip every group whose member set did not change — re-encoding it is a no-op by construction."""
+
+    def __init__(self, n: int, device):
+        self.first = torch.full((max(n, 1),), -1, dtype=torch.int64, device=device)
+        self.meta = torch.full((max(n, 1),), -1, dtype=torch.int64, device=device)
+        self.round = 0
+
+
 @torch.no_grad()
 def reencode_round(model: RQVAE, codes: torch.Tensor, data, residual: Optional[torch.Tensor] = None,
-                   verbose_round: Optional[int] = None) -> int:
+                   verbose_round: Optional[int] = None, records: Optional[_GroupRecords] = None) -> Tuple[int, int]:
     """ONE round of the loop at infer.py:116-129, in place on `codes`: every group of items sharing a full code goes
     through `model.get_indices(data[group], use_sk=True)` — as in the reference the WHOLE model runs again on the group's
     rows alone (encoder, arg-min levels, Sinkhorn on the last level), in the arithmetic the reference uses for a batch of
     that size (csrc/small_batch.cu), and all L codes of the members are overwritten.  Groups of one round are disjoint
     and are all found before anything is rewritten, so the round is a pure function of the codes it starts from.
-    Returns the number of groups (0: nothing to do)."""
+    `records` (rounds of one driver run): groups that are member-for-member a group of the previous round are skipped —
+    they are fixed points.  Returns (groups found, groups re-encoded); (0, 0): nothing collides."""
     lib = _cabi.lib()
     dev = codes.device
     data = _as_rows(data)
     last = model.rq.vq_layers[-1]
     if last.sk_epsilon is None or last.sk_epsilon <= 0:
-        return 0
+        return 0, 0
     model._sync()
-    items, offsets, max_group = collision_groups(model, codes)
+    n, Lv = codes.shape
+    if records is None:
+        items, offsets, max_group = collision_groups(model, codes)
+        n_total = offsets.numel() - 1
+    else:
+        items = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+        offsets = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+        ng, ni, mg, nt = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        check(lib.rqb200_collision_groups_changed(model._handle, ptr(codes), n, Lv, _cabi.int_array(model.num_emb_list),
+                                                  ptr(records.first), ptr(records.meta), records.round, ptr(items),
+                                                  ptr(offsets), ctypes.byref(ng), ctypes.byref(ni), ctypes.byref(mg),
+                                                  ctypes.byref(nt), stream_ptr(dev)))
+        records.round += 1
+        items, offsets, max_group, n_total = items[:ni.value], offsets[:ng.value + 1], int(mg.value), int(nt.value)
     n_groups = offsets.numel() - 1
+    if verbose_round is not None and n_total > 0:
+        print(f"Iteration {verbose_round}: Found {n_total} collision groups")
     if n_groups <= 0:
-        return 0
-    if verbose_round is not None:
-        print(f"Iteration {verbose_round}: Found {n_groups} collision groups")
+        return n_total, 0
     if residual is None:
-        residual = torch.empty((codes.shape[0], model.e_dim), dtype=torch.float32, device=dev)
+        residual = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
     if data.is_cuda:
         x, gathered = data, 0
     else:
@@ -153,26 +177,39 @@ def reencode_round(model: RQVAE, codes: torch.Tensor, data, residual: Optional[t
                                       stream_ptr(dev)))
     if max_group > cap:
         _regroup_oversized(model, residual, items, offsets, cap, codes)
-    return n_groups
+    return n_total, n_groups
 
 
 @torch.no_grad()
-def resolve_rounds(model: RQVAE, codes: torch.Tensor, data, max_rounds: int = 30, verbose: bool = False
-                   ) -> Tuple[torch.Tensor, int]:
+def resolve_rounds(model: RQVAE, codes: torch.Tensor, data, max_rounds: int = 30, verbose: bool = False,
+                   stats: Optional[dict] = None) -> Tuple[torch.Tensor, int]:
     """Pass 2 (infer.py:109-130): ≤ max_rounds rounds of `reencode_round`, until no two items share a full code.
     `codes` is updated in place.  `data`: the catalogue rows — a CUDA tensor (members gathered on the device) or a host
-    tensor / array (members gathered on the host and uploaded per round).  Returns (codes, rounds)."""
+    tensor / array (members gathered on the host and uploaded per round).  Once every remaining group is a fixed point
+    the remaining rounds of the reference are no-ops; they are counted, not run.  Returns (codes, rounds)."""
     # infer.py:109-110 — only the last level keeps its Sinkhorn epsilon
     for vq in model.rq.vq_layers[:-1]:
         vq.sk_epsilon = 0.0
     last = model.rq.vq_layers[-1]
     rounds = 0
+    work = []
     if last.sk_epsilon is not None and last.sk_epsilon > 0:
         residual = torch.empty((codes.shape[0], model.e_dim), dtype=torch.float32, device=codes.device)
+        records = _GroupRecords(codes.shape[0], codes.device)
         while rounds < max_rounds:
-            if reencode_round(model, codes, data, residual, rounds if verbose else None) == 0:
+            found, done = reencode_round(model, codes, data, residual, rounds if verbose else None, records)
+            if found == 0:
                 break
+            work.append(done)
             rounds += 1
+            if done == 0:                      # only fixed points are left: the reference spins until tt == 30 without effect
+                if verbose:
+                    for t in range(rounds, max_rounds):
+                        print(f"Iteration {t}: Found {found} collision groups")
+                rounds = max_rounds
+                break
+    if stats is not None:
+        stats["groups_reencoded_per_round"] = work
     return codes, rounds
 
 
@@ -204,8 +241,10 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
     model.eval()
     try:
         codes = encode_codes_fast(model, data, chunk_rows) if fast else encode_codes_exact(model, data, chunk_rows)
-        codes, rounds = resolve_rounds(model, codes, data, max_rounds=max_rounds, verbose=verbose)
+        rstats = {}
+        codes, rounds = resolve_rounds(model, codes, data, max_rounds=max_rounds, verbose=verbose, stats=rstats)
         out, stats = suffix_dedup(model, codes)
+        stats.update(rstats)
         stats["rounds"] = rounds
         stats["pass1_route"] = "tensor-core" if fast else "exact"
         return out, stats

@@ -10,8 +10,12 @@ dedup, inputs resident in HBM → final [N, L+1] int64 semantic ids resident in 
        ranks written back the same way) so ids are unique catalogue-wide.
 `e2e` is the same work through the host-buffer C-ABI call (rqb200_generate_codes_host): pinned host
 embeddings in, host semantic ids out, H2D/D2H inside the timed region.
-`--impl reference` times the CPU restatement of the reference path (oracle/, all host threads) on a bounded
-sample of the same workload.
+`--impl reference` times the reference's own CPU implementation of the step on the box's host cores, on a bounded sample
+of the same workload: the REAL PyTorch `RQVAE.get_indices` (reference RQ-VAE/models/rqvae.py:67-71, copied unmodified
+into the git-ignored oracle/_ref/ by oracle/make_ref.py; all host threads, batch 65 536) followed by the suffix column
+(oracle C restatement of infer.py:152-163 — the reference's own O(N·G) loop is timed separately on a bounded number of
+duplicated codes and reported, not run in full).  Without oracle/_ref it falls back to the oracle C port (kind "port").
+`config.extra` (N > 1): BASELINE configs[2] (10 M items, strong-scaled over the N GPUs) and, at N = 8, configs[4] (100 M).
 """
 import argparse
 import ctypes
@@ -24,7 +28,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "rqvae_semantic_id_encode_items_per_s"
 UNIT = "items/s"
@@ -98,32 +101,100 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def golden_model(device):
-    from conftest import build_model, load_golden
+def golden_model(device, with_sk=False):
+    from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden
     g, cfg, cbs = load_golden(GOLDEN)
-    cfg = dict(cfg, sk_epsilons=[0.0] * len(cfg["num_emb_list"]))      # bench step = pass 1 + suffix dedup (no Sinkhorn rounds)
+    if not with_sk:
+        cfg = dict(cfg, sk_epsilons=[0.0] * len(cfg["num_emb_list"]))  # bench step = pass 1 + suffix dedup (no Sinkhorn rounds)
     return build_model(cfg, cbs, device=device), cfg, cbs
 
 
-def cpu_reference_leg(sample_rows, threads, x_host=None):
-    """The reference path on the host cores: CPU restatement (oracle/) of get_indices + suffix dedup."""
+def sample_rows_host(sample, in_dim):
     import numpy as np
-    from conftest import load_golden, synth_weights
-    from oracle import oracle as O
     from ai_education_generative_recommendation_b200 import synth
+    return np.concatenate([synth.synth_items(SEED, r0, min(65536, sample - r0), in_dim, N_PER_GPU)
+                           for r0 in range(0, sample, 65536)])
+
+
+_REF_MODEL = {}
+
+
+def reference_torch_model():
+    """The UNMODIFIED reference RQVAE (oracle/_ref/models, see oracle/make_ref.py) with the bench weights, or None."""
+    if GOLDEN in _REF_MODEL:
+        return _REF_MODEL[GOLDEN]
+    model = None
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "models", "rqvae.py")):
+        import torch
+        from ai_education_generative_recommendation_b200.fixtures import load_golden, synth_weights
+        sys.path.insert(0, ref_dir)
+        try:
+            from models.rqvae import RQVAE as RefRQVAE
+            g, cfg, cbs = load_golden(GOLDEN)
+            sd, _, _ = synth_weights(cfg)
+            for l, c in enumerate(cbs):
+                sd[f"rq.vq_layers.{l}.embedding.weight"] = c
+            model = RefRQVAE(in_dim=cfg["in_dim"], num_emb_list=cfg["num_emb_list"], e_dim=cfg["e_dim"], layers=cfg["layers"],
+                             dropout_prob=0.0, bn=False, loss_type="mse", kmeans_init=False,
+                             sk_epsilons=[0.0] * len(cfg["num_emb_list"]), sk_iters=cfg["sk_iters"])
+            model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
+            model.eval()
+        finally:
+            sys.path.remove(ref_dir)
+    _REF_MODEL[GOLDEN] = model
+    return model
+
+
+def cpu_reference_leg(sample_rows, threads, x_host=None, kind="auto"):
+    """The reference path on the host cores → (items/s, seconds, ids, kind).  kind "reference": the real PyTorch
+    get_indices (all threads, batch 65 536) + suffix column; "port": the oracle C restatement of both."""
+    import numpy as np
+    from ai_education_generative_recommendation_b200.fixtures import load_golden, synth_weights
+    from oracle import oracle as O
     O.build()
     g, cfg, cbs = load_golden(GOLDEN)
-    _, (ew, eb), _ = synth_weights(cfg)
     if x_host is None:
-        x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample_rows - r0), cfg["in_dim"], N_PER_GPU)
-                                 for r0 in range(0, sample_rows, 65536)])
+        x_host = sample_rows_host(sample_rows, cfg["in_dim"])
     x = np.ascontiguousarray(x_host[:sample_rows])
+    ref = reference_torch_model() if kind in ("auto", "reference") else None
+    if ref is not None:
+        import torch
+        torch.set_num_threads(threads)
+        xt = torch.from_numpy(x)
+        with torch.no_grad():
+            ref.get_indices(xt[:4096], use_sk=False)               # warm-up
+            t0 = time.perf_counter()
+            codes = torch.cat([ref.get_indices(xt[i:i + 65536], use_sk=False) for i in range(0, sample_rows, 65536)]).numpy()
+        ids = O.suffix_dedup(codes)
+        dt = time.perf_counter() - t0
+        return sample_rows / dt, dt, ids, "reference"
+    _, (ew, eb), _ = synth_weights(cfg)
     O.get_indices(x[:4096], ew, eb, cbs, threads=threads)     # warm-up
     t0 = time.perf_counter()
     codes = O.get_indices(x, ew, eb, cbs, threads=threads)
     ids = O.suffix_dedup(codes)
     dt = time.perf_counter() - t0
-    return sample_rows / dt, dt, ids
+    return sample_rows / dt, dt, ids, "port"
+
+
+def reference_dedup_lane(codes, max_dups=200):
+    """B-dedup lane: the reference's own suffix loop (infer.py:152-163: np.unique + one np.where scan per
+    duplicated code), verbatim, on at most `max_dups` duplicated codes → seconds per duplicated code at this N."""
+    import numpy as np
+    arr = np.hstack((codes, np.zeros((codes.shape[0], 1), dtype=int)))
+    t0 = time.perf_counter()
+    unique_codes, counts = np.unique(arr, axis=0, return_counts=True)
+    t_unique = time.perf_counter() - t0
+    duplicates = unique_codes[counts > 1]
+    t0 = time.perf_counter()
+    for duplicate in duplicates[:max_dups]:
+        duplicate_indices = np.where((arr == duplicate).all(axis=1))[0]
+        for i, idx in enumerate(duplicate_indices):
+            arr[idx, -1] = i
+    per_dup = (time.perf_counter() - t0) / max(1, min(max_dups, len(duplicates)))
+    return {"n": int(codes.shape[0]), "np_unique_s": t_unique, "duplicated_codes": int(len(duplicates)),
+            "s_per_duplicated_code": per_dup, "projected_total_s": t_unique + per_dup * len(duplicates)}
 
 
 def run_reference_arm(args):
@@ -132,27 +203,103 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     sample = 262144
-    import numpy as np
-    from conftest import load_golden
-    from ai_education_generative_recommendation_b200 import synth
+    from ai_education_generative_recommendation_b200.fixtures import load_golden
     in_dim = json.loads(str(load_golden(GOLDEN)[0]["cfg"]))["in_dim"]
-    x_host = np.concatenate([synth.synth_items(SEED, r0, min(65536, sample - r0), in_dim, N_PER_GPU)
-                             for r0 in range(0, sample, 65536)])          # generated once, outside the timed steps
+    x_host = sample_rows_host(sample, in_dim)          # generated once, outside the timed steps
     vals = []
+    kind = "port"
     for i in range(args.warmup + args.steps):
-        v, dt, _ = cpu_reference_leg(sample, threads, x_host=x_host)
+        v, dt, ids, kind = cpu_reference_leg(sample, threads, x_host=x_host)
         if i >= args.warmup:
             vals.append((v, dt))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    what = ("the reference's own PyTorch RQVAE.get_indices (oracle/_ref, unmodified; batch 65536, all host threads) + suffix column "
+            "(oracle C restatement of infer.py:152-163)" if kind == "reference"
+            else "oracle C restatement of get_indices + suffix dedup, pthreads (oracle/_ref absent)")
+    import torch
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"{sample} rows of the same catalogue per step"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} rows/step: oracle C restatement of get_indices + suffix dedup, pthreads"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{sample} rows/step: {what}", "torch": torch.__version__,
+                             "reference_dedup_lane": reference_dedup_lane(ids[:, :-1])},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+KEEP_ALIVE = []
+
+
+def run_extra(key, n_total, rank, world, dev, group, args):
+    """BASELINE configs[2] (10 M x 768, 4 x 256 codes, e 64) / configs[4] (100 M x 1024, 4 x 1024 codes, e 64): the catalogue
+    is split into contiguous shards over the `world` GPUs (strong scaling), every rank encodes its shard (tensor-core
+    route) and the suffix column is global (peer-memory dedup).  Returns the per-config record (rank 0) — items/s over all
+    GPUs, per-stage ms of rank 0, and a sampled fast == exact check on this rank's first rows."""
+    import torch
+    import torch.distributed as dist
+    import ai_education_generative_recommendation_b200 as rq
+    from ai_education_generative_recommendation_b200 import _cabi, sharding
+    global GOLDEN, WORKLOAD
+    saved = (GOLDEN, WORKLOAD)
+    GOLDEN, WORKLOAD = CONFIGS[key]
+    try:
+        lib = _cabi.lib()
+        model, cfg, cbs = golden_model(dev)
+        model.encode_mode = _cabi.ENCODE_FAST
+        lo, hi = sharding.shard_range(n_total, rank, world)
+        n = hi - lo
+        in_dim, Ks = cfg["in_dim"], cfg["num_emb_list"]
+        x = torch.empty((n, in_dim), dtype=torch.float32, device=dev)
+        _cabi.check(lib.rqb200_synth_items(SEED, lo, n, in_dim, n_total, x.data_ptr(), _cabi.stream_ptr()))
+        peer = sharding.PeerShardDedup(model, group, max_local_items=n + 1)
+
+        def step():
+            return peer(model.get_indices(x, use_sk=False), Ks)
+
+        for _ in range(2):
+            out = step()
+        dist.barrier(); torch.cuda.synchronize()
+        lib.rqb200_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            out = step()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        prof_ms = (ctypes.c_double * 12)()
+        prof_cnt = (ctypes.c_longlong * 12)()
+        lib.rqb200_profile_read(prof_ms, prof_cnt, 12)
+        lib.rqb200_profile_enable(0)
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # sampled parity: tensor-core route == exact route on this rank's first rows; ids unique catalogue-wide
+        ns = min(n, 200_000)
+        fast_codes = model.get_indices(x[:ns], use_sk=False)
+        model.encode_mode = _cabi.ENCODE_EXACT
+        exact_codes = model.get_indices(x[:ns], use_sk=False)
+        ok = torch.tensor([int(torch.equal(fast_codes, exact_codes))], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        dup = torch.tensor([int((out[:, -1] > 0).sum())], dtype=torch.int64, device=dev)
+        dist.all_reduce(dup, op=dist.ReduceOp.SUM)
+        dist.barrier(); torch.cuda.synchronize()
+        KEEP_ALIVE.append(peer)          # peer-mapped buffers stay mapped until the process exits (all ranks tear down together)
+        del x, out, model
+        torch.cuda.empty_cache()
+        step_ms = float(ms.item())
+        return {"workload": WORKLOAD, "global_items": n_total, "items_per_gpu": n, "scaling": "strong", "ms_per_step": step_ms,
+                "value": n_total / (step_ms * 1e-3), "unit": UNIT,
+                "stage_ms_rank0": {"tc_linear0": prof_ms[4] / reps, "tc_linear_rest": prof_ms[6] / reps,
+                                   "quantize": prof_ms[2] / reps, "rerun_tier": prof_ms[7] / reps,
+                                   "exact_rescue_tier": prof_ms[8] / reps, "dedup": prof_ms[3] / reps},
+                "hbm_frac_layer1_rank0": (4.0 * in_dim * n / (prof_ms[4] / reps * 1e-3) / 1e9 / float(load_peaks()[0]["hbm_gbs"]))
+                if prof_ms[4] > 0 else None,
+                "fast_equals_exact_on_sample": bool(ok.item()), "sample_rows_per_gpu": ns,
+                "items_with_nonzero_suffix": int(dup.item())}
+    finally:
+        GOLDEN, WORKLOAD = saved
 
 
 def main():
@@ -164,6 +311,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RQB200_MODE", "auto"), choices=["auto", "exact", "fast"])
     ap.add_argument("--items", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the configs[2] / configs[4] runs under config.extra")
+    ap.add_argument("--no-full-driver", action="store_true", help="skip the full_driver leg (passes 1-3 with Sinkhorn rounds)")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--e2e-items", type=int, default=0,
                     help="rows per rank of the host-buffer (e2e) leg; 0 = the same rows as the device leg, capped at 2M "
@@ -303,6 +452,17 @@ def main():
     if world == 1 and ne == n:
         assert np.array_equal(ids_host.numpy(), out.cpu().numpy()), "host-buffer path and device path disagree"
 
+    # ---- the other BASELINE configurations, strong-scaled over this run's GPUs (N > 1 only; reported under config.extra)
+    extras = {}
+    if world > 1 and not args.no_extra:
+        del xh, ids_host
+        x = None
+        out = None
+        barrier()
+        torch.cuda.empty_cache()
+        plan = [("c3", 10_000_000)] + ([("c5", 100_000_000)] if world >= 8 else [])
+        for key, total in plan:
+            extras[key] = run_extra(key, total, rank, world, dev, group, args)
     if rank == 0:
         peaks, peak_src = load_peaks()
         # dominant kernel: the encoder's first Linear — linear_tc2_kernel (fast route) / linear_exact_kernel (exact route).
@@ -362,20 +522,57 @@ def main():
                            "step": "get_indices(use_sk=False) + suffix dedup" + (" (global: keys routed to owner ranks over NVLink peer memory)" if world > 1 else ""),
                            "l2": f"inputs {n * in_dim * 4 / 1e9:.2f} GB per GPU per step, larger than the 126 MB L2 (no flush needed)",
                            "parallelism": f"items sharded x{world}, codebooks replicated",
-                           "multi_gpu_ids_equal_single_gpu": multi_check},
+                           "multi_gpu_ids_equal_single_gpu": multi_check, "extra": extras or None},
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ne * in_dim * 4),
                         "d2h_bytes_per_step": int(ne * (len(Ks) + 1) * 8), "items_per_gpu": ne,
                         "api": "rqb200_generate_codes_host (pinned host buffers)"},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_full_driver:
+            # the WHOLE driver (generate_code.py / infer.py semantics): pass 1 + the <= 30 Sinkhorn re-encode rounds
+            # (eps on the last level as in the fixture's config) + suffix column, catalogue resident in HBM
+            model_sk, cfg_sk, _ = golden_model(dev, with_sk=True)
+            ids_sk, st_sk = rq.generate_codes(model_sk, x)                  # warm-up (workspaces, attributes)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 2
+            for _ in range(reps):
+                ids_sk, st_sk = rq.generate_codes(model_sk, x)
+            torch.cuda.synchronize()
+            fd_s = (time.perf_counter() - t0) / reps
+            full = {"value": n / fd_s, "unit": UNIT, "seconds": fd_s, "items": n, "sk_epsilons": cfg_sk["sk_epsilons"],
+                    "rounds": st_sk["rounds"], "groups_reencoded_per_round": st_sk.get("groups_reencoded_per_round"),
+                    "collision_rate_after": st_sk["collision_rate"], "max_conflicts": st_sk["max_conflicts"],
+                    "what": "rq.generate_codes: pass 1 (tensor-core route) + re-encode rounds (every group through the whole model "
+                            "as its own batch, reference arithmetic; fixed-point groups skipped after their first round) + suffix dedup"}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                from ai_education_generative_recommendation_b200.fixtures import synth_weights
+                ns = min(n, 20000)
+                _, (ew, eb), _ = synth_weights(cfg_sk)
+                xs = x[:ns].cpu().numpy()
+                t0 = time.perf_counter()
+                ref_ids, ref_st = O.generate_codes(xs, ew, eb, cbs, cfg_sk["sk_epsilons"], cfg_sk["sk_iters"], group_order=True)
+                cs = time.perf_counter() - t0
+                sub_ids, _ = rq.generate_codes(model_sk, x[:ns].contiguous())
+                full["cpu_port"] = {"value": ns / cs, "unit": UNIT, "seconds": cs, "items": ns, "rounds": ref_st["rounds"],
+                                    "ids_equal_gpu_on_the_same_items": bool(np.array_equal(ref_ids, sub_ids.cpu().numpy())),
+                                    "what": "oracle.generate_codes(group_order=True), one host process"}
+            line["full_driver"] = full
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sample = min(ne, 1_000_000)
-            v, dt, ids = cpu_reference_leg(sample, threads, x_host=xh.numpy())
+            v, dt, ids, kind = cpu_reference_leg(sample, threads, x_host=xh.numpy())
             same = bool(np.array_equal(ids[:, :n_levels], ids_host.numpy()[:sample, :n_levels]))
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} rows of the same catalogue, {dt:.1f} s: oracle C restatement of "
-                                              f"get_indices + suffix dedup (pthreads); codes equal to GPU: {same}"}
+            what = ("the reference's own PyTorch RQVAE.get_indices (oracle/_ref, unmodified; batch 65536, all host threads) + "
+                    "suffix column (oracle C restatement)" if kind == "reference"
+                    else "oracle C restatement of get_indices + suffix dedup (pthreads)")
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{sample} rows of the same catalogue, {dt:.1f} s: {what}; codes equal to GPU: {same}"}
+            if kind == "reference":      # the C port beside it (what round 1 reported)
+                pv, pdt, pids, _ = cpu_reference_leg(sample, threads, x_host=xh.numpy(), kind="port")
+                line["cpu_baseline"]["port_value"] = pv
+                line["cpu_baseline"]["port_codes_equal_reference"] = bool(np.array_equal(pids, ids))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -194,6 +194,15 @@ int rqb200_collision_groups(rqb200_model *m, const int64_t *codes_dev, int64_t n
                             const int *K_host, int64_t *items_dev, int64_t *offsets_dev,
                             int64_t *n_groups_host,
                             int64_t *n_items_host, int64_t *max_group_host, void *stream);
+/* The same, for the rounds of the collision loop (infer.py:112-130): groups whose member set is exactly a group that
+ * was re-encoded in the previous round are fixed points of the round (the re-encode is a pure function of the member
+ * rows) and are left out of items/offsets; n_groups_total_host still counts them.  prev_first_dev / prev_meta_dev:
+ * int64[n] records owned by the caller (any content before round 0), round = 0, 1, 2 … in call order.            */
+int rqb200_collision_groups_changed(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L, const int *K_host,
+                                    int64_t *prev_first_dev, int64_t *prev_meta_dev, int round,
+                                    int64_t *items_dev, int64_t *offsets_dev, int64_t *n_groups_host,
+                                    int64_t *n_items_host, int64_t *max_group_host, int64_t *n_groups_total_host,
+                                    void *stream);
 /* Generic building blocks used by the multi-GPU dedup exchange: pack codes to u64 keys and
  * stable-sort (key, value) pairs by key; segmented rank = position inside the equal-key run. */
 int rqb200_pack_keys(const int64_t *codes_dev, int64_t n, int L, const int *K_host,

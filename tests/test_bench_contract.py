@@ -1,5 +1,5 @@
 """bench.py on a box without a GPU: the product arm refuses to run (no CPU fallback), the reference arm
-(`--impl reference`: the CPU restatement on the host cores) prints one JSON line with the contract's keys."""
+(`--impl reference`: the reference's own PyTorch get_indices from oracle/_ref — the oracle port without it — on the host cores) prints one JSON line with the contract's keys."""
 import json
 import os
 import subprocess
@@ -30,7 +30,10 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "items/s" and line["higher_is_better"] is True
     assert line["metric"] == "rqvae_semantic_id_encode_items_per_s" and line["vs_baseline"] is None
     assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "models", "rqvae.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")      # the real PyTorch reference when it is there
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["cpu_baseline"]["reference_dedup_lane"]["s_per_duplicated_code"] > 0
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]

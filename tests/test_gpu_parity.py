@@ -245,7 +245,7 @@ def test_generate_codes_reproduces_reference_infer_exactly(oracle):
     xt = torch.from_numpy(x).to(DEV)
     codes = torch.from_numpy(trace[0].copy()).to(DEV)
     for t in range(f["rounds"]):
-        assert rq.generate_code.reencode_round(m, codes, xt) > 0
+        assert rq.generate_code.reencode_round(m, codes, xt)[0] > 0
         assert np.array_equal(codes.cpu().numpy(), trace[t + 1]), t
 
 
