@@ -44,6 +44,7 @@ _PROTOS = {
     "rqb200_model_set_screen": (c_int, [c_void_p, c_int, c_float]),
     "rqb200_model_last_tier_rows": (c_int, [c_void_p, POINTER(c_int64)]),
     "rqb200_debug_linear_tc": (c_int, [c_void_p, c_int, c_int, _P, c_int64, _P, c_int, c_int, _P]),
+    "rqb200_debug_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, c_int, _P]),
     "rqb200_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P]),
     "rqb200_mlp_exact": (c_int, [c_void_p, c_int, _P, _P, c_int64, _P, _P]),
     "rqb200_quantize": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P, _P]),
@@ -51,6 +52,7 @@ _PROTOS = {
     "rqb200_forward": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P]),
     "rqb200_sinkhorn_regroup": (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, c_double, c_int, _P, _P]),
     "rqb200_reencode_groups": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "rqb200_reencode_rows": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, _P, _P, _P]),
     "rqb200_sinkhorn_group_cap": (c_int, [c_void_p]),
     "rqb200_sinkhorn_regroup_large": (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int64, _P, c_double, c_int, _P, _P]),
     "rqb200_sinkhorn": (c_int, [_P, c_int64, c_int, c_double, c_int, _P]),
@@ -92,7 +94,7 @@ _PROTOS = {
     "rqb200_offset_tokens": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "rqb200_gather_item_tokens": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
     "rqb200_synth_items": (c_int, [c_uint64, c_int64, c_int64, c_int, c_int64, _P, _P]),
-    "rqb200_generate_codes_host": (c_int, [c_void_p, c_int, _P, c_int64, c_int64, _P, POINTER(c_int64)]),
+    "rqb200_generate_codes_host": (c_int, [c_void_p, c_int, _P, c_int64, c_int64, _P, POINTER(c_int64), _P]),
 }
 
 

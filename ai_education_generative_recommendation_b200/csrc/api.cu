@@ -114,6 +114,7 @@ static void free_linear(Linear &l) {
     if (l.b) cudaFree(l.b);
     if (l.W_tc) cudaFree(l.W_tc);
     if (l.W_tc2) cudaFree(l.W_tc2);
+    if (l.W_tf32) cudaFree(l.W_tf32);
     if (l.absW_rowmax) cudaFree(l.absW_rowmax);
     l = Linear();
 }
@@ -248,6 +249,8 @@ extern "C" int rqb200_model_set_linear(rqb200_model *m, int which, int layer, co
     }
     if (l.W_tc) { cudaFree(l.W_tc); l.W_tc = nullptr; l.W_tc_bytes = 0; }   // stale tensor-core images
     if (l.W_tc2) { cudaFree(l.W_tc2); l.W_tc2 = nullptr; }
+    if (l.W_tf32) { cudaFree(l.W_tf32); l.W_tf32 = nullptr; }
+    RQB_CUDA(cudaDeviceSynchronize());       // device-to-device copies above are asynchronous to callers on non-blocking streams
     l.set = true;
     return 0;
 }
@@ -275,7 +278,9 @@ extern "C" int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_a
 extern "C" int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma1) {
     RQB_CHECK(m != nullptr, "model is NULL");
     RQB_CHECK(gamma1 >= 0.0f, "gate parameters must be non-negative");
+    RQB_CHECK(enabled >= 0 && enabled <= 2, "enabled must be 0 (off), 1 (one fp16 pass through all layers) or 2 (TF32 first layer fed by TMA)");
     m->screen_enabled = enabled != 0;
+    if (enabled) m->screen_kind = enabled == 2 ? 1 : 0;
     if (gamma1 > 0.0f) m->screen_gamma = gamma1;
     return 0;
 }
@@ -303,7 +308,21 @@ extern "C" int rqb200_mlp_tc(rqb200_model *m, int which, const float *x_dev, int
     return mlp_tc(m, which, x_dev, n, y_dev, (cudaStream_t)stream);
 }
 
-// diagnostics / tools: one tensor-core Linear of the model in isolation (passes = 1 or 3)
+// diagnostics / tools: the tensor-core MLP at a chosen precision — passes = 3 (split-fp16), 1 (one fp16 pass), 2 (TF32 first
+// layer fed by TMA + three-pass tail: what the screening tier computes)
+extern "C" int rqb200_debug_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, int passes, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(which == 0 || which == 1, "which must be 0 or 1");
+    RQB_CHECK(passes >= 1 && passes <= 3, "passes must be 1, 2 or 3");
+    if (n == 0) return 0;
+    RQB_CHECK(x_dev != nullptr && y_dev != nullptr, "NULL buffer");
+    for (int i = 0; i < m->n_layers; ++i)
+        if (!(which == 0 ? m->enc[i].set : m->dec[i].set)) { set_error("layer %d not loaded", i); return RQB200_ESTATE; }
+    RQB_CUDA(cudaSetDevice(m->device));
+    return mlp_tc(m, which, x_dev, n, y_dev, (cudaStream_t)stream, passes);
+}
+
+// diagnostics / tools: one tensor-core Linear of the model in isolation (passes = 1 or 3; 2 = the TF32 screening kernel)
 extern "C" int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
                                       int passes, int relu, void *stream) {
     RQB_CHECK(m != nullptr, "model is NULL");
@@ -314,6 +333,7 @@ extern "C" int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, con
     Linear &l = which == 0 ? m->enc[layer] : m->dec[layer];
     RQB_CHECK(l.set, "layer not loaded");
     RQB_CUDA(cudaSetDevice(m->device));
+    if (passes == 2) return linear_tf32(l, x_dev, n, y_dev, relu != 0, (cudaStream_t)stream, false);      // TF32 screening kernel
     return linear_tc(l, x_dev, n, y_dev, relu != 0, (cudaStream_t)stream, passes);
 }
 
@@ -416,7 +436,10 @@ extern "C" int rqb200_get_indices(rqb200_model *m, int mode, const float *x_dev,
     RQB_TRY(check_encoder(m));
     RQB_TRY(check_codebooks(m));
     RQB_CUDA(cudaSetDevice(m->device));
-    if (mode == RQB200_ENCODE_FAST) return get_indices_fast(m, x_dev, n, codes_dev, z_out_dev, stats_host, s);
+    // batches of fewer than 16 rows: the reference's CPU GEMM uses its small-batch summation order (small_batch.cu) — only
+    // the exact kernels restate it
+    if (mode == RQB200_ENCODE_FAST && n >= 16) return get_indices_fast(m, x_dev, n, codes_dev, z_out_dev, stats_host, s);
+    if (mode == RQB200_ENCODE_FAST) mode = RQB200_ENCODE_EXACT;
     RQB_CHECK(mode == RQB200_ENCODE_EXACT, "unknown mode %d", mode);
     float *z = z_out_dev;
     if (!z) {
@@ -455,7 +478,7 @@ extern "C" int rqb200_forward(rqb200_model *m, const float *x_dev, int64_t n, fl
 // infer.py:88-103 (pass 1) + infer.py:139-177 (suffix) for a catalogue that lives in host memory:
 // chunked H2D on a copy stream, double-buffered against the encode kernels.
 extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float *x_host, int64_t n,
-                                          int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host) {
+                                          int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host, void *stream) {
     RQB_CHECK(m != nullptr, "model is NULL");
     RQB_CHECK(n >= 0, "n < 0");
     if (stats_host) { stats_host[0] = 0; stats_host[1] = 0; stats_host[2] = 0; }
@@ -467,21 +490,22 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
     if (chunk_rows <= 0) chunk_rows = 131072;
     if (chunk_rows > n) chunk_rows = n;
     const int in = m->dims[0], L = m->L;
-    const size_t chunk_bytes = sizeof(float) * (size_t)chunk_rows * in;
+    // a tail of fewer than 16 rows rides with the previous chunk (a call with < 16 rows would take the small-batch order)
+    const size_t chunk_bytes = sizeof(float) * (size_t)(chunk_rows + 16) * in;
     RQB_TRY(ws_reserve(m->hostpipe[0], chunk_bytes + sizeof(int64_t) * (size_t)n * (2 * L + 1)));
     RQB_TRY(ws_reserve(m->hostpipe[1], chunk_bytes));
     float *xbuf[2] = {(float *)m->hostpipe[0].ptr, (float *)m->hostpipe[1].ptr};
     int64_t *codes = (int64_t *)((char *)m->hostpipe[0].ptr + chunk_bytes);
     int64_t *out = codes + (size_t)n * L;
     cudaStream_t cs = m->copy_stream;
-    cudaStream_t ks = 0;
+    cudaStream_t ks = (cudaStream_t)stream;
     // ev[0], ev[1]: chunk in buffer b copied;  ev[2], ev[3]: buffer b consumed
     int64_t rescued = 0;
-    int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
-    for (int64_t c = 0; c < nchunks; ++c) {
+    int64_t r0 = 0;
+    for (int64_t c = 0; r0 < n; ++c) {
         const int b = (int)(c & 1);
-        const int64_t r0 = c * chunk_rows;
-        const int64_t rows = (n - r0) < chunk_rows ? (n - r0) : chunk_rows;
+        const int64_t left = n - r0;
+        const int64_t rows = (left - chunk_rows < 16) ? left : chunk_rows;
         if (c >= 2) RQB_CUDA(cudaStreamWaitEvent(cs, m->ev[2 + b], 0));
         RQB_CUDA(cudaMemcpyAsync(xbuf[b], x_host + (size_t)r0 * in, sizeof(float) * (size_t)rows * in,
                                  cudaMemcpyHostToDevice, cs));
@@ -491,6 +515,7 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
         RQB_TRY(rqb200_get_indices(m, mode, xbuf[b], rows, codes + (size_t)r0 * L, nullptr, &st, ks));
         rescued += st;
         RQB_CUDA(cudaEventRecord(m->ev[2 + b], ks));
+        r0 += rows;
     }
     int64_t distinct = 0, maxgroup = 0;
     RQB_TRY(rqb200_suffix_dedup(m, codes, n, L, m->K, out, stats_host ? &distinct : nullptr,

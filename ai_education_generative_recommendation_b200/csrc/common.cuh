@@ -68,6 +68,7 @@ struct Linear {
     float *absW_rowmax = nullptr;
     int tc_scale_exp = 0;    // W_tc holds W * 2^tc_scale_exp
     void *W_tc2 = nullptr;   // image for the 2-CTA kernel (each CTA of a pair stages half of the output features)
+    float *W_tf32 = nullptr; // W rounded to the TF32 mantissa (screening kernel, encode_tf32.cu)
 };
 
 // "Do this once per device": cudaFuncSetAttribute is a per-device setting, and one process may drive several devices
@@ -118,7 +119,8 @@ struct rqb200_model {
     int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced
     bool force_simt_quantizer = false;      // diagnostics: keep the SIMT quantizer behind the tensor-core encoder
     float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
-    bool screen_enabled = false;            // tier 1 (opt-in): one fp16 pass over every row, only gated rows get the 3-pass run
+    bool screen_enabled = false;            // tier 1 (opt-in): one reduced-precision pass over every row, only gated rows get the 3-pass run
+    int screen_kind = 1;                    // 1: TF32 first layer fed by TMA + three-pass tail (encode_tf32.cu); 0: one fp16 pass through all layers
     float screen_gamma = 4.8828125e-04f;    // 2^-11: calibrated gate of the one-pass tier
     int64_t last_tier_rows[2] = {0, 0};     // rows re-run by tier 2 / tier 3 in the last fast get_indices
     cudaStream_t copy_stream = nullptr;
@@ -130,8 +132,10 @@ namespace rqb {
 int ws_reserve(Workspace &w, size_t bytes);
 
 // linear_exact.cu
+// batch_rows: how many rows the reference would have in the batch these n rows belong to (decides the summation order,
+// small_batch.cu); -1 = n.  Internal callers that recompute a SUBSET of a large batch (rescue tier) pass the batch size.
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s);
+                 bool relu, cudaStream_t s, int64_t batch_rows = -1);
 // small_batch.cu: the reference's order for batches of 2..15 rows (and per-row batch sizes for the group re-encode)
 int linear_small(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu, cudaStream_t s);
 int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, const int *msize, int m_uniform, int64_t n,
@@ -141,6 +145,9 @@ int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, 
 bool linear_tc2_supported(const Linear &l);
 int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
                const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
+// encode_tf32.cu: TMA-fed one-pass TF32 first layer (screening tier)
+bool linear_tf32_supported(const Linear &l);
+int linear_tf32(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out);
 // encode_tc3.cu (experimental, off unless RQB200_TC3=1 or debug flag 4096): same contract as the plain three-pass linear_tc2
 bool linear_tc3_enabled();
 int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out, int passes = 3);
@@ -164,7 +171,7 @@ int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int6
 int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
                    const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
-                   float *margin_out, cudaStream_t s);
+                   float *margin_out, cudaStream_t s, int64_t batch_rows = -1);
 int distances_exact(const rqb200_model *m, int level, const float *r, int64_t n, float *d,
                     cudaStream_t s);
 int recon_error(const float *out, const float *x, int64_t count, double *recon_sum, cudaStream_t s);

@@ -725,6 +725,12 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
         RQB_TRY(ws_reserve(m->act[0], sizeof(float) * n_pad * maxdim));
         if (m->n_layers > 2) RQB_TRY(ws_reserve(m->act[1], sizeof(float) * n_pad * maxdim));
     }
+    // passes == 2: the screening tier — first layer as ONE TF32 pass fed by TMA (encode_tf32.cu), the tail three-pass
+    const bool tf32_first = passes == 2;
+    if (tf32_first) {
+        RQB_CHECK(which == 0 && rows == nullptr && n_dev == nullptr && linear_tf32_supported(ls[0]), "TF32 screening pass: unsupported call");
+        passes = 3;
+    }
     const float *cur = x;
     bool cur_tiled = false;             // `cur` holds split-fp16 UMMA tiles (written by the 2-CTA kernel for the fused kernel)
     for (int i = 0; i < m->n_layers; ++i) {
@@ -747,7 +753,8 @@ int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cuda
         // first layer of a 3-layer three-pass MLP whose tail is fused: emit the tiles the fused kernel bulk-loads
         const bool tiled = i == 0 && m->n_layers == 3 && passes == 3 && linear_tc2_supported(ls[0]) && ls[0].out == 256 &&
                            mlp23_supported(ls[1], ls[2]) && !env_unfused() && !env_untiled();
-        RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev, tiled));
+        if (i == 0 && tf32_first) RQB_TRY(linear_tf32(ls[0], cur, n, dst, !last, s, tiled));
+        else RQB_TRY(linear_tc(ls[i], cur, n, dst, !last, s, passes, i == 0 ? rows : nullptr, n_dev, tiled));
         cur = dst;
         cur_tiled = tiled;
     }
@@ -799,7 +806,8 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
     RQB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), s));
     unsigned long long h[2] = {0, 0};
     if (screen) {
-        RQB_TRY(mlp_tc(m, 0, x, n, z1, s, 1, nullptr, nullptr, true));
+        const bool tf32 = m->screen_kind == 1 && linear_tf32_supported(m->enc[0]) && (((uintptr_t)x & 15) == 0) && n < ((int64_t)1 << 31);
+        RQB_TRY(mlp_tc(m, 0, x, n, z1, s, tf32 ? 2 : 1, nullptr, nullptr, true));
         {
             ProfScope ps(PROF_QUANTIZE, s);
             RQB_TRY(quantize_tc(m, z1, n, codes, list1, counts, s, m->screen_gamma));
@@ -847,10 +855,10 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
         for (int i = 0; i < m->n_layers; ++i) {
             const bool last = i == m->n_layers - 1;
             float *dst = last ? zr : (float *)m->rescue_act[i & 1].ptr;
-            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list2 : nullptr, nr, dst, !last, s));
+            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list2 : nullptr, nr, dst, !last, s, n));      // order of the n-row batch
             cur = dst;
         }
-        RQB_TRY(quantize_exact(m, zr, nr, codes, list2, nullptr, nullptr, nullptr, nullptr, s));
+        RQB_TRY(quantize_exact(m, zr, nr, codes, list2, nullptr, nullptr, nullptr, nullptr, s, n));
         if (z_out) RQB_TRY(scatter_rows(zr, list2, nr, m->e, z_out, s));      // keep the caller's latent exact on rescued rows
     }
     return 0;

@@ -93,7 +93,7 @@ extern "C" int rqb200_kmeans_assign(const float *x_dev, int64_t n, int e, const 
     tmp.cb[0] = const_cast<float *>(centers_dev);
     tmp.cc[0] = cnorm_scratch_dev;
     RQB_TRY(codebook_norms(centers_dev, K, e, cnorm_scratch_dev, s));
-    return quantize_exact(&tmp, x_dev, n, assign_dev, nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    return quantize_exact(&tmp, x_dev, n, assign_dev, nullptr, nullptr, nullptr, nullptr, nullptr, s, (int64_t)1 << 30);
 }
 
 extern "C" int rqb200_kmeans_distances(const float *x_dev, int64_t n, int e, const float *centers_dev, int K,

@@ -246,14 +246,14 @@ int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, fl
 }  // namespace
 
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s) {
+                 bool relu, cudaStream_t s, int64_t batch_rows) {
     if (n == 0) return 0;
     RQB_CHECK(lin.set, "linear layer not loaded");
     RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
     RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);
     RQB_CHECK(n <= (int64_t)2147483647 * 128, "too many rows");
     // a batch of 2..15 rows: the reference's CPU GEMM switches to its small-batch summation order (small_batch.cu)
-    if (small_batch_lane16(n, lin.in)) return linear_small(lin, x, rows, n, y, relu, s);
+    if (small_batch_lane16(batch_rows < 0 ? n : batch_rows, lin.in)) return linear_small(lin, x, rows, n, y, relu, s);
     if (lin.out > 64) return launch<128, 128, 8, 8>(lin, x, rows, n, y, relu, s);
     if (lin.out > 32) return launch<128, 64, 8, 4>(lin, x, rows, n, y, relu, s);
     return launch<128, 32, 4, 4>(lin, x, rows, n, y, relu, s);

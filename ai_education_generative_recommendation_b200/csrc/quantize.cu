@@ -630,11 +630,11 @@ int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s) {
 
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
                    const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
-                   float *margin_out, cudaStream_t s) {
+                   float *margin_out, cudaStream_t s, int64_t batch_rows) {
     if (n == 0) return 0;
     ProfScope ps(PROF_QUANTIZE, s);
     // a batch of 2..15 rows with 24·n <= e: matmul(latent, E.t()) runs in the reference's small-batch order (small_batch.cu)
-    if (small_batch_lane16(n, m->e) && !last_residual && !margin_out)
+    if (small_batch_lane16(batch_rows < 0 ? n : batch_rows, m->e) && !last_residual && !margin_out)
         return quantize_small(m, z, rows_out, nullptr, (int)n, n, m->L, codes, nullptr, xq, sumsq, nullptr, 0, s);
     // few rows and codes only: share a row between QS lanes so that the whole GPU works on it (measured: faster than a row
     // per thread up to about half a wave of 128-row CTAs, slower beyond — the row-per-thread kernel then fills the SMs)

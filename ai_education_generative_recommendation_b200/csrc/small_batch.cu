@@ -325,32 +325,10 @@ int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, 
 
 using namespace rqb;
 
-// infer.py:120-122 for ALL collision groups of one round, up to (not including) the last level:
-//   for every group g and every member i:  z = encoder(x_i) in the order of a batch of |g| rows,
-//   codes[i, 0..L-2] = arg-min codes of the first L-1 levels (distance product in the order of that batch size),
-//   residual[i, :]   = residual entering the last level.
-// The last level (Sinkhorn over the group's distance matrix) is rqb200_sinkhorn_regroup on `residual`.
-extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
-                                      const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
-                                      int64_t *codes_dev, float *residual_dev, void *stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    RQB_CHECK(m != nullptr, "model is NULL");
-    if (n_groups == 0 || n_items == 0) return 0;
-    RQB_CHECK(x_dev && items_dev && offsets_dev && codes_dev && residual_dev, "NULL buffer");
-    for (int i = 0; i < m->n_layers; ++i) RQB_CHECK(m->enc[i].set, "encoder layer %d not loaded", i);
-    for (int l = 0; l < m->L; ++l) RQB_CHECK(m->cb_set[l], "codebook %d not loaded", l);
-    RQB_CUDA(cudaSetDevice(m->device));
-    int maxdim = m->e;
-    for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
-    const size_t act = sizeof(float) * (size_t)n_items * maxdim;
-    const size_t msz = ((sizeof(int) * (size_t)n_items + 255) / 256) * 256;
-    RQB_TRY(ws_reserve(m->groupws, msz + 2 * act));
-    int *msize = (int *)m->groupws.ptr;
-    float *buf[2] = {(float *)((char *)m->groupws.ptr + msz), (float *)((char *)m->groupws.ptr + msz + act)};
-    ProfScope ps(PROF_REENCODE, s);
-    rqb::count_launch();
-    group_sizes_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(offsets_dev, n_groups, n_items, msize);
-    RQB_LAUNCH_CHECK();
+// shared body: every listed row is re-encoded up to (not including) the last level in the order of ITS batch size
+static int reencode_rows_impl(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev, const int *msize,
+                              int64_t n_items, float *buf0, float *buf1, int64_t *codes_dev, float *residual_dev, cudaStream_t s) {
+    float *buf[2] = {buf0, buf1};
     const float *cur = x_dev;
     for (int i = 0; i < m->n_layers; ++i) {
         const bool last = i == m->n_layers - 1;
@@ -360,4 +338,56 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
         cur = dst;
     }
     return quantize_small(m, cur, items_dev, msize, 0, n_items, m->L - 1, codes_dev, residual_dev, nullptr, nullptr, nullptr, 0, s);
+}
+
+static int reencode_check(rqb200_model *m) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    for (int i = 0; i < m->n_layers; ++i) RQB_CHECK(m->enc[i].set, "encoder layer %d not loaded", i);
+    for (int l = 0; l < m->L; ++l) RQB_CHECK(m->cb_set[l], "codebook %d not loaded", l);
+    return 0;
+}
+
+// infer.py:120-122 for ALL collision groups of one round, up to (not including) the last level:
+//   for every group g and every member i:  z = encoder(x_i) in the order of a batch of |g| rows,
+//   codes[i, 0..L-2] = arg-min codes of the first L-1 levels (distance product in the order of that batch size),
+//   residual[i, :]   = residual entering the last level.
+// The last level (Sinkhorn over the group's distance matrix) is rqb200_sinkhorn_regroup on `residual`.
+extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
+                                      const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
+                                      int64_t *codes_dev, float *residual_dev, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_TRY(reencode_check(m));
+    if (n_groups == 0 || n_items == 0) return 0;
+    RQB_CHECK(x_dev && items_dev && offsets_dev && codes_dev && residual_dev, "NULL buffer");
+    RQB_CUDA(cudaSetDevice(m->device));
+    int maxdim = m->e;
+    for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
+    const size_t act = sizeof(float) * (size_t)n_items * maxdim;
+    const size_t msz = ((sizeof(int) * (size_t)n_items + 255) / 256) * 256;
+    RQB_TRY(ws_reserve(m->groupws, msz + 2 * act));
+    int *msize = (int *)m->groupws.ptr;
+    ProfScope ps(PROF_REENCODE, s);
+    rqb::count_launch();
+    group_sizes_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(offsets_dev, n_groups, n_items, msize);
+    RQB_LAUNCH_CHECK();
+    return reencode_rows_impl(m, x_dev, x_is_gathered, items_dev, msize, n_items, (float *)((char *)m->groupws.ptr + msz),
+                              (float *)((char *)m->groupws.ptr + msz + act), codes_dev, residual_dev, s);
+}
+
+// The same for rows that are members of groups whose other members live elsewhere (sharded catalogue): the caller
+// supplies the size of every row's group (msize_dev, int32 [n_rows]) instead of the group lists.
+extern "C" int rqb200_reencode_rows(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *rows_dev,
+                                    const int *msize_dev, int64_t n_rows, int64_t *codes_dev, float *residual_dev, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    RQB_TRY(reencode_check(m));
+    if (n_rows == 0) return 0;
+    RQB_CHECK(x_dev && rows_dev && msize_dev && codes_dev && residual_dev, "NULL buffer");
+    RQB_CUDA(cudaSetDevice(m->device));
+    int maxdim = m->e;
+    for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
+    const size_t act = sizeof(float) * (size_t)n_rows * maxdim;
+    RQB_TRY(ws_reserve(m->groupws, 2 * act));
+    ProfScope ps(PROF_REENCODE, s);
+    return reencode_rows_impl(m, x_dev, x_is_gathered, rows_dev, msize_dev, n_rows, (float *)m->groupws.ptr,
+                              (float *)((char *)m->groupws.ptr + act), codes_dev, residual_dev, s);
 }

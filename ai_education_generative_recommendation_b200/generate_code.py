@@ -27,6 +27,16 @@ from .rqvae import RQVAE
 MAX_LEVELS_OF_REFERENCE_DRIVER = 5     # prefix list ["<a_{}>",…,"<e_{}>"] has 5 entries (infer.py:90)
 
 
+def _chunks(n: int, chunk_rows: int):
+    """[lo, hi) row ranges of about chunk_rows rows.  Pass 1 treats the catalogue as ONE batch (the reference with a
+    catalogue-sized batch); a tail of fewer than 16 rows is merged into the previous chunk, because a call with < 16 rows
+    would be computed in the reference's small-batch summation order (csrc/small_batch.cu)."""
+    bounds = list(range(0, n, chunk_rows)) + [n]
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] < 16:
+        del bounds[-2]
+    return list(zip(bounds[:-1], bounds[1:]))
+
+
 def _as_rows(data):
     if isinstance(data, np.ndarray):
         return torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
@@ -43,8 +53,7 @@ def encode_latents(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Tensor
     z = torch.empty((n, model.e_dim), dtype=torch.float32, device=dev)
     model._sync()
     L = _cabi.lib()
-    for r0 in range(0, n, chunk_rows):
-        r1 = min(n, r0 + chunk_rows)
+    for r0, r1 in _chunks(n, chunk_rows):
         chunk = data[r0:r1]
         if not chunk.is_cuda:
             chunk = chunk.contiguous().to(dev, non_blocking=True)
@@ -106,8 +115,7 @@ def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Ten
     model._sync()
     L = _cabi.lib()
     stats = (ctypes.c_int64 * 4)()
-    for r0 in range(0, n, chunk_rows):
-        r1 = min(n, r0 + chunk_rows)
+    for r0, r1 in _chunks(n, chunk_rows):
         chunk = data[r0:r1]
         if not chunk.is_cuda:
             chunk = chunk.contiguous().to(dev, non_blocking=True)

@@ -340,19 +340,22 @@ class RQVAE(nn.Module):
         return (not self.bn and dims[0] % 8 == 0 and all(d in (32, 64, 128, 256) for d in dims[1:])
                 and self.e_dim in (16, 32, 48, 64))
 
-    def set_screen(self, enabled: bool, gamma1: float = 0.0):
-        """Screening tier of the fast route (one fp16 pass over every row; see rqb200_model_set_screen)."""
+    def set_screen(self, enabled, gamma1: float = 0.0):
+        """Screening tier of the fast route (rqb200_model_set_screen): 0 / False off, 2 / "tf32" the TMA-fed TF32 first
+        layer, 1 / True one fp16 pass through all layers."""
         self._ensure_handle()
-        check(_cabi.lib().rqb200_model_set_screen(self._handle, int(bool(enabled)), float(gamma1)))
+        kind = 2 if enabled == "tf32" else int(enabled)
+        check(_cabi.lib().rqb200_model_set_screen(self._handle, kind, float(gamma1)))
 
     @torch.no_grad()
-    def encode_tc(self, x: torch.Tensor) -> torch.Tensor:
-        """Encoder MLP on the tensor cores (fp32-class accuracy, not bit-exact) — diagnostic / building block."""
+    def encode_tc(self, x: torch.Tensor, passes: int = 3) -> torch.Tensor:
+        """Encoder MLP on the tensor cores (not bit-exact) — diagnostic / building block.  passes = 3: split-fp16,
+        fp32-class accuracy; 2: TF32 first layer fed by TMA + three-pass tail (screening tier); 1: one fp16 pass."""
         _require_cuda_tensor(x, "input")
         self._sync()
         x2 = x.reshape(-1, self.in_dim).contiguous()
         y = torch.empty((x2.shape[0], self.e_dim), dtype=torch.float32, device=x.device)
-        check(_cabi.lib().rqb200_mlp_tc(self._handle, 0, ptr(x2), x2.shape[0], ptr(y), stream_ptr(x.device)))
+        check(_cabi.lib().rqb200_debug_mlp_tc(self._handle, 0, ptr(x2), x2.shape[0], ptr(y), int(passes), stream_ptr(x.device)))
         return y
 
     # ---- building blocks -----------------------------------------------------------------

@@ -5,9 +5,10 @@ The reference is single-process; this is new design for BASELIN
   * global collision handling needs ONE exchange step: every item's packed code is routed to the rank
     that owns the key (all-to-all), the owner ranks equal keys in ascending GLOBAL item order, and the
     ranks travel back (all-to-all).  The result is bit-identical to the single-GPU suffix column;
-  * the Sinkhorn re-encode rounds (reference infer.py:109-130) only ever touch the last level, so items are
-    routed once by the hash of their PREFIX codes together with the residual entering the last level; the
-    owner runs all rounds and the suffix ranking locally (`generate_codes_sharded`).
+  * the Sinkhorn re-encode rounds (reference infer.py:109-130): per round the full codes travel to the key's owner,
+    which finds the groups; every member's home rank — which holds the item's embedding — re-encodes it as the reference
+    does (whole model, in the arithmetic of a batch of the group's size), the residuals entering the last level meet
+    at the owner for the group's Sinkhorn pass, and the new last-level codes travel home (`generate_codes_sharded`).
 Collectives go through torch.distributed (NCCL over NVLink on the GPU box, gloo in the CPU tests); the
 per-rank work is behind a small `ops` object — `CudaShardOps` (C-ABI kernels) in production, an
 oracle-backed numpy twin only inside tests/.
@@ -77,19 +78,72 @@ class CudaShardOps:
 
 
     # ---- the complete sharded driver (generate_codes_sharded) ----
-    def encode_shard(self, data):
-        """Pass 1 on this rank's shard: (codes[n, L], residual entering the last level [n, e])."""
-        from .generate_code import encode_codes_and_residual
-        return encode_codes_and_residual(self.model, data)
+    def encode_codes(self, data):
+        """Pass 1 on this rank's shard: codes[n, L] (tensor-core route where the shapes allow it — every row certified by
+        the margin gate or recomputed exactly — else the exact route)."""
+        from .generate_code import encode_codes_exact, encode_codes_fast
+        fast = self.model.fast_route_supported()
+        return encode_codes_fast(self.model, data) if fast else encode_codes_exact(self.model, data)
 
-    def resolve_owned(self, codes: torch.Tensor, residual: torch.Tensor, max_rounds: int):
-        """Passes 2-3 over the items this rank owns (they arrive in ascending global item order)."""
-        from .generate_code import resolve_rounds, suffix_dedup
-        if codes.shape[0] == 0:
-            return torch.empty((0, codes.shape[1] + 1), dtype=torch.int64, device=codes.device), 0
-        codes, rounds = resolve_rounds(self.model, codes.contiguous(), residual.contiguous(), max_rounds=max_rounds)
-        out, _ = suffix_dedup(self.model, codes)
-        return out, rounds
+    def last_level_sinkhorn(self) -> bool:
+        last = self.model.rq.vq_layers[-1]
+        return last.sk_epsilon is not None and last.sk_epsilon > 0
+
+    def resolve_local(self, codes, data, max_rounds):
+        from .generate_code import resolve_rounds
+        return resolve_rounds(self.model, codes, data, max_rounds=max_rounds)
+
+    def groups(self, codes: torch.Tensor):
+        """Collision groups among `codes` (rows in arrival order) → (items, offsets, sizes[n] with 1 = in no group)."""
+        from .generate_code import collision_groups
+        n = codes.shape[0]
+        sizes = torch.ones((n,), dtype=torch.int64, device=codes.device)
+        if n == 0:
+            return codes.new_zeros((0,)), codes.new_zeros((1,)), sizes
+        items, offsets, _ = collision_groups(self.model, codes.contiguous())
+        if items.numel():
+            sizes[items] = torch.repeat_interleave(offsets[1:] - offsets[:-1], offsets[1:] - offsets[:-1])
+        return items, offsets, sizes
+
+    def reencode_members(self, data, members: torch.Tensor, msize: torch.Tensor, codes: torch.Tensor) -> torch.Tensor:
+        """Re-encode the listed local items as members of groups of the given sizes (infer.py:120-122 up to the last
+        level): codes[members, :L-1] are overwritten, the residuals entering the last level are returned [m, e]."""
+        from .generate_code import _as_rows
+        m = self.model
+        dev = codes.device
+        k = members.numel()
+        out = torch.empty((k, m.e_dim), dtype=torch.float32, device=dev)
+        if k == 0:
+            return out
+        data = _as_rows(data)
+        residual = torch.empty((codes.shape[0], m.e_dim), dtype=torch.float32, device=dev)
+        if data.is_cuda:
+            x, gathered = data, 0
+        else:
+            x, gathered = data[members.cpu()].contiguous().to(dev), 1
+        m._sync()
+        check(_cabi.lib().rqb200_reencode_rows(m._handle, ptr(x), gathered, ptr(members.contiguous()),
+                                               ptr(msize.to(torch.int32).contiguous()), k, ptr(codes), ptr(residual),
+                                               stream_ptr(dev)))
+        return residual[members]
+
+    def sinkhorn_groups(self, codes: torch.Tensor, items, offsets, residual_rows: torch.Tensor):
+        """Last level of the re-encode for the groups found by `groups` (vq.py:74-83 over each group's distance matrix):
+        codes[item, L-1] overwritten in place.  residual_rows[n, e]: rows of the members are filled."""
+        from .generate_code import _regroup_oversized
+        m = self.model
+        lib = _cabi.lib()
+        last = m.rq.vq_layers[-1]
+        n_groups = offsets.numel() - 1
+        if n_groups <= 0:
+            return
+        max_group = int((offsets[1:] - offsets[:-1]).max().item())
+        cap = lib.rqb200_sinkhorn_group_cap(m._handle)
+        m._sync()
+        check(lib.rqb200_sinkhorn_regroup(m._handle, ptr(residual_rows), ptr(items), ptr(offsets), n_groups, min(max_group, cap),
+                                          float(last.sk_epsilon), int(last.sk_iters), ptr(codes), stream_ptr(codes.device)))
+        if max_group > cap:
+            _regroup_oversized(m, residual_rows, items, offsets, cap, codes)
 
 
 class PeerShardDedup:
@@ -196,44 +250,82 @@ def global_suffix(codes: torch.Tensor, num_emb_list, ops, group=None) -> torch.T
     return out
 
 
+def _segment_counts(mask: torch.Tensor, splits: List[int]) -> List[int]:
+    """How many True entries of `mask` fall into each consecutive segment of the given lengths (one host read)."""
+    cs = torch.cat([mask.new_zeros((1,), dtype=torch.int64), torch.cumsum(mask.to(torch.int64), 0)])
+    bounds = torch.tensor([0] + list(_accumulate(splits)), dtype=torch.int64, device=mask.device)
+    return (cs[bounds[1:]] - cs[bounds[:-1]]).cpu().tolist()
+
+
+def _accumulate(xs):
+    t = 0
+    for v in xs:
+        t += int(v)
+        yield t
+
+
 def generate_codes_sharded(model, data_shard, group=None, max_rounds: int = 30, ops=None) -> Tuple[torch.Tensor, dict]:
     """The whole encode driver (reference infer.py:88-177) over a catalogue sharded by contiguous item ranges:
     `data_shard` = this rank's rows; returns this rank's [n_local, L+1] semantic ids, identical to the rows a
     single-GPU `generate_codes` of the concatenated catalogue produces.
 
-    Levels < L-1 never change during the Sinkhorn rounds (infer.py:109-110), so every collision group — in any
-    round — lives inside one PREFIX (first L-1 codes) class.  Items are therefore routed ONCE to
-    owner = hash(prefix) mod G together with the residual entering the last level (all-to-all: 8(L+1) + 4e bytes
-    per item); the owner holds them in ascending global item order, runs the ≤30 re-encode rounds and the suffix
-    ranking locally with the single-GPU kernels, and the finished rows travel back (all-to-all, 8(L+1) bytes per
-    item).  Two exchanges in total, none per round."""
+    A round of the re-encode loop (infer.py:116-129), sharded:
+      1. every item's full code travels to owner = hash(key) mod G (all-to-all; arrival order = ascending global item
+         index), the owner finds the groups and answers every item with the size of its group (1 = no collision);
+      2. the HOME rank of a member — it holds the embedding — re-encodes it as the reference does: encoder and arg-min
+         levels in the arithmetic of a batch of that size (csrc/small_batch.cu); the first L-1 codes are final;
+      3. the members' residuals entering the last level travel to the owner (4e bytes per member), which runs the
+         Sinkhorn pass over each group's distance matrix, and the new last-level codes travel home.
+    Four small exchanges per round, all sized by the number of colliding items except the first; the loop ends as soon
+    as no rank owns a group.  The suffix column is one more exchange (`global_suffix`)."""
     ops = ops if ops is not None else CudaShardOps(model)
     Ks = list(model.num_emb_list)
     Lv = len(Ks)
-    codes, residual = ops.encode_shard(data_shard)
+    codes = ops.encode_codes(data_shard)
     world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
+    rounds = 0
     if world == 1:
-        out, rounds = ops.resolve_owned(codes, residual, max_rounds)
+        codes, rounds = ops.resolve_local(codes, data_shard, max_rounds)
+        out = global_suffix(codes, Ks, ops, None)
         stats = global_stats(out, None)
         stats["rounds"] = rounds
         return out, stats
-    if Lv > 1:
-        prefix = ops.pack_keys(codes[:, :Lv - 1].contiguous(), Ks[:Lv - 1])
-    else:
-        prefix = torch.zeros((codes.shape[0],), dtype=torch.int64, device=codes.device)   # one class: a single owner
-    owner = owner_of(prefix, world)
-    order, send_counts = ops.bucket_by_owner(owner, world)        # stable: ascending item index inside a bucket
-    sc, rc = _exchange_counts(send_counts, group)
-    recv_codes = _all_to_all(codes[order], sc, rc, group)         # arrival order = (source rank, local index)
-    recv_res = _all_to_all(residual[order], sc, rc, group)        #               = ascending global item index
-    owned, rounds = ops.resolve_owned(recv_codes, recv_res, max_rounds)
-    back = _all_to_all(owned, rc, sc, group)
-    out = torch.empty((codes.shape[0], Lv + 1), dtype=torch.int64, device=codes.device)
-    out[order] = back
-    r = torch.tensor([rounds], dtype=torch.int64, device=codes.device)
-    dist.all_reduce(r, op=dist.ReduceOp.MAX, group=group)
+    if ops.last_level_sinkhorn():
+        n = codes.shape[0]
+        dev = codes.device
+        while rounds < max_rounds:
+            keys = ops.pack_keys(codes, Ks)
+            owner = owner_of(keys, world)
+            order, send_counts = ops.bucket_by_owner(owner, world)        # stable: ascending item index inside a bucket
+            sc, rc = _exchange_counts(send_counts, group)
+            recv_codes = _all_to_all(codes[order], sc, rc, group)         # arrival order = (source rank, local index)
+            items, offsets, sizes = ops.groups(recv_codes)
+            busy = torch.tensor([int(items.numel() > 0)], dtype=torch.int64, device=dev)
+            dist.all_reduce(busy, op=dist.ReduceOp.MAX, group=group)
+            if int(busy.item()) == 0:
+                break
+            size_back = _all_to_all(sizes, rc, sc, group)
+            msize = torch.ones((n,), dtype=torch.int64, device=dev)
+            msize[order] = size_back
+            members = torch.nonzero(msize > 1).flatten()
+            res_members = ops.reencode_members(data_shard, members, msize[members], codes)
+            residual = torch.zeros((n, res_members.shape[1]), dtype=torch.float32, device=dev)
+            residual[members] = res_members
+            sel = msize[order] > 1                                        # members, in send order
+            sc_m = _segment_counts(sel, sc)
+            mem_recv = sizes > 1                                          # members, in arrival order
+            rc_m = _segment_counts(mem_recv, rc)
+            res_recv = _all_to_all(residual[order[sel]], sc_m, rc_m, group)
+            res_rows = torch.zeros((recv_codes.shape[0], residual.shape[1]), dtype=torch.float32, device=dev)
+            pos = torch.nonzero(mem_recv).flatten()
+            res_rows[pos] = res_recv
+            ops.sinkhorn_groups(recv_codes, items, offsets, res_rows)
+            last_back = _all_to_all(recv_codes[pos, Lv - 1].contiguous(), rc_m, sc_m, group)
+            codes[order[sel], Lv - 1] = last_back
+            rounds += 1
+    out = global_suffix(codes, Ks, ops, group)
     stats = global_stats(out, group)
-    stats["rounds"] = int(r.item())
+    stats["rounds"] = rounds
     return out, stats
 
 

@@ -435,7 +435,8 @@ def main():
     mode_id = _cabi.ENCODE_FAST if fast_ok else _cabi.ENCODE_EXACT
 
     def e2e_step():
-        _cabi.check(lib.rqb200_generate_codes_host(model._handle, mode_id, xh.data_ptr(), ne, 131072, ids_host.data_ptr(), stats))
+        _cabi.check(lib.rqb200_generate_codes_host(model._handle, mode_id, xh.data_ptr(), ne, 131072, ids_host.data_ptr(), stats,
+                                                   _cabi.stream_ptr()))
 
     for _ in range(2):
         e2e_step()

@@ -64,10 +64,13 @@ int rqb200_profile_read(double *ms_out, long long *count_out, int nslots);
 int rqb200_debug_tc_trace(long long *buf_dev);
 /* Diagnostics: ablation switches of the tensor-core linear kernel (tools/ablate_tc.py); 0 = production. */
 int rqb200_debug_tc_flags(int flags);
-/* Diagnostics: one tensor-core Linear (+bias, optional ReLU) of the model in isolation; passes = 3 (split-fp16)
- * or 1 (fp16 screening pass).  Used by tools/ to time and ablate the kernels.                        */
+/* Diagnostics: one tensor-core Linear (+bias, optional ReLU) of the model in isolation; passes = 3 (split-fp16),
+ * 1 (fp16 screening pass) or 2 (the TMA-fed TF32 kernel, first layer only).  Used by tools/ to time and ablate.   */
 int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
                            int passes, int relu, void *stream);
+/* Diagnostics: the whole tensor-core MLP at a chosen precision — passes = 3, 1, or 2 (TF32 first layer + three-pass
+ * tail: the latent the screening tier certifies).  Used by tools/calibrate_gate.py.                               */
+int rqb200_debug_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, int passes, void *stream);
 
 /* ---- model lifetime ---------------------------------------------------------------
  * Replaces the module tree RQVAE.__init__ builds (rqvae.py:45-58): an encoder MLP
@@ -89,11 +92,12 @@ int rqb200_model_set_codebook(rqb200_model *m, int level, const float *E);
  * |z~ - z| <= gamma * (|z| + floor_abs) per row; rows whose top-2 distance gap could be closed by
  * such an error are re-run by the exact kernels.  Defaults: gamma = 2^-15, floor_abs = 1e-3.       */
 int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_abs);
-/* Screening tier of the fast route: when enabled (default), every row first takes ONE fp16 tensor pass and is
- * certified with the same margin gate at the looser bound gamma1 (default 2^-11; 0 keeps the current value);
- * only rows inside that gate are re-run with the three-pass split-fp16 kernels, and only rows inside the
- * tight gate of rqb200_model_set_gate go to the exact kernels.  rqb200_model_last_tier_rows: rows re-run by
- * the three-pass tier [0] and by the exact tier [1] in the last RQB200_ENCODE_FAST call.                  */
+/* Screening tier of the fast route (opt-in).  enabled = 2: the wide first encoder layer runs as ONE TF32 tensor pass
+ * fed by TMA straight from the fp32 rows (csrc/encode_tf32.cu), the narrow layers three-pass; enabled = 1: one fp16
+ * pass through all layers; 0: off.  Rows are certified with the same margin gate at the looser bound gamma1 (default
+ * 2^-11; 0 keeps the current value); only rows inside that gate are re-run with the three-pass split-fp16 kernels, and
+ * only rows inside the tight gate of rqb200_model_set_gate go to the exact kernels.  rqb200_model_last_tier_rows: rows
+ * re-run by the three-pass tier [0] and by the exact tier [1] in the last RQB200_ENCODE_FAST call.                  */
 int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma1);
 int rqb200_model_last_tier_rows(rqb200_model *m, int64_t *out2);
 /* Copy the current codebook of `level` back (host or device destination). */
@@ -155,6 +159,10 @@ int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const in
 int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
                            const int64_t *offsets_dev, int64_t n_groups, int64_t n_items, int64_t *codes_dev,
                            float *residual_dev, void *stream);
+/* The same for rows whose group mates live on other GPUs (sharded catalogue): the size of every row's group is given
+ * (msize_dev, int32 [n_rows]) instead of the group lists; rows_dev = the rows' indices into x / codes / residual.   */
+int rqb200_reencode_rows(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *rows_dev,
+                         const int *msize_dev, int64_t n_rows, int64_t *codes_dev, float *residual_dev, void *stream);
 /* Largest group (rows) rqb200_sinkhorn_regroup handles in shared memory for this model; larger
  * groups are skipped by it and must go through rqb200_distances + rqb200_sinkhorn_assign.   */
 int rqb200_sinkhorn_group_cap(rqb200_model *m);
@@ -325,10 +333,11 @@ int rqb200_synth_items(uint64_t seed, int64_t first_row, int64_t n, int dim, int
 /* ---- host-buffer end-to-end call (what infer.py:88-177 does, use_sk=False pass + suffix)
  * x_host[n,in] pinned or pageable host memory → codes_host[n,L+1] int64; chunks of
  * `chunk_rows` are copied H2D on a side stream while the previous chunk is encoded.
- * Synchronises before returning.  stats_host (may be NULL): [0] rows rescued by the exact
+ * Kernels and the final D2H copy run on `stream` (NULL = the legacy default stream); the call synchronises that
+ * stream before returning.  stats_host (may be NULL): [0] rows rescued by the exact
  * kernels, [1] distinct codes, [2] largest collision group (infer.py:132-137).           */
 int rqb200_generate_codes_host(rqb200_model *m, int mode, const float *x_host, int64_t n,
-                               int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host);
+                               int64_t chunk_rows, int64_t *codes_host, int64_t *stats_host, void *stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -269,6 +269,55 @@ def make_infer_c3():
     make_infer("c3_infer", cfg, 20000, 10_000_000, (0, 4096), (64,), dup=dup)
 
 
+def make_small_batches():
+    """Module-level calls on SMALL batches (2 … 20 rows): the reference's CPU GEMM switches its summation order below 16
+    rows, so `get_indices` / `forward` of the same rows give other last bits than inside a large batch.  Pins the oracle's
+    small-batch restatement and gives the GPU tests golden bits for RQVAE.get_indices / forward at those batch sizes."""
+    out = {}
+    names = []
+    for tag, base in (("c2", "c2_slice"), ("c3", "c3_slice")):
+        g = np.load(os.path.join(GOLD, f"{base}.npz"))
+        cfg = json.loads(str(g["cfg"]))
+        cbs = [g[f"codebook{l}"] for l in range(len(cfg["num_emb_list"]))]
+        sd = synth.synth_state_dict(SEED, cfg["in_dim"], cfg["layers"], cfg["e_dim"], cfg["num_emb_list"])
+        for l, c in enumerate(cbs):
+            sd[f"rq.vq_layers.{l}.embedding.weight"] = c
+        m = ref_model(cfg, sd)
+        m.eval()
+        nl = len(cfg["layers"]) + 1
+        ew, eb = weights_of(sd, "encoder", nl)
+        dw, db = weights_of(sd, "decoder", nl)
+        x_all = synth.synth_items(SEED, 0, 4096, cfg["in_dim"], int(g["n_total"]))
+        eps = [0.0] * (len(cbs) - 1) + [0.003]
+        for M in (2, 3, 5, 6, 10, 11, 15, 16, 20):
+            x = np.ascontiguousarray(x_all[100:100 + M])
+            xt = torch.from_numpy(x)
+            with torch.no_grad():
+                z = m.encoder(xt).numpy()
+                codes = m.get_indices(xt, use_sk=False).numpy()
+                o, rq_loss, _ = m(xt, use_sk=False)
+                for vq, e_ in zip(m.rq.vq_layers, eps):
+                    vq.sk_epsilon = e_
+                codes_sk = m.get_indices(xt, use_sk=True).numpy()
+            zo = O.mlp_group(x, ew, eb)
+            assert np.array_equal(zo.view(np.int32), z.view(np.int32)), (tag, M, "latent")
+            pc, r = O.reencode_prefix(x, ew, eb, cbs)
+            mine_sk = np.concatenate([pc, O.sinkhorn_last_level(r, cbs[-1], eps[-1], cfg["sk_iters"])[:, None]], 1)
+            assert np.array_equal(mine_sk, codes_sk), (tag, M, "use_sk codes")
+            assert np.array_equal(pc, codes[:, :-1]), (tag, M, "prefix codes")
+            key = f"{tag}_m{M}"
+            names.append(key)
+            out[f"{key}_z"] = z
+            out[f"{key}_codes"] = codes.astype(np.int16)
+            out[f"{key}_codes_sk"] = codes_sk.astype(np.int16)
+            out[f"{key}_out"] = o.numpy()[:, :16].copy()
+            out[f"{key}_rq_loss"] = np.float64(rq_loss)
+        print(f"small batches {tag}: oracle bit-equal to the reference for M in 2..20 (latent, prefix codes, use_sk codes)")
+    out["names"] = np.array(names)
+    out["first_row"] = np.int64(100)
+    np.savez_compressed(os.path.join(GOLD, "small_batch.npz"), **out)
+
+
 def make_sinkhorn_cases():
     from models.vq import VectorQuantizer
     rng = np.random.default_rng(SEED)
@@ -336,6 +385,9 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     print("torch", torch.__version__, "| sklearn", __import__("sklearn").__version__, "| numpy", np.__version__)
+    if sys.argv[1:] == ["small"]:
+        make_small_batches()
+        sys.exit(0)
     if sys.argv[1:] == ["infer"]:        # only the infer() fixtures
         make_infer_c1()
         make_infer_c2()
@@ -358,4 +410,5 @@ if __name__ == "__main__":
     make_infer_c1()
     make_infer_c2()
     make_infer_c3()
+    make_small_batches()
     make_odd_slices()

@@ -128,12 +128,14 @@ def small_batch_plan(M: int, K: int, N: int) -> int:
     return 0
 
 
-def linear_group(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool) -> np.ndarray:
-    """``nn.Linear`` (+ReLU) on ONE small batch, in the order the reference's CPU GEMM uses for that batch size."""
+def linear_group(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bool,
+                 batch_size: Optional[int] = None) -> np.ndarray:
+    """``nn.Linear`` (+ReLU) on ONE small batch, in the order the reference's CPU GEMM uses for that batch size
+    (batch_size: the rows given are only SOME rows of a batch of that size — every row is computed independently)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     W = np.ascontiguousarray(W, dtype=np.float32)
     n, k = x.shape
-    kind = small_batch_plan(n, k, W.shape[0])
+    kind = small_batch_plan(n if batch_size is None else int(batch_size), k, W.shape[0])
     if kind == 0:
         return linear(x, W, b, relu, threads=1)
     y = np.empty((n, W.shape[0]), dtype=np.float32)
@@ -145,12 +147,38 @@ def linear_group(x: np.ndarray, W: np.ndarray, b: Optional[np.ndarray], relu: bo
     return y
 
 
-def mlp_group(x: np.ndarray, weights, biases) -> np.ndarray:
+def mlp_group(x: np.ndarray, weights, biases, batch_size: Optional[int] = None) -> np.ndarray:
     """``MLPLayers.forward`` on one small batch (a collision group), layer by layer in the batch-size-dependent order."""
     h = x
     for i, (W, b) in enumerate(zip(weights, biases)):
-        h = linear_group(h, W, b, relu=(i != len(weights) - 1))
+        h = linear_group(h, W, b, relu=(i != len(weights) - 1), batch_size=batch_size)
     return h
+
+
+def reencode_prefix(xg: np.ndarray, enc_w, enc_b, codebooks, batch_size: Optional[int] = None):
+    """The part of ``get_indices(data[group], use_sk=True)`` before the last level, for rows of a batch of
+    ``batch_size`` rows (default: the rows given ARE the batch): (codes[m, L-1], residual entering the last level)."""
+    M = xg.shape[0] if batch_size is None else int(batch_size)
+    r = mlp_group(np.ascontiguousarray(xg, dtype=np.float32), enc_w, enc_b, batch_size=M).copy()
+    out = []
+    for cb in codebooks[:-1]:
+        cb = np.ascontiguousarray(cb, dtype=np.float32)
+        idx = quantize(r, [cb], want_xq=False, threads=1, dot_kind=small_batch_plan(M, r.shape[1], cb.shape[0]))[0][:, 0]
+        q = cb[idx]
+        xres = r + (q - r)
+        r = r - xres
+        out.append(idx)
+    codes = np.stack(out, axis=-1).astype(np.int64) if out else np.zeros((xg.shape[0], 0), dtype=np.int64)
+    return codes, r
+
+
+def sinkhorn_last_level(residual: np.ndarray, cb_last: np.ndarray, eps: float, iters: int) -> np.ndarray:
+    """Last level of the re-encode of ONE group: distances of the group's residual rows (in the order the reference's
+    matmul uses for that many rows), centred over the group, fp64 Sinkhorn, arg-max (vq.py:71-83)."""
+    cb = np.ascontiguousarray(cb_last, dtype=np.float32)
+    r = np.ascontiguousarray(residual, dtype=np.float32)
+    d = quantize(r, [cb], want_xq=False, dist_level=0, threads=1, dot_kind=small_batch_plan(r.shape[0], r.shape[1], cb.shape[0]))[3]
+    return sinkhorn_assign(d, eps, iters)
 
 
 def mlp(x: np.ndarray, weights: Sequence[np.ndarray], biases: Sequence[np.ndarray],

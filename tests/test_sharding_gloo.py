@@ -35,38 +35,52 @@ class NumpyShardOps:
 
 
 class NumpyDriverOps(NumpyShardOps):
-    """Oracle-backed twin of CudaShardOps.encode_shard / resolve_owned (tests only)."""
+    """Oracle-backed twin of the per-rank pieces CudaShardOps provides to generate_codes_sharded (tests only)."""
 
     def __init__(self, enc_w, enc_b, cbs, eps, iters):
         self.enc_w, self.enc_b, self.cbs, self.eps, self.iters = enc_w, enc_b, cbs, eps, iters
 
-    def encode_shard(self, data):
+    def encode_codes(self, data):
         from oracle import oracle as O
         z = O.mlp(data.numpy(), self.enc_w, self.enc_b, threads=1)
-        codes = O.quantize(z, self.cbs, want_xq=False, threads=1)[0]
-        r = z.copy()
-        for l in range(len(self.cbs) - 1):                    # vq.py:95, rq.py:47
-            q = self.cbs[l][codes[:, l]]
-            r = r - (r + (q - r))
-        return torch.from_numpy(codes), torch.from_numpy(r)
+        return torch.from_numpy(O.quantize(z, self.cbs, want_xq=False, threads=1)[0])
 
-    def resolve_owned(self, codes, residual, max_rounds):
+    def last_level_sinkhorn(self):
+        return self.eps > 0
+
+    def resolve_local(self, codes, data, max_rounds):
+        raise AssertionError("world == 1 is the single-process driver; not exercised here")
+
+    def groups(self, codes):
         from oracle import oracle as O
-        codes, residual = codes.numpy().copy(), residual.numpy()
-        if codes.shape[0] == 0:
-            return torch.zeros((0, codes.shape[1] + 1), dtype=torch.int64), 0
-        rounds = 0
-        while rounds < max_rounds:
-            groups = O.collision_groups(codes)
-            if not groups:
-                break
-            new = codes.copy()
-            for g in groups:
-                d = O.quantize(residual[g], [self.cbs[-1]], want_xq=False, dist_level=0, threads=1)[3]
-                new[g, -1] = O.sinkhorn_assign(d, self.eps, self.iters)
-            codes = new
-            rounds += 1
-        return torch.from_numpy(O.suffix_dedup(codes)), rounds
+        n = codes.shape[0]
+        sizes = torch.ones((n,), dtype=torch.int64)
+        groups = O.collision_groups(codes.numpy()) if n else []
+        groups.sort(key=lambda g: tuple(codes[int(g[0])].tolist()))          # any order: groups are disjoint
+        items = np.concatenate(groups).astype(np.int64) if groups else np.zeros(0, dtype=np.int64)
+        offsets = np.cumsum([0] + [len(g) for g in groups]).astype(np.int64)
+        for g in groups:
+            sizes[torch.from_numpy(np.asarray(g))] = len(g)
+        return torch.from_numpy(items), torch.from_numpy(offsets), sizes
+
+    def reencode_members(self, data, members, msize, codes):
+        from oracle import oracle as O
+        out = torch.zeros((members.numel(), self.cbs[0].shape[1]), dtype=torch.float32)
+        x = data.numpy()
+        for M in sorted(set(msize.tolist())):
+            sel = torch.nonzero(msize == M).flatten()
+            rows = members[sel].numpy()
+            pc, r = O.reencode_prefix(x[rows], self.enc_w, self.enc_b, self.cbs, batch_size=int(M))
+            codes[members[sel], :len(self.cbs) - 1] = torch.from_numpy(pc)
+            out[sel] = torch.from_numpy(r)
+        return out
+
+    def sinkhorn_groups(self, codes, items, offsets, residual_rows):
+        from oracle import oracle as O
+        items, offsets, res = items.numpy(), offsets.numpy(), residual_rows.numpy()
+        for a, b in zip(offsets[:-1], offsets[1:]):
+            g = items[a:b]
+            codes[torch.from_numpy(g), -1] = torch.from_numpy(O.sinkhorn_last_level(res[g], self.cbs[-1], self.eps, self.iters))
 
 
 class _Cfg:
@@ -90,7 +104,7 @@ def test_sharded_driver_matches_single_process_driver(tmp_path, oracle, world):
     n = 600
     x = synth.synth_items(2024, 0, n, cfg["in_dim"], 1_000_000)
     x[300:340] = x[10:50]                                   # exact duplicates across the shard boundary
-    ref, rstats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"])
+    ref, rstats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"], group_order=True)
     assert rstats["rounds"] >= 1
     res = run_world(_driver_job, (torch.from_numpy(x), ew, eb, cbs, float(cfg["sk_epsilons"][-1]), cfg["sk_iters"]),
                     tmp_path, world=world)

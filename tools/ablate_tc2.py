@@ -2,8 +2,7 @@
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import build_model, load_golden
+from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden
 from ai_education_generative_recommendation_b200 import _cabi
 lib = _cabi.lib()
 n = 1_000_000

@@ -7,8 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import build_model, load_golden          # noqa: E402
+from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden          # noqa: E402
 from ai_education_generative_recommendation_b200 import _cabi   # noqa: E402
 
 DEV = "cuda:0"
@@ -24,8 +23,11 @@ for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
     # is the error mostly a uniform shrink (truncating accumulation)?  best scalar fit z ≈ s * z~
     s_opt = float((zt.double() * z.double()).sum() / (zt.double() * zt.double()).sum())
     rel2 = (zt * s_opt - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
+    zs = m.encode_tc(x, passes=2)                      # the screening tier's latent: TF32 first layer + three-pass tail
+    rel_s = (zs - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
     exact = m.get_indices(x)
-    out = {"config": name, "rows": n, "rel_err_max": float(rel.max()), "rel_err_mean": float(rel.mean()),
+    out = {"config": name, "tf32_screen_rel_err_max": float(rel_s.max()), "tf32_screen_rel_err_mean": float(rel_s.mean()),
+           "tf32_screen_rel_err_log2_max": float(torch.log2(rel_s.max())), "rows": n, "rel_err_max": float(rel.max()), "rel_err_mean": float(rel.mean()),
            "rel_err_log2_max": float(torch.log2(rel.max())), "best_scale_minus_1": s_opt - 1.0,
            "rel_err_after_scale_max": float(rel2.max()), "rel_err_after_scale_mean": float(rel2.mean())}
     m.encode_mode = _cabi.ENCODE_FAST
@@ -35,10 +37,10 @@ for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
         fast = m.get_indices(x)
         out[f"gamma=2^{gamma_log2}"] = {"rescued": m.last_stats["rescued_rows"],
                                         "mismatching_rows": int((fast != exact).any(1).sum())}
-    # screening tier (one fp16 pass): rows sent on to the three-pass tier, rows mis-coded if the tight gate were off
+    # screening tier (TF32 first layer): rows sent on to the three-pass tier, rows mis-coded if the tight gate were off
     m.set_gate(2.0 ** -15, 1e-3)
-    for g1 in (-14, -13, -12.5, -12, -11.5, -11, -10.5, -10, -9):
-        m.set_screen(True, 2.0 ** g1)
+    for g1 in (-16, -15, -14, -13.5, -13, -12.5, -12, -11.5, -11, -10):
+        m.set_screen("tf32", 2.0 ** g1)
         fast = m.get_indices(x)
         out[f"screen=2^{g1}"] = {"three_pass_rows": m.last_stats["three_pass_rows"], "rescued": m.last_stats["rescued_rows"],
                                  "mismatching_rows": int((fast != exact).any(1).sum())}

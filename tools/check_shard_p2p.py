@@ -13,10 +13,9 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ai_education_generative_recommendation_b200 as rq           # noqa: E402
 from ai_education_generative_recommendation_b200 import sharding    # noqa: E402
-from conftest import build_model, load_golden                        # noqa: E402
+from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden                        # noqa: E402
 
 
 def main():

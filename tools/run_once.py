@@ -6,8 +6,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import build_model, load_golden          # noqa: E402
+from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden          # noqa: E402
 from ai_education_generative_recommendation_b200 import _cabi   # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_slice"
