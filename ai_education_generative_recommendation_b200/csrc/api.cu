@@ -115,6 +115,7 @@ static void free_linear(Linear &l) {
     if (l.W_tc) cudaFree(l.W_tc);
     if (l.W_tc2) cudaFree(l.W_tc2);
     if (l.W_tf32) cudaFree(l.W_tf32);
+    if (l.Wt) cudaFree(l.Wt);
     if (l.absW_rowmax) cudaFree(l.absW_rowmax);
     l = Linear();
 }
@@ -250,6 +251,7 @@ extern "C" int rqb200_model_set_linear(rqb200_model *m, int which, int layer, co
     if (l.W_tc) { cudaFree(l.W_tc); l.W_tc = nullptr; l.W_tc_bytes = 0; }   // stale tensor-core images
     if (l.W_tc2) { cudaFree(l.W_tc2); l.W_tc2 = nullptr; }
     if (l.W_tf32) { cudaFree(l.W_tf32); l.W_tf32 = nullptr; }
+    if (l.Wt) { cudaFree(l.Wt); l.Wt = nullptr; }
     RQB_CUDA(cudaDeviceSynchronize());       // device-to-device copies above are asynchronous to callers on non-blocking streams
     l.set = true;
     return 0;
@@ -280,6 +282,7 @@ extern "C" int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma
     RQB_CHECK(gamma1 >= 0.0f, "gate parameters must be non-negative");
     RQB_CHECK(enabled >= 0 && enabled <= 2, "enabled must be 0 (off), 1 (one fp16 pass through all layers) or 2 (TF32 first layer fed by TMA)");
     m->screen_enabled = enabled != 0;
+    m->screen_auto = false;
     if (enabled) m->screen_kind = enabled == 2 ? 1 : 0;
     if (gamma1 > 0.0f) m->screen_gamma = gamma1;
     return 0;

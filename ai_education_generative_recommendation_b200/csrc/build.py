@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "librqvae_b200.so")
-SOURCES = ["api.cu", "linear_exact.cu", "quantize.cu", "dedup.cu", "dedup_list.cu", "sinkhorn.cu", "kmeans.cu", "synth.cu",
-           "encode_tc.cu", "encode_tc2.cu", "encode_tc3.cu", "quantize_tc.cu", "train.cu", "tokens.cu", "small_batch.cu", "encode_tf32.cu"]
+SOURCES = ["api.cu", "linear_exact.cu", "quantize.cu", "dedup.cu", "sinkhorn.cu", "kmeans.cu", "synth.cu",
+           "encode_tc.cu", "encode_tc2.cu", "quantize_tc.cu", "train.cu", "tokens.cu", "small_batch.cu", "encode_tf32.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]

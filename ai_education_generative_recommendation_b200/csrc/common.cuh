@@ -69,6 +69,7 @@ struct Linear {
     int tc_scale_exp = 0;    // W_tc holds W * 2^tc_scale_exp
     void *W_tc2 = nullptr;   // image for the 2-CTA kernel (each CTA of a pair stages half of the output features)
     float *W_tf32 = nullptr; // W rounded to the TF32 mantissa (screening kernel, encode_tf32.cu)
+    mutable float *Wt = nullptr;   // [in, out] transposed copy (small-batch kernel, small_batch.cu), built on first use
 };
 
 // "Do this once per device": cudaFuncSetAttribute is a per-device setting, and one process may drive several devices
@@ -119,9 +120,10 @@ struct rqb200_model {
     int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced
     bool force_simt_quantizer = false;      // diagnostics: keep the SIMT quantizer behind the tensor-core encoder
     float gate_floor = 1.0e-3f;             // absolute floor added to |z| in that bound
-    bool screen_enabled = false;            // tier 1 (opt-in): one reduced-precision pass over every row, only gated rows get the 3-pass run
+    bool screen_enabled = false;            // tier 1: one reduced-precision pass over every row, only gated rows get the 3-pass run
+    bool screen_auto = true;                // until rqb200_model_set_screen is called: TF32 screening where it pays (see get_indices_fast)
     int screen_kind = 1;                    // 1: TF32 first layer fed by TMA + three-pass tail (encode_tf32.cu); 0: one fp16 pass through all layers
-    float screen_gamma = 4.8828125e-04f;    // 2^-11: calibrated gate of the one-pass tier
+    float screen_gamma = 4.8828125e-04f;    // 2^-11: calibrated gate of the screening tier (tools/calibrate_gate.py)
     int64_t last_tier_rows[2] = {0, 0};     // rows re-run by tier 2 / tier 3 in the last fast get_indices
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -148,14 +150,6 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
 // encode_tf32.cu: TMA-fed one-pass TF32 first layer (screening tier)
 bool linear_tf32_supported(const Linear &l);
 int linear_tf32(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out);
-// encode_tc3.cu (experimental, off unless RQB200_TC3=1 or debug flag 4096): same contract as the plain three-pass linear_tc2
-bool linear_tc3_enabled();
-int linear_tc3(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, bool tiled_out, int passes = 3);
-// dedup_list.cu (experimental, off unless RQB200_DEDUP_LIST=1 or debug flag 8192): suffix column from a hash table with
-// per-code item lists instead of a sort; *done = 0 ⇒ the caller runs the sort path
-bool dedup_list_enabled();
-int suffix_dedup_list(rqb200_model *m, const int64_t *codes, int64_t n, int L, const int *K_host, int64_t *out,
-                      int64_t *n_distinct_host, int64_t *max_group_host, cudaStream_t s, int *done);
 // encode_tc.cu
 int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStream_t s, int passes = 3,
               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);

@@ -883,11 +883,6 @@ extern "C" int rqb200_suffix_dedup(rqb200_model *m, const int64_t *codes_dev, in
     int buf = 0;
     ProfScope ps(PROF_DEDUP, s);
     const bool stats = n_distinct_host || max_group_host;
-    if (stats && dedup_list_enabled()) {        // experimental sort-free path (dedup_list.cu); falls through when it declines
-        int done = 0;
-        RQB_TRY(suffix_dedup_list(m, codes_dev, n, L, K_host, out_dev, n_distinct_host, max_group_host, s, &done));
-        if (done) return 0;
-    }
     RQB_TRY(sort_codes(m, codes_dev, n, L, K_host, sc, &buf, s));
     RQB_TRY(run_seg_rank(sc, buf, n, nullptr, codes_dev, L, out_dev, stats, s));
     if (stats) {

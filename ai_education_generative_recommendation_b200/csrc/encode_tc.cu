@@ -795,7 +795,15 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
     // workspace: z~[n,e] | z2[n,e] (compact, tier 2) | list1[n] | list2[n] | count1, count2
     const size_t zb = (sizeof(float) * (size_t)n * m->e + 255) & ~(size_t)255;
     const size_t lb = (sizeof(int64_t) * (size_t)n + 255) & ~(size_t)255;
-    const bool screen = m->screen_enabled && quantize_tc_supported(m) && !m->force_simt_quantizer;
+    // Screening pays when the first layer dominates the row: the TF32 pass saves about a third of that layer, the rows it
+    // cannot certify (5-15 %) pay the three-pass encoder AND the tensor-core quantizer a second time.  Measured
+    // (profiles/r2_check_tf32_*.txt): a gain with 3 x 256 codes of 32 dims, a loss with 4 x 1024 codes of 64 dims.
+    long long quant_work = 0;
+    for (int l = 0; l < m->L; ++l) quant_work += (long long)m->K[l] * m->e;
+    const bool screen_on = m->screen_auto ? (m->screen_kind == 1 && linear_tf32_supported(m->enc[0]) && m->n_layers == 3 &&
+                                             quant_work <= 32768)
+                                          : m->screen_enabled;
+    const bool screen = screen_on && quantize_tc_supported(m) && !m->force_simt_quantizer;
     RQB_TRY(ws_reserve(m->misc, 2 * zb + 2 * lb + 512));
     char *base = (char *)m->misc.ptr;
     float *z1 = z_out ? z_out : (float *)base;

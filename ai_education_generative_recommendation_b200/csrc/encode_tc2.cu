@@ -335,7 +335,6 @@ int linear_tc2(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaSt
         return launch_tc2<3, true>(l, x, n, y, relu, rows, n_dev, s, tiled_out);
     }
     RQB_CHECK(n_dev == nullptr, "a device-side row count needs the gather variant");
-    if (linear_tc3_enabled()) return linear_tc3(l, x, n, y, relu, s, tiled_out, passes);
     return passes == 1 ? launch_tc2<1, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out)
                        : launch_tc2<3, false>(l, x, n, y, relu, nullptr, nullptr, s, tiled_out);
 }

@@ -19,6 +19,7 @@
 // the rest is re-run by the three-pass kernels and, if still uncertified, by the exact SIMT kernels.  Algorithmic
 // traffic: 4·K bytes per row read once (HBM-bound: 2·K·256 flop per row at the TF32 rate take about as long).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -294,10 +295,13 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
 }
 
-// W[256,K] fp32 → the same matrix with every element rounded to nearest-even at the TF32 mantissa (10 bits)
-__global__ void round_w_tf32_kernel(const float *__restrict__ W, int64_t count, float *__restrict__ out) {
+// W[256,K] fp32 → W·comp with every element rounded to nearest-even at the TF32 mantissa (10 bits).
+// comp > 1 compensates the hardware's TRUNCATION of the X operand to 10 mantissa bits: trunc(x) = x·(1 - u), u in
+// [0, 2^-10) with mean ≈ 0.72·2^-11 for log-uniform mantissas — a systematic shrink of every product that would otherwise
+// dominate the error of the pass (measured: mean relative error of the latent 2^-11.1 without, see tools/calibrate_gate.py).
+__global__ void round_w_tf32_kernel(const float *__restrict__ W, int64_t count, float comp, float *__restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t u = __float_as_uint(W[i]);
+        uint32_t u = __float_as_uint(W[i] * comp);
         u += 0x0FFFu + ((u >> 13) & 1u);
         out[i] = __uint_as_float(u & 0xFFFFE000u);
     }
@@ -351,7 +355,9 @@ int linear_tf32(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaS
         void *p = nullptr;
         RQB_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)l.out * l.in));
         count_launch();
-        round_w_tf32_kernel<<<kNumSMs, 256, 0, s>>>(l.W, (int64_t)l.out * l.in, (float *)p);
+        float comp = 1.0f + 0.72f * 4.8828125e-4f;                 // 1 + 0.72·2^-11
+        if (const char *ev = getenv("RQB200_TF32_COMP")) comp = 1.0f + (float)atof(ev) * 4.8828125e-4f;   // diagnostics: in units of 2^-11
+        round_w_tf32_kernel<<<kNumSMs, 256, 0, s>>>(l.W, (int64_t)l.out * l.in, comp, (float *)p);
         RQB_LAUNCH_CHECK();
         l.W_tf32 = (float *)p;
     }

@@ -13,9 +13,9 @@
 // arithmetic (see the derivation at `tau` below).  Rows on the list are recomputed by the exact
 // kernels; all other rows provably have the reference's codes.
 //
-// CTA = 320 threads: warps 0-3 and 4-7 are two independent "row groups" (one 128-row tile each, thread
-// = row), warp 8 issues the MMAs for both groups, warp 9 streams codebook chunks.  While one group is
-// in its top-2 epilogue the tensor core works for the other.
+// CTA = 576 threads: four independent "row groups" of four warps each (one 128-row tile per group, thread
+// = row), warp 16 issues the MMAs for all groups, warp 17 streams codebook chunks.  While one group is
+// in its top-2 epilogue the tensor core works for the others.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -30,20 +30,11 @@ constexpr int QCH = 128;                   // codes per MMA (UMMA N)
 constexpr int QB = 1;                      // TMEM accumulator buffers per group (QG * QB * QCH <= 512 columns).  Measured on C2/C3/C5
                                            // (ms per 1M rows): 4 groups x 1 x 128 codes 0.43/0.83/2.7 (this), 4 x 2 x 64 0.50/0.95/3.2
                                            // (N=64 MMAs are shared-memory-bound), 2 x 2 x 128 0.51/0.88/2.8, 2 x 1 x 256 0.47/1.05/3.0
-#ifndef QTC_GROUPS
-#define QTC_GROUPS 4
-#endif
-#ifndef QTC_A_HI_TMEM
-#define QTC_A_HI_TMEM 0
-#endif
-constexpr int QG = QTC_GROUPS;             // row groups per CTA (one 128-row tile each, thread = row)
-// EXPERIMENTAL A/B build (-DQTC_A_HI_TMEM=1 -DQTC_GROUPS=3, tools/build_variant.sh; not yet run on a GPU): the hi half of the
-// residual tile is ALSO written to tensor memory (32 columns per group behind the accumulators) and the two MMA passes that
-// use it take A from there — 16 KB instead of 24 KB of shared-memory operand reads per 16-wide K step (the N = 128 MMAs read A
-// and B at exactly the port rate).  Tensor memory then holds three groups: 3 x 128 + 3 x 32 = 480 columns.
-constexpr bool Q_TS = QTC_A_HI_TMEM != 0;
-constexpr int Q_A_TMEM_COL0 = QG * QB * QCH;                // first tensor-memory column of the A_hi blocks (32 columns per group)
-static_assert(QG * QB * QCH + (Q_TS ? QG * 32 : 0) <= 512, "tensor memory: accumulators + A_hi blocks");
+constexpr int QG = 4;                      // row groups per CTA (one 128-row tile each, thread = row)
+// (Measured and dropped in round 2: the hi half of the residual tile additionally kept in tensor memory as the A operand of two
+// of the three MMA passes, three row groups — bit-identical, 2.61 vs 2.67 ms on the 4 x 1024-code shape, no gain at 3 x 256:
+// profiles/r2_first_call_summary.txt.)
+static_assert(QG * QB * QCH <= 512, "tensor memory: accumulators");
 constexpr int Q_MMA_WARP = 4 * QG, Q_LOAD_WARP = 4 * QG + 1;
 constexpr int QTC_THREADS = (4 * QG + 2) * 32;              // 576
 constexpr int Q_STAGES = 2;
@@ -63,24 +54,6 @@ struct QtcArgs {
     float inv_scale[RQB200_MAX_LEVELS];
     int L;
 };
-
-// A from tensor memory (TS form), B from shared memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// this thread's row (tensor-memory lane): four 32-bit columns = 8 fp16 along K
-__device__ __forceinline__ void tmem_st_row_x4(uint32_t taddr, const uint4 &v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait_q() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ int q_swz(int rloc, int c) {          // byte offset of 16-byte chunk c of row rloc (SW128 K-major tile)
     return (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
@@ -154,12 +127,6 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
         unsigned char *a_hi = a_base + g * 2 * Q_A_BYTES;
         unsigned char *a_lo = a_hi + Q_A_BYTES;
         const uint32_t t_group = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * QB * QCH);
-        const uint32_t t_ahi = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(Q_A_TMEM_COL0 + g * 32);   // (Q_TS)
-        if (Q_TS) {            // columns past E (+ the augmented one) of the 64-wide K slab stay zero for the whole kernel
-#pragma unroll
-            for (int c = 0; c < 8; ++c) tmem_st_row_x4(t_ahi + 4 * c, make_uint4(0, 0, 0, 0));
-            tmem_st_wait_q();
-        }
         uint32_t round = 0;                       // chunks consumed by this group so far: buffer = round % QB
         for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
             const int64_t tile = batch * QG + g;
@@ -185,7 +152,6 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     split2(v1.x, v1.y, hi.z, lo.z); split2(v1.z, v1.w, hi.w, lo.w);
                     *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = hi;
                     *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = lo;
-                    if (Q_TS) tmem_st_row_x4(t_ahi + 4 * c, hi);
                 }
                 xx = s0 + s1;
             }
@@ -195,11 +161,6 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
             for (int l = 0; l < qa.L; cc_base += (qa.K[l] + QCH - 1) / QCH * QCH, ++l) {
                 if (AUG)   // augmented K column E: A = 2^t, B = |c_j|^2 * 2^(s-t)  ⇒  the MMA itself adds the code norm
                     *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, E / 8)) = make_uint4(qa.aug_half[l], 0, 0, 0);
-                if (Q_TS) {
-                    if (AUG) tmem_st_row_x4(t_ahi + 4 * (E / 8), make_uint4(qa.aug_half[l], 0, 0, 0));
-                    tmem_st_wait_q();
-                    tc_fence_before();
-                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
@@ -307,7 +268,6 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                         split2(rn[4], rn[5], nh.z, nl.z); split2(rn[6], rn[7], nh.w, nl.w);
                         *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = nh;
                         *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = nl;
-                        if (Q_TS) tmem_st_row_x4(t_ahi + 4 * c, nh);
                     }
                     xx = s0 + s1;
                 }
@@ -357,14 +317,8 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                             for (int kk = 0; kk < (E + (AUG ? 1 : 0) + 15) / 16; ++kk) {      // E residual columns (+ the augmented norm column)
                                 const uint64_t ko = (uint64_t)(2 * kk);                      // 32 bytes along K = 2 descriptor units
                                 umma_f16(d_tmem, da_lo[g] + ko, dw_hi + ko, idesc, kk != 0);
-                                if (Q_TS) {
-                                    const uint32_t a_t = tmem_base + (uint32_t)(Q_A_TMEM_COL0 + g * 32 + 8 * kk);
-                                    umma_f16_ts(d_tmem, a_t, dw_lo + ko, idesc, 1);
-                                    umma_f16_ts(d_tmem, a_t, dw_hi + ko, idesc, 1);
-                                } else {
-                                    umma_f16(d_tmem, da_hi[g] + ko, dw_lo + ko, idesc, 1);
-                                    umma_f16(d_tmem, da_hi[g] + ko, dw_hi + ko, idesc, 1);
-                                }
+                                umma_f16(d_tmem, da_hi[g] + ko, dw_lo + ko, idesc, 1);
+                                umma_f16(d_tmem, da_hi[g] + ko, dw_hi + ko, idesc, 1);
                             }
                             umma_commit(&d_full[QB * g + buf]);
                         }

@@ -23,7 +23,8 @@ namespace rqb {
 namespace {
 
 constexpr int LS_THREADS = 128;
-constexpr int LS_ROWS = 4;
+constexpr int LS_ROWS = 16;                 // slots per CTA (rows staged in shared memory)
+constexpr int LS_TN = 2;                    // output features per thread: j and j + 128
 
 // slot -> size of the group it belongs to (items are stored group by group, offsets[g] .. offsets[g+1])
 __global__ void group_sizes_kernel(const int64_t *__restrict__ offsets, int64_t n_groups, int64_t n_items,
@@ -47,25 +48,54 @@ __device__ __forceinline__ float fold_lane16(const float (&acc)[16]) {
     return __fadd_rn(__fadd_rn(s[0], s[1]), __fadd_rn(s[2], s[3]));
 }
 
+// W[N,K] → Wt[K,N] so that the threads of a warp (consecutive output features) read consecutive addresses
+__global__ void transpose_w_kernel(const float *__restrict__ W, int N, int K, float *__restrict__ Wt) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int nn = n0 + i, kk = k0 + threadIdx.x;
+        tile[i][threadIdx.x] = (nn < N && kk < K) ? W[(size_t)nn * K + kk] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int kk = k0 + i, nn = n0 + threadIdx.x;
+        if (kk < K && nn < N) Wt[(size_t)kk * N + nn] = tile[threadIdx.x][i];
+    }
+}
+
 // Y[slot, :] = act(X[row(slot), :] · Wᵀ + b) where every slot uses the order of ITS batch size (msize[slot], or m_uniform).
-// CTA = LS_ROWS consecutive slots (rows staged in shared memory), thread = output feature(s).
+// CTA = LS_ROWS consecutive slots x 256 output features (blockIdx.y selects the 256-column block), thread = features j, j + 128.
+// The rows sit in shared memory LANE-MAJOR — element k of a row at [k mod 16][k div 16] — so a lane of the small-batch order
+// (k ≡ l mod 16, ascending) is contiguous: one LDS.128 (broadcast) feeds 4 k-steps x LS_TN features.  The lanes are walked
+// in the order of the fold, (l = q, q+4, q+8, q+12 for q = 0..3), which needs only four running values per output:
+//   s_q = ((P_q + P_{q+4}) + P_{q+8}) + P_{q+12};   result = (s_0 + s_1) + (s_2 + s_3);   + bias last.
+// Rows whose batch size takes the catalogue order (K-blocks of sequential chains, bias first) are computed by a second,
+// scalar-k pass over the same staged rows — rare (groups of 16 or more members).
 __global__ void __launch_bounds__(LS_THREADS)
 linear_small_kernel(const float *__restrict__ X, const int64_t *__restrict__ rows, const int *__restrict__ msize,
-                    int m_uniform, int64_t n, const float *__restrict__ W, const float *__restrict__ bias,
+                    int m_uniform, int64_t n, const float *__restrict__ Wt, const float *__restrict__ bias,
                     float *__restrict__ Y, int K, int N, int relu, int nblk, const int kb0, const int kb1, const int kb2,
                     const int kb3, const int kb4, const int kb5, const int kb6, const int kb7) {
-    extern __shared__ __align__(16) float xs[];           // [LS_ROWS][K]
+    extern __shared__ __align__(16) float xs[];           // [LS_ROWS][16][KCP]
     __shared__ int s_kind[LS_ROWS];
+    const int KC = (K + 15) >> 4;                          // elements per lane
+    const int KCP = (KC + 3) & ~3;                         // padded to whole float4s (zero filled: fma(0, w, acc) == acc)
     const int64_t slot0 = (int64_t)blockIdx.x * LS_ROWS;
     const int nr = (int)((n - slot0) < LS_ROWS ? (n - slot0) : LS_ROWS);
+    for (int i = threadIdx.x; i < LS_ROWS * 16 * KCP; i += LS_THREADS) xs[i] = 0.0f;
+    __syncthreads();
     for (int i = threadIdx.x; i < LS_ROWS * (K / 4); i += LS_THREADS) {
-        const int r = i / (K / 4), c = i % (K / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r = i / (K / 4), c4 = i % (K / 4);
         if (r < nr) {
             const int64_t src = rows ? rows[slot0 + r] : slot0 + r;
-            v = *reinterpret_cast<const float4 *>(X + src * K + 4 * c);
+            const float4 v = *reinterpret_cast<const float4 *>(X + src * K + 4 * c4);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int k = 4 * c4 + t;
+                xs[((size_t)r * 16 + (k & 15)) * KCP + (k >> 4)] = e[t];
+            }
         }
-        *reinterpret_cast<float4 *>(xs + (size_t)r * K + 4 * c) = v;
     }
     if (threadIdx.x < LS_ROWS) {
         const int r = threadIdx.x;
@@ -77,75 +107,119 @@ linear_small_kernel(const float *__restrict__ X, const int64_t *__restrict__ row
 #pragma unroll
     for (int r = 0; r < LS_ROWS; ++r) { any_lane |= s_kind[r] == 1; any_blk |= s_kind[r] == 0; }
     const int kb[8] = {kb0, kb1, kb2, kb3, kb4, kb5, kb6, kb7};
+    const int j0 = blockIdx.y * (LS_THREADS * LS_TN) + threadIdx.x;
+    bool live[LS_TN];
+    float bj[LS_TN];
+#pragma unroll
+    for (int t = 0; t < LS_TN; ++t) {
+        live[t] = j0 + t * LS_THREADS < N;
+        bj[t] = (live[t] && bias) ? bias[j0 + t * LS_THREADS] : 0.0f;
+    }
+    const float *w0 = Wt + (live[0] ? j0 : 0);
+    const float *w1 = Wt + (live[1] ? j0 + LS_THREADS : 0);
 
-    for (int j = threadIdx.x; j < N; j += LS_THREADS) {
-        const float *w = W + (size_t)j * K;
-        const float bj = bias ? bias[j] : 0.0f;
-        float out[LS_ROWS];
-        if (any_lane) {
-            float acc[LS_ROWS][16];
+    float out[LS_ROWS][LS_TN];
+    if (any_lane) {
+        float tt[LS_ROWS][LS_TN], uu[LS_ROWS][LS_TN];
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            float ss[LS_ROWS][LS_TN];
+#pragma unroll 1
+            for (int p = 0; p < 4; ++p) {
+                const int l = q + 4 * p;
+                float acc[LS_ROWS][LS_TN];
 #pragma unroll
-            for (int r = 0; r < LS_ROWS; ++r)
+                for (int r = 0; r < LS_ROWS; ++r)
 #pragma unroll
-                for (int l = 0; l < 16; ++l) acc[r][l] = 0.0f;
-            int k = 0;
-            for (; k + 16 <= K; k += 16) {
-                float wv[16];
+                    for (int t = 0; t < LS_TN; ++t) acc[r][t] = 0.0f;
+                for (int c = 0; c < KC; c += 4) {
+                    float wa[4], wb[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4 *>(w + k + 4 * q);
-                    wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 16 * (c + i) + l;
+                        const bool ok = k < K;
+                        wa[i] = ok ? w0[(size_t)k * N] : 0.0f;
+                        wb[i] = ok ? w1[(size_t)k * N] : 0.0f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < LS_ROWS; ++r) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(xs + ((size_t)r * 16 + l) * KCP + c);
+                        const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (c + i < KC) {          // ascending k inside the lane; the padded tail adds nothing
+                                acc[r][0] = __fmaf_rn(xe[i], wa[i], acc[r][0]);
+                                acc[r][1] = __fmaf_rn(xe[i], wb[i], acc[r][1]);
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int r = 0; r < LS_ROWS; ++r)
 #pragma unroll
-                    for (int l = 0; l < 16; ++l) acc[r][l] = __fmaf_rn(xs[(size_t)r * K + k + l], wv[l], acc[r][l]);
-            }
-            // masked tail (K not a multiple of 16): lane l takes element k + l if it exists
-#pragma unroll
-            for (int l = 0; l < 16; ++l)
-                if (k + l < K) {
-#pragma unroll
-                    for (int r = 0; r < LS_ROWS; ++r) acc[r][l] = __fmaf_rn(xs[(size_t)r * K + k + l], w[k + l], acc[r][l]);
-                }
-#pragma unroll
-            for (int r = 0; r < LS_ROWS; ++r)
-                if (s_kind[r] == 1) out[r] = __fadd_rn(fold_lane16(acc[r]), bj);
-        }
-        if (any_blk) {
-            float o[LS_ROWS];
-#pragma unroll
-            for (int r = 0; r < LS_ROWS; ++r) o[r] = bj;
-            int k0 = 0;
-            for (int blk = 0; blk < nblk; ++blk) {
-                const int k1 = k0 + kb[blk];
-                float acc[LS_ROWS];
-#pragma unroll
-                for (int r = 0; r < LS_ROWS; ++r) acc[r] = 0.0f;
-                for (int k = k0; k < k1; k += 4) {
-                    const float4 t = *reinterpret_cast<const float4 *>(w + k);
-                    const float wv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-#pragma unroll
-                        for (int r = 0; r < LS_ROWS; ++r) acc[r] = __fmaf_rn(xs[(size_t)r * K + k + q], wv[q], acc[r]);
-                }
-#pragma unroll
-                for (int r = 0; r < LS_ROWS; ++r) o[r] = __fadd_rn(o[r], acc[r]);
-                k0 = k1;
+                    for (int t = 0; t < LS_TN; ++t) ss[r][t] = p == 0 ? acc[r][t] : __fadd_rn(ss[r][t], acc[r][t]);
             }
 #pragma unroll
             for (int r = 0; r < LS_ROWS; ++r)
-                if (s_kind[r] == 0) out[r] = o[r];
+#pragma unroll
+                for (int t = 0; t < LS_TN; ++t) {
+                    if (q == 0) tt[r][t] = ss[r][t];
+                    else if (q == 1) tt[r][t] = __fadd_rn(tt[r][t], ss[r][t]);
+                    else if (q == 2) uu[r][t] = ss[r][t];
+                    else tt[r][t] = __fadd_rn(tt[r][t], __fadd_rn(uu[r][t], ss[r][t]));
+                }
         }
 #pragma unroll
         for (int r = 0; r < LS_ROWS; ++r)
-            if (r < nr) {
-                float v = out[r];
-                if (relu) v = (v != v) ? v : (v > 0.0f ? v : 0.0f);
-                Y[(slot0 + r) * N + j] = v;
-            }
+#pragma unroll
+            for (int t = 0; t < LS_TN; ++t)
+                if (s_kind[r] == 1) out[r][t] = __fadd_rn(tt[r][t], bj[t]);
     }
+    if (any_blk) {
+        float o[LS_ROWS][LS_TN];
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+            for (int t = 0; t < LS_TN; ++t) o[r][t] = bj[t];
+        int k0 = 0;
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int k1 = k0 + kb[blk];
+            float acc[LS_ROWS][LS_TN];
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+                for (int t = 0; t < LS_TN; ++t) acc[r][t] = 0.0f;
+            for (int k = k0; k < k1; ++k) {
+                const float wa = w0[(size_t)k * N], wb = w1[(size_t)k * N];
+                const float *xk = xs + (size_t)(k & 15) * KCP + (k >> 4);
+#pragma unroll
+                for (int r = 0; r < LS_ROWS; ++r) {
+                    const float xv = xk[(size_t)r * 16 * KCP];
+                    acc[r][0] = __fmaf_rn(xv, wa, acc[r][0]);
+                    acc[r][1] = __fmaf_rn(xv, wb, acc[r][1]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+                for (int t = 0; t < LS_TN; ++t) o[r][t] = __fadd_rn(o[r][t], acc[r][t]);
+            k0 = k1;
+        }
+#pragma unroll
+        for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+            for (int t = 0; t < LS_TN; ++t)
+                if (s_kind[r] == 0) out[r][t] = o[r][t];
+    }
+#pragma unroll
+    for (int r = 0; r < LS_ROWS; ++r)
+#pragma unroll
+        for (int t = 0; t < LS_TN; ++t)
+            if (r < nr && live[t]) {
+                float v = out[r][t];
+                if (relu) v = (v != v) ? v : (v > 0.0f ? v : 0.0f);
+                Y[(slot0 + r) * N + j0 + t * LS_THREADS] = v;
+            }
 }
 
 // torch.sum(v*v) for a runtime length (ATen order; twin of sinkhorn.cu's helper, kept local to this unit)
@@ -281,18 +355,27 @@ int launch_linear_small(const Linear &lin, const float *x, const int64_t *rows, 
     RQB_CHECK(lin.set, "linear layer not loaded");
     RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
     RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);
-    for (int i = 0; i < lin.nblk; ++i) RQB_CHECK(lin.kblocks[i] % 4 == 0, "K-block %d not a multiple of 4", lin.kblocks[i]);
-    const size_t smem = sizeof(float) * LS_ROWS * (size_t)lin.in;
+    const int KC = (lin.in + 15) / 16, KCP = (KC + 3) & ~3;
+    const size_t smem = sizeof(float) * LS_ROWS * 16 * (size_t)KCP;
     RQB_CHECK(smem <= 200 * 1024, "in_features %d too large for the small-batch kernel", lin.in);
     static rqb::DeviceOnce attr_once;
     if (attr_once.first())
         RQB_CUDA(cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (!lin.Wt) {
+        float *p = nullptr;
+        RQB_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)lin.in * lin.out));
+        rqb::count_launch();
+        transpose_w_kernel<<<dim3((lin.in + 31) / 32, (lin.out + 31) / 32), dim3(32, 8), 0, s>>>(lin.W, lin.out, lin.in, p);
+        RQB_LAUNCH_CHECK();
+        lin.Wt = p;
+    }
     int kb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < lin.nblk; ++i) kb[i] = lin.kblocks[i];
     rqb::count_launch();
-    linear_small_kernel<<<(unsigned)((n + LS_ROWS - 1) / LS_ROWS), LS_THREADS, smem, s>>>(
-        x, rows, msize, m_uniform, n, lin.W, lin.b, y, lin.in, lin.out, relu ? 1 : 0, lin.nblk, kb[0], kb[1], kb[2], kb[3],
-        kb[4], kb[5], kb[6], kb[7]);
+    const dim3 grid((unsigned)((n + LS_ROWS - 1) / LS_ROWS), (unsigned)((lin.out + LS_THREADS * LS_TN - 1) / (LS_THREADS * LS_TN)));
+    linear_small_kernel<<<grid, LS_THREADS, smem, s>>>(x, rows, msize, m_uniform, n, lin.Wt, lin.b, y, lin.in, lin.out,
+                                                       relu ? 1 : 0, lin.nblk, kb[0], kb[1], kb[2], kb[3], kb[4], kb[5], kb[6],
+                                                       kb[7]);
     RQB_LAUNCH_CHECK();
     return 0;
 }

@@ -311,6 +311,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RQB200_MODE", "auto"), choices=["auto", "exact", "fast"])
     ap.add_argument("--items", type=int, default=N_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--screen", default="auto", choices=["auto", "off", "tf32", "fp16"],
+                    help="screening tier of the tensor-core route: auto = the library's rule (TF32 screen where it pays)")
     ap.add_argument("--no-extra", action="store_true", help="N > 1: skip the configs[2] / configs[4] runs under config.extra")
     ap.add_argument("--no-full-driver", action="store_true", help="skip the full_driver leg (passes 1-3 with Sinkhorn rounds)")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
@@ -354,7 +356,10 @@ def main():
             model.encode_mode = _cabi.ENCODE_EXACT
     else:
         fast_ok = False
-    mode_name = "fast(tcgen05 split-fp16 + margin gate + exact rescue)" if fast_ok else "exact(SIMT fp32, reference order)"
+    if args.screen != "auto":
+        model.set_screen({"off": 0, "tf32": "tf32", "fp16": 1}[args.screen])
+    mode_name = ("fast(TMA-fed TF32 screening pass + tcgen05 split-fp16 three-pass tier + margin gates + exact rescue)"
+                 if fast_ok else "exact(SIMT fp32, reference order)")
 
     n = args.items
     n_total = n * world
@@ -472,15 +477,20 @@ def main():
         k_ms = prof_ms[slot] / max(prof_cnt[slot], 1)
         alg_bytes = 4.0 * in_dim * n
         alg_flops = 2.0 * in_dim * first_out * n
-        tc3 = os.environ.get("RQB200_TC3", "0")[:1] == "1"      # experimental first-layer kernel (csrc/encode_tc3.cu)
-        l1_kernel = "linear_tc3_kernel" if tc3 else "linear_tc2_kernel"
-        kname = ((l1_kernel + " (encoder layer 1: tcgen05 cta_group::2, split-fp16, 3 MMA passes"
-                  + (", A operand in tensor memory)" if tc3 else ")")) if slot == 4
+        screen_active = fast_ok and model.last_stats.get("three_pass_rows", 0) > 0     # the TF32 screening tier ran
+        l1_kernel = "linear_tf32_kernel" if screen_active else "linear_tc2_kernel"
+        l1_desc = ("encoder layer 1 over every row: ONE tcgen05 kind::tf32 pass, cta_group::2, operands delivered by TMA "
+                   "(cp.async.bulk.tensor) straight from the fp32 rows" if screen_active
+                   else "encoder layer 1: tcgen05 cta_group::2, split-fp16, 3 MMA passes")
+        kname = (f"{l1_kernel} ({l1_desc})" if slot == 4
                  else "linear_exact_kernel<128,128,8,8> (encoder layer 1, fp32 FMA chains)")
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):           # dram bytes per launch from the committed ncu --set full capture (null if not captured)
-            traffic = json.load(open(tpath)).get(l1_kernel if slot == 4 else "linear_exact_kernel")
+        for tname in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):       # dram bytes per launch from the committed ncu --set full capture (null if not captured)
+                traffic = json.load(open(tpath)).get(l1_kernel if slot == 4 else "linear_exact_kernel")
+                if traffic is not None:
+                    break
         gbs = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         tfl = alg_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         hbm_peak = float(peaks["hbm_gbs"])
@@ -512,7 +522,8 @@ def main():
                     "peak_source": f"{peak_src} hbm_gbs; SURVEY §8d: a bf16-rate pass over this shape is HBM-bound (AI 96 flop/B < ridge 207)",
                     "algorithmic_bytes_per_launch": alg_bytes,
                     "tensor_view": {"achieved_tflops": tfl, "peak_tflops": tc_peak, "frac": tfl / tc_peak if tc_peak else None,
-                                    "note": "algorithmic flops of ONE pass; the kernel issues 3 fp16 passes for fp32-class accuracy"},
+                                    "note": ("algorithmic flops of ONE pass = what the TF32 kernel issues; the TF32 rate is half the bf16 rate the peak is quoted at"
+                                             if screen_active else "algorithmic flops of ONE pass; the kernel issues 3 fp16 passes for fp32-class accuracy")},
                     "step_share": (prof_ms[slot] / args.steps) / ms_step if ms_step else None,
                     "whole_step_hbm_frac": (value / world) * (4 * in_dim + 8 * n_levels) / (hbm_peak * 1e9),
                     "stage_ms_per_step": stage, "stages": stages}
@@ -535,15 +546,24 @@ def main():
             model_sk, cfg_sk, _ = golden_model(dev, with_sk=True)
             ids_sk, st_sk = rq.generate_codes(model_sk, x)                  # warm-up (workspaces, attributes)
             torch.cuda.synchronize()
+            lib.rqb200_profile_enable(1)
             t0 = time.perf_counter()
             reps = 2
             for _ in range(reps):
                 ids_sk, st_sk = rq.generate_codes(model_sk, x)
             torch.cuda.synchronize()
             fd_s = (time.perf_counter() - t0) / reps
+            fd_ms = (ctypes.c_double * 12)()
+            fd_cnt = (ctypes.c_longlong * 12)()
+            lib.rqb200_profile_read(fd_ms, fd_cnt, 12)
+            lib.rqb200_profile_enable(0)
             full = {"value": n / fd_s, "unit": UNIT, "seconds": fd_s, "items": n, "sk_epsilons": cfg_sk["sk_epsilons"],
                     "rounds": st_sk["rounds"], "groups_reencoded_per_round": st_sk.get("groups_reencoded_per_round"),
                     "collision_rate_after": st_sk["collision_rate"], "max_conflicts": st_sk["max_conflicts"],
+                    "stage_ms": {"group_reencode (small-batch encoder + arg-min levels)": fd_ms[9] / reps,
+                                 "sinkhorn (one CTA per group, fp64)": fd_ms[5] / reps,
+                                 "pass1_layer1": fd_ms[4] / reps, "pass1_quantize": fd_ms[2] / reps,
+                                 "sort / group extraction / suffix (dedup slot)": fd_ms[3] / reps},
                     "what": "rq.generate_codes: pass 1 (tensor-core route) + re-encode rounds (every group through the whole model "
                             "as its own batch, reference arithmetic; fixed-point groups skipped after their first round) + suffix dedup"}
             if not args.no_cpu_baseline:

@@ -377,9 +377,14 @@ def test_host_buffer_end_to_end_call(oracle):
     out = torch.empty((n, 4), dtype=torch.int64).pin_memory()
     stats = (ctypes.c_int64 * 4)()
     _cabi.check(_cabi.lib().rqb200_generate_codes_host(m._handle, _cabi.ENCODE_EXACT, xh.data_ptr(), n, 1024,
-                                                       out.data_ptr(), stats))
+                                                       out.data_ptr(), stats, _cabi.stream_ptr()))
     ref = oracle.suffix_dedup(oracle.get_indices(x, ew, eb, cbs))
     assert np.array_equal(out.numpy(), ref)
+    side = torch.cuda.Stream()                                  # the call runs on the stream it is given
+    out2 = torch.empty_like(out).pin_memory()
+    _cabi.check(_cabi.lib().rqb200_generate_codes_host(m._handle, _cabi.ENCODE_FAST, xh.data_ptr(), n, 1000,
+                                                       out2.data_ptr(), stats, ctypes.c_void_p(side.cuda_stream)))
+    assert np.array_equal(out2.numpy(), ref)
     assert stats[1] == len(np.unique(ref[:, :3], axis=0))
 
 

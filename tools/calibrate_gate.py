@@ -11,7 +11,12 @@ from ai_education_generative_recommendation_b200.fixtures import build_model, lo
 from ai_education_generative_recommendation_b200 import _cabi   # noqa: E402
 
 DEV = "cuda:0"
-for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
+# RQB200_TF32_COMP (units of 2^-11, read when the TF32 weight image is packed): compensation of the operand truncation
+comps = [c for c in os.environ.get("CALIBRATE_COMPS", "").split(",") if c] or [None]
+names = [a for a in sys.argv[1:]] or ["c2_slice", "c3_slice", "c5_slice"]
+for name, comp in [(nm, c) for nm in names for c in comps]:
+    if comp is not None:
+        os.environ["RQB200_TF32_COMP"] = comp
     g, cfg, cbs = load_golden(name)
     m = build_model(cfg, cbs)
     n = 1_000_000 if cfg["in_dim"] == 768 else 400_000
@@ -26,7 +31,8 @@ for name in sys.argv[1:] or ["c2_slice", "c3_slice", "c5_slice"]:
     zs = m.encode_tc(x, passes=2)                      # the screening tier's latent: TF32 first layer + three-pass tail
     rel_s = (zs - z).norm(dim=1) / (z.norm(dim=1) + 1e-3)
     exact = m.get_indices(x)
-    out = {"config": name, "tf32_screen_rel_err_max": float(rel_s.max()), "tf32_screen_rel_err_mean": float(rel_s.mean()),
+    ss = float((zs.double() * z.double()).sum() / (zs.double() * zs.double()).sum())
+    out = {"config": name, "tf32_comp_in_2^-11": comp, "tf32_best_residual_scale_minus_1": ss - 1.0, "tf32_screen_rel_err_max": float(rel_s.max()), "tf32_screen_rel_err_mean": float(rel_s.mean()),
            "tf32_screen_rel_err_log2_max": float(torch.log2(rel_s.max())), "rows": n, "rel_err_max": float(rel.max()), "rel_err_mean": float(rel.mean()),
            "rel_err_log2_max": float(torch.log2(rel.max())), "best_scale_minus_1": s_opt - 1.0,
            "rel_err_after_scale_max": float(rel2.max()), "rel_err_after_scale_mean": float(rel2.mean())}
