@@ -20,7 +20,7 @@ What changes underneath:
 """
 from __future__ import annotations
 
-import heapq
+import collections
 import logging
 import os
 from time import time
@@ -87,8 +87,6 @@ class Trainer(object):
         self.warmup_steps = params["warmup_epochs"] * data_num
         self.max_steps = params["epochs"] * data_num
         self.save_limit = params["save_limit"]
-        self.best_save_heap = []
-        self.newest_save_queue = []
         self.eval_step = min(params["eval_step"], self.epochs)
         self.device = torch.device(params["device"])
         self.ckpt_dir = params["ckpt_dir"]
@@ -218,11 +216,16 @@ class Trainer(object):
         chunks = []
         for data in valid_data:
             data = data.to(self.device, non_blocking=True)
-            chunks.append(self.model.get_indices(data).view(-1, len(self.model.num_emb_list)))
-        codes = torch.cat(chunks)
+            if self.world > 1 and self.slice_batches:   # every rank iterates over the same batches: keep this rank's rows,
+                lo, hi = (self.rank * data.shape[0]) // self.world, ((self.rank + 1) * data.shape[0]) // self.world
+                data = data[lo:hi].contiguous()         # so that every item is counted once in the global statistics
+            if data.shape[0]:
+                chunks.append(self.model.get_indices(data).view(-1, len(self.model.num_emb_list)))
+        codes = torch.cat(chunks) if chunks else torch.zeros((0, len(self.model.num_emb_list)), dtype=torch.int64, device=self.device)
         if self.world > 1:
             from .sharding import CudaShardOps, global_stats, global_suffix
-            out = global_suffix(codes, self.model.num_emb_list, CudaShardOps(self.model), self.group)
+            ops = getattr(self, "shard_ops", None) or CudaShardOps(self.model)
+            out = global_suffix(codes, self.model.num_emb_list, ops, self.group)
             return global_stats(out, self.group)["collision_rate"]
         _, stats = suffix_dedup(self.model, codes)
         return stats["collision_rate"]
@@ -244,42 +247,57 @@ class Trainer(object):
         return ckpt_path
 
     def fit(self, data):
-        cur_eval_step = 0
-        for epoch_idx in range(self.epochs):
-            t0 = time()
-            train_loss, train_recon_loss = self._train_epoch(data, epoch_idx)
+        """train.py:186-250: epochs of training; every `eval_step` epochs the collision rate is measured, the two
+        "best" checkpoints are refreshed and an epoch checkpoint is written and filed with the keeper."""
+        keeper = _CheckpointKeeper(self.save_limit, self.rank)
+        self.checkpoints = keeper
+        for epoch in range(self.epochs):
+            started = time()
+            loss, recon = self._train_epoch(data, epoch)
             self.logger.info("epoch %d training [time: %.2fs, train loss: %.4f, reconstruction loss: %.4f]"
-                             % (epoch_idx, time() - t0, train_loss, train_recon_loss))
-            if (epoch_idx + 1) % self.eval_step == 0:
-                t1 = time()
-                collision_rate = self._valid_epoch(data)
-                if train_loss < self.best_loss:
-                    self.best_loss = train_loss
-                    self._save_checkpoint(epoch=epoch_idx, ckpt_file=self.best_loss_ckpt)
-                if collision_rate < self.best_collision_rate:
-                    self.best_collision_rate = collision_rate
-                    cur_eval_step = 0
-                    self._save_checkpoint(epoch_idx, collision_rate=collision_rate, ckpt_file=self.best_collision_ckpt)
-                else:
-                    cur_eval_step += 1
-                self.logger.info("epoch %d evaluating [time: %.2fs, collision_rate: %f]"
-                                 % (epoch_idx, time() - t1, collision_rate))
-                ckpt_path = self._save_checkpoint(epoch_idx, collision_rate=collision_rate)
-                now_save = (-collision_rate, ckpt_path)
-                if len(self.newest_save_queue) < self.save_limit:
-                    self.newest_save_queue.append(now_save)
-                    heapq.heappush(self.best_save_heap, now_save)
-                else:                                   # rotation rule of train.py:237-248
-                    old_save = self.newest_save_queue.pop(0)
-                    self.newest_save_queue.append(now_save)
-                    if collision_rate < -self.best_save_heap[0][0]:
-                        bad_save = heapq.heappop(self.best_save_heap)
-                        heapq.heappush(self.best_save_heap, now_save)
-                        if bad_save not in self.newest_save_queue:
-                            _delete_file(bad_save[1], self.rank)
-                    if old_save not in self.best_save_heap:
-                        _delete_file(old_save[1], self.rank)
+                             % (epoch, time() - started, loss, recon))
+            if (epoch + 1) % self.eval_step:
+                continue
+            started = time()
+            rate = self._valid_epoch(data)
+            if loss < self.best_loss:
+                self.best_loss = loss
+                self._save_checkpoint(epoch=epoch, ckpt_file=self.best_loss_ckpt)
+            if rate < self.best_collision_rate:
+                self.best_collision_rate = rate
+                self._save_checkpoint(epoch, collision_rate=rate, ckpt_file=self.best_collision_ckpt)
+            self.logger.info("epoch %d evaluating [time: %.2fs, collision_rate: %f]" % (epoch, time() - started, rate))
+            keeper.file(rate, self._save_checkpoint(epoch, collision_rate=rate))
         return self.best_loss, self.best_collision_rate
+
+
+class _CheckpointKeeper:
+    """Which epoch checkpoints stay on disk (the rule of train.py:232-248, stated as sets): the `limit` most recent ones
+    and the `limit` with the lowest collision rate; a file is removed when it belongs to neither set any more.  As in
+    the reference a checkpoint enters the "best" set only while that set is not full or when it beats the worst member
+    (ties: the worst member is the one with the highest rate, then the smallest path)."""
+
+    def __init__(self, limit: int, rank: int = 0):
+        self.limit, self.rank = int(limit), rank
+        self.recent = collections.deque()
+        self.best = []
+
+    def file(self, rate: float, path: str):
+        entry = (rate, path)
+        if len(self.recent) < self.limit:
+            self.recent.append(entry)
+            self.best.append(entry)
+            return
+        leaving = [self.recent.popleft()]
+        self.recent.append(entry)
+        worst = min(self.best, key=lambda e: (-e[0], e[1]))
+        if rate < worst[0]:
+            self.best.remove(worst)
+            self.best.append(entry)
+            leaving.insert(0, worst)
+        for old in leaving:
+            if old not in self.recent and old not in self.best:
+                _delete_file(old[1], self.rank)
 
 
 def _delete_file(path, rank=0):

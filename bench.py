@@ -232,6 +232,34 @@ def run_reference_arm(args):
 KEEP_ALIVE = []
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off BEFORE the pinned host buffers are allocated and
+    first touched, so that the e2e leg's H2D stream reads node-local memory (at N = 8 eight ranks stream 3 GB each)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local)
+        bdf = None
+        if hasattr(props, "pci_bus_id"):
+            bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, getattr(props, "pci_device_id", 0))
+        else:
+            q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                               capture_output=True, text=True, timeout=10).stdout.strip().lower()
+            bdf = q[-12:] if q else None
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as exc:          # placement is an optimisation
+        return {"numa_node": None, "note": f"not bound ({type(exc).__name__})"}
+
+
 def run_extra(key, n_total, rank, world, dev, group, args):
     """BASELINE configs[2] (10 M x 768, 4 x 256 codes, e 64) / configs[4] (100 M x 1024, 4 x 1024 codes, e 64): the catalogue
     is split into contiguous shards over the `world` GPUs (strong scaling), every rank encodes its shard (tensor-core
@@ -338,6 +366,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -455,6 +485,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = ne * world / float(e2e_s.item())
+    os.sched_setaffinity(0, all_cpus)          # the CPU baseline below gets every host core again
     if world == 1 and ne == n:
         assert np.array_equal(ids_host.numpy(), out.cpu().numpy()), "host-buffer path and device path disagree"
 
@@ -538,7 +569,7 @@ def main():
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ne * in_dim * 4),
                         "d2h_bytes_per_step": int(ne * (len(Ks) + 1) * 8), "items_per_gpu": ne,
-                        "api": "rqb200_generate_codes_host (pinned host buffers)"},
+                        "api": "rqb200_generate_codes_host (pinned host buffers)", "host_placement_rank0": numa},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_full_driver:
             # the WHOLE driver (generate_code.py / infer.py semantics): pass 1 + the <= 30 Sinkhorn re-encode rounds

@@ -214,3 +214,68 @@ def test_shard_ranges_cover_the_catalogue():
             r = [sharding.shard_range(n, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+class _FakeModel:
+    """Stands in for the RQVAE in Trainer._valid_epoch: codes are a fixed function of the rows (CPU)."""
+    num_emb_list = [4, 4, 4]
+
+    def eval(self):
+        return self
+
+    def get_indices(self, data):
+        return (data[:, :3].abs() * 3.999).long().clamp_(0, 3)
+
+
+def _valid_epoch_job(rank, world, x_all, batch):
+    import types
+    from ai_education_generative_recommendation_b200.trainer import Trainer
+    me = types.SimpleNamespace(model=_FakeModel(), device=torch.device("cpu"), world=world, rank=rank, slice_batches=True,
+                               group=dist.group.WORLD, shard_ops=NumpyShardOps())
+    loader = [x_all[i:i + batch] for i in range(0, x_all.shape[0], batch)]
+    return Trainer._valid_epoch(me, loader)
+
+
+def test_data_parallel_collision_rate_counts_every_item_once(tmp_path, oracle):
+    """Trainer._valid_epoch with sliced batches (every rank iterates over the SAME batches, train.py:126-151): the global
+    collision rate equals the single-process value — every item enters the statistics exactly once."""
+    torch.manual_seed(3)
+    x = torch.rand(1003, 8)
+    codes = _FakeModel().get_indices(x).numpy()
+    want = 1.0 - len(np.unique(codes, axis=0)) / len(codes)
+    res = run_world(_valid_epoch_job, (x, 64), tmp_path, world=2)
+    assert abs(res[0] - want) < 1e-12 and abs(res[1] - want) < 1e-12
+
+
+def test_checkpoint_keeper_follows_the_reference_rotation_rule(monkeypatch):
+    """_CheckpointKeeper against the heap / queue rule of train.py:232-248 replayed verbatim on random histories."""
+    import heapq
+    import random
+    import ai_education_generative_recommendation_b200.trainer as T
+    gone = []
+    monkeypatch.setattr(T, "_delete_file", lambda p, rank=0: gone.append(p))
+    random.seed(1)
+    for _ in range(100):
+        limit = random.choice([1, 2, 3, 5])
+        keeper = T._CheckpointKeeper(limit)
+        gone.clear()
+        heap, queue, ref_gone = [], [], []
+        for e in range(30):
+            rate = random.choice([0.1, 0.2, 0.3, 0.05, 0.5])
+            path = f"epoch_{e}_collision_{rate:.4f}_model.pth"
+            keeper.file(rate, path)
+            now = (-rate, path)
+            if len(queue) < limit:
+                queue.append(now)
+                heapq.heappush(heap, now)
+            else:
+                old = queue.pop(0)
+                queue.append(now)
+                if rate < -heap[0][0]:
+                    bad = heapq.heappop(heap)
+                    heapq.heappush(heap, now)
+                    if bad not in queue:
+                        ref_gone.append(bad[1])
+                if old not in heap:
+                    ref_gone.append(old[1])
+        assert sorted(ref_gone) == sorted(gone)
