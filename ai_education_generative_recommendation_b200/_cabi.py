@@ -44,6 +44,7 @@ _PROTOS = {
     "rqb200_model_set_screen": (c_int, [c_void_p, c_int, c_float]),
     "rqb200_model_last_tier_rows": (c_int, [c_void_p, POINTER(c_int64)]),
     "rqb200_debug_linear_tc": (c_int, [c_void_p, c_int, c_int, _P, c_int64, _P, c_int, c_int, _P]),
+    "rqb200_debug_check_division": (c_int, [ctypes.c_uint64, c_int, ctypes.c_uint64, POINTER(ctypes.c_uint64), _P]),
     "rqb200_debug_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, c_int, _P]),
     "rqb200_mlp_tc": (c_int, [c_void_p, c_int, _P, c_int64, _P, _P]),
     "rqb200_mlp_exact": (c_int, [c_void_p, c_int, _P, _P, c_int64, _P, _P]),

@@ -12,6 +12,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace rqb {
@@ -46,7 +48,15 @@ static cudaEvent_t prof_get_event() {
     cudaEventCreate(&e);
     return e;
 }
+// NVTX range per stage (always on: a push / pop costs a few ns when no tool is attached), so that a timeline tool shows
+// the stages of a step by name; the CUDA-event timing below is what bench.py reads.
+static const char *const kStageNames[PROF_NSLOTS] = {
+    "rqb200/linear_exact layer 1", "rqb200/linear_exact other layers", "rqb200/quantize", "rqb200/sort+dedup",
+    "rqb200/tensor-core layer 1", "rqb200/sinkhorn", "rqb200/tensor-core layers 2+3", "rqb200/three-pass re-run tier",
+    "rqb200/exact rescue tier", "rqb200/group re-encode", "rqb200/slot10", "rqb200/slot11"};
+
 void prof_begin(int slot, cudaStream_t s) {
+    if (slot >= 0 && slot < PROF_NSLOTS) nvtxRangePushA(kStageNames[slot]);
     if (!g_prof.enabled || slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e = prof_get_event();
@@ -54,6 +64,7 @@ void prof_begin(int slot, cudaStream_t s) {
     g_prof.open_ev[slot] = e;
 }
 void prof_end(int slot, cudaStream_t s) {
+    if (slot >= 0 && slot < PROF_NSLOTS) nvtxRangePop();
     if (!g_prof.enabled || slot < 0) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof.open_ev[slot]) return;

@@ -155,6 +155,7 @@ int linear_tc(Linear &l, const float *x, int64_t n, float *y, bool relu, cudaStr
               const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool tiled_out = false);
 int mlp_tc(rqb200_model *m, int which, const float *x, int64_t n, float *y, cudaStream_t s, int passes = 3,
            const int64_t *rows = nullptr, const unsigned long long *n_dev = nullptr, bool profile = true);
+int scatter_rows(const float *src, const int64_t *rows, int64_t nr, int e, float *dst, cudaStream_t s);   // encode_tc.cu: dst[rows[i]] = src[i]
 // quantize_tc.cu
 bool quantize_tc_supported(const rqb200_model *m);
 // rows (may be NULL): row i of z is item rows[i] (codes / list entries use the item index); n_dev: device-resident

@@ -254,6 +254,9 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
     RQB_CHECK(n <= (int64_t)2147483647 * 128, "too many rows");
     // a batch of 2..15 rows: the reference's CPU GEMM switches to its small-batch summation order (small_batch.cu)
     if (small_batch_lane16(batch_rows < 0 ? n : batch_rows, lin.in)) return linear_small(lin, x, rows, n, y, relu, s);
+    // few rows (rescue tier, collision groups): 128 x 128 tiles leave most SMs idle (6.9 k rows x 256 features = 108 CTAs);
+    // 64 x 64 tiles give four times the CTAs.  Same chains, same bits.
+    if (lin.out > 64 && n <= 24576) return launch<64, 64, 4, 4>(lin, x, rows, n, y, relu, s);
     if (lin.out > 64) return launch<128, 128, 8, 8>(lin, x, rows, n, y, relu, s);
     if (lin.out > 32) return launch<128, 64, 8, 4>(lin, x, rows, n, y, relu, s);
     return launch<128, 32, 4, 4>(lin, x, rows, n, y, relu, s);

@@ -87,6 +87,27 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// a / b for MANY numerators over ONE denominator, without a division per element: y = RN(1/b) once, then
+//   q0 = RN(a·y);  r0 = a − b·q0 (exact, fma);  q1 = RN(q0 + r0·y)  → faithful;  r1 = a − b·q1 (exact);  q = RN(q1 + r1·y)
+// which is the correctly rounded quotient RN(a/b) (Markstein's final-step theorem for a faithful q1 and a correctly rounded
+// reciprocal) for normal, finite, non-zero operands — the only ones the Sinkhorn matrix holds (entries are exp() of bounded
+// arguments divided by positive sums); everything else takes the hardware division.  Same bits as `a / b`, one multiply + four
+// fmas instead of a ≈ 30-instruction fp64 division: the kernel is bound by exactly these.  rqb200_debug_check_division compares
+// the two on 2^32 operand pairs per call (tests/test_gpu_parity.py).
+__device__ __noinline__ double div_slow(double a, double b) { return a / b; }
+
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q0 = a * y;
+    const double q1 = __fma_rn(__fma_rn(-q0, b, a), y, q0);
+    const double q = __fma_rn(__fma_rn(-q1, b, a), y, q1);
+    // |a|, |b|, |q| in [2^-900, 2^900]: no underflow / overflow anywhere in the sequence; otherwise (zeros, subnormals, inf, NaN) divide
+    const unsigned ea = (unsigned)((__double_as_longlong(a) >> 52) & 0x7ff), eb = (unsigned)((__double_as_longlong(b) >> 52) & 0x7ff),
+                   eq = (unsigned)((__double_as_longlong(q) >> 52) & 0x7ff);
+    const bool safe = ea - 123u < 1801u && eb - 123u < 1801u && eq - 123u < 1801u;
+    if (__builtin_expect(!safe, 0)) return div_slow(a, b);      // a real branch: the division must not be evaluated on the fast path
+    return q;
+}
+
 __device__ double block_sum(double v, double *s_red) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -111,7 +132,10 @@ __device__ void sinkhorn_cta(double *Q, int B, int K, int iters, double *s_red) 
         if (lane == 0) part += rs;
     }
     double total = block_sum(part, s_red);
-    for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = Q[i] / total;
+    {
+        const double ytot = 1.0 / total;
+        for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = div_by(Q[i], total, ytot);
+    }
     __syncthreads();
     const double dB = (double)B, dK = (double)K;
     // `Q /= B` / `Q /= K` with a power-of-two divisor: x / 2^k and x * 2^-k are the correctly rounded value of the same real
@@ -124,16 +148,18 @@ __device__ void sinkhorn_cta(double *Q, int B, int K, int iters, double *s_red) 
             double rs = 0.0;
             for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
             rs = warp_sum(rs);
-            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / rs) * invB; }
-            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / rs) / dB; }
+            const double yr = 1.0 / rs;
+            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], rs, yr) * invB; }
+            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], rs, yr), dB, invB); }
         }
         __syncthreads();
         // Q /= Q.sum(dim=0, keepdim=True);  Q /= K
         for (int j = tid; j < K; j += SK_THREADS) {
             double cs = 0.0;
             for (int i = 0; i < B; ++i) cs += Q[(size_t)i * K + j];
-            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / cs) * invK; }
-            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = (Q[(size_t)i * K + j] / cs) / dK; }
+            const double yc = 1.0 / cs;
+            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], cs, yc) * invK; }
+            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], cs, yc), dK, invK); }
         }
         __syncthreads();
     }
@@ -236,6 +262,114 @@ sinkhorn_regroup_kernel(const float *__restrict__ residual, const int64_t *__res
     argmax_rows(Q, B, K, gi, codes, L, nullptr);
 }
 
+
+// Groups of 2 … SKW_MAX_ROWS rows — the bulk of every round after the first — one WARP per group, no block barriers.
+// Bit-identical to sinkhorn_regroup_kernel by construction: every sum runs in the same order (row sums: lane-strided
+// partials + xor butterfly; the total: row sums added in row order; column sums: rows in order), every quotient through the
+// same div_by, the same centre / exp expressions, the same arg-max rule.
+constexpr int SKW_MAX_ROWS = 8;
+__global__ void __launch_bounds__(128)
+sinkhorn_regroup_warp_kernel(const float *__restrict__ residual, const int64_t *__restrict__ items,
+                             const int64_t *__restrict__ offsets, int64_t n_groups, int e, const float *__restrict__ cb,
+                             const float *__restrict__ cc, int K, int L, double epsilon, int iters, int warps_per_cta,
+                             int64_t *__restrict__ codes) {
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid >= warps_per_cta) return;
+    const int64_t g = (int64_t)blockIdx.x * warps_per_cta + wid;
+    if (g >= n_groups) return;
+    const int64_t g0 = offsets[g];
+    const int64_t B64 = offsets[g + 1] - g0;
+    if (B64 < 2 || B64 > SKW_MAX_ROWS) return;
+    const int B = (int)B64;
+    const size_t per_warp = sizeof(double) * SKW_MAX_ROWS * (size_t)K + sizeof(float) * SKW_MAX_ROWS * (size_t)(e + 1);
+    double *Q = reinterpret_cast<double *>(sk_smem + (size_t)wid * per_warp);          // [B][K]
+    float *s_r = reinterpret_cast<float *>(Q + (size_t)SKW_MAX_ROWS * K);              // [B][e]
+    float *s_xx = s_r + (size_t)SKW_MAX_ROWS * e;                                      // [B]
+    const int64_t *gi = items + g0;
+    for (int i = lane; i < B * e; i += 32) s_r[i] = residual[gi[i / e] * e + (i % e)];
+    __syncwarp();
+    if (lane < B) s_xx[lane] = sumsq_aten_rt(s_r + (size_t)lane * e, e);
+    __syncwarp();
+    float mx = -__int_as_float(0x7f800000), mn = __int_as_float(0x7f800000);
+    for (int p = lane; p < B * K; p += 32) {
+        const int i = p / K, j = p % K;
+        const float acc = dot_for_batch(s_r + (size_t)i * e, cb + (size_t)j * e, e, B);
+        const float d = __fsub_rn(__fadd_rn(s_xx[i], cc[j]), __fmul_rn(2.0f, acc));
+        Q[p] = (double)d;
+        mx = fmaxf(mx, d);
+        mn = fminf(mn, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    const float middle = __fdiv_rn(__fadd_rn(mx, mn), 2.0f);
+    const float amplitude = __fadd_rn(__fsub_rn(mx, middle), 1e-5f);
+    for (int p = lane; p < B * K; p += 32) {
+        const float c = __fdiv_rn(__fsub_rn((float)Q[p], middle), amplitude);
+        Q[p] = exp(-((double)c) / epsilon);
+    }
+    __syncwarp();
+    // sum_Q = Q.sum(-1).sum(-2);  Q /= sum_Q
+    double total = 0.0;
+    for (int i = 0; i < B; ++i) {
+        double rs = 0.0;
+        for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
+        total += warp_sum(rs);
+    }
+    {
+        const double ytot = 1.0 / total;
+        for (int p = lane; p < B * K; p += 32) Q[p] = div_by(Q[p], total, ytot);
+    }
+    __syncwarp();
+    const double dB = (double)B, dK = (double)K;
+    const bool b_pow2 = (B & (B - 1)) == 0, k_pow2 = (K & (K - 1)) == 0;
+    const double invB = 1.0 / dB, invK = 1.0 / dK;
+    for (int it = 0; it < iters; ++it) {
+        for (int i = 0; i < B; ++i) {
+            double rs = 0.0;
+            for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
+            rs = warp_sum(rs);
+            const double yr = 1.0 / rs;
+            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], rs, yr) * invB; }
+            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], rs, yr), dB, invB); }
+        }
+        __syncwarp();
+        for (int j = lane; j < K; j += 32) {
+            double cs = 0.0;
+            for (int i = 0; i < B; ++i) cs += Q[(size_t)i * K + j];
+            const double yc = 1.0 / cs;
+            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], cs, yc) * invK; }
+            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], cs, yc), dK, invK); }
+        }
+        __syncwarp();
+    }
+    for (int p = lane; p < B * K; p += 32) Q[p] = Q[p] * dB;
+    __syncwarp();
+    // arg-max per row (first maximum wins; NaN counts as maximum like torch.argmax)
+    for (int i = 0; i < B; ++i) {
+        double best = 0.0;
+        int bj = -1;
+        for (int j = lane; j < K; j += 32) {
+            const double v = Q[(size_t)i * K + j];
+            const bool take = bj < 0 || (!(best != best) && ((v != v) || v > best));
+            if (take) { best = v; bj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (oj >= 0) {
+                const bool onan = ov != ov, bnan = best != best;
+                const bool take = bj < 0 || (onan && (!bnan || oj < bj)) || (!onan && !bnan && (ov > best || (ov == best && oj < bj)));
+                if (take) { best = ov; bj = oj; }
+            }
+        }
+        if (lane == 0) codes[gi[i] * L + (L - 1)] = bj;
+    }
+}
 
 // collision groups too large for shared memory: same computation, the fp64 matrix and the row norms live in a global
 // scratch slice (offset given per listed group).  One CTA per listed group.
@@ -438,10 +572,55 @@ sinkhorn_assign_grid_kernel(const float *__restrict__ d, double *__restrict__ ws
     argmax_rows(Q, rows, K, nullptr, nullptr, 0, idx_out + row0);
 }
 
+// div_by against the hardware division on pseudo-random operand pairs: mantissas uniform, exponents spread over ±span binades,
+// a fraction of the denominators with all-ones / all-zeros mantissa tails (the hard cases of reciprocal-based division)
+__global__ void check_division_kernel(unsigned long long seed, int span, unsigned long long per_thread, unsigned long long *bad) {
+    unsigned long long st = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    auto next = [&]() {
+        st += 0x9E3779B97F4A7C15ull;
+        unsigned long long z = st;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    unsigned long long mism = 0;
+    for (unsigned long long t = 0; t < per_thread; ++t) {
+        const unsigned long long ra = next(), rb = next(), rc = next();
+        unsigned long long mb = rb & 0xFFFFFFFFFFFFFull;
+        if ((rc & 7) == 0) mb |= (1ull << (rc >> 58)) - 1;            // trailing ones
+        if ((rc & 7) == 1) mb &= ~((1ull << (rc >> 58)) - 1);         // trailing zeros
+        const long long expa = 1023 + (long long)((ra >> 52) % (unsigned long long)(2 * span + 1)) - span;
+        const long long expb = 1023 + (long long)((rb >> 52) % (unsigned long long)(2 * span + 1)) - span;
+        const double a = __longlong_as_double((long long)((unsigned long long)expa << 52 | (ra & 0xFFFFFFFFFFFFFull)));
+        const double b = __longlong_as_double((long long)((unsigned long long)expb << 52 | mb));
+        const double y = 1.0 / b;
+        if (__double_as_longlong(div_by(a, b, y)) != __double_as_longlong(a / b)) ++mism;
+    }
+    if (mism) atomicAdd(bad, mism);
+}
+
 }  // namespace
 }  // namespace rqb
 
 using namespace rqb;
+
+// diagnostics: number of operand pairs (of `pairs` tried) on which the kernel's reciprocal-based division differs from `a / b`
+extern "C" int rqb200_debug_check_division(unsigned long long seed, int exponent_span, unsigned long long pairs,
+                                           unsigned long long *mismatches_host, void *stream) {
+    RQB_CHECK(mismatches_host != nullptr, "NULL argument");
+    RQB_CHECK(exponent_span >= 0 && exponent_span <= 1000, "exponent_span out of range");
+    unsigned long long *bad = nullptr;
+    RQB_CUDA(cudaMalloc(&bad, sizeof(*bad)));
+    RQB_CUDA(cudaMemsetAsync(bad, 0, sizeof(*bad), (cudaStream_t)stream));
+    const unsigned blocks = kNumSMs * 8, threads = 256;
+    const unsigned long long per_thread = (pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+    rqb::count_launch();
+    check_division_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(seed, exponent_span, per_thread, bad);
+    RQB_CUDA(cudaMemcpyAsync(mismatches_host, bad, sizeof(*bad), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RQB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    RQB_CUDA(cudaFree(bad));
+    return 0;
+}
 
 extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const int64_t *items_dev,
                                        const int64_t *offsets_dev, int64_t n_groups, int max_group,
@@ -471,6 +650,21 @@ extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_de
     ProfScope ps(PROF_SINKHORN, (cudaStream_t)stream);
     const int bounds[4] = {8, 24, 48, top};
     int lo = 2;
+    {
+        // groups of 2 … 8 rows: one warp per group (same bits as the CTA kernel below, no block barriers)
+        const size_t per_warp = sizeof(double) * SKW_MAX_ROWS * (size_t)K + sizeof(float) * SKW_MAX_ROWS * (size_t)(e + 1);
+        int wpc = (int)((size_t)(100 * 1024) / per_warp);
+        wpc = wpc > 4 ? 4 : wpc;
+        if (wpc >= 1 && (per_warp % 16) == 0) {
+            static rqb::DeviceOnce warp_attr_once;
+            if (warp_attr_once.first())
+                RQB_CUDA(cudaFuncSetAttribute(sinkhorn_regroup_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+            rqb::count_launch();
+            sinkhorn_regroup_warp_kernel<<<(unsigned)((n_groups + wpc - 1) / wpc), 128, per_warp * wpc, (cudaStream_t)stream>>>(
+                residual_dev, items_dev, offsets_dev, n_groups, e, m->cb[L - 1], m->cc[L - 1], K, L, epsilon, iters, wpc, codes_dev);
+            lo = SKW_MAX_ROWS + 1;
+        }
+    }
     for (int c = 0; c < 4 && lo <= top; ++c) {
         const int hi = bounds[c] < top ? bounds[c] : top;
         if (hi < lo) continue;

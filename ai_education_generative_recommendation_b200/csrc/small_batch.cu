@@ -40,6 +40,32 @@ __global__ void group_sizes_kernel(const int64_t *__restrict__ offsets, int64_t 
     msize[i] = sz > 2147483647 ? 2147483647 : (int)sz;
 }
 
+// slots → two compact lists: members of groups with fewer than 16 rows (small-batch arithmetic) and the rest (catalogue
+// arithmetic in every layer: the fast exact kernels take those).  Order inside a list is irrelevant: rows are independent.
+__global__ void partition_by_size_kernel(const int64_t *__restrict__ items, const int *__restrict__ msize, int64_t n_items,
+                                         int64_t *__restrict__ small_items, int *__restrict__ small_msize,
+                                         int64_t *__restrict__ big_items, unsigned long long *__restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_items;
+    const bool big = live && msize[i] >= 16;
+    const unsigned mb = __ballot_sync(0xffffffffu, big), ms = __ballot_sync(0xffffffffu, live && !big);
+    const int lane = threadIdx.x & 31;
+    unsigned long long base_b = 0, base_s = 0;
+    if (lane == 0) {
+        if (mb) base_b = atomicAdd(&counts[1], (unsigned long long)__popc(mb));
+        if (ms) base_s = atomicAdd(&counts[0], (unsigned long long)__popc(ms));
+    }
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    base_s = __shfl_sync(0xffffffffu, base_s, 0);
+    const unsigned below = (1u << lane) - 1;
+    if (big) big_items[base_b + __popc(mb & below)] = items[i];
+    else if (live) {
+        const unsigned long long p = base_s + __popc(ms & below);
+        small_items[p] = items[i];
+        small_msize[p] = msize[i];
+    }
+}
+
 __device__ __forceinline__ float fold_lane16(const float (&acc)[16]) {
     float s[4];
 #pragma unroll
@@ -299,16 +325,32 @@ quantize_small_kernel(const float *__restrict__ z, const int64_t *__restrict__ i
 #pragma unroll
                 for (int q = 0; q < 16; ++q) acc[q] = 0.0f;
                 int k = 0;
-                for (; k + 16 <= e; k += 16)
+                for (; k + 16 <= e; k += 16) {
+                    float cv[16], rv[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
+                    for (int q = 0; q < 4; ++q) {           // e is a multiple of 4 and the rows are 16-byte aligned: 128-bit loads
+                        const float4 a = *reinterpret_cast<const float4 *>(c + k + 4 * q), b = *reinterpret_cast<const float4 *>(r + k + 4 * q);
+                        cv[4 * q] = a.x; cv[4 * q + 1] = a.y; cv[4 * q + 2] = a.z; cv[4 * q + 3] = a.w;
+                        rv[4 * q] = b.x; rv[4 * q + 1] = b.y; rv[4 * q + 2] = b.z; rv[4 * q + 3] = b.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc[q] = __fmaf_rn(rv[q], cv[q], acc[q]);
+                }
 #pragma unroll
                 for (int q = 0; q < 16; ++q)
                     if (k + q < e) acc[q] = __fmaf_rn(r[k + q], c[k + q], acc[q]);
                 dot = fold_lane16(acc);
             } else {
+                // one sequential chain over k; the operands of the next 8 steps are fetched ahead as two 128-bit loads each
                 dot = 0.0f;
-                for (int k = 0; k < e; ++k) dot = __fmaf_rn(r[k], c[k], dot);
+                int k = 0;
+                for (; k + 8 <= e; k += 8) {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(c + k), a1 = *reinterpret_cast<const float4 *>(c + k + 4);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(r + k), b1 = *reinterpret_cast<const float4 *>(r + k + 4);
+                    dot = __fmaf_rn(b0.x, a0.x, dot); dot = __fmaf_rn(b0.y, a0.y, dot); dot = __fmaf_rn(b0.z, a0.z, dot); dot = __fmaf_rn(b0.w, a0.w, dot);
+                    dot = __fmaf_rn(b1.x, a1.x, dot); dot = __fmaf_rn(b1.y, a1.y, dot); dot = __fmaf_rn(b1.z, a1.z, dot); dot = __fmaf_rn(b1.w, a1.w, dot);
+                }
+                for (; k < e; ++k) dot = __fmaf_rn(r[k], c[k], dot);
             }
             const float d = __fsub_rn(__fadd_rn(xx, cc[j]), __fmul_rn(2.0f, dot));
             if (dist_out) dist_out[slot * K + j] = d;
@@ -396,6 +438,7 @@ int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, 
     for (int l = 0; l < m->L; ++l) { qa.cb[l] = m->cb[l]; qa.cc[l] = m->cc[l]; qa.K[l] = m->K[l]; }
     const size_t smem = sizeof(float) * QS_WARPS * 2 * (size_t)m->e;
     RQB_CHECK(smem <= 48 * 1024, "e_dim %d too large for the small-batch quantizer", m->e);
+    RQB_CHECK(m->e % 4 == 0, "e_dim must be a multiple of 4 (got %d)", m->e);
     rqb::count_launch();
     quantize_small_kernel<<<(unsigned)((n + QS_WARPS - 1) / QS_WARPS), QS_WARPS * 32, smem, s>>>(
         z, items, msize, m_uniform, n, m->e, qa, dist_out ? 1 : levels_run, codes, residual_out, xq_out, sumsq_out, dist_out,
@@ -445,16 +488,56 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
     RQB_CUDA(cudaSetDevice(m->device));
     int maxdim = m->e;
     for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
-    const size_t act = sizeof(float) * (size_t)n_items * maxdim;
+    const size_t isz = ((sizeof(int64_t) * (size_t)n_items + 255) / 256) * 256;
     const size_t msz = ((sizeof(int) * (size_t)n_items + 255) / 256) * 256;
-    RQB_TRY(ws_reserve(m->groupws, msz + 2 * act));
-    int *msize = (int *)m->groupws.ptr;
+    // msize | small msize | small items | big items | counts | two activation buffers (sized once the split is known)
+    const size_t head = 2 * msz + 2 * isz + 256;
+    RQB_TRY(ws_reserve(m->groupws, head));
+    char *base = (char *)m->groupws.ptr;
+    int *msize = (int *)base;
+    int *small_msize = (int *)(base + msz);
+    int64_t *small_items = (int64_t *)(base + 2 * msz);
+    int64_t *big_items = (int64_t *)(base + 2 * msz + isz);
+    unsigned long long *counts = (unsigned long long *)(base + 2 * msz + 2 * isz);
     ProfScope ps(PROF_REENCODE, s);
     rqb::count_launch();
     group_sizes_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(offsets_dev, n_groups, n_items, msize);
-    RQB_LAUNCH_CHECK();
-    return reencode_rows_impl(m, x_dev, x_is_gathered, items_dev, msize, n_items, (float *)((char *)m->groupws.ptr + msz),
-                              (float *)((char *)m->groupws.ptr + msz + act), codes_dev, residual_dev, s);
+    unsigned long long h[2] = {(unsigned long long)n_items, 0};
+    if (!x_is_gathered) {
+        // groups of 16 or more rows use the catalogue arithmetic in every layer: hand those rows to the fast exact kernels
+        RQB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), s));
+        rqb::count_launch();
+        partition_by_size_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(items_dev, msize, n_items, small_items, small_msize,
+                                                                                 big_items, counts);
+        RQB_LAUNCH_CHECK();
+        RQB_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));
+        RQB_CUDA(cudaStreamSynchronize(s));
+    }
+    const int64_t n_small = (int64_t)h[0], n_big = (int64_t)h[1];
+    if (n_small > 0) {
+        const size_t act = sizeof(float) * (size_t)n_small * maxdim;
+        RQB_TRY(ws_reserve(m->rescue_act[0], act));
+        RQB_TRY(ws_reserve(m->rescue_act[1], act));
+        RQB_TRY(reencode_rows_impl(m, x_dev, x_is_gathered, x_is_gathered ? items_dev : small_items, x_is_gathered ? msize : small_msize,
+                                   n_small, (float *)m->rescue_act[0].ptr, (float *)m->rescue_act[1].ptr, codes_dev, residual_dev, s));
+    }
+    if (n_big > 0) {
+        const int64_t batch = (int64_t)1 << 30;               // "a large batch": catalogue order in every layer
+        RQB_TRY(ws_reserve(m->rescue_act[0], sizeof(float) * (size_t)n_big * maxdim));
+        RQB_TRY(ws_reserve(m->rescue_act[1], sizeof(float) * (size_t)n_big * maxdim));
+        RQB_TRY(ws_reserve(m->rescue, sizeof(float) * (size_t)n_big * m->e));
+        const float *cur = x_dev;
+        for (int i = 0; i < m->n_layers; ++i) {
+            float *dst = (float *)m->rescue_act[i & 1].ptr;
+            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? big_items : nullptr, n_big, dst, i != m->n_layers - 1, s, batch));
+            cur = dst;
+        }
+        float *res_compact = (float *)m->rescue.ptr;
+        // all L arg-min levels are written; the Sinkhorn pass then overwrites the last one
+        RQB_TRY(quantize_exact(m, cur, n_big, codes_dev, big_items, nullptr, nullptr, res_compact, nullptr, s, batch));
+        RQB_TRY(scatter_rows(res_compact, big_items, n_big, m->e, residual_dev, s));
+    }
+    return 0;
 }
 
 // The same for rows that are members of groups whose other members live elsewhere (sharded catalogue): the caller

@@ -235,11 +235,15 @@ def encode_codes_exact(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Te
 
 @torch.no_grad()
 def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 262144, verbose: bool = False,
-                   fast: Optional[bool] = None) -> Tuple[torch.Tensor, dict]:
+                   fast: Optional[bool] = None, batch_size: Optional[int] = None) -> Tuple[torch.Tensor, dict]:
     """Passes 1–3 for one catalogue on one GPU.  Returns ([N, L+1] int64 CUDA tensor, stats).
 
     fast (default: whenever the model's shapes allow it): pass 1 runs on the tensor-core route (every row certified by
-    the margin gate or recomputed by the exact kernels); the re-encode rounds always run on the exact kernels."""
+    the margin gate or recomputed by the exact kernels); the re-encode rounds always run on the exact kernels.
+    batch_size (the reference's `params["batch_size"]`, infer.py:85): the reference encodes the catalogue in DataLoader
+    batches; full batches of 16 or more rows all share the catalogue arithmetic, but a LAST batch of 2..15 rows is
+    computed in its small-batch order (csrc/small_batch.cu) — given batch_size, those rows are encoded that way too.
+    (A last batch of exactly one row takes the reference's matrix-vector kernel, which is not restated.)"""
     Lv = len(model.num_emb_list)
     if Lv > MAX_LEVELS_OF_REFERENCE_DRIVER:
         raise IndexError("list index out of range")        # what prefix[i] raises in the reference
@@ -249,6 +253,13 @@ def generate_codes(model: RQVAE, data, max_rounds: int = 30, chunk_rows: int = 2
     model.eval()
     try:
         codes = encode_codes_fast(model, data, chunk_rows) if fast else encode_codes_exact(model, data, chunk_rows)
+        tail = codes.shape[0] % int(batch_size) if batch_size else 0
+        if 2 <= tail <= 15 and codes.shape[0] > tail:
+            rows = _as_rows(data)[codes.shape[0] - tail:]
+            rows = (rows if rows.is_cuda else rows.contiguous().to(model._device())).contiguous()
+            model._sync()
+            check(_cabi.lib().rqb200_get_indices(model._handle, _cabi.ENCODE_EXACT, ptr(rows), tail,
+                                                 ptr(codes[codes.shape[0] - tail:]), 0, None, stream_ptr(model._device())))
         rstats = {}
         codes, rounds = resolve_rounds(model, codes, data, max_rounds=max_rounds, verbose=verbose, stats=rstats)
         out, stats = suffix_dedup(model, codes)
@@ -325,7 +336,7 @@ def infer(params):
     model = model.to(device)
     model.eval()
     print("Generating codes...")
-    codes, stats = generate_codes(model, data.embeddings, verbose=True)
+    codes, stats = generate_codes(model, data.embeddings, verbose=True, batch_size=params.get("batch_size"))
     codes_array = codes.cpu().numpy()
     print("All indices number: ", len(codes_array))
     print("Max number of conflicts: ", stats["max_conflicts"])

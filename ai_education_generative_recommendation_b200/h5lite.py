@@ -130,7 +130,15 @@ class _Dataset:
                 raise H5LiteError(f"filter id {fid} is not supported by h5lite (deflate, shuffle, fletcher32 are)")
         return raw
 
-    def read(self) -> np.ndarray:
+    def read_rows(self, lo: int, hi: int) -> np.ndarray:
+        """Rows [lo, hi) along the first axis, touching only the bytes / chunks that hold them (a rank of a sharded job
+        reads its contiguous item range, not the catalogue)."""
+        if not self.shape:
+            raise H5LiteError("read_rows needs an array dataset")
+        lo, hi = max(0, int(lo)), min(int(hi), self.shape[0])
+        return self.read(rows=(lo, max(lo, hi)))
+
+    def read(self, rows=None) -> np.ndarray:
         b = self._one(0x0008, "data layout")
         version = b[0]
         O, Lz = self.f.off_size, self.f.len_size
@@ -164,6 +172,14 @@ class _Dataset:
         elif cls == 1:                                          # contiguous
             addr = int.from_bytes(b[2:2 + O], "little")
             size = int.from_bytes(b[2 + O:2 + O + Lz], "little")
+            if rows is not None:
+                row_items = int(np.prod(self.shape[1:], dtype=np.int64))
+                row_bytes = row_items * self.dtype.itemsize
+                nrows = rows[1] - rows[0]
+                if addr == UNDEF or nrows == 0:
+                    return np.zeros((nrows,) + tuple(self.shape[1:]), dtype=self.dtype)
+                raw = self.f._read(addr + rows[0] * row_bytes, nrows * row_bytes)
+                return np.frombuffer(raw, dtype=self.dtype, count=nrows * row_items).reshape((nrows,) + tuple(self.shape[1:])).copy()
             if addr == UNDEF:
                 arr = np.zeros(count, dtype=self.dtype)
             else:
@@ -174,21 +190,31 @@ class _Dataset:
             cdims = struct.unpack_from(f"<{nd1}I", b, 3 + O)
             if nd1 - 1 != len(self.shape):
                 raise H5LiteError("chunk rank does not match the dataspace")
-            arr = np.zeros(self.shape, dtype=self.dtype)
+            r0, r1 = rows if rows is not None else (0, self.shape[0] if self.shape else 0)
+            arr = np.zeros((r1 - r0,) + tuple(self.shape[1:]), dtype=self.dtype) if rows is not None else np.zeros(self.shape, dtype=self.dtype)
             if btree != UNDEF:
                 for offs, size, mask, addr in self.f._chunk_leaves(btree, nd1):
+                    if rows is not None and (offs[0] >= r1 or offs[0] + cdims[0] <= r0):
+                        continue                               # chunk holds none of the requested rows: not read, not inflated
                     raw = self._unfilter(self.f._read(addr, size), mask)
                     chunk = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(cdims[:-1]))).reshape(cdims[:-1])
                     sel_d, sel_c = [], []
-                    for o, c, s in zip(offs[:-1], cdims[:-1], self.shape):
+                    for ax, (o, c, s) in enumerate(zip(offs[:-1], cdims[:-1], self.shape)):
                         n = min(c, s - o)
-                        sel_d.append(slice(o, o + n))
-                        sel_c.append(slice(0, n))
+                        a, z = o, o + n
+                        if ax == 0 and rows is not None:
+                            a, z = max(o, r0), min(o + n, r1)
+                            sel_d.append(slice(a - r0, z - r0))
+                        else:
+                            sel_d.append(slice(a, z))
+                        sel_c.append(slice(a - o, z - o))
                     arr[tuple(sel_d)] = chunk[tuple(sel_c)]
             return arr
         else:
             raise H5LiteError(f"data layout class {cls}")
         arr = arr.reshape(self.shape) if self.shape else arr.reshape(())
+        if rows is not None:
+            return arr[rows[0]:rows[1]].copy()
         return arr.copy()
 
     def __getitem__(self, key):

@@ -330,6 +330,73 @@ def run_extra(key, n_total, rank, world, dev, group, args):
         GOLDEN, WORKLOAD = saved
 
 
+def run_sharded_checks(rank, world, dev, group):
+    """N > 1, driver-visible evidence for the two other cross-GPU steps of the path: the Sinkhorn re-encode
+    rounds over a sharded catalogue (ids must equal the single-GPU driver's) and the sharded k-means statistics all-reduce
+    (centres must equal a single-GPU fit of the gathered samples)."""
+    import torch
+    import torch.distributed as dist
+    import ai_education_generative_recommendation_b200 as rq
+    from ai_education_generative_recommendation_b200 import _cabi, sharding
+    from ai_education_generative_recommendation_b200.fixtures import build_model, load_golden
+    lib = _cabi.lib()
+    out = {}
+    g, cfg, cbs = load_golden("c2_slice")                    # sk_epsilons [0, 0, 0.003]: the re-encode rounds are live
+    n_total = 200_000
+    lo, hi = sharding.shard_range(n_total, rank, world)
+    model = build_model(cfg, cbs, device=dev)
+    x = torch.empty((hi - lo, cfg["in_dim"]), dtype=torch.float32, device=dev)
+    _cabi.check(lib.rqb200_synth_items(SEED, lo, hi - lo, cfg["in_dim"], 1_000_000, x.data_ptr(), _cabi.stream_ptr()))
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mine, stats = sharding.generate_codes_sharded(model, x, group)
+    torch.cuda.synchronize(); dist.barrier()
+    t_sh = time.perf_counter() - t0
+    pad = max(b - a for a, b in (sharding.shard_range(n_total, r, world) for r in range(world)))
+    buf = torch.full((pad, mine.shape[1]), -7, dtype=torch.int64, device=dev)
+    buf[:mine.shape[0]] = mine
+    xb = torch.zeros((pad, x.shape[1]), dtype=torch.float32, device=dev)
+    xb[:x.shape[0]] = x
+    ids_all = [torch.empty_like(buf) for _ in range(world)]
+    x_all = [torch.empty_like(xb) for _ in range(world)]
+    dist.all_gather(ids_all, buf)
+    dist.all_gather(x_all, xb)
+    if rank == 0:
+        sizes = [sharding.shard_range(n_total, r, world) for r in range(world)]
+        full = torch.cat([ids_all[r][:b - a] for r, (a, b) in enumerate(sizes)])
+        xs = torch.cat([x_all[r][:b - a] for r, (a, b) in enumerate(sizes)])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref, rstats = rq.generate_codes(build_model(cfg, cbs, device=dev), xs)
+        torch.cuda.synchronize()
+        out["sharded_driver"] = {"items": n_total, "rounds": stats["rounds"], "ids_equal_single_gpu": bool(torch.equal(ref, full)),
+                                 "seconds_sharded": t_sh, "seconds_single_gpu": time.perf_counter() - t0,
+                                 "what": "sharding.generate_codes_sharded: passes 1-3 incl. the <= 30 Sinkhorn re-encode rounds, codes / group "
+                                         "sizes / residuals exchanged per round (NCCL all-to-all), vs rq.generate_codes on one GPU"}
+    del ids_all, x_all, xb, buf
+    # sharded k-means: per-cluster sums / counts all-reduced every Lloyd iteration
+    e, K, per = 64, 256, 131072
+    xs = torch.empty((per, e), dtype=torch.float32, device=dev)
+    _cabi.check(lib.rqb200_synth_items(SEED, rank * per, per, e, per * world, xs.data_ptr(), _cabi.stream_ptr()))
+    gathered = [torch.empty_like(xs) for _ in range(world)]
+    dist.all_gather(gathered, xs)
+    init = torch.cat(gathered)[:: (per * world) // K][:K].contiguous()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    c_sh = rq.kmeans(xs, K, 10, init=init, group=group, tol=0.0)
+    torch.cuda.synchronize(); dist.barrier()
+    t_km = time.perf_counter() - t0
+    if rank == 0:
+        c_one = rq.kmeans(torch.cat(gathered), K, 10, init=init, tol=0.0)
+        out["sharded_kmeans"] = {"samples": per * world, "e": e, "K": K, "lloyd_iterations": 10, "seconds": t_km,
+                                 "max_abs_diff_vs_single_gpu": float((c_sh - c_one).abs().max()),
+                                 "bit_equal_single_gpu": bool(torch.equal(c_sh, c_one)),
+                                 "what": "rq.kmeans(group=WORLD): fp64 per-cluster sums + counts all-reduced (NCCL) per iteration"}
+    del gathered
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -500,6 +567,7 @@ def main():
         plan = [("c3", 10_000_000)] + ([("c5", 100_000_000)] if world >= 8 else [])
         for key, total in plan:
             extras[key] = run_extra(key, total, rank, world, dev, group, args)
+        extras.update(run_sharded_checks(rank, world, dev, group) or {})
     if rank == 0:
         peaks, peak_src = load_peaks()
         # dominant kernel: the encoder's first Linear — linear_tc2_kernel (fast route) / linear_exact_kernel (exact route).

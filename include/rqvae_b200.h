@@ -68,6 +68,11 @@ int rqb200_debug_tc_flags(int flags);
  * 1 (fp16 screening pass) or 2 (the TMA-fed TF32 kernel, first layer only).  Used by tools/ to time and ablate.   */
 int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
                            int passes, int relu, void *stream);
+/* Diagnostics: the Sinkhorn kernels divide many matrix entries by one row / column sum through the sum's correctly rounded
+ * reciprocal and two fma corrections (same bits as `a / b`, csrc/sinkhorn.cu: div_by); this compares the two on `pairs`
+ * pseudo-random operand pairs spread over ±exponent_span binades and returns the number of differing quotients.       */
+int rqb200_debug_check_division(unsigned long long seed, int exponent_span, unsigned long long pairs,
+                                unsigned long long *mismatches_host, void *stream);
 /* Diagnostics: the whole tensor-core MLP at a chosen precision — passes = 3, 1, or 2 (TF32 first layer + three-pass
  * tail: the latent the screening tier certifies).  Used by tools/calibrate_gate.py.                               */
 int rqb200_debug_mlp_tc(rqb200_model *m, int which, const float *x_dev, int64_t n, float *y_dev, int passes, void *stream);

@@ -354,7 +354,7 @@ def reencode_group(xg: np.ndarray, enc_w, enc_b, codebooks, eps, sk_iters: int, 
 
 def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters: int,
                    max_rounds: int = 30, threads: Optional[int] = None, group_order: bool = False,
-                   trace: Optional[list] = None) -> Tuple[np.ndarray, dict]:
+                   trace: Optional[list] = None, batch_size: Optional[int] = None) -> Tuple[np.ndarray, dict]:
     """The encode driver of infer.py:88-177 / generate_code.py:82-178: pass 1 (argmin codes),
     ≤30 rounds of per-group re-encoding with Sinkhorn on the last level only (infer.py:109-130),
     then the suffix column.  Returns ([N, L+1] int64, stats).
@@ -367,6 +367,16 @@ def generate_codes(x: np.ndarray, enc_w, enc_b, codebooks, sk_epsilons, sk_iters
         raise IndexError("list index out of range")      # prefix list has 5 entries (infer.py:90)
     z = mlp(x, enc_w, enc_b, threads=threads)
     codes = quantize(z, codebooks, want_xq=False, threads=threads)[0]
+    tail = len(x) % int(batch_size) if batch_size else 0
+    if 2 <= tail <= 15 and len(x) > tail:        # the reference's last DataLoader batch (infer.py:85,93-96) is a small batch
+        zt = mlp_group(np.ascontiguousarray(x[len(x) - tail:], dtype=np.float32), enc_w, enc_b)
+        r = zt.copy()
+        for l, cb in enumerate(codebooks):
+            cb = np.ascontiguousarray(cb, dtype=np.float32)
+            idx = quantize(r, [cb], want_xq=False, threads=1, dot_kind=small_batch_plan(tail, r.shape[1], cb.shape[0]))[0][:, 0]
+            codes[len(x) - tail:, l] = idx
+            q = cb[idx]
+            r = r - (r + (q - r))
     eps = [0.0] * (L - 1) + [float(sk_epsilons[-1])]
     rounds = 0
     if trace is not None:

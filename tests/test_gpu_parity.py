@@ -226,6 +226,15 @@ def test_sinkhorn_cases_match_reference_golden(oracle):
         assert np.allclose(Q, Qo, rtol=1e-9, atol=1e-300)
 
 
+def test_sinkhorn_division_is_the_ieee_quotient():
+    """The Sinkhorn kernels divide through a correctly rounded reciprocal + two fma corrections (csrc/sinkhorn.cu: div_by);
+    the quotient must have the bits of `a / b`: 2^32 operand pairs per exponent spread, hard denominators included."""
+    bad = ctypes.c_uint64(0)
+    for seed, span in ((1, 2), (2, 40), (3, 300), (4, 900)):
+        _cabi.check(_cabi.lib().rqb200_debug_check_division(seed, span, 1 << 32, ctypes.byref(bad), _cabi.stream_ptr()))
+        assert bad.value == 0, (span, bad.value)
+
+
 def test_generate_codes_reproduces_reference_infer_exactly(oracle):
     """BASELINE config 1 end to end: 707 items, K=8, 30 Sinkhorn rounds, suffix column — the reference's verbatim
     infer() output on ALL rows, and the reference's codes after EVERY round (no tolerance: integer output)."""
@@ -234,11 +243,13 @@ def test_generate_codes_reproduces_reference_infer_exactly(oracle):
     n = f["n"]
     for fast in (False, True):
         m = build_model(cfg, f["codebooks"])
-        out, stats = rq.generate_codes(m, x, fast=fast)
+        # batch_size = 64 as in the reference run: its last DataLoader batch has 707 % 64 = 3 rows (small-batch arithmetic)
+        out, stats = rq.generate_codes(m, x, fast=fast, batch_size=64)
         out = out.cpu().numpy()
         assert out.shape == (n, 4) and out.dtype == np.int64
         assert np.array_equal(out, golden)
         assert stats["rounds"] == f["rounds"]
+        assert np.array_equal(rq.generate_codes(build_model(cfg, f["codebooks"]), x, fast=fast)[0].cpu().numpy(), golden)
     m = build_model(cfg, f["codebooks"])
     for vq in m.rq.vq_layers[:-1]:
         vq.sk_epsilon = 0.0                                                    # infer.py:109-110

@@ -56,7 +56,8 @@ def test_oracle_driver_reproduces_reference_infer_exactly(oracle):
     _, (ew, eb), _ = synth_weights(cfg)
     assert golden.shape == (707, 4) and len(np.unique(golden, axis=0)) == 707
     mine = []
-    got, stats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"], group_order=True, trace=mine)
+    got, stats = oracle.generate_codes(x, ew, eb, cbs, cfg["sk_epsilons"], cfg["sk_iters"], group_order=True, trace=mine,
+                                       batch_size=64)          # the reference ran with batch 64: a last batch of 3 rows
     assert np.array_equal(got, golden)
     assert stats["rounds"] == f["rounds"] == len(mine) - 1
     for a, b in zip(mine, trace):

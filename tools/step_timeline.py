@@ -38,8 +38,9 @@ def main():
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
-    # last step = kernels after the last linear_tc2 launch
-    starts = [i for i, e in enumerate(evs) if "linear_tc2" in e.name]
+    # last step = kernels after the last first-layer launch over all rows (the TF32 screening kernel, else the three-pass kernel)
+    first = "linear_tf32" if any("linear_tf32" in e.name for e in evs) else "linear_tc2"
+    starts = [i for i, e in enumerate(evs) if first in e.name]
     evs = evs[starts[-1]:]
     t0 = evs[0].time_range.start
     prev_end = t0

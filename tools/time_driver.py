@@ -31,17 +31,28 @@ def main():
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         print(f"{name} n={n} pass1={'tensor-core' if fast else 'exact'}: {dt * 1e3:.1f} ms total, {stats}", flush=True)
-    # one round in isolation
-    codes, residual = rq.generate_code.encode_codes_and_residual(m, x)
+    # one round in isolation, stage by stage (CUDA events of the library)
+    import ctypes
+    codes = rq.generate_code.encode_codes_exact(m, x)
+    for vq in m.rq.vq_layers[:-1]:
+        vq.sk_epsilon = 0.0
     items, offsets, max_group = rq.collision_groups(m, codes)
     sizes = (offsets[1:] - offsets[:-1])
     print(f"groups {offsets.numel() - 1} items {items.numel()} max {max_group} mean {float(sizes.float().mean()):.1f}")
     for rep in range(3):
+        c = codes.clone()
+        lib.rqb200_profile_enable(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        c2, rounds = rq.generate_code.resolve_rounds(m, codes, residual, max_rounds=1)
+        found, done = rq.generate_code.reencode_round(m, c, x)
         torch.cuda.synchronize()
-        print(f"one re-encode round: {(time.perf_counter() - t0) * 1e3:.2f} ms")
+        dt = time.perf_counter() - t0
+        ms = (ctypes.c_double * 12)()
+        cnt = (ctypes.c_longlong * 12)()
+        lib.rqb200_profile_read(ms, cnt, 12)
+        lib.rqb200_profile_enable(0)
+        print(f"one re-encode round over {done} groups: {dt * 1e3:.2f} ms (group extraction {ms[3]:.2f}, small-batch re-encode {ms[9]:.2f}, "
+              f"Sinkhorn {ms[5]:.2f})")
 
 
 if __name__ == "__main__":
