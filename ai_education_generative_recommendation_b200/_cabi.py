@@ -53,6 +53,11 @@ _PROTOS = {
     "rqb200_forward": (c_int, [c_void_p, _P, c_int64, _P, _P, _P, _P, _P]),
     "rqb200_sinkhorn_regroup": (c_int, [c_void_p, _P, _P, _P, c_int64, c_int, c_double, c_int, _P, _P]),
     "rqb200_reencode_groups": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "rqb200_debug_sinkhorn_variant": (c_int, [c_int]),
+    "rqb200_model_levels": (c_int, [c_void_p]),
+    "rqb200_model_e_dim": (c_int, [c_void_p]),
+    "rqb200_reencode_classes": (c_int, [c_void_p]),
+    "rqb200_reencode_groups_memo": (c_int, [c_void_p, _P, _P, _P, c_int64, c_int64, _P, _P, c_int64, _P, _P, _P, _P]),
     "rqb200_reencode_rows": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, _P, _P, _P]),
     "rqb200_sinkhorn_group_cap": (c_int, [c_void_p]),
     "rqb200_sinkhorn_regroup_large": (c_int, [c_void_p, _P, _P, _P, _P, _P, c_int64, _P, c_double, c_int, _P, _P]),

@@ -136,6 +136,14 @@ static void free_linear(Linear &l) {
 using namespace rqb;
 
 extern "C" int rqb200_abi_version(void) { return RQB200_ABI_VERSION; }
+extern "C" int rqb200_model_levels(const rqb200_model *m) {
+    if (!m) { rqb::set_error("model is NULL"); return 0; }
+    return m->L;
+}
+extern "C" int rqb200_model_e_dim(const rqb200_model *m) {
+    if (!m) { rqb::set_error("model is NULL"); return 0; }
+    return m->e;
+}
 extern "C" const char *rqb200_last_error(void) { return rqb::g_err; }
 
 extern "C" long long rqb200_launch_count(void) { return rqb::g_launches.load(); }
@@ -222,7 +230,7 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
         if (m->ccs_tc[l]) cudaFree(m->ccs_tc[l]);
     }
     Workspace *ws[] = {&m->act[0], &m->act[1], &m->sortws, &m->misc, &m->hostpipe[0], &m->hostpipe[1],
-                       &m->rescue, &m->rescue_act[0], &m->rescue_act[1], &m->groupws};
+                       &m->rescue, &m->rescue_act[0], &m->rescue_act[1], &m->groupws, &m->skws};
     for (Workspace *w : ws)
         if (w->ptr) cudaFree(w->ptr);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);

@@ -115,6 +115,7 @@ struct rqb200_model {
     rqb::Workspace hostpipe[2];     // device chunks of the host-buffer pipeline
     rqb::Workspace rescue;          // exact latent of gated rows
     rqb::Workspace groupws;         // per-group re-encode: group sizes + activations of the colliding items
+    rqb::Workspace skws;            // Sinkhorn re-encode: per-size-class group lists + tickets
     rqb::Workspace rescue_act[2];
     float gate_gamma = 3.0517578125e-05f;   // 2^-15: bound on |z~ - z| / |z| of the tensor-core encoder
     int use_2cta = -1;                      // -1: decide from RQB200_TC2 env (default on), 0/1: forced

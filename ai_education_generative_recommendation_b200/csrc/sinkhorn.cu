@@ -90,21 +90,46 @@ __device__ __forceinline__ double warp_sum(double v) {
 // a / b for MANY numerators over ONE denominator, without a division per element: y = RN(1/b) once, then
 //   q0 = RN(a·y);  r0 = a − b·q0 (exact, fma);  q1 = RN(q0 + r0·y)  → faithful;  r1 = a − b·q1 (exact);  q = RN(q1 + r1·y)
 // which is the correctly rounded quotient RN(a/b) (Markstein's final-step theorem for a faithful q1 and a correctly rounded
-// reciprocal) for normal, finite, non-zero operands — the only ones the Sinkhorn matrix holds (entries are exp() of bounded
-// arguments divided by positive sums); everything else takes the hardware division.  Same bits as `a / b`, one multiply + four
-// fmas instead of a ≈ 30-instruction fp64 division: the kernel is bound by exactly these.  rqb200_debug_check_division compares
+// reciprocal) as long as nothing in the sequence under- or overflows: a, b, q normal with exponents inside ±960, which makes
+// the residuals exactly representable.  The window is checked on the NUMERATOR alone: for a given b the exponent of q is that
+// of a minus that of b (or one less), so "a and q inside ±960" is one range test on the high word of a against bounds that
+// are computed once per denominator (two integer instructions per quotient; a zero, subnormal, negative, infinite or NaN
+// numerator falls outside every window).  Everything outside takes the hardware division.  Same bits as `a / b`, one multiply
+// + four fmas instead of a division: the Sinkhorn kernels are bound by exactly these.  rqb200_debug_check_division compares
 // the two on 2^32 operand pairs per call (tests/test_gpu_parity.py).
 __device__ __noinline__ double div_slow(double a, double b) { return a / b; }
 
-__device__ __forceinline__ double div_by(double a, double b, double y) {
-    const double q0 = a * y;
-    const double q1 = __fma_rn(__fma_rn(-q0, b, a), y, q0);
-    const double q = __fma_rn(__fma_rn(-q1, b, a), y, q1);
-    // |a|, |b|, |q| in [2^-900, 2^900]: no underflow / overflow anywhere in the sequence; otherwise (zeros, subnormals, inf, NaN) divide
-    const unsigned ea = (unsigned)((__double_as_longlong(a) >> 52) & 0x7ff), eb = (unsigned)((__double_as_longlong(b) >> 52) & 0x7ff),
-                   eq = (unsigned)((__double_as_longlong(q) >> 52) & 0x7ff);
-    const bool safe = ea - 123u < 1801u && eb - 123u < 1801u && eq - 123u < 1801u;
-    if (__builtin_expect(!safe, 0)) return div_slow(a, b);      // a real branch: the division must not be evaluated on the fast path
+struct DivCtx {
+    double b, y;            // denominator and RN(1/b)
+    unsigned lo, span;      // numerators with (hi32(a) - lo) < span take the fma sequence
+};
+
+__device__ __forceinline__ DivCtx make_div(double b) {
+    DivCtx c;
+    c.b = b;
+    c.y = 1.0 / b;
+    // a >= 2^-968 keeps both residuals (multiples of 2^(e_a - 104)) representable; q >= 2^-1021 keeps every quotient normal;
+    // |e_b| <= 960 keeps b, 1/b and the products far from the ends of the range
+    const unsigned eb = (unsigned)__double2hiint(b) >> 20;         // sign bit included: a negative b is "out of range"
+    const bool b_ok = eb - 63u <= 1920u;                           // 2^-960 <= b < 2^961, finite, positive
+    const int lo_e = max(55, (int)eb - 1020), hi_e = min(1983, (int)eb + 960);
+    c.lo = b_ok ? (unsigned)lo_e << 20 : 0xffffffffu;
+    c.span = b_ok ? (unsigned)(hi_e + 1 - lo_e) << 20 : 0u;
+    return c;
+}
+
+// the fma sequence alone (the caller has checked the window for a whole batch of numerators: straight-line code, so the
+// independent quotients of a row or column overlap in the fp64 pipe)
+__device__ __forceinline__ double div_fast(double a, const DivCtx &c) {
+    const double q0 = a * c.y;
+    const double q1 = __fma_rn(__fma_rn(-q0, c.b, a), c.y, q0);
+    return __fma_rn(__fma_rn(-q1, c.b, a), c.y, q1);
+}
+__device__ __forceinline__ bool div_outside(double a, const DivCtx &c) { return (unsigned)__double2hiint(a) - c.lo >= c.span; }
+
+__device__ __forceinline__ double div_ctx(double a, const DivCtx &c) {
+    const double q = div_fast(a, c);
+    if (__builtin_expect(div_outside(a, c), 0)) return div_slow(a, c.b);   // a real branch
     return q;
 }
 
@@ -133,8 +158,8 @@ __device__ void sinkhorn_cta(double *Q, int B, int K, int iters, double *s_red) 
     }
     double total = block_sum(part, s_red);
     {
-        const double ytot = 1.0 / total;
-        for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = div_by(Q[i], total, ytot);
+        const DivCtx ct = make_div(total);
+        for (int i = tid; i < B * K; i += SK_THREADS) Q[i] = div_ctx(Q[i], ct);
     }
     __syncthreads();
     const double dB = (double)B, dK = (double)K;
@@ -142,24 +167,25 @@ __device__ void sinkhorn_cta(double *Q, int B, int K, int iters, double *s_red) 
     // number, hence the same bits — one fp64 division less per element and half-iteration (the kernel is division-bound)
     const bool b_pow2 = (B & (B - 1)) == 0, k_pow2 = (K & (K - 1)) == 0;
     const double invB = 1.0 / dB, invK = 1.0 / dK;
+    const DivCtx cB = make_div(dB), cK = make_div(dK);
     for (int it = 0; it < iters; ++it) {
         // Q /= Q.sum(dim=1, keepdim=True);  Q /= B
         for (int i = wid; i < B; i += NW) {
             double rs = 0.0;
             for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
             rs = warp_sum(rs);
-            const double yr = 1.0 / rs;
-            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], rs, yr) * invB; }
-            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], rs, yr), dB, invB); }
+            const DivCtx cr = make_div(rs);
+            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_ctx(Q[(size_t)i * K + j], cr) * invB; }
+            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_ctx(div_ctx(Q[(size_t)i * K + j], cr), cB); }
         }
         __syncthreads();
         // Q /= Q.sum(dim=0, keepdim=True);  Q /= K
         for (int j = tid; j < K; j += SK_THREADS) {
             double cs = 0.0;
             for (int i = 0; i < B; ++i) cs += Q[(size_t)i * K + j];
-            const double yc = 1.0 / cs;
-            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], cs, yc) * invK; }
-            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], cs, yc), dK, invK); }
+            const DivCtx cc_ = make_div(cs);
+            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_ctx(Q[(size_t)i * K + j], cc_) * invK; }
+            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_ctx(div_ctx(Q[(size_t)i * K + j], cc_), cK); }
         }
         __syncthreads();
     }
@@ -320,29 +346,30 @@ sinkhorn_regroup_warp_kernel(const float *__restrict__ residual, const int64_t *
         total += warp_sum(rs);
     }
     {
-        const double ytot = 1.0 / total;
-        for (int p = lane; p < B * K; p += 32) Q[p] = div_by(Q[p], total, ytot);
+        const DivCtx ct = make_div(total);
+        for (int p = lane; p < B * K; p += 32) Q[p] = div_ctx(Q[p], ct);
     }
     __syncwarp();
     const double dB = (double)B, dK = (double)K;
     const bool b_pow2 = (B & (B - 1)) == 0, k_pow2 = (K & (K - 1)) == 0;
     const double invB = 1.0 / dB, invK = 1.0 / dK;
+    const DivCtx cB = make_div(dB), cK = make_div(dK);
     for (int it = 0; it < iters; ++it) {
         for (int i = 0; i < B; ++i) {
             double rs = 0.0;
             for (int j = lane; j < K; j += 32) rs += Q[(size_t)i * K + j];
             rs = warp_sum(rs);
-            const double yr = 1.0 / rs;
-            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], rs, yr) * invB; }
-            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], rs, yr), dB, invB); }
+            const DivCtx cr = make_div(rs);
+            if (b_pow2) { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_ctx(Q[(size_t)i * K + j], cr) * invB; }
+            else { for (int j = lane; j < K; j += 32) Q[(size_t)i * K + j] = div_ctx(div_ctx(Q[(size_t)i * K + j], cr), cB); }
         }
         __syncwarp();
         for (int j = lane; j < K; j += 32) {
             double cs = 0.0;
             for (int i = 0; i < B; ++i) cs += Q[(size_t)i * K + j];
-            const double yc = 1.0 / cs;
-            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(Q[(size_t)i * K + j], cs, yc) * invK; }
-            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_by(div_by(Q[(size_t)i * K + j], cs, yc), dK, invK); }
+            const DivCtx cc_ = make_div(cs);
+            if (k_pow2) { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_ctx(Q[(size_t)i * K + j], cc_) * invK; }
+            else { for (int i = 0; i < B; ++i) Q[(size_t)i * K + j] = div_ctx(div_ctx(Q[(size_t)i * K + j], cc_), cK); }
         }
         __syncwarp();
     }
@@ -368,6 +395,504 @@ sinkhorn_regroup_warp_kernel(const float *__restrict__ residual, const int64_t *
             }
         }
         if (lane == 0) codes[gi[i] * L + (L - 1)] = bj;
+    }
+}
+
+// ---- column-owner kernels: the fp64 matrix lives in REGISTERS ------------------------------------------------------------
+// A team of WARPS warps owns one group; thread (w, l) of the team holds the columns j = l + 32·(w + WARPS·u), u < CPT, of every
+// row (K = 32·WARPS·CPT), BMAX·CPT doubles in registers.  The column pass (sum over the rows in order, divide) is then
+// register-local: no shared memory, no barrier.  The row pass needs Σ_j Q[i][j] in the order every Sinkhorn kernel of this
+// file uses — lane l adds its columns l, l+32, l+64 … in ascending order, then the xor butterfly — which for WARPS = 1 is
+// again register-local (one warp per group, several groups per CTA; EXACT: the launch serves groups of exactly BMAX rows, so
+// every row loop is resolved at compile time and the loop body stays small enough for the instruction cache); for WARPS = 8
+// the values pass once through a shared exchange tile ([row][column], conflict-free both ways), warp i mod 8 folds row i and
+// publishes the row's division context.
+// Same sums in the same order, the same quotients, centre / exp expressions and arg-max rule as sinkhorn_regroup_kernel ⇒
+// bit-identical codes (tests/test_gpu_zz_late_fixtures.py compares the two on real groups).  Groups are taken from a per-size-
+// class list (sk_class_lists_kernel) through an atomic ticket, so a launch is persistent and self-balancing.
+constexpr int SK_MAX_CLASSES = 12;
+struct SkClassArgs {
+    int n_classes;
+    int lo[SK_MAX_CLASSES], hi[SK_MAX_CLASSES];       // class c holds groups with lo[c] <= rows <= hi[c]
+};
+
+__global__ void sk_class_lists_kernel(const int64_t *__restrict__ offsets, int64_t n_groups, SkClassArgs ca,
+                                      int *__restrict__ lists, unsigned *__restrict__ counts) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = -1;
+    if (g < n_groups) {
+        const int64_t B = offsets[g + 1] - offsets[g];
+        for (int k = 0; k < ca.n_classes; ++k)
+            if (B >= ca.lo[k] && B <= ca.hi[k]) c = k;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < ca.n_classes; ++k) {
+        const unsigned mk = __ballot_sync(0xffffffffu, c == k);
+        if (!mk) continue;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counts[k], (unsigned)__popc(mk));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (c == k) lists[(size_t)k * n_groups + base + __popc(mk & ((1u << lane) - 1))] = (int)g;
+    }
+}
+
+// A pass whose numerators are not all inside the windows of their contexts (rare: an entry next to the bottom of the fp64
+// range): the reference's literal two divisions, element by element, on a copy of the thread's elements in shared memory —
+// compact looped code that stays out of the hot loop body.  elem(i, u) at el[i·is + u·us]; den[d·dpitch] is the row sum
+// (by_row) or the column sum of the element.
+__device__ __noinline__ void sk_slow_pass(double *el, int is, int us, const double *den, int dpitch, int B, int ncol, bool by_row,
+                                          bool pow2, double inv, double dcount) {
+    const DivCtx cD = make_div(dcount);
+    for (int i = 0; i < B; ++i)
+        for (int u = 0; u < ncol; ++u) {
+            const double d = den[(by_row ? i : u) * dpitch];
+            double *x = el + (size_t)i * is + (size_t)u * us;
+            *x = pow2 ? (*x / d) * inv : div_ctx(*x / d, cD);
+        }
+}
+
+template <int CPT, int WARPS, int BMAX, int E, bool EXACT>
+__global__ void __launch_bounds__(WARPS == 1 ? 128 : 32 * WARPS)
+sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *__restrict__ items,
+                            const int64_t *__restrict__ offsets, const int *__restrict__ glist,
+                            const unsigned *__restrict__ gcount, unsigned *__restrict__ gnext,
+                            const float *__restrict__ cb, const float *__restrict__ cc, int L, double epsilon, int iters,
+                            int64_t *__restrict__ codes) {
+    constexpr int K = 32 * WARPS * CPT;
+    constexpr int TEAMS = WARPS == 1 ? 4 : 1;
+    constexpr bool K_POW2 = (K & (K - 1)) == 0;
+    static_assert(E % 16 == 0, "e_dim must be a multiple of 16");
+    static_assert(!EXACT || WARPS == 1, "exact row counts are a property of the one-warp launches");
+    extern __shared__ __align__(16) unsigned char sk_smem[];
+    const int lane = threadIdx.x & 31;
+    const int w = WARPS == 1 ? 0 : (threadIdx.x >> 5);
+    const int team = WARPS == 1 ? (threadIdx.x >> 5) : 0;
+    const int tid_team = WARPS == 1 ? lane : threadIdx.x;
+    constexpr int TEAM_THREADS = 32 * WARPS;
+    // shared memory per team: rows float[BMAX][E], norms float[BMAX], the row sums of the pass double[BMAX], the thread's
+    // column sums double[CPT][threads]; WARPS = 1: a scratch copy of every thread's elements for the slow pass; WARPS > 1: the
+    // exchange tile double[BMAX][K] (doubles as that scratch), one division context per row, per-warp partials
+    constexpr size_t ROWS_BYTES = (sizeof(float) * BMAX * (E + 1) + 15) / 16 * 16;
+    constexpr size_t TEAM_DOUBLES = (size_t)BMAX + (size_t)CPT * TEAM_THREADS + (WARPS == 1 ? (size_t)BMAX * CPT * 32 : 0);
+    constexpr size_t TEAM_BYTES = (ROWS_BYTES + sizeof(double) * TEAM_DOUBLES + 15) / 16 * 16;
+    float *s_r = reinterpret_cast<float *>(sk_smem + (size_t)team * TEAM_BYTES);
+    float *s_xx = s_r + BMAX * E;
+    double *den_row = reinterpret_cast<double *>(sk_smem + (size_t)team * TEAM_BYTES + ROWS_BYTES);          // [BMAX]
+    double *den_col = den_row + BMAX + tid_team;                                                             // [CPT], pitch TEAM_THREADS
+    double *ex = reinterpret_cast<double *>(sk_smem + (size_t)TEAMS * TEAM_BYTES);                           // WARPS > 1 only
+    DivCtx *s_ctx = reinterpret_cast<DivCtx *>(ex + (size_t)BMAX * K);
+    double *s_part = reinterpret_cast<double *>(s_ctx + BMAX);           // [WARPS]
+    float *s_mm = reinterpret_cast<float *>(s_part + WARPS);             // [2][WARPS]
+    // where this thread's element (i, u) sits while a slow pass works on it
+    double *el = WARPS == 1 ? den_row + BMAX + (size_t)CPT * TEAM_THREADS + lane : ex + lane + 32 * w;
+    constexpr int EL_IS = WARPS == 1 ? CPT * 32 : K, EL_US = WARPS == 1 ? 32 : 32 * WARPS;
+    __shared__ unsigned s_ticket;
+    auto team_sync = [&]() { if (WARPS == 1) __syncwarp(); else __syncthreads(); };
+    const unsigned n_listed = *gcount;
+
+    for (;;) {
+        unsigned ticket;
+        if (WARPS == 1) {
+            __syncwarp();
+            ticket = 0;
+            if (lane == 0) ticket = atomicAdd(gnext, 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        } else {
+            __syncthreads();                                  // the previous group's arg-max has left the exchange tile
+            if (threadIdx.x == 0) s_ticket = atomicAdd(gnext, 1u);
+            __syncthreads();
+            ticket = s_ticket;
+        }
+        if (ticket >= n_listed) return;
+        const int64_t g = glist[ticket];
+        const int64_t g0 = offsets[g];
+        const int B = EXACT ? BMAX : (int)(offsets[g + 1] - g0);
+        const int64_t *gi = items + g0;
+        for (int i = tid_team; i < B * (E / 4); i += TEAM_THREADS) {
+            const int r = i / (E / 4), q4 = i % (E / 4);
+            reinterpret_cast<float4 *>(s_r + r * E)[q4] = reinterpret_cast<const float4 *>(residual + gi[r] * E)[q4];
+        }
+        team_sync();
+        for (int i = tid_team; i < B; i += TEAM_THREADS) s_xx[i] = sumsq_aten_rt(s_r + i * E, E);
+        team_sync();
+
+        // d[i][j] = (xx_i + cc_j) - 2 <r_i, c_j>  (vq.py:71-73), the product in the order of a batch of B rows
+        double Q[BMAX][CPT];
+        float mx = -__int_as_float(0x7f800000), mn = __int_as_float(0x7f800000);
+        const bool l16 = small_batch_lane16(B, E);
+#pragma unroll 1
+        for (int u = 0; u < CPT; ++u) {
+            const int j = lane + 32 * (w + WARPS * u);
+            const float *c = cb + (size_t)j * E;
+            const float ccj = cc[j];
+            float dist[BMAX];
+            if (!l16) {
+                float acc[BMAX];
+#pragma unroll
+                for (int i = 0; i < BMAX; ++i) acc[i] = 0.0f;
+#pragma unroll 1
+                for (int k0 = 0; k0 < E; k0 += 16) {
+                    float cv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a = *reinterpret_cast<const float4 *>(c + k0 + 4 * q);
+                        cv[4 * q] = a.x; cv[4 * q + 1] = a.y; cv[4 * q + 2] = a.z; cv[4 * q + 3] = a.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i) {
+                        if (i < B) {
+                            const float *r = s_r + i * E + k0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 b = *reinterpret_cast<const float4 *>(r + 4 * q);
+                                acc[i] = __fmaf_rn(b.x, cv[4 * q], acc[i]);
+                                acc[i] = __fmaf_rn(b.y, cv[4 * q + 1], acc[i]);
+                                acc[i] = __fmaf_rn(b.z, cv[4 * q + 2], acc[i]);
+                                acc[i] = __fmaf_rn(b.w, cv[4 * q + 3], acc[i]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < BMAX; ++i) dist[i] = __fsub_rn(__fadd_rn(s_xx[i < B ? i : 0], ccj), __fmul_rn(2.0f, acc[i]));
+            } else {
+                // small-batch order (2 <= B and 24·B <= E, i.e. B <= E/24 rows): 16 interleaved chains per product, folded
+                constexpr int LB = (E / 24 < BMAX ? E / 24 : BMAX) > 0 ? (E / 24 < BMAX ? E / 24 : BMAX) : 1;
+                float a16[LB][16];
+#pragma unroll
+                for (int i = 0; i < LB; ++i)
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) a16[i][q] = 0.0f;
+#pragma unroll 1
+                for (int k0 = 0; k0 < E; k0 += 16) {
+                    float cv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 a = *reinterpret_cast<const float4 *>(c + k0 + 4 * q);
+                        cv[4 * q] = a.x; cv[4 * q + 1] = a.y; cv[4 * q + 2] = a.z; cv[4 * q + 3] = a.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < LB; ++i) {
+                        if (i < B) {
+                            const float *r = s_r + i * E + k0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float4 b = *reinterpret_cast<const float4 *>(r + 4 * q);
+                                a16[i][4 * q] = __fmaf_rn(b.x, cv[4 * q], a16[i][4 * q]);
+                                a16[i][4 * q + 1] = __fmaf_rn(b.y, cv[4 * q + 1], a16[i][4 * q + 1]);
+                                a16[i][4 * q + 2] = __fmaf_rn(b.z, cv[4 * q + 2], a16[i][4 * q + 2]);
+                                a16[i][4 * q + 3] = __fmaf_rn(b.w, cv[4 * q + 3], a16[i][4 * q + 3]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < BMAX; ++i) dist[i] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
+                    float s4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        s4[q] = __fadd_rn(__fadd_rn(__fadd_rn(a16[i][q], a16[i][q + 4]), a16[i][q + 8]), a16[i][q + 12]);
+                    const float acc = __fadd_rn(__fadd_rn(s4[0], s4[1]), __fadd_rn(s4[2], s4[3]));
+                    dist[i] = __fsub_rn(__fadd_rn(s_xx[i < B ? i : 0], ccj), __fmul_rn(2.0f, acc));
+                }
+            }
+            // the column loop is rolled (u is a run-time value here): the thread's matrix is addressed with static indices
+            // only, so the distances of this column are routed to their registers by a compile-time switch
+#pragma unroll
+            for (int uu = 0; uu < CPT; ++uu) {
+                if (uu == u) {
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i) {
+                        if (i < B) {
+                            Q[i][uu] = (double)dist[i];
+                            mx = fmaxf(mx, dist[i]);
+                            mn = fminf(mn, dist[i]);
+                        }
+                    }
+                }
+            }
+        }
+        // centre over the whole group (vq.py:51-61), exp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if (WARPS > 1) {
+            if (lane == 0) { s_mm[w] = mx; s_mm[WARPS + w] = mn; }
+            __syncthreads();
+            for (int v = 0; v < WARPS; ++v) { mx = fmaxf(mx, s_mm[v]); mn = fminf(mn, s_mm[WARPS + v]); }
+        }
+        const float middle = __fdiv_rn(__fadd_rn(mx, mn), 2.0f);
+        const float amplitude = __fadd_rn(__fsub_rn(mx, middle), 1e-5f);
+#pragma unroll
+        for (int i = 0; i < BMAX; ++i) {
+            if (i < B) {
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) {
+                    const float cd = __fdiv_rn(__fsub_rn((float)Q[i][u], middle), amplitude);
+                    Q[i][u] = exp(-((double)cd) / epsilon);
+                }
+            }
+        }
+
+        auto publish = [&]() {                                  // WARPS > 1: every thread stores its columns of every row
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) ex[i * K + lane + 32 * (w + WARPS * u)] = Q[i][u];
+                }
+            }
+        };
+        auto lane_row_sum = [&](int i) {                        // WARPS = 1
+            double rs = 0.0;
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) rs += Q[i][u];
+            return warp_sum(rs);
+        };
+        auto ex_row_sum = [&](int i) {                          // WARPS > 1, called by the warp that owns row i
+            double rs = 0.0;
+            for (int j = lane; j < K; j += 32) rs += ex[i * K + j];
+            return warp_sum(rs);
+        };
+        // the thread's elements [u0, u0 + NC) of every row → scratch, the literal divisions there, and back (see sk_slow_pass)
+        auto slow_rows = [&](bool pow2, double inv, double dcount) {
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) el[(size_t)i * EL_IS + (size_t)u * EL_US] = Q[i][u];
+                }
+            }
+            sk_slow_pass(el, EL_IS, EL_US, den_row, 1, B, CPT, true, pow2, inv, dcount);
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) Q[i][u] = el[(size_t)i * EL_IS + (size_t)u * EL_US];
+                }
+            }
+        };
+        // every element of the thread divided by ONE number, literally (the denominator goes through the thread's own
+        // column-sum slots, which are free outside the column pass)
+        auto slow_all = [&](double d) {
+#pragma unroll
+            for (int u = 0; u < CPT; ++u) den_col[(size_t)u * TEAM_THREADS] = d;
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) el[(size_t)i * EL_IS + (size_t)u * EL_US] = Q[i][u];
+                }
+            }
+            sk_slow_pass(el, EL_IS, EL_US, den_col, TEAM_THREADS, B, CPT, false, true, 1.0, 1.0);
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) Q[i][u] = el[(size_t)i * EL_IS + (size_t)u * EL_US];
+                }
+            }
+        };
+
+        // sum_Q = Q.sum(-1).sum(-2);  Q /= sum_Q      (row sums added per warp in row order, warps in order: as sinkhorn_cta)
+        double total;
+        if (WARPS == 1) {
+            total = 0.0;
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i)
+                if (i < B) total += lane_row_sum(i);
+        } else {
+            publish();
+            __syncthreads();
+            double part = 0.0;
+            for (int i = w; i < B; i += WARPS) part += ex_row_sum(i);
+            if (lane == 0) s_part[w] = part;
+            __syncthreads();
+            total = 0.0;
+            for (int v = 0; v < WARPS; ++v) total += s_part[v];
+        }
+        {
+            const DivCtx ct = make_div(total);
+            bool outside = false;
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) outside |= div_outside(Q[i][u], ct);
+                }
+            }
+            if (__builtin_expect(!outside, 1)) {
+#pragma unroll
+                for (int i = 0; i < BMAX; ++i) {
+                    if (i < B) {
+#pragma unroll
+                        for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], ct);
+                    }
+                }
+            } else {
+                slow_all(total);
+            }
+        }
+        // Every pass below is "divide a batch of numerators by their row / column sum, then by B / K".  With a power-of-two
+        // B (K) the second division is an exact scaling, so the pair is ONE quotient by sum·B (an exact product): the same
+        // bits as long as that quotient is normal.  A pass first tests all its numerators against the windows of their
+        // contexts (two integer instructions each); if all are inside — the rule — the quotients are straight-line fma
+        // sequences that overlap in the fp64 pipe; otherwise the pass is redone with the reference's literal two divisions.
+        const double dB = (double)B, dK = (double)K;
+        const bool b_pow2 = (B & (B - 1)) == 0;
+        const double invB = 1.0 / dB, invK = 1.0 / dK;
+        const DivCtx cB = make_div(dB);
+        for (int it = 0; it < iters; ++it) {
+            // Q /= Q.sum(dim=1, keepdim=True);  Q /= B
+            if (WARPS > 1) {
+                publish();
+                __syncthreads();
+                for (int i = w; i < B; i += WARPS) {
+                    const double rs = ex_row_sum(i);
+                    if (lane == 0) { s_ctx[i] = make_div(b_pow2 ? rs * dB : rs); den_row[i] = rs; }
+                }
+                __syncthreads();
+            }
+            {
+                constexpr int NCR = WARPS == 1 ? BMAX : 1;      // WARPS > 1: the contexts stay in shared memory
+                DivCtx cr[NCR];
+                bool outside = false;
+#pragma unroll
+                for (int i = 0; i < BMAX; ++i) {
+                    if (i < B) {
+                        if (WARPS == 1) {
+                            const double rs = lane_row_sum(i);
+                            cr[i % NCR] = make_div(b_pow2 ? rs * dB : rs);
+                        }
+                        const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[i];
+#pragma unroll
+                        for (int u = 0; u < CPT; ++u) outside |= div_outside(Q[i][u], c);
+                    }
+                }
+                if (__builtin_expect(!outside, 1)) {
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i) {
+                        if (i < B) {
+                            const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[i];
+#pragma unroll
+                            for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], c);
+                        }
+                    }
+                    if (!b_pow2) {                              // Q /= B as a second batch of quotients
+                        bool out2 = false;
+#pragma unroll
+                        for (int i = 0; i < BMAX; ++i) {
+                            if (i < B) {
+#pragma unroll
+                                for (int u = 0; u < CPT; ++u) out2 |= div_outside(Q[i][u], cB);
+                            }
+                        }
+                        if (__builtin_expect(!out2, 1)) {
+#pragma unroll
+                            for (int i = 0; i < BMAX; ++i) {
+                                if (i < B) {
+#pragma unroll
+                                    for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], cB);
+                                }
+                            }
+                        } else {
+                            slow_all(dB);
+                        }
+                    }
+                } else {
+                    if (WARPS == 1) {
+#pragma unroll
+                        for (int i = 0; i < BMAX; ++i)
+                            if (i < B) den_row[i] = b_pow2 ? cr[i % NCR].b * invB : cr[i % NCR].b;   // the row sum itself (exact un-scaling)
+                    }
+                    slow_rows(b_pow2, invB, dB);
+                }
+            }
+            // Q /= Q.sum(dim=0, keepdim=True);  Q /= K      (a column lives in one thread); eight columns at a time
+            constexpr int CCH = CPT < 8 ? CPT : 8;
+#pragma unroll
+            for (int u0 = 0; u0 < CPT; u0 += CCH) {
+                DivCtx ccol[CCH];
+                bool outside = false;
+#pragma unroll
+                for (int v = 0; v < CCH; ++v) {
+                    double cs = 0.0;
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i)
+                        if (i < B) cs += Q[i][u0 + v];
+                    ccol[v] = make_div(K_POW2 ? cs * dK : cs);
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i)
+                        if (i < B) outside |= div_outside(Q[i][u0 + v], ccol[v]);
+                }
+                if (__builtin_expect(!outside && K_POW2, 1)) {
+#pragma unroll
+                    for (int v = 0; v < CCH; ++v) {
+#pragma unroll
+                        for (int i = 0; i < BMAX; ++i)
+                            if (i < B) Q[i][u0 + v] = div_fast(Q[i][u0 + v], ccol[v]);
+                    }
+                } else {
+                    // only this chunk goes through the literal divisions: columns are independent in this pass
+#pragma unroll
+                    for (int v = 0; v < CCH; ++v) den_col[(size_t)v * TEAM_THREADS] = K_POW2 ? ccol[v].b * invK : ccol[v].b;   // the column sum itself
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i) {
+                        if (i < B) {
+#pragma unroll
+                            for (int v = 0; v < CCH; ++v) el[(size_t)i * EL_IS + (size_t)v * EL_US] = Q[i][u0 + v];
+                        }
+                    }
+                    sk_slow_pass(el, EL_IS, EL_US, den_col, TEAM_THREADS, B, CCH, false, K_POW2, invK, dK);
+#pragma unroll
+                    for (int i = 0; i < BMAX; ++i) {
+                        if (i < B) {
+#pragma unroll
+                            for (int v = 0; v < CCH; ++v) Q[i][u0 + v] = el[(size_t)i * EL_IS + (size_t)v * EL_US];
+                        }
+                    }
+                }
+            }
+        }
+        // Q *= B;  arg-max per row (first maximum wins; NaN counts as maximum like torch.argmax)
+        if (WARPS == 1) {
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+                    double best = 0.0;
+                    int bj = -1;
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) {
+                        const double v = Q[i][u] * dB;
+                        const bool take = bj < 0 || (!(best != best) && ((v != v) || v > best));
+                        if (take) { best = v; bj = lane + 32 * u; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                        const bool onan = ov != ov, bnan = best != best;
+                        const bool take = (onan && (!bnan || oj < bj)) || (!onan && !bnan && (ov > best || (ov == best && oj < bj)));
+                        if (take) { best = ov; bj = oj; }
+                    }
+                    if (lane == 0) codes[gi[i] * L + (L - 1)] = bj;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < BMAX; ++i) {
+                if (i < B) {
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) ex[i * K + lane + 32 * (w + WARPS * u)] = Q[i][u] * dB;
+                }
+            }
+            __syncthreads();
+            argmax_rows(ex, B, K, gi, codes, L, nullptr);
+        }
     }
 }
 
@@ -593,8 +1118,8 @@ __global__ void check_division_kernel(unsigned long long seed, int span, unsigne
         const long long expb = 1023 + (long long)((rb >> 52) % (unsigned long long)(2 * span + 1)) - span;
         const double a = __longlong_as_double((long long)((unsigned long long)expa << 52 | (ra & 0xFFFFFFFFFFFFFull)));
         const double b = __longlong_as_double((long long)((unsigned long long)expb << 52 | mb));
-        const double y = 1.0 / b;
-        if (__double_as_longlong(div_by(a, b, y)) != __double_as_longlong(a / b)) ++mism;
+        const DivCtx c = make_div(b);
+        if (__double_as_longlong(div_ctx(a, c)) != __double_as_longlong(a / b)) ++mism;
     }
     if (mism) atomicAdd(bad, mism);
 }
@@ -619,6 +1144,91 @@ extern "C" int rqb200_debug_check_division(unsigned long long seed, int exponent
     RQB_CUDA(cudaMemcpyAsync(mismatches_host, bad, sizeof(*bad), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     RQB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     RQB_CUDA(cudaFree(bad));
+    return 0;
+}
+
+static int g_sk_variant = 0;      // 0: column-owner register kernels where the shape allows; 1: shared-memory kernels only
+extern "C" int rqb200_debug_sinkhorn_variant(int v) {
+    g_sk_variant = v;
+    return 0;
+}
+
+template <int CPT, int WARPS, int BMAX, int E, bool EXACT>
+static int launch_own(const rqb200_model *m, const float *residual, const int64_t *items, const int64_t *offsets, int64_t n_groups,
+                      const int *glist, const unsigned *gcount, unsigned *gnext, double epsilon, int iters, int64_t *codes,
+                      cudaStream_t s) {
+    constexpr int K = 32 * WARPS * CPT;
+    constexpr int TEAMS = WARPS == 1 ? 4 : 1;
+    constexpr int TEAM_THREADS = 32 * WARPS;
+    constexpr size_t rows_bytes = (sizeof(float) * BMAX * (E + 1) + 15) / 16 * 16;
+    constexpr size_t team_doubles = (size_t)BMAX + (size_t)CPT * TEAM_THREADS + (WARPS == 1 ? (size_t)BMAX * CPT * 32 : 0);
+    constexpr size_t team_bytes = (rows_bytes + sizeof(double) * team_doubles + 15) / 16 * 16;
+    constexpr size_t smem = WARPS == 1 ? TEAMS * team_bytes
+                                       : team_bytes + sizeof(double) * BMAX * K + sizeof(DivCtx) * BMAX + sizeof(double) * WARPS +
+                                             sizeof(float) * 2 * WARPS + 16;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static rqb::DeviceOnce once;
+    if (once.first())
+        RQB_CUDA(cudaFuncSetAttribute(sinkhorn_regroup_own_kernel<CPT, WARPS, BMAX, E, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    const int L = m->L;
+    int64_t ctas = (n_groups + TEAMS - 1) / TEAMS;
+    if (ctas > kNumSMs * 8) ctas = kNumSMs * 8;             // persistent: groups are taken through an atomic ticket
+    rqb::count_launch();
+    sinkhorn_regroup_own_kernel<CPT, WARPS, BMAX, E, EXACT><<<(unsigned)ctas, WARPS == 1 ? 128 : 32 * WARPS, smem, s>>>(
+        residual, items, offsets, glist, gcount, gnext, m->cb[L - 1], m->cc[L - 1], L, epsilon, iters, codes);
+    RQB_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int E>
+static int regroup_own(rqb200_model *m, const float *residual, const int64_t *items, const int64_t *offsets, int64_t n_groups,
+                       int top, double epsilon, int iters, int64_t *codes, cudaStream_t s, int *covered_up_to) {
+    const int K = m->K[m->L - 1];
+    SkClassArgs ca;
+    ca.n_classes = 0;
+    for (int k = 0; k < SK_MAX_CLASSES; ++k) { ca.lo[k] = 0; ca.hi[k] = -1; }
+    auto add = [&](int lo, int hi) { ca.lo[ca.n_classes] = lo; ca.hi[ca.n_classes] = hi; ++ca.n_classes; };
+    if (K == 256) {
+        for (int b = 2; b <= 8; ++b) add(b, b);             // one launch per row count: one warp per group, rows resolved at compile time
+        add(9, 16);
+        add(17, 32);
+    } else {
+        add(2, 2);
+        add(3, 16);
+    }
+    RQB_TRY(ws_reserve(m->skws, sizeof(int) * (size_t)ca.n_classes * n_groups + 128));
+    unsigned *counts = (unsigned *)m->skws.ptr;              // [16] listed groups per class, [16] tickets
+    unsigned *next = counts + 16;
+    int *lists = (int *)((char *)m->skws.ptr + 128);
+    RQB_CUDA(cudaMemsetAsync(counts, 0, 128, s));
+    rqb::count_launch();
+    sk_class_lists_kernel<<<(unsigned)((n_groups + 255) / 256), 256, 0, s>>>(offsets, n_groups, ca, lists, counts);
+    RQB_LAUNCH_CHECK();
+#define RQB_OWN(CPT, WARPS, BMAX, EXACT) \
+    RQB_TRY((launch_own<CPT, WARPS, BMAX, E, EXACT>(m, residual, items, offsets, n_groups, lists + (size_t)c * n_groups, counts + c, next + c, \
+                                                    epsilon, iters, codes, s)))
+    for (int c = 0; c < ca.n_classes; ++c) {
+        if (ca.lo[c] > top) break;
+        if (K == 256) {
+            switch (c) {
+                case 0: RQB_OWN(8, 1, 2, true); break;
+                case 1: RQB_OWN(8, 1, 3, true); break;
+                case 2: RQB_OWN(8, 1, 4, true); break;
+                case 3: RQB_OWN(8, 1, 5, true); break;
+                case 4: RQB_OWN(8, 1, 6, true); break;
+                case 5: RQB_OWN(8, 1, 7, true); break;
+                case 6: RQB_OWN(8, 1, 8, true); break;
+                case 7: RQB_OWN(1, 8, 16, false); break;
+                default: RQB_OWN(1, 8, 32, false); break;
+            }
+        } else {
+            if (c == 0) RQB_OWN(32, 1, 2, true);
+            else RQB_OWN(4, 8, 16, false);
+        }
+    }
+#undef RQB_OWN
+    *covered_up_to = ca.hi[ca.n_classes - 1];
     return 0;
 }
 
@@ -650,7 +1260,15 @@ extern "C" int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_de
     ProfScope ps(PROF_SINKHORN, (cudaStream_t)stream);
     const int bounds[4] = {8, 24, 48, top};
     int lo = 2;
-    {
+    if (g_sk_variant == 0 && (K == 256 || K == 1024) && (e == 32 || e == 64) && n_groups < ((int64_t)1 << 31)) {
+        // register-resident kernels for the bulk of the groups; what is larger falls through to the shared-memory kernel
+        int covered = 0;
+        if (e == 32) RQB_TRY(regroup_own<32>(m, residual_dev, items_dev, offsets_dev, n_groups, top, epsilon, iters, codes_dev,
+                                             (cudaStream_t)stream, &covered));
+        else RQB_TRY(regroup_own<64>(m, residual_dev, items_dev, offsets_dev, n_groups, top, epsilon, iters, codes_dev,
+                                     (cudaStream_t)stream, &covered));
+        lo = covered + 1;
+    } else {
         // groups of 2 … 8 rows: one warp per group (same bits as the CTA kernel below, no block barriers)
         const size_t per_warp = sizeof(double) * SKW_MAX_ROWS * (size_t)K + sizeof(float) * SKW_MAX_ROWS * (size_t)(e + 1);
         int wpc = (int)((size_t)(100 * 1024) / per_warp);

@@ -66,6 +66,97 @@ __global__ void partition_by_size_kernel(const int64_t *__restrict__ items, cons
     }
 }
 
+
+// ---- memo of the per-item part of the re-encode ------------------------------------------------------------------------
+// What rqb200_reencode_groups computes for a member — its codes on the first L-1 levels and the residual entering the last
+// level — depends on the item and on the SIZE of its group only through which products take the lane16 order, i.e. through
+// a handful of thresholds (min(15, K/24) per product).  The sizes between two thresholds form a class; (item, class) → result
+// is a pure function, so a member that was already re-encoded inside a group of the same class is answered from the memo.
+struct SizeClasses {
+    int nb;                 // number of thresholds; classes 0 … nb (class nb: every product in the catalogue order)
+    int bound[8];           // ascending; class(M) = #{k : bound[k] < M}
+};
+__device__ __forceinline__ int size_class(const SizeClasses &sc, int M) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c += (k < sc.nb && sc.bound[k] < M) ? 1 : 0;
+    return c;
+}
+
+// slots → (a) members found in the memo: nothing listed (memo_restore_kernel copies them), (b) misses of groups with fewer
+// than 16 rows, (c) misses of larger groups.  counts[0] = small misses, counts[1] = big misses.
+__global__ void memo_classify_kernel(const int64_t *__restrict__ items, const int *__restrict__ msize, int64_t n_items,
+                                     SizeClasses sc, const unsigned *__restrict__ have, int64_t *__restrict__ small_items,
+                                     int *__restrict__ small_msize, int64_t *__restrict__ big_items,
+                                     unsigned long long *__restrict__ counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n_items;
+    int M = 0;
+    int64_t item = 0;
+    bool miss = false;
+    if (live) {
+        M = msize[i];
+        item = items[i];
+        miss = !((have[item] >> size_class(sc, M)) & 1u);
+    }
+    const bool big = miss && M >= 16, small = miss && M < 16;
+    const unsigned mb = __ballot_sync(0xffffffffu, big), ms = __ballot_sync(0xffffffffu, small);
+    const int lane = threadIdx.x & 31;
+    unsigned long long base_b = 0, base_s = 0;
+    if (lane == 0) {
+        if (mb) base_b = atomicAdd(&counts[1], (unsigned long long)__popc(mb));
+        if (ms) base_s = atomicAdd(&counts[0], (unsigned long long)__popc(ms));
+    }
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    base_s = __shfl_sync(0xffffffffu, base_s, 0);
+    const unsigned below = (1u << lane) - 1;
+    if (big) big_items[base_b + __popc(mb & below)] = item;
+    else if (small) {
+        const unsigned long long p = base_s + __popc(ms & below);
+        small_items[p] = item;
+        small_msize[p] = M;
+    }
+}
+
+// members found in the memo: codes[item, 0..L-2] and residual[item, :] from the memo (thread = one float4 of one slot)
+__global__ void memo_restore_kernel(const int64_t *__restrict__ items, const int *__restrict__ msize, int64_t n_items,
+                                    SizeClasses sc, const unsigned *__restrict__ have, const float *__restrict__ memo_res,
+                                    const int *__restrict__ memo_codes, int64_t n_cat, int e, int L,
+                                    int64_t *__restrict__ codes, float *__restrict__ residual) {
+    const int e4 = e >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = t / e4;
+    const int q = (int)(t % e4);
+    if (slot >= n_items) return;
+    const int64_t item = items[slot];
+    const int c = size_class(sc, msize[slot]);
+    if (!((have[item] >> c) & 1u)) return;
+    const size_t row = (size_t)c * n_cat + item;
+    reinterpret_cast<float4 *>(residual + item * e)[q] = reinterpret_cast<const float4 *>(memo_res + row * e)[q];
+    if (q == 0)
+        for (int l = 0; l < L - 1; ++l) codes[item * L + l] = memo_codes[row * (L - 1) + l];
+}
+
+// freshly computed members → memo.  msize == nullptr: every listed item is of class sc.nb (groups of 16 or more rows)
+__global__ void memo_store_kernel(const int64_t *__restrict__ list, const int *__restrict__ msize, int64_t n_list,
+                                  SizeClasses sc, unsigned *__restrict__ have, float *__restrict__ memo_res,
+                                  int *__restrict__ memo_codes, int64_t n_cat, int e, int L,
+                                  const int64_t *__restrict__ codes, const float *__restrict__ residual) {
+    const int e4 = e >> 2;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = t / e4;
+    const int q = (int)(t % e4);
+    if (slot >= n_list) return;
+    const int64_t item = list[slot];
+    const int c = msize ? size_class(sc, msize[slot]) : sc.nb;
+    const size_t row = (size_t)c * n_cat + item;
+    reinterpret_cast<float4 *>(memo_res + row * e)[q] = reinterpret_cast<const float4 *>(residual + item * e)[q];
+    if (q == 0) {
+        for (int l = 0; l < L - 1; ++l) memo_codes[row * (L - 1) + l] = (int)codes[item * L + l];
+        have[item] |= 1u << c;            // an item is a member of at most one group per round: no other thread touches this word
+    }
+}
+
 __device__ __forceinline__ float fold_lane16(const float (&acc)[16]) {
     float s[4];
 #pragma unroll
@@ -473,18 +564,41 @@ static int reencode_check(rqb200_model *m) {
     return 0;
 }
 
+// batch-size classes of this model (see SizeClasses): one threshold min(15, K/24) >= 2 per product on the way to the last level
+static SizeClasses size_classes_of(const rqb200_model *m) {
+    int t[RQB200_MAX_LAYERS + 1], nt = 0;
+    for (int i = 0; i < m->n_layers; ++i) t[nt++] = m->enc[i].in / 24;
+    t[nt++] = m->e / 24;
+    SizeClasses sc;
+    sc.nb = 0;
+    for (int k = 0; k < 8; ++k) sc.bound[k] = 0;
+    for (int v = 2; v <= 15; ++v) {                 // ascending, distinct
+        bool present = false;
+        for (int i = 0; i < nt; ++i) present |= (t[i] > 15 ? 15 : t[i]) == v;
+        if (present && sc.nb < 8) sc.bound[sc.nb++] = v;
+    }
+    return sc;
+}
+
+struct ReencodeMemo {
+    unsigned *have = nullptr;     // [n_cat] bit c: (item, class c) is in the memo
+    float *res = nullptr;         // [n_classes][n_cat][e]
+    int *codes = nullptr;         // [n_classes][n_cat][L-1]
+    int64_t n_cat = 0;
+};
+
 // infer.py:120-122 for ALL collision groups of one round, up to (not including) the last level:
 //   for every group g and every member i:  z = encoder(x_i) in the order of a batch of |g| rows,
 //   codes[i, 0..L-2] = arg-min codes of the first L-1 levels (distance product in the order of that batch size),
 //   residual[i, :]   = residual entering the last level.
 // The last level (Sinkhorn over the group's distance matrix) is rqb200_sinkhorn_regroup on `residual`.
-extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
-                                      const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
-                                      int64_t *codes_dev, float *residual_dev, void *stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+static int reencode_groups_impl(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
+                                const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
+                                int64_t *codes_dev, float *residual_dev, const ReencodeMemo *memo, cudaStream_t s) {
     RQB_TRY(reencode_check(m));
     if (n_groups == 0 || n_items == 0) return 0;
     RQB_CHECK(x_dev && items_dev && offsets_dev && codes_dev && residual_dev, "NULL buffer");
+    RQB_CHECK(!memo || !x_is_gathered, "the memo needs the catalogue on the device (x_is_gathered = 0)");
     RQB_CUDA(cudaSetDevice(m->device));
     int maxdim = m->e;
     for (int i = 0; i < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
@@ -499,6 +613,8 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
     int64_t *small_items = (int64_t *)(base + 2 * msz);
     int64_t *big_items = (int64_t *)(base + 2 * msz + isz);
     unsigned long long *counts = (unsigned long long *)(base + 2 * msz + 2 * isz);
+    const SizeClasses sc = size_classes_of(m);
+    const int e4 = m->e / 4;
     ProfScope ps(PROF_REENCODE, s);
     rqb::count_launch();
     group_sizes_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(offsets_dev, n_groups, n_items, msize);
@@ -507,8 +623,17 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
         // groups of 16 or more rows use the catalogue arithmetic in every layer: hand those rows to the fast exact kernels
         RQB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), s));
         rqb::count_launch();
-        partition_by_size_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(items_dev, msize, n_items, small_items, small_msize,
-                                                                                 big_items, counts);
+        if (memo) {
+            memo_classify_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(items_dev, msize, n_items, sc, memo->have, small_items,
+                                                                                 small_msize, big_items, counts);
+            rqb::count_launch();
+            memo_restore_kernel<<<(unsigned)((n_items * e4 + 255) / 256), 256, 0, s>>>(items_dev, msize, n_items, sc, memo->have, memo->res,
+                                                                                      memo->codes, memo->n_cat, m->e, m->L, codes_dev,
+                                                                                      residual_dev);
+        } else {
+            partition_by_size_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, s>>>(items_dev, msize, n_items, small_items, small_msize,
+                                                                                     big_items, counts);
+        }
         RQB_LAUNCH_CHECK();
         RQB_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));
         RQB_CUDA(cudaStreamSynchronize(s));
@@ -520,6 +645,13 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
         RQB_TRY(ws_reserve(m->rescue_act[1], act));
         RQB_TRY(reencode_rows_impl(m, x_dev, x_is_gathered, x_is_gathered ? items_dev : small_items, x_is_gathered ? msize : small_msize,
                                    n_small, (float *)m->rescue_act[0].ptr, (float *)m->rescue_act[1].ptr, codes_dev, residual_dev, s));
+        if (memo) {
+            rqb::count_launch();
+            memo_store_kernel<<<(unsigned)((n_small * e4 + 255) / 256), 256, 0, s>>>(small_items, small_msize, n_small, sc, memo->have,
+                                                                                    memo->res, memo->codes, memo->n_cat, m->e, m->L,
+                                                                                    codes_dev, residual_dev);
+            RQB_LAUNCH_CHECK();
+        }
     }
     if (n_big > 0) {
         const int64_t batch = (int64_t)1 << 30;               // "a large batch": catalogue order in every layer
@@ -536,8 +668,43 @@ extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x
         // all L arg-min levels are written; the Sinkhorn pass then overwrites the last one
         RQB_TRY(quantize_exact(m, cur, n_big, codes_dev, big_items, nullptr, nullptr, res_compact, nullptr, s, batch));
         RQB_TRY(scatter_rows(res_compact, big_items, n_big, m->e, residual_dev, s));
+        if (memo) {
+            rqb::count_launch();
+            memo_store_kernel<<<(unsigned)((n_big * e4 + 255) / 256), 256, 0, s>>>(big_items, nullptr, n_big, sc, memo->have, memo->res,
+                                                                                  memo->codes, memo->n_cat, m->e, m->L, codes_dev,
+                                                                                  residual_dev);
+            RQB_LAUNCH_CHECK();
+        }
     }
     return 0;
+}
+
+extern "C" int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
+                                      const int64_t *offsets_dev, int64_t n_groups, int64_t n_items,
+                                      int64_t *codes_dev, float *residual_dev, void *stream) {
+    return reencode_groups_impl(m, x_dev, x_is_gathered, items_dev, offsets_dev, n_groups, n_items, codes_dev, residual_dev, nullptr,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int rqb200_reencode_classes(const rqb200_model *m) {
+    if (!m) return 0;
+    return size_classes_of(m).nb + 1;
+}
+
+extern "C" int rqb200_reencode_groups_memo(rqb200_model *m, const float *x_dev, const int64_t *items_dev,
+                                           const int64_t *offsets_dev, int64_t n_groups, int64_t n_items, int64_t *codes_dev,
+                                           float *residual_dev, int64_t n_catalogue, unsigned *memo_have_dev, float *memo_residual_dev,
+                                           int *memo_codes_dev, void *stream) {
+    RQB_CHECK(m != nullptr, "model is NULL");
+    RQB_CHECK(memo_have_dev && memo_residual_dev && (memo_codes_dev || m->L == 1), "NULL memo buffer");
+    RQB_CHECK(n_catalogue > 0, "n_catalogue must be positive");
+    ReencodeMemo memo;
+    memo.have = memo_have_dev;
+    memo.res = memo_residual_dev;
+    memo.codes = memo_codes_dev;
+    memo.n_cat = n_catalogue;
+    return reencode_groups_impl(m, x_dev, 0, items_dev, offsets_dev, n_groups, n_items, codes_dev, residual_dev, &memo,
+                                (cudaStream_t)stream);
 }
 
 // The same for rows that are members of groups whose other members live elsewhere (sharded catalogue): the caller

@@ -125,6 +125,34 @@ def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Ten
     return codes
 
 
+class _ReencodeMemo:
+    """Device memo of the per-item part of the group re-encode (csrc/small_batch.cu, rqb200_reencode_groups_memo): the
+    codes of the first L-1 levels and the residual entering the last level are a pure function of (item, size class of its
+    group), so rounds after the first answer almost every member from here instead of running the model again."""
+
+    def __init__(self, model: RQVAE, n: int, device):
+        self.classes = int(_cabi.lib().rqb200_reencode_classes(model._handle))
+        Lv = len(model.num_emb_list)
+        self.have = torch.zeros((max(n, 1),), dtype=torch.int32, device=device)
+        self.res = torch.empty((self.classes, max(n, 1), model.e_dim), dtype=torch.float32, device=device)
+        self.codes = torch.empty((self.classes, max(n, 1), max(Lv - 1, 1)), dtype=torch.int32, device=device)
+
+    @staticmethod
+    def try_create(model: RQVAE, n: int, device, data):
+        """None when the catalogue is not on the device or the memo does not fit next to it (the rounds then recompute)."""
+        if not (torch.is_tensor(data) and data.is_cuda):
+            return None
+        classes = int(_cabi.lib().rqb200_reencode_classes(model._handle))
+        need = classes * n * 4 * (model.e_dim + len(model.num_emb_list)) + 4 * n
+        free, _total = torch.cuda.mem_get_info(device)
+        if need > 0.6 * free:
+            return None
+        try:
+            return _ReencodeMemo(model, n, device)
+        except torch.cuda.OutOfMemoryError:
+            return None
+
+
 class _GroupRecords:
     """Per-item record of the group an item was last re-encoded in (csrc/dedup.cu: group_unchanged_kernel): lets the
     rounds after the first skip every group whose member set did not change — re-encoding it is a no-op by construction."""
@@ -137,14 +165,16 @@ class _GroupRecords:
 
 @torch.no_grad()
 def reencode_round(model: RQVAE, codes: torch.Tensor, data, residual: Optional[torch.Tensor] = None,
-                   verbose_round: Optional[int] = None, records: Optional[_GroupRecords] = None) -> Tuple[int, int]:
+                   verbose_round: Optional[int] = None, records: Optional[_GroupRecords] = None,
+                   memo: Optional[_ReencodeMemo] = None) -> Tuple[int, int]:
     """ONE round of the loop at infer.py:116-129, in place on `codes`: every group of items sharing a full code goes
     through `model.get_indices(data[group], use_sk=True)` — as in the reference the WHOLE model runs again on the group's
     rows alone (encoder, arg-min levels, Sinkhorn on the last level), in the arithmetic the reference uses for a batch of
     that size (csrc/small_batch.cu), and all L codes of the members are overwritten.  Groups of one round are disjoint
     and are all found before anything is rewritten, so the round is a pure function of the codes it starts from.
     `records` (rounds of one driver run): groups that are member-for-member a group of the previous round are skipped —
-    they are fixed points.  Returns (groups found, groups re-encoded); (0, 0): nothing collides."""
+    they are fixed points.  `memo` (same): members already re-encoded in a group of the same size class are answered
+    from it.  Returns (groups found, groups re-encoded); (0, 0): nothing collides."""
     lib = _cabi.lib()
     dev = codes.device
     data = _as_rows(data)
@@ -178,8 +208,13 @@ def reencode_round(model: RQVAE, codes: torch.Tensor, data, residual: Optional[t
     else:
         x, gathered = data[items.cpu()].contiguous().to(dev), 1
     cap = lib.rqb200_sinkhorn_group_cap(model._handle)
-    check(lib.rqb200_reencode_groups(model._handle, ptr(x), gathered, ptr(items), ptr(offsets), n_groups, items.numel(),
-                                     ptr(codes), ptr(residual), stream_ptr(dev)))
+    if memo is not None and not gathered:
+        check(lib.rqb200_reencode_groups_memo(model._handle, ptr(x), ptr(items), ptr(offsets), n_groups, items.numel(),
+                                              ptr(codes), ptr(residual), n, ptr(memo.have), ptr(memo.res), ptr(memo.codes),
+                                              stream_ptr(dev)))
+    else:
+        check(lib.rqb200_reencode_groups(model._handle, ptr(x), gathered, ptr(items), ptr(offsets), n_groups, items.numel(),
+                                         ptr(codes), ptr(residual), stream_ptr(dev)))
     check(lib.rqb200_sinkhorn_regroup(model._handle, ptr(residual), ptr(items), ptr(offsets), n_groups,
                                       min(max_group, cap), float(last.sk_epsilon), int(last.sk_iters), ptr(codes),
                                       stream_ptr(dev)))
@@ -204,8 +239,10 @@ def resolve_rounds(model: RQVAE, codes: torch.Tensor, data, max_rounds: int = 30
     if last.sk_epsilon is not None and last.sk_epsilon > 0:
         residual = torch.empty((codes.shape[0], model.e_dim), dtype=torch.float32, device=codes.device)
         records = _GroupRecords(codes.shape[0], codes.device)
+        data = _as_rows(data)
+        memo = _ReencodeMemo.try_create(model, codes.shape[0], codes.device, data)
         while rounds < max_rounds:
-            found, done = reencode_round(model, codes, data, residual, rounds if verbose else None, records)
+            found, done = reencode_round(model, codes, data, residual, rounds if verbose else None, records, memo)
             if found == 0:
                 break
             work.append(done)

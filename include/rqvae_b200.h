@@ -68,6 +68,9 @@ int rqb200_debug_tc_flags(int flags);
  * 1 (fp16 screening pass) or 2 (the TMA-fed TF32 kernel, first layer only).  Used by tools/ to time and ablate.   */
 int rqb200_debug_linear_tc(rqb200_model *m, int which, int layer, const float *x_dev, int64_t n, float *y_dev,
                            int passes, int relu, void *stream);
+/* Diagnostics: 1 = rqb200_sinkhorn_regroup uses the shared-memory kernels only (the register-resident kernels are the
+ * default where K is 256 or 1024 and e_dim 32 or 64; both give the same codes, tests compare them); 0 = default.   */
+int rqb200_debug_sinkhorn_variant(int variant);
 /* Diagnostics: the Sinkhorn kernels divide many matrix entries by one row / column sum through the sum's correctly rounded
  * reciprocal and two fma corrections (same bits as `a / b`, csrc/sinkhorn.cu: div_by); this compares the two on `pairs`
  * pseudo-random operand pairs spread over ±exponent_span binades and returns the number of differing quotients.       */
@@ -105,6 +108,9 @@ int rqb200_model_set_gate(rqb200_model *m, float gamma, float floor_abs);
  * re-run by the three-pass tier [0] and by the exact tier [1] in the last RQB200_ENCODE_FAST call.                  */
 int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma1);
 int rqb200_model_last_tier_rows(rqb200_model *m, int64_t *out2);
+/* Shape accessors: number of quantizer levels L and the latent width e_dim of a handle (0 + last_error for NULL). */
+int rqb200_model_levels(const rqb200_model *m);
+int rqb200_model_e_dim(const rqb200_model *m);
 /* Copy the current codebook of `level` back (host or device destination). */
 int rqb200_model_get_codebook(rqb200_model *m, int level, float *E_out);
 
@@ -160,10 +166,24 @@ int rqb200_sinkhorn_regroup(rqb200_model *m, const float *residual_dev, const in
  * order of ITS group's size.  Writes codes[item, 0..L-2] and residual[item, :] (the residual entering the last
  * level; [N,e], indexed by item like codes) for the members only; rqb200_sinkhorn_regroup on that residual finishes
  * the round.  x_dev: the catalogue [N,in] (x_is_gathered = 0: row of member i is items[i]) or the members' rows in
- * list order [n_items,in] (x_is_gathered = 1).  Nothing synchronises.                                            */
+ * list order [n_items,in] (x_is_gathered = 1).  With x_is_gathered = 0 the call synchronises once (it reads back how
+ * many members belong to groups of fewer than 16 rows).                                                           */
 int rqb200_reencode_groups(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *items_dev,
                            const int64_t *offsets_dev, int64_t n_groups, int64_t n_items, int64_t *codes_dev,
                            float *residual_dev, void *stream);
+/* rqb200_reencode_groups with a memo.  What the call computes for a member depends on the item and on the size of its
+ * group only through WHICH products take the small-batch order — a few size classes (rqb200_reencode_classes: one
+ * threshold min(15, K/24) per product).  (item, class) → (codes of the first L-1 levels, residual) is a pure function,
+ * so a member already re-encoded in a group of the same class (an earlier round of infer.py:112-130) is answered from
+ * the memo instead of running the model again; new results are added.  Caller-owned device buffers, n_catalogue = rows
+ * of x / codes / residual:  memo_have_dev uint32[n_catalogue] (zero before the first call),
+ * memo_residual_dev float[classes][n_catalogue][e], memo_codes_dev int32[classes][n_catalogue][L-1].
+ * Same outputs, bit for bit, as rqb200_reencode_groups(x_is_gathered = 0).  Synchronises once (miss counts).          */
+int rqb200_reencode_classes(const rqb200_model *m);
+int rqb200_reencode_groups_memo(rqb200_model *m, const float *x_dev, const int64_t *items_dev,
+                                const int64_t *offsets_dev, int64_t n_groups, int64_t n_items, int64_t *codes_dev,
+                                float *residual_dev, int64_t n_catalogue, unsigned *memo_have_dev,
+                                float *memo_residual_dev, int *memo_codes_dev, void *stream);
 /* The same for rows whose group mates live on other GPUs (sharded catalogue): the size of every row's group is given
  * (msize_dev, int32 [n_rows]) instead of the group lists; rows_dev = the rows' indices into x / codes / residual.   */
 int rqb200_reencode_rows(rqb200_model *m, const float *x_dev, int x_is_gathered, const int64_t *rows_dev,

@@ -290,6 +290,15 @@ def test_reencode_rounds_against_reference_infer_at_catalogue_shapes(oracle, nam
     rq.generate_code.reencode_round(m, codes_d, xt)
     rq.generate_code.reencode_round(m, codes_h, x)
     assert torch.equal(codes_d, codes_h)
+    # the memo of the per-item part (rqb200_reencode_groups_memo) changes nothing: a chain of rounds with and without it
+    memo = rq.generate_code._ReencodeMemo(m, xt.shape[0], xt.device)
+    codes_m = torch.from_numpy(trace[0].copy()).to(DEV)
+    codes_p = codes_m.clone()
+    for t in range(min(6, f["rounds"])):
+        rq.generate_code.reencode_round(m, codes_m, xt, memo=memo)
+        rq.generate_code.reencode_round(m, codes_p, xt)
+        assert torch.equal(codes_m, codes_p), t
+    assert int((memo.have != 0).sum()) > 0
 
 
 def test_generate_codes_matches_oracle_driver_at_scale(oracle):

@@ -24,11 +24,14 @@ for vq in m.rq.vq_layers[:-1]:
     vq.sk_epsilon = 0.0
 import ctypes
 lib = _cabi.lib()
+use_memo = os.environ.get("RQB200_NO_MEMO", "0") != "1"
+memo = rq.generate_code._ReencodeMemo(m, n, x.device) if use_memo else None
+lib.rqb200_debug_sinkhorn_variant(int(os.environ.get("RQB200_SK_VARIANT", "0")))
 for r in range(rounds):
     lib.rqb200_profile_enable(1)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    found, done = rq.generate_code.reencode_round(m, codes, x)
+    found, done = rq.generate_code.reencode_round(m, codes, x, memo=memo)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ms = (ctypes.c_double * 12)()
