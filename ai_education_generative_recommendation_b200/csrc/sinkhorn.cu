@@ -609,6 +609,8 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
                             Q[i][uu] = (double)dist[i];
                             mx = fmaxf(mx, dist[i]);
                             mn = fminf(mn, dist[i]);
+                        } else {
+                            Q[i][uu] = 0.0;                   // rows beyond the group stay exactly zero (see for_rows)
                         }
                     }
                 }
@@ -638,14 +640,26 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
             }
         }
 
-        auto publish = [&]() {                                  // WARPS > 1: every thread stores its columns of every row
+        // Row loops of the hot path.  The rows are walked in blocks of RB: one uniform branch per block, straight-line code
+        // inside, so the independent quotients of a block overlap in the fp64 pipe.  Rows of the last block beyond the group
+        // ("not live") hold exactly 0.0 and are carried along: 0 / x = 0 through the fma sequence, and a trailing + 0.0 changes
+        // no column sum; their window tests are masked.  With EXACT every row is live and all of this folds away.
+        constexpr int RB = 4, NBLK = (BMAX + RB - 1) / RB;
+        auto for_rows = [&](auto &&f) {
 #pragma unroll
-            for (int i = 0; i < BMAX; ++i) {
-                if (i < B) {
+            for (int blk = 0; blk < NBLK; ++blk) {
+                if (EXACT || blk * RB < B) {
 #pragma unroll
-                    for (int u = 0; u < CPT; ++u) ex[i * K + lane + 32 * (w + WARPS * u)] = Q[i][u];
+                    for (int ii = 0; ii < RB; ++ii)
+                        if (blk * RB + ii < BMAX) f(blk * RB + ii, EXACT || blk * RB + ii < B);
                 }
             }
+        };
+        auto publish = [&]() {                                  // WARPS > 1: every thread stores its columns of every row
+            for_rows([&](int i, bool) {
+#pragma unroll
+                for (int u = 0; u < CPT; ++u) ex[i * K + lane + 32 * (w + WARPS * u)] = Q[i][u];
+            });
         };
         auto lane_row_sum = [&](int i) {                        // WARPS = 1
             double rs = 0.0;
@@ -658,8 +672,8 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
             for (int j = lane; j < K; j += 32) rs += ex[i * K + j];
             return warp_sum(rs);
         };
-        // the thread's elements [u0, u0 + NC) of every row → scratch, the literal divisions there, and back (see sk_slow_pass)
-        auto slow_rows = [&](bool pow2, double inv, double dcount) {
+        // the thread's elements → scratch, the literal divisions there, and back (see sk_slow_pass)
+        auto to_scratch = [&]() {
 #pragma unroll
             for (int i = 0; i < BMAX; ++i) {
                 if (i < B) {
@@ -667,7 +681,8 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
                     for (int u = 0; u < CPT; ++u) el[(size_t)i * EL_IS + (size_t)u * EL_US] = Q[i][u];
                 }
             }
-            sk_slow_pass(el, EL_IS, EL_US, den_row, 1, B, CPT, true, pow2, inv, dcount);
+        };
+        auto from_scratch = [&]() {
 #pragma unroll
             for (int i = 0; i < BMAX; ++i) {
                 if (i < B) {
@@ -675,28 +690,22 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
                     for (int u = 0; u < CPT; ++u) Q[i][u] = el[(size_t)i * EL_IS + (size_t)u * EL_US];
                 }
             }
+        };
+        auto slow_rows = [&](bool pow2, double inv, double dcount) {      // by the row sums in den_row
+            to_scratch();
+            sk_slow_pass(el, EL_IS, EL_US, den_row, 1, B, CPT, true, pow2, inv, dcount);
+            from_scratch();
         };
         // every element of the thread divided by ONE number, literally (the denominator goes through the thread's own
         // column-sum slots, which are free outside the column pass)
         auto slow_all = [&](double d) {
 #pragma unroll
             for (int u = 0; u < CPT; ++u) den_col[(size_t)u * TEAM_THREADS] = d;
-#pragma unroll
-            for (int i = 0; i < BMAX; ++i) {
-                if (i < B) {
-#pragma unroll
-                    for (int u = 0; u < CPT; ++u) el[(size_t)i * EL_IS + (size_t)u * EL_US] = Q[i][u];
-                }
-            }
+            to_scratch();
             sk_slow_pass(el, EL_IS, EL_US, den_col, TEAM_THREADS, B, CPT, false, true, 1.0, 1.0);
-#pragma unroll
-            for (int i = 0; i < BMAX; ++i) {
-                if (i < B) {
-#pragma unroll
-                    for (int u = 0; u < CPT; ++u) Q[i][u] = el[(size_t)i * EL_IS + (size_t)u * EL_US];
-                }
-            }
+            from_scratch();
         };
+        const DivCtx cOne = make_div(1.0);
 
         // sum_Q = Q.sum(-1).sum(-2);  Q /= sum_Q      (row sums added per warp in row order, warps in order: as sinkhorn_cta)
         double total;
@@ -708,31 +717,32 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
         } else {
             publish();
             __syncthreads();
-            double part = 0.0;
-            for (int i = w; i < B; i += WARPS) part += ex_row_sum(i);
-            if (lane == 0) s_part[w] = part;
+            for (int i = w; i < B; i += WARPS) {
+                const double rs = ex_row_sum(i);
+                if (lane == 0) den_row[i] = rs;
+            }
             __syncthreads();
+            // sinkhorn_cta's order: eight partials (rows i ≡ v mod 8 in ascending order), added in order
             total = 0.0;
-            for (int v = 0; v < WARPS; ++v) total += s_part[v];
+            for (int v = 0; v < SK_THREADS / 32; ++v) {
+                double part = 0.0;
+                for (int i = v; i < B; i += SK_THREADS / 32) part += den_row[i];
+                total += part;
+            }
+            __syncthreads();                                  // den_row is rewritten by the first row pass
         }
         {
             const DivCtx ct = make_div(total);
             bool outside = false;
+            for_rows([&](int i, bool live) {
 #pragma unroll
-            for (int i = 0; i < BMAX; ++i) {
-                if (i < B) {
-#pragma unroll
-                    for (int u = 0; u < CPT; ++u) outside |= div_outside(Q[i][u], ct);
-                }
-            }
+                for (int u = 0; u < CPT; ++u) outside |= live && div_outside(Q[i][u], ct);
+            });
             if (__builtin_expect(!outside, 1)) {
+                for_rows([&](int i, bool) {
 #pragma unroll
-                for (int i = 0; i < BMAX; ++i) {
-                    if (i < B) {
-#pragma unroll
-                        for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], ct);
-                    }
-                }
+                    for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], ct);
+                });
             } else {
                 slow_all(total);
             }
@@ -751,9 +761,32 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
             if (WARPS > 1) {
                 publish();
                 __syncthreads();
-                for (int i = w; i < B; i += WARPS) {
-                    const double rs = ex_row_sum(i);
-                    if (lane == 0) { s_ctx[i] = make_div(b_pow2 ? rs * dB : rs); den_row[i] = rs; }
+                // this warp's rows (i = w, w + WARPS, …) are summed TOGETHER — independent chains, one butterfly pass for all —
+                // and lane r turns row r's sum into its division context, so the phase costs one division latency, not one
+                // per row.  Rows beyond the group read stale tile rows; their sums go nowhere.
+                constexpr int RPW = (BMAX + WARPS - 1) / WARPS;
+                double rs[RPW];
+#pragma unroll
+                for (int r = 0; r < RPW; ++r) rs[r] = 0.0;
+#pragma unroll
+                for (int t = 0; t < K / 32; ++t) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r)
+                        if (w + r * WARPS < BMAX) rs[r] += ex[(w + r * WARPS) * K + lane + 32 * t];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], o);
+                }
+                double mine = rs[0];
+#pragma unroll
+                for (int r = 1; r < RPW; ++r)
+                    if (lane == r) mine = rs[r];
+                if (lane < RPW && w + lane * WARPS < B) {
+                    const int i = w + lane * WARPS;
+                    s_ctx[i] = make_div(b_pow2 ? mine * dB : mine);
+                    den_row[i] = mine;
                 }
                 __syncthreads();
             }
@@ -761,44 +794,32 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
                 constexpr int NCR = WARPS == 1 ? BMAX : 1;      // WARPS > 1: the contexts stay in shared memory
                 DivCtx cr[NCR];
                 bool outside = false;
-#pragma unroll
-                for (int i = 0; i < BMAX; ++i) {
-                    if (i < B) {
-                        if (WARPS == 1) {
-                            const double rs = lane_row_sum(i);
-                            cr[i % NCR] = make_div(b_pow2 ? rs * dB : rs);
-                        }
-                        const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[i];
-#pragma unroll
-                        for (int u = 0; u < CPT; ++u) outside |= div_outside(Q[i][u], c);
+                for_rows([&](int i, bool live) {
+                    if (WARPS == 1) {
+                        const double rs = lane_row_sum(i);
+                        cr[i % NCR] = make_div(b_pow2 ? rs * dB : rs);
                     }
-                }
+                    const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[live ? i : 0];
+#pragma unroll
+                    for (int u = 0; u < CPT; ++u) outside |= live && div_outside(Q[i][u], c);
+                });
                 if (__builtin_expect(!outside, 1)) {
+                    for_rows([&](int i, bool live) {
+                        const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[live ? i : 0];       // a dead row: 0 / (any row's sum) = 0
 #pragma unroll
-                    for (int i = 0; i < BMAX; ++i) {
-                        if (i < B) {
-                            const DivCtx c = WARPS == 1 ? cr[i % NCR] : s_ctx[i];
-#pragma unroll
-                            for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], c);
-                        }
-                    }
+                        for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], c);
+                    });
                     if (!b_pow2) {                              // Q /= B as a second batch of quotients
                         bool out2 = false;
+                        for_rows([&](int i, bool live) {
 #pragma unroll
-                        for (int i = 0; i < BMAX; ++i) {
-                            if (i < B) {
-#pragma unroll
-                                for (int u = 0; u < CPT; ++u) out2 |= div_outside(Q[i][u], cB);
-                            }
-                        }
+                            for (int u = 0; u < CPT; ++u) out2 |= live && div_outside(Q[i][u], cB);
+                        });
                         if (__builtin_expect(!out2, 1)) {
+                            for_rows([&](int i, bool) {
 #pragma unroll
-                            for (int i = 0; i < BMAX; ++i) {
-                                if (i < B) {
-#pragma unroll
-                                    for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], cB);
-                                }
-                            }
+                                for (int u = 0; u < CPT; ++u) Q[i][u] = div_fast(Q[i][u], cB);
+                            });
                         } else {
                             slow_all(dB);
                         }
@@ -818,28 +839,28 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
             for (int u0 = 0; u0 < CPT; u0 += CCH) {
                 DivCtx ccol[CCH];
                 bool outside = false;
+                double cs[CCH];
 #pragma unroll
-                for (int v = 0; v < CCH; ++v) {
-                    double cs = 0.0;
+                for (int v = 0; v < CCH; ++v) cs[v] = 0.0;
+                for_rows([&](int i, bool) {
 #pragma unroll
-                    for (int i = 0; i < BMAX; ++i)
-                        if (i < B) cs += Q[i][u0 + v];
-                    ccol[v] = make_div(K_POW2 ? cs * dK : cs);
+                    for (int v = 0; v < CCH; ++v) cs[v] += Q[i][u0 + v];
+                });
 #pragma unroll
-                    for (int i = 0; i < BMAX; ++i)
-                        if (i < B) outside |= div_outside(Q[i][u0 + v], ccol[v]);
-                }
+                for (int v = 0; v < CCH; ++v) ccol[v] = make_div(K_POW2 ? cs[v] * dK : cs[v]);
+                for_rows([&](int i, bool live) {
+#pragma unroll
+                    for (int v = 0; v < CCH; ++v) outside |= live && div_outside(Q[i][u0 + v], ccol[v]);
+                });
                 if (__builtin_expect(!outside && K_POW2, 1)) {
+                    for_rows([&](int i, bool) {
 #pragma unroll
-                    for (int v = 0; v < CCH; ++v) {
-#pragma unroll
-                        for (int i = 0; i < BMAX; ++i)
-                            if (i < B) Q[i][u0 + v] = div_fast(Q[i][u0 + v], ccol[v]);
-                    }
+                        for (int v = 0; v < CCH; ++v) Q[i][u0 + v] = div_fast(Q[i][u0 + v], ccol[v]);
+                    });
                 } else {
                     // only this chunk goes through the literal divisions: columns are independent in this pass
 #pragma unroll
-                    for (int v = 0; v < CCH; ++v) den_col[(size_t)v * TEAM_THREADS] = K_POW2 ? ccol[v].b * invK : ccol[v].b;   // the column sum itself
+                    for (int v = 0; v < CCH; ++v) den_col[(size_t)v * TEAM_THREADS] = cs[v];
 #pragma unroll
                     for (int i = 0; i < BMAX; ++i) {
                         if (i < B) {
@@ -891,7 +912,24 @@ sinkhorn_regroup_own_kernel(const float *__restrict__ residual, const int64_t *_
                 }
             }
             __syncthreads();
-            argmax_rows(ex, B, K, gi, codes, L, nullptr);
+            for (int i = w; i < B; i += WARPS) {
+                double best = 0.0;
+                int bj = -1;
+                for (int j = lane; j < K; j += 32) {
+                    const double v = ex[i * K + j];
+                    const bool take = bj < 0 || (!(best != best) && ((v != v) || v > best));
+                    if (take) { best = v; bj = j; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                    const bool onan = ov != ov, bnan = best != best;
+                    const bool take = (onan && (!bnan || oj < bj)) || (!onan && !bnan && (ov > best || (ov == best && oj < bj)));
+                    if (take) { best = ov; bj = oj; }
+                }
+                if (lane == 0) codes[gi[i] * L + (L - 1)] = bj;
+            }
         }
     }
 }
@@ -1193,6 +1231,7 @@ static int regroup_own(rqb200_model *m, const float *residual, const int64_t *it
         for (int b = 2; b <= 8; ++b) add(b, b);             // one launch per row count: one warp per group, rows resolved at compile time
         add(9, 16);
         add(17, 32);
+        add(33, 64);
     } else {
         add(2, 2);
         add(3, 16);
@@ -1219,8 +1258,9 @@ static int regroup_own(rqb200_model *m, const float *residual, const int64_t *it
                 case 4: RQB_OWN(8, 1, 6, true); break;
                 case 5: RQB_OWN(8, 1, 7, true); break;
                 case 6: RQB_OWN(8, 1, 8, true); break;
-                case 7: RQB_OWN(1, 8, 16, false); break;
-                default: RQB_OWN(1, 8, 32, false); break;
+                case 7: RQB_OWN(4, 2, 16, false); break;       // 64 doubles per thread in every class
+                case 8: RQB_OWN(2, 4, 32, false); break;
+                default: RQB_OWN(1, 8, 64, false); break;
             }
         } else {
             if (c == 0) RQB_OWN(32, 1, 2, true);
