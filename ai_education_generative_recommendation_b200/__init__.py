@@ -5,7 +5,7 @@
 Every compute call goes through `librqvae_b200.so` (hand-written sm_100a CUDA behind a C ABI);
 there is no CPU fallback.
 """
-from . import _cabi
+from . import _cabi, torch_ops
 from ._cabi import ENCODE_EXACT, ENCODE_FAST, RQB200Error
 from .rqvae import (MLPLayers, RQVAE, ResidualVectorQuantizer, VectorQuantizer, activation_layer, kmeans,
                     sinkhorn_algorithm)

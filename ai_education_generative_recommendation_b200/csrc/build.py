@@ -55,5 +55,29 @@ def build(force=False, verbose=False):
     return OUT
 
 
+TORCH_OPS_OUT = os.path.join(PKG, "librqvae_b200_torch.so")
+
+
+def build_torch_ops(force=False):
+    """g++ → librqvae_b200_torch.so: the TORCH_LIBRARY registration of the ops (csrc/torch_ops.cpp), a thin layer over
+    the C ABI linked against librqvae_b200.so ($ORIGIN) and libtorch.  No kernels in it."""
+    src = os.path.join(HERE, "torch_ops.cpp")
+    hdr = os.path.join(PKG, "..", "include", "rqvae_b200.h")
+    if (not force and os.path.exists(TORCH_OPS_OUT)
+            and os.path.getmtime(TORCH_OPS_OUT) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(__file__))):
+        return TORCH_OPS_OUT
+    import torch
+    from torch.utils import cpp_extension as ce
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", src, "-o", TORCH_OPS_OUT,
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    cmd += [f"-I{p}" for p in ce.include_paths("cuda")]
+    cmd += [f"-L{tlib}", f"-L{PKG}", "-L/usr/local/cuda/lib64", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+            "-lrqvae_b200", "-lcudart", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}", "-Wl,--no-as-needed"]
+    subprocess.check_call(cmd)
+    return TORCH_OPS_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_ops(force="--force" in sys.argv))

@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch import nn
 
-from . import _cabi
+from . import _cabi, torch_ops
 from ._cabi import check, ptr, stream_ptr
 
 
@@ -500,14 +500,21 @@ class RQVAE(nn.Module):
         self._sync()
         x2 = xs.reshape(-1, self.in_dim).contiguous()
         n, Lv = x2.shape[0], len(self.num_emb_list)
-        codes = torch.empty((n, Lv), dtype=torch.int64, device=xs.device)
-        stats = (ctypes.c_int64 * 4)()
-        check(_cabi.lib().rqb200_get_indices(self._handle, int(self.encode_mode), ptr(x2), n, ptr(codes), 0, stats,
-                                             stream_ptr(xs.device)))
         tiers = (ctypes.c_int64 * 2)()
-        check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
-        self.last_stats = {"rescued_rows": int(stats[0]),
-                           "three_pass_rows": int(tiers[0]) if self.encode_mode == _cabi.ENCODE_FAST else 0}
+        if torch_ops.available():
+            # the registered op (csrc/torch_ops.cpp): same C-ABI call, output from the caching allocator, current stream
+            codes = torch.ops.rqvae_b200.encode_indices(torch_ops.handle(self), x2, int(self.encode_mode))
+            check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
+            rescued = int(tiers[1])
+        else:
+            codes = torch.empty((n, Lv), dtype=torch.int64, device=xs.device)
+            stats = (ctypes.c_int64 * 4)()
+            check(_cabi.lib().rqb200_get_indices(self._handle, int(self.encode_mode), ptr(x2), n, ptr(codes), 0, stats,
+                                                 stream_ptr(xs.device)))
+            check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
+            rescued = int(stats[0])
+        fast = self.encode_mode == _cabi.ENCODE_FAST
+        self.last_stats = {"rescued_rows": rescued if fast else 0, "three_pass_rows": int(tiers[0]) if fast else 0}
         return codes.view(*xs.shape[:-1], Lv)
 
     def compute_loss(self, out, quant_loss, xs=None):

@@ -23,6 +23,19 @@ def test_library_exports_every_declared_symbol():
     assert _cabi.lib().rqb200_abi_version() == 1
 
 
+def test_torch_library_ops_are_registered():
+    """csrc/torch_ops.cpp: the TORCH_LIBRARY layer over the C ABI loads without a GPU, declares the ops of SURVEY.md §8b with
+    CUDA kernels only (a CPU tensor has no implementation to fall back on)."""
+    from ai_education_generative_recommendation_b200 import torch_ops
+    torch_ops.load()
+    for name in torch_ops.OPS:
+        assert hasattr(torch.ops.rqvae_b200, name), name
+        dump = torch._C._dispatch_dump(f"rqvae_b200::{name}")
+        assert "CUDA: registered" in dump and "CPU: registered" not in dump, dump
+    with pytest.raises(NotImplementedError):
+        torch.ops.rqvae_b200.sinkhorn_assign(torch.zeros(2, 8), 0.003, 50)
+
+
 def test_product_does_not_reference_the_oracle():
     pkg = os.path.join(ROOT, "ai_education_generative_recommendation_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -66,6 +66,37 @@ def test_get_indices_and_forward_match_reference_golden(oracle, name):
     assert np.array_equal(out.cpu().numpy().view(np.int32), oracle.mlp(xqo, dw, db).view(np.int32))
 
 
+def test_registered_torch_ops_equal_the_ctypes_binding():
+    """torch.ops.rqvae_b200.* (csrc/torch_ops.cpp) and the ctypes binding call the same C ABI: same tensors out."""
+    from ai_education_generative_recommendation_b200 import torch_ops
+    torch_ops.load()
+    g, cfg, cbs = load_golden("c2_slice")
+    m = build_model(cfg, cbs)
+    n = 3000
+    xt = torch.from_numpy(synth.synth_items(2024, 0, n, cfg["in_dim"], 1_000_000)).to(DEV)
+    h = torch_ops.handle(m)
+    want = g["codes"][:n].astype(np.int64)
+    for mode in (_cabi.ENCODE_EXACT, _cabi.ENCODE_FAST):
+        assert np.array_equal(torch.ops.rqvae_b200.encode_indices(h, xt, mode).cpu().numpy(), want)
+    z = torch.ops.rqvae_b200.encode_latents(h, xt)
+    assert torch.equal(z, m.encoder(xt))
+    idx, xq, sumsq = torch.ops.rqvae_b200.quantize(h, z)
+    x_q, _, codes = m.rq(z, use_sk=False)
+    assert np.array_equal(idx.cpu().numpy(), want) and torch.equal(idx, codes) and torch.equal(xq, x_q)
+    ids = torch.ops.rqvae_b200.resolve_collisions(h, idx, list(cfg["num_emb_list"]))
+    ref, stats = rq.suffix_dedup(m, idx)
+    assert torch.equal(ids, ref)
+    assert tuple(torch.ops.rqvae_b200.collision_rate(h, idx, list(cfg["num_emb_list"]))) == (stats["distinct"], stats["max_conflicts"])
+    d = torch.rand(24, 256, device=DEV)
+    a = torch.ops.rqvae_b200.sinkhorn_assign(d, 0.003, 50)
+    scratch = torch.empty((24, 256), dtype=torch.float64, device=DEV)
+    b = torch.empty((24,), dtype=torch.int64, device=DEV)
+    _cabi.check(_cabi.lib().rqb200_sinkhorn_assign(d.data_ptr(), 24, 256, 0.003, 50, scratch.data_ptr(), b.data_ptr(), _cabi.stream_ptr()))
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor|CPU"):
+        torch.ops.rqvae_b200.encode_indices(h, xt.cpu(), 0)
+
+
 def test_ragged_and_empty_batches(oracle):
     g, cfg, cbs = load_golden("c2_slice")
     m = build_model(cfg, cbs)
