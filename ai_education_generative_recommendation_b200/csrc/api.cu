@@ -521,17 +521,26 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
     int64_t *out = codes + (size_t)n * L;
     cudaStream_t cs = m->copy_stream;
     cudaStream_t ks = (cudaStream_t)stream;
-    // ev[0], ev[1]: chunk in buffer b copied;  ev[2], ev[3]: buffer b consumed
+    // ev[0], ev[1]: chunk in buffer b copied;  ev[2], ev[3]: buffer b consumed.
+    // The copy of chunk c+1 is enqueued BEFORE the kernels of chunk c: rqb200_get_indices(FAST) waits on the host for the
+    // row count of its exact tier, and a copy enqueued behind that wait would leave the PCIe link idle for as long as the
+    // tensor-core tiers of every chunk run.
     int64_t rescued = 0;
-    int64_t r0 = 0;
-    for (int64_t c = 0; r0 < n; ++c) {
+    auto rows_of = [&](int64_t r0) { const int64_t left = n - r0; return (left - chunk_rows < 16) ? left : chunk_rows; };
+    auto enqueue_copy = [&](int64_t c, int64_t r0) -> int {
         const int b = (int)(c & 1);
-        const int64_t left = n - r0;
-        const int64_t rows = (left - chunk_rows < 16) ? left : chunk_rows;
         if (c >= 2) RQB_CUDA(cudaStreamWaitEvent(cs, m->ev[2 + b], 0));
-        RQB_CUDA(cudaMemcpyAsync(xbuf[b], x_host + (size_t)r0 * in, sizeof(float) * (size_t)rows * in,
+        RQB_CUDA(cudaMemcpyAsync(xbuf[b], x_host + (size_t)r0 * in, sizeof(float) * (size_t)rows_of(r0) * in,
                                  cudaMemcpyHostToDevice, cs));
         RQB_CUDA(cudaEventRecord(m->ev[b], cs));
+        return 0;
+    };
+    int64_t r0 = 0;
+    RQB_TRY(enqueue_copy(0, 0));
+    for (int64_t c = 0; r0 < n; ++c) {
+        const int b = (int)(c & 1);
+        const int64_t rows = rows_of(r0);
+        if (r0 + rows < n) RQB_TRY(enqueue_copy(c + 1, r0 + rows));     // needs "buffer consumed" of chunk c-1: recorded last turn
         RQB_CUDA(cudaStreamWaitEvent(ks, m->ev[b], 0));
         int64_t st = 0;
         RQB_TRY(rqb200_get_indices(m, mode, xbuf[b], rows, codes + (size_t)r0 * L, nullptr, &st, ks));
