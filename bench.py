@@ -672,12 +672,17 @@ def main():
                 _, (ew, eb), _ = synth_weights(cfg_sk)
                 xs = x[:ns].cpu().numpy()
                 t0 = time.perf_counter()
-                ref_ids, ref_st = O.generate_codes(xs, ew, eb, cbs, cfg_sk["sk_epsilons"], cfg_sk["sk_iters"], group_order=True)
-                cs = time.perf_counter() - t0
-                sub_ids, _ = rq.generate_codes(model_sk, x[:ns].contiguous())
-                full["cpu_port"] = {"value": ns / cs, "unit": UNIT, "seconds": cs, "items": ns, "rounds": ref_st["rounds"],
-                                    "ids_equal_gpu_on_the_same_items": bool(np.array_equal(ref_ids, sub_ids.cpu().numpy())),
-                                    "what": "oracle.generate_codes(group_order=True), one host process"}
+                try:
+                    ref_ids, ref_st = O.generate_codes(xs, ew, eb, cbs, cfg_sk["sk_epsilons"], cfg_sk["sk_iters"], group_order=True)
+                    cs = time.perf_counter() - t0
+                    sub_ids, _ = rq.generate_codes(model_sk, x[:ns].contiguous())
+                    full["cpu_port"] = {"value": ns / cs, "unit": UNIT, "seconds": cs, "items": ns, "rounds": ref_st["rounds"],
+                                        "ids_equal_gpu_on_the_same_items": bool(np.array_equal(ref_ids, sub_ids.cpu().numpy())),
+                                        "what": "oracle.generate_codes(group_order=True), one host process"}
+                except KeyError as exc:
+                    # a group size whose reference arithmetic is not restated by the oracle (1024 -> 256 with 16..175 rows: the
+                    # reference's own result depends on its thread count there): no CPU twin for this catalogue
+                    full["cpu_port"] = {"unavailable": str(exc)}
             line["full_driver"] = full
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
