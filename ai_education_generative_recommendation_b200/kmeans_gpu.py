@@ -65,7 +65,10 @@ def _all_reduce(t, group):
 def kmeans_pp_seed(x: torch.Tensor, K: int, gen: torch.Generator, ops, group=None) -> torch.Tensor:
     """Greedy k-means++ seeding (like scikit-learn: 2 + log K candidates per step, keep the one that lowers the
     potential most).  Sharded mode: every rank draws the same uniform numbers; the rank that owns a selected
-    global position contributes the row through an all-reduce, potentials are all-reduced."""
+    global position contributes the row through an all-reduce, potentials are all-reduced.
+    The whole loop stays on the device: every decision (degenerate weights, which rank owns a draw, the best candidate)
+    is a tensor expression, so a step is a fixed sequence of launches with no host read — the K steps queue up behind each
+    other instead of paying a device round trip per centre."""
     import math
     n, e = x.shape
     dev = x.device
@@ -75,44 +78,46 @@ def kmeans_pp_seed(x: torch.Tensor, K: int, gen: torch.Generator, ops, group=Non
     else:
         rank, world = 0, 1
     trials = 2 + int(math.log(K)) if K > 1 else 1
+    uniforms = torch.rand((K, trials), generator=gen, dtype=torch.float64).to(dev)        # the same numbers on every rank
     centers = torch.empty((K, e), dtype=torch.float32, device=dev)
+    ones = torch.ones((n,), dtype=torch.float64, device=dev)
+    counts = torch.zeros(world, dtype=torch.float64, device=dev)
+    counts[rank] = float(n)
+    _all_reduce(counts, group)
+    ranks = torch.arange(world, device=dev)
     mind = None                                   # current min squared distance of every local sample
     for k in range(K):
         T = 1 if k == 0 else trials
-        u = torch.rand((T,), generator=gen, dtype=torch.float64).to(dev)
-        w_local = torch.ones((n,), dtype=torch.float64, device=dev) if mind is None else mind.to(torch.float64)
+        u = uniforms[k, :T]
+        w_local = ones if mind is None else mind.to(torch.float64)
         tot = torch.zeros(world, dtype=torch.float64, device=dev)
         tot[rank] = w_local.sum()
         _all_reduce(tot, group)
+        degenerate = ~(tot.sum() > 0)             # all remaining samples coincide with a centre: draw uniformly
+        w_local = torch.where(degenerate, ones, w_local)
+        tot = torch.where(degenerate, counts, tot)
         total = tot.sum()
-        if not bool(total > 0):                   # all remaining samples coincide with a centre
-            w_local = torch.ones((n,), dtype=torch.float64, device=dev)
-            tot = torch.zeros(world, dtype=torch.float64, device=dev)
-            tot[rank] = float(n)
-            _all_reduce(tot, group)
-            total = tot.sum()
         target = u * total                        # [T] positions in the global cumulative weight
-        before = tot[:rank].sum()
+        before = (torch.cumsum(tot, 0) - tot)[rank]
         mine = tot[rank]
-        last_nonempty = int(torch.nonzero(tot > 0).max().item()) if bool((tot > 0).any()) else 0
+        last_nonempty = (ranks * (tot > 0)).max()
         cands = torch.zeros((T, e), dtype=torch.float32, device=dev)
-        if n > 0 and bool(mine > 0):
+        if n > 0:
             cs = torch.cumsum(w_local, 0)
             local_t = target - before
-            own = (local_t >= 0) & (local_t < mine)
-            if rank == last_nonempty:
-                own = own | (local_t >= mine)
+            own = ((local_t >= 0) & (local_t < mine)) | ((last_nonempty == rank) & (local_t >= mine))
+            own = own & (mine > 0)
             j = torch.searchsorted(cs, local_t.clamp(min=0)).clamp(0, n - 1)
-            cands[own] = x[j[own]]
+            cands = torch.where(own[:, None], x[j], cands)
         _all_reduce(cands, group)
         d = ops.sqdist(x, cands)                  # [n, T]
         if mind is not None:
             d = torch.minimum(d, mind[:, None])
         pot = d.to(torch.float64).sum(0)
         _all_reduce(pot, group)
-        best = int(torch.argmin(pot).item())
-        centers[k] = cands[best]
-        mind = d[:, best].contiguous()
+        best = torch.argmin(pot).reshape(1)       # stays on the device
+        centers[k] = cands.index_select(0, best)[0]
+        mind = d.index_select(1, best).reshape(-1).contiguous()
     return centers
 
 

@@ -397,12 +397,18 @@ class RQVAE(nn.Module):
             indices = torch.argmin(d, dim=-1)
         else:
             indices = self._sinkhorn_assign(d, q.sk_epsilon, q.sk_iters)
-        cb = q.embedding.weight.detach()
-        x_q = cb[indices].view(x.shape)
-        mse = torch.mean((x_q - x) ** 2)
+        # gather, straight-through output and the loss numerator in one kernel (vq.py:87-95): x_q = x + (E[idx] - x)
+        cb = q.embedding.weight.detach().contiguous()
+        n = latent.shape[0]
+        x_q = torch.empty_like(latent)
+        r_next = torch.empty_like(latent)
+        sumsq = torch.zeros((1,), dtype=torch.float64, device=latent.device)
+        if n:
+            check(_cabi.lib().rqb200_rq_level_apply(ptr(latent), ptr(indices), ptr(cb), n, self.e_dim, 1, ptr(x_q), ptr(r_next),
+                                                    ptr(sumsq), stream_ptr(latent.device)))
+        mse = (sumsq[0] / float(max(n * self.e_dim, 1))).to(torch.float32)
         loss = mse + q.beta * mse
-        x_q = x + (x_q - x)
-        return x_q, loss, indices.view(x.shape[:-1])
+        return x_q.view(x.shape), loss, indices.view(x.shape[:-1])
 
     @torch.no_grad()
     def _rq(self, x: torch.Tensor, use_sk: bool):
