@@ -203,6 +203,12 @@ extern "C" int rqb200_model_create(rqb200_model **out, int device, int n_layers,
             return RQB200_ENOMEM;
         }
     }
+    if (cudaMalloc(&m->tier_counts_dev, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        delete m;
+        return RQB200_ENOMEM;
+    }
+    (void)cudaMemset(m->tier_counts_dev, 0, 2 * sizeof(unsigned long long));
     if (cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         rqb200_model_destroy(m);
@@ -233,6 +239,7 @@ extern "C" void rqb200_model_destroy(rqb200_model *m) {
                        &m->rescue, &m->rescue_act[0], &m->rescue_act[1], &m->groupws, &m->skws};
     for (Workspace *w : ws)
         if (w->ptr) cudaFree(w->ptr);
+    if (m->tier_counts_dev) cudaFree(m->tier_counts_dev);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     for (int i = 0; i < 4; ++i)
         if (m->ev[i]) cudaEventDestroy(m->ev[i]);
@@ -309,6 +316,15 @@ extern "C" int rqb200_model_set_screen(rqb200_model *m, int enabled, float gamma
 
 extern "C" int rqb200_model_last_tier_rows(rqb200_model *m, int64_t *out2) {
     RQB_CHECK(m != nullptr && out2 != nullptr, "NULL argument");
+    if (m->tier_counts_pending) {           // the fast route left the counts on the device: fetch them (waits for that stream)
+        unsigned long long h[2] = {0, 0};
+        RQB_CUDA(cudaSetDevice(m->device));
+        RQB_CUDA(cudaMemcpyAsync(h, m->tier_counts_dev, sizeof(h), cudaMemcpyDeviceToHost, m->tier_counts_stream));
+        RQB_CUDA(cudaStreamSynchronize(m->tier_counts_stream));
+        m->last_tier_rows[0] = (int64_t)h[0];
+        m->last_tier_rows[1] = (int64_t)h[1];
+        m->tier_counts_pending = false;
+    }
     out2[0] = m->last_tier_rows[0];
     out2[1] = m->last_tier_rows[1];
     return 0;
@@ -515,16 +531,20 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
     // a tail of fewer than 16 rows rides with the previous chunk (a call with < 16 rows would take the small-batch order)
     const size_t chunk_bytes = sizeof(float) * (size_t)(chunk_rows + 16) * in;
     RQB_TRY(ws_reserve(m->hostpipe[0], chunk_bytes + sizeof(int64_t) * (size_t)n * (2 * L + 1)));
-    RQB_TRY(ws_reserve(m->hostpipe[1], chunk_bytes));
+    const int64_t n_chunks = (n + chunk_rows - 1) / chunk_rows + 1;
+    const size_t cnt_bytes = sizeof(unsigned long long) * 2 * (size_t)n_chunks;
+    RQB_TRY(ws_reserve(m->hostpipe[1], chunk_bytes + cnt_bytes));       // + the tier row counts of every chunk (read once, at the end)
     float *xbuf[2] = {(float *)m->hostpipe[0].ptr, (float *)m->hostpipe[1].ptr};
     int64_t *codes = (int64_t *)((char *)m->hostpipe[0].ptr + chunk_bytes);
     int64_t *out = codes + (size_t)n * L;
+    unsigned long long *chunk_counts = (unsigned long long *)((char *)m->hostpipe[1].ptr + chunk_bytes);
     cudaStream_t cs = m->copy_stream;
     cudaStream_t ks = (cudaStream_t)stream;
+    RQB_CUDA(cudaMemsetAsync(chunk_counts, 0, cnt_bytes, ks));
     // ev[0], ev[1]: chunk in buffer b copied;  ev[2], ev[3]: buffer b consumed.
-    // The copy of chunk c+1 is enqueued BEFORE the kernels of chunk c: rqb200_get_indices(FAST) waits on the host for the
-    // row count of its exact tier, and a copy enqueued behind that wait would leave the PCIe link idle for as long as the
-    // tensor-core tiers of every chunk run.
+    // The copy of chunk c+1 is enqueued BEFORE the kernels of chunk c, and no call in the loop waits for the device (the
+    // fast route keeps its tier row counts on the device; they are collected per chunk and read once at the end), so the
+    // PCIe link never idles behind host-side work.
     int64_t rescued = 0;
     auto rows_of = [&](int64_t r0) { const int64_t left = n - r0; return (left - chunk_rows < 16) ? left : chunk_rows; };
     auto enqueue_copy = [&](int64_t c, int64_t r0) -> int {
@@ -542,9 +562,9 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
         const int64_t rows = rows_of(r0);
         if (r0 + rows < n) RQB_TRY(enqueue_copy(c + 1, r0 + rows));     // needs "buffer consumed" of chunk c-1: recorded last turn
         RQB_CUDA(cudaStreamWaitEvent(ks, m->ev[b], 0));
-        int64_t st = 0;
-        RQB_TRY(rqb200_get_indices(m, mode, xbuf[b], rows, codes + (size_t)r0 * L, nullptr, &st, ks));
-        rescued += st;
+        RQB_TRY(rqb200_get_indices(m, mode, xbuf[b], rows, codes + (size_t)r0 * L, nullptr, nullptr, ks));      // nothing waits
+        if (mode == RQB200_ENCODE_FAST && m->tier_counts_pending)
+            RQB_CUDA(cudaMemcpyAsync(chunk_counts + 2 * c, m->tier_counts_dev, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, ks));
         RQB_CUDA(cudaEventRecord(m->ev[2 + b], ks));
         r0 += rows;
     }
@@ -552,6 +572,12 @@ extern "C" int rqb200_generate_codes_host(rqb200_model *m, int mode, const float
     RQB_TRY(rqb200_suffix_dedup(m, codes, n, L, m->K, out, stats_host ? &distinct : nullptr,
                                 stats_host ? &maxgroup : nullptr, ks));
     RQB_CUDA(cudaMemcpyAsync(codes_host, out, sizeof(int64_t) * (size_t)n * (L + 1), cudaMemcpyDeviceToHost, ks));
+    if (stats_host) {
+        std::vector<unsigned long long> hc(2 * (size_t)n_chunks);
+        RQB_CUDA(cudaMemcpyAsync(hc.data(), chunk_counts, cnt_bytes, cudaMemcpyDeviceToHost, ks));
+        RQB_CUDA(cudaStreamSynchronize(ks));
+        for (int64_t c = 0; c < n_chunks; ++c) rescued += (int64_t)hc[2 * c + 1];
+    }
     RQB_CUDA(cudaStreamSynchronize(ks));
     if (stats_host) { stats_host[0] = rescued; stats_host[1] = distinct; stats_host[2] = maxgroup; }
     return 0;

@@ -126,6 +126,9 @@ struct rqb200_model {
     int screen_kind = 1;                    // 1: TF32 first layer fed by TMA + three-pass tail (encode_tf32.cu); 0: one fp16 pass through all layers
     float screen_gamma = 4.8828125e-04f;    // 2^-11: calibrated gate of the screening tier (tools/calibrate_gate.py)
     int64_t last_tier_rows[2] = {0, 0};     // rows re-run by tier 2 / tier 3 in the last fast get_indices
+    unsigned long long *tier_counts_dev = nullptr;   // the same two counts on the device (the fast route does not wait for them)
+    cudaStream_t tier_counts_stream = nullptr;
+    bool tier_counts_pending = false;       // last_tier_rows is stale until rqb200_model_last_tier_rows reads tier_counts_dev
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -137,8 +140,9 @@ int ws_reserve(Workspace &w, size_t bytes);
 // linear_exact.cu
 // batch_rows: how many rows the reference would have in the batch these n rows belong to (decides the summation order,
 // small_batch.cu); -1 = n.  Internal callers that recompute a SUBSET of a large batch (rescue tier) pass the batch size.
+// n_dev (may be NULL): the row count lives on the device (n = capacity; persistent grid) — the exact tier of the fast route.
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s, int64_t batch_rows = -1);
+                 bool relu, cudaStream_t s, int64_t batch_rows = -1, const unsigned long long *n_dev = nullptr);
 // small_batch.cu: the reference's order for batches of 2..15 rows (and per-row batch sizes for the group re-encode)
 int linear_small(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu, cudaStream_t s);
 int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, const int *msize, int m_uniform, int64_t n,
@@ -167,7 +171,8 @@ int quantize_tc(rqb200_model *m, const float *z, int64_t n, int64_t *codes, int6
 int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s);
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
                    const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
-                   float *margin_out, cudaStream_t s, int64_t batch_rows = -1);
+                   float *margin_out, cudaStream_t s, int64_t batch_rows = -1, const unsigned long long *n_dev = nullptr,
+                   int64_t n_hint = 0);
 int distances_exact(const rqb200_model *m, int level, const float *r, int64_t n, float *d,
                     cudaStream_t s);
 int recon_error(const float *out, const float *x, int64_t count, double *recon_sum, cudaStream_t s);

@@ -843,31 +843,40 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
             RQB_LAUNCH_CHECK();
         }
     }
-    RQB_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));
-    RQB_CUDA(cudaStreamSynchronize(s));
-    if (stats_host) stats_host[0] = (int64_t)h[1];
-    m->last_tier_rows[0] = (int64_t)h[0];
-    m->last_tier_rows[1] = (int64_t)h[1];
-    if (h[1] > 0) {
-        // exact route for the gated rows: gather → exact MLP → exact quantizer → scatter codes
+    // Tier 3: the exact SIMT kernels over the rows of list2 — gather → exact MLP → exact quantizer → scatter codes.  The row
+    // count stays on the device (counts[1]): the kernels run persistent grids over "row tiles below the count", their
+    // activations live in the MLP's own ping-pong buffers (free by now, sized for every row) and the latent in z2, so no size
+    // has to come back to the host and nothing in this call waits for the device.
+    {
         ProfScope ps(PROF_RESCUE, s);
-        const int64_t nr = (int64_t)h[1];
-        Workspace &zw = m->rescue;
-        RQB_TRY(ws_reserve(zw, sizeof(float) * (size_t)nr * m->e));
-        float *zr = (float *)zw.ptr;
-        int maxdim = 0;
-        for (int i = 0; i + 1 < m->n_layers; ++i) maxdim = m->enc[i].out > maxdim ? m->enc[i].out : maxdim;
-        RQB_TRY(ws_reserve(m->rescue_act[0], sizeof(float) * (size_t)nr * maxdim));
-        RQB_TRY(ws_reserve(m->rescue_act[1], sizeof(float) * (size_t)nr * maxdim));
+        const unsigned long long *nr_dev = counts + 1;
+        const int64_t hint = m->last_tier_rows[1] > 0 ? m->last_tier_rows[1] : n / 64 + 1;      // picks the quantizer mapping only
+        float *zr = z2;                                                    // [n, e]: tier 2 has consumed it
         const float *cur = x;
         for (int i = 0; i < m->n_layers; ++i) {
             const bool last = i == m->n_layers - 1;
-            float *dst = last ? zr : (float *)m->rescue_act[i & 1].ptr;
-            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list2 : nullptr, nr, dst, !last, s, n));      // order of the n-row batch
+            float *dst = last ? zr : (float *)m->act[i & 1].ptr;
+            RQB_TRY(linear_exact(m->enc[i], cur, i == 0 ? list2 : nullptr, n, dst, !last, s, n < 16 ? 16 : n, nr_dev));   // order of the n-row batch
             cur = dst;
         }
-        RQB_TRY(quantize_exact(m, zr, nr, codes, list2, nullptr, nullptr, nullptr, nullptr, s, n));
-        if (z_out) RQB_TRY(scatter_rows(zr, list2, nr, m->e, z_out, s));      // keep the caller's latent exact on rescued rows
+        RQB_TRY(quantize_exact(m, zr, n, codes, list2, nullptr, nullptr, nullptr, nullptr, s, n < 16 ? 16 : n, nr_dev, hint));
+        if (z_out) {                                                       // keep the caller's latent exact on rescued rows
+            count_launch();
+            scatter_rows_dev_kernel<<<kNumSMs * 4, 256, 0, s>>>(zr, list2, nr_dev, m->e, z_out);
+            RQB_LAUNCH_CHECK();
+        }
+    }
+    // the tier row counts: kept on the device for rqb200_model_last_tier_rows; read back here only if the caller asks
+    RQB_CUDA(cudaMemcpyAsync(m->tier_counts_dev, counts, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
+    m->tier_counts_stream = s;
+    m->tier_counts_pending = true;
+    if (stats_host) {
+        RQB_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));
+        RQB_CUDA(cudaStreamSynchronize(s));
+        stats_host[0] = (int64_t)h[1];
+        m->last_tier_rows[0] = (int64_t)h[0];
+        m->last_tier_rows[1] = (int64_t)h[1];
+        m->tier_counts_pending = false;
     }
     return 0;
 }

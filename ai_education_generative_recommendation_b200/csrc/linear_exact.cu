@@ -27,7 +27,11 @@ linear_exact_kernel(const float *__restrict__ X, const int64_t *__restrict__ row
                     const float *__restrict__ W, const float *__restrict__ bias,
                     float *__restrict__ Y, int K, int N, int relu,
                     const int nblk, const int kb0, const int kb1, const int kb2, const int kb3,
-                    const int kb4, const int kb5, const int kb6, const int kb7) {
+                    const int kb4, const int kb5, const int kb6, const int kb7,
+                    const unsigned long long *__restrict__ n_dev) {
+    // n_dev (may be NULL): the row count lives on the device (rescue tier: rows the margin gate listed); n is then the
+    // capacity and the grid is persistent — every CTA walks row tiles blockIdx.x, blockIdx.x + gridDim.x, …
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     constexpr int NTX = BN / TN;           // threads along n
     constexpr int NTY = BM / TM;           // threads along m
     static_assert(NTX * NTY == NTHREADS, "tile/thread mismatch");
@@ -42,9 +46,12 @@ linear_exact_kernel(const float *__restrict__ X, const int64_t *__restrict__ row
 
     const int tid = threadIdx.x;
     const int tx = tid % NTX, ty = tid / NTX;
-    const int64_t row0 = (int64_t)blockIdx.x * BM;
     const int col0 = blockIdx.y * BN;
     const int kbs[8] = {kb0, kb1, kb2, kb3, kb4, kb5, kb6, kb7};
+    const int64_t n_row_tiles = (n + BM - 1) / BM;
+    for (int64_t row_tile = blockIdx.x; row_tile < n_row_tiles; row_tile += gridDim.x) {
+    if (row_tile != (int64_t)blockIdx.x) __syncthreads();         // the previous tile's shared-memory reads are done
+    const int64_t row0 = row_tile * BM;
 
     // ---- per-thread load coordinates
     const float *a_src[A_F4];
@@ -221,11 +228,12 @@ linear_exact_kernel(const float *__restrict__ X, const int64_t *__restrict__ row
             }
         }
     }
+    }   // row tiles
 }
 
 template <int BM, int BN, int TM, int TN>
 int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu,
-           cudaStream_t s) {
+           cudaStream_t s, const unsigned long long *n_dev = nullptr) {
     auto kern = linear_exact_kernel<BM, BN, TM, TN>;
     size_t stash = lin.nblk > 1 ? sizeof(float) * TM * TN * NTHREADS : 0;
     static rqb::DeviceOnce attr_once;   // per template instantiation
@@ -236,9 +244,13 @@ int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, fl
     int kb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < lin.nblk; ++i) kb[i] = lin.kblocks[i];
     dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)((lin.out + BN - 1) / BN));
+    if (n_dev) {                                       // persistent over the row tiles: about three CTAs per SM in total
+        const unsigned cap = (unsigned)((kNumSMs * 3 + grid.y - 1) / grid.y);
+        if (grid.x > cap) grid.x = cap;
+    }
     rqb::count_launch();
     kern<<<grid, NTHREADS, stash, s>>>(x, rows, n, lin.W, lin.b, y, lin.in, lin.out, relu ? 1 : 0,
-                                       lin.nblk, kb[0], kb[1], kb[2], kb[3], kb[4], kb[5], kb[6], kb[7]);
+                                       lin.nblk, kb[0], kb[1], kb[2], kb[3], kb[4], kb[5], kb[6], kb[7], n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -246,8 +258,18 @@ int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, fl
 }  // namespace
 
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s, int64_t batch_rows) {
+                 bool relu, cudaStream_t s, int64_t batch_rows, const unsigned long long *n_dev) {
     if (n == 0) return 0;
+    if (n_dev) {
+        // device-counted rows (rescue tier): n is the capacity; always a subset of a large batch (catalogue order)
+        RQB_CHECK(lin.set, "linear layer not loaded");
+        RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
+        RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);
+        RQB_CHECK(!small_batch_lane16(batch_rows, lin.in), "device-counted rows must belong to a batch of 16 or more rows");
+        if (lin.out > 64) return launch<64, 64, 4, 4>(lin, x, rows, n, y, relu, s, n_dev);
+        if (lin.out > 32) return launch<128, 64, 8, 4>(lin, x, rows, n, y, relu, s, n_dev);
+        return launch<128, 32, 4, 4>(lin, x, rows, n, y, relu, s, n_dev);
+    }
     RQB_CHECK(lin.set, "linear layer not loaded");
     RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
     RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);

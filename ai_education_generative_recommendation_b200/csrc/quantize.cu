@@ -285,14 +285,18 @@ constexpr int QS_ROWS = QT / QS;           // rows per CTA
 template <int E>
 __global__ void __launch_bounds__(QT)
 quantize_sliced_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
-                       const int64_t *__restrict__ rows_out) {
+                       const int64_t *__restrict__ rows_out, const unsigned long long *__restrict__ n_dev) {
+    // n_dev (may be NULL): device-resident row count (n = capacity), persistent grid over the row tiles
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ __align__(16) float smem[];
     constexpr int PITCH = E + 4;
     constexpr int CH = (CHUNK_FLOATS / PITCH) / QS * QS;    // codes per chunk (multiple of QS)
     float *s_cb = smem;                     // [CH][PITCH]
     float *s_cc = smem + CH * PITCH;        // [CH]
     const int tid = threadIdx.x, sl = tid % QS;
-    const int64_t row = (int64_t)blockIdx.x * QS_ROWS + tid / QS;
+    const int64_t n_row_tiles = (n + QS_ROWS - 1) / QS_ROWS;
+    for (int64_t row_tile = blockIdx.x; row_tile < n_row_tiles; row_tile += gridDim.x) {
+    const int64_t row = row_tile * QS_ROWS + tid / QS;
     const bool live = row < n;
     float r[E];
 #pragma unroll
@@ -385,11 +389,12 @@ quantize_sliced_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int
             }
         }
     }
+    }   // row tiles (every chunk staging starts with a block barrier, so the shared buffers are free again)
 }
 
 template <int E>
 int launch_quant_sliced(const rqb200_model *m, const float *z, int64_t n, int64_t *codes, const int64_t *rows_out,
-                        cudaStream_t s) {
+                        cudaStream_t s, const unsigned long long *n_dev = nullptr) {
     auto kern = quantize_sliced_kernel<E>;
     constexpr int PITCH = E + 4;
     constexpr int CH = (CHUNK_FLOATS / PITCH) / QS * QS;
@@ -399,8 +404,9 @@ int launch_quant_sliced(const rqb200_model *m, const float *z, int64_t n, int64_
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     unsigned grid = (unsigned)((n + QS_ROWS - 1) / QS_ROWS);
+    if (n_dev && grid > (unsigned)kNumSMs * 8) grid = (unsigned)kNumSMs * 8;
     rqb::count_launch();
-    kern<<<grid, QT, smem, s>>>(z, n, make_args(m), codes, rows_out);
+    kern<<<grid, QT, smem, s>>>(z, n, make_args(m), codes, rows_out, n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -418,7 +424,9 @@ constexpr int QTL_ROWS = 64, QTL_THREADS = 256, QTL_CODES = 128;     // rows per
 template <int E>
 __global__ void __launch_bounds__(QTL_THREADS, 2)
 quantize_tiled_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int64_t *__restrict__ codes,
-                      const int64_t *__restrict__ rows_out) {
+                      const int64_t *__restrict__ rows_out, const unsigned long long *__restrict__ n_dev) {
+    // n_dev (may be NULL): device-resident row count (n = capacity), persistent grid over the row tiles
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ __align__(16) float smem[];
     constexpr int PITCH = E + 4;
     float *s_r = smem;                                   // [64][PITCH]  residual tile
@@ -426,7 +434,10 @@ quantize_tiled_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int6
     float *s_cc = s_cb + 2 * QTL_CODES * PITCH;          // [2][QTL_CODES]
     float *s_xx = s_cc + 2 * QTL_CODES;                  // [64]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t row0 = (int64_t)blockIdx.x * QTL_ROWS;
+    const int64_t n_row_tiles = (n + QTL_ROWS - 1) / QTL_ROWS;
+    for (int64_t row_tile = blockIdx.x; row_tile < n_row_tiles; row_tile += gridDim.x) {
+    if (row_tile != (int64_t)blockIdx.x) __syncthreads();         // the previous tile's shared-memory reads are done
+    const int64_t row0 = row_tile * QTL_ROWS;
     for (int i = tid; i < QTL_ROWS * (E / 4); i += QTL_THREADS) {
         const int rr = i / (E / 4), k4 = i % (E / 4);
         const float4 v = row0 + rr < n ? *reinterpret_cast<const float4 *>(z + (row0 + rr) * E + 4 * k4) : make_float4(0, 0, 0, 0);
@@ -555,11 +566,12 @@ quantize_tiled_kernel(const float *__restrict__ z, int64_t n, QuantArgs qa, int6
             }
         }
     }
+    }   // row tiles
 }
 
 template <int E>
 int launch_quant_tiled(const rqb200_model *m, const float *z, int64_t n, int64_t *codes, const int64_t *rows_out,
-                       cudaStream_t s) {
+                       cudaStream_t s, const unsigned long long *n_dev = nullptr) {
     auto kern = quantize_tiled_kernel<E>;
     constexpr int PITCH = E + 4;
     size_t smem = sizeof(float) * (QTL_ROWS * PITCH + 2 * QTL_CODES * PITCH + 2 * QTL_CODES + QTL_ROWS);
@@ -568,8 +580,9 @@ int launch_quant_tiled(const rqb200_model *m, const float *z, int64_t n, int64_t
         RQB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     unsigned grid = (unsigned)((n + QTL_ROWS - 1) / QTL_ROWS);
+    if (n_dev && grid > (unsigned)kNumSMs * 4) grid = (unsigned)kNumSMs * 4;
     rqb::count_launch();
-    kern<<<grid, QTL_THREADS, smem, s>>>(z, n, make_args(m), codes, rows_out);
+    kern<<<grid, QTL_THREADS, smem, s>>>(z, n, make_args(m), codes, rows_out, n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -630,9 +643,17 @@ int codebook_norms(const float *cb, int K, int e, float *cc, cudaStream_t s) {
 
 int quantize_exact(const rqb200_model *m, const float *z, int64_t n, int64_t *codes,
                    const int64_t *rows_out, float *xq, double *sumsq, float *last_residual,
-                   float *margin_out, cudaStream_t s, int64_t batch_rows) {
+                   float *margin_out, cudaStream_t s, int64_t batch_rows, const unsigned long long *n_dev, int64_t n_hint) {
     if (n == 0) return 0;
     ProfScope ps(PROF_QUANTIZE, s);
+    if (n_dev) {
+        // device-counted rows (rescue tier; codes only, rows of a large batch): n is the capacity, n_hint the expected count
+        RQB_CHECK(!xq && !sumsq && !last_residual && !margin_out && m->e <= 64, "device-counted quantizer: codes only, e_dim <= 64");
+        RQB_CHECK(!small_batch_lane16(batch_rows, m->e), "device-counted rows must belong to a batch of 16 or more rows");
+        if (n_hint <= (int64_t)kNumSMs * QT / 2) { RQB_DISPATCH_E(m->e, return (launch_quant_sliced<E>(m, z, n, codes, rows_out, s, n_dev))); }
+        else { RQB_DISPATCH_E(m->e, return (launch_quant_tiled<E>(m, z, n, codes, rows_out, s, n_dev))); }
+        return 0;
+    }
     // a batch of 2..15 rows with 24·n <= e: matmul(latent, E.t()) runs in the reference's small-batch order (small_batch.cu)
     if (small_batch_lane16(batch_rows < 0 ? n : batch_rows, m->e) && !last_residual && !margin_out)
         return quantize_small(m, z, rows_out, nullptr, (int)n, n, m->L, codes, nullptr, xq, sumsq, nullptr, 0, s);

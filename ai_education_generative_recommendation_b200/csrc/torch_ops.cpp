@@ -44,11 +44,10 @@ at::Tensor encode_indices(int64_t handle, const at::Tensor &x, int64_t mode) {
     check_input(x, at::kFloat, 2, "x");
     const c10::cuda::CUDAGuard guard(x.device());
     const int64_t n = x.size(0);
-    int64_t stats[4] = {0, 0, 0, 0};
     const int L = rqb200_model_levels(as_model(handle));
     TORCH_CHECK(L > 0, "rqvae_b200::encode_indices: ", rqb200_last_error());
     at::Tensor idx = at::empty({n, L}, x.options().dtype(at::kLong));
-    ok(rqb200_get_indices(as_model(handle), (int)mode, x.data_ptr<float>(), n, idx.data_ptr<int64_t>(), nullptr, stats, cur_stream(x)),
+    ok(rqb200_get_indices(as_model(handle), (int)mode, x.data_ptr<float>(), n, idx.data_ptr<int64_t>(), nullptr, nullptr, cur_stream(x)),
        "encode_indices");
     return idx;
 }

@@ -114,13 +114,12 @@ def encode_codes_fast(model: RQVAE, data, chunk_rows: int = 262144) -> torch.Ten
     codes = torch.empty((n, Lv), dtype=torch.int64, device=dev)
     model._sync()
     L = _cabi.lib()
-    stats = (ctypes.c_int64 * 4)()
     for r0, r1 in _chunks(n, chunk_rows):
         chunk = data[r0:r1]
         if not chunk.is_cuda:
             chunk = chunk.contiguous().to(dev, non_blocking=True)
         chunk = chunk.contiguous()
-        check(L.rqb200_get_indices(model._handle, _cabi.ENCODE_FAST, ptr(chunk), r1 - r0, ptr(codes[r0:r1]), 0, stats,
+        check(L.rqb200_get_indices(model._handle, _cabi.ENCODE_FAST, ptr(chunk), r1 - r0, ptr(codes[r0:r1]), 0, None,
                                    stream_ptr(dev)))
     return codes
 

@@ -253,7 +253,7 @@ class RQVAE(nn.Module):
         self._synced = {}
         self.encode_mode = _cabi.ENCODE_EXACT     # or _cabi.ENCODE_FAST (tensor-core path, same codes)
         self.kblocks = {}                          # optional {("enc"|"dec", layer): [k-block sizes]}
-        self.last_stats = {}
+        self._stats_fast = False
 
     # ---- C handle management -------------------------------------------------------------
     def __del__(self):
@@ -494,6 +494,16 @@ class RQVAE(nn.Module):
         out = MLPFunction.apply(x_q, p, seed * 2 + 1, seed_dev, *self._mlp_params(self.decoder))
         return out.view(*x.shape[:-1], self.in_dim), rq_loss, indices.view(*x.shape[:-1], len(layers))
 
+    @property
+    def last_stats(self) -> dict:
+        """Rows the last fast-route `get_indices` re-ran on its three-pass and exact tiers (rqb200_model_last_tier_rows: the
+        counts stay on the device until somebody asks, so get_indices itself never waits for the GPU)."""
+        if not getattr(self, "_stats_fast", False) or not self._handle.value:
+            return {"rescued_rows": 0, "three_pass_rows": 0}
+        tiers = (ctypes.c_int64 * 2)()
+        check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
+        return {"rescued_rows": int(tiers[1]), "three_pass_rows": int(tiers[0])}
+
     @torch.no_grad()
     def get_indices(self, xs, use_sk=False):
         """rqvae.py:67-71.  With use_sk=False (the catalogue pass) this is one fused C-ABI call."""
@@ -506,21 +516,14 @@ class RQVAE(nn.Module):
         self._sync()
         x2 = xs.reshape(-1, self.in_dim).contiguous()
         n, Lv = x2.shape[0], len(self.num_emb_list)
-        tiers = (ctypes.c_int64 * 2)()
         if torch_ops.available():
             # the registered op (csrc/torch_ops.cpp): same C-ABI call, output from the caching allocator, current stream
             codes = torch.ops.rqvae_b200.encode_indices(torch_ops.handle(self), x2, int(self.encode_mode))
-            check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
-            rescued = int(tiers[1])
         else:
             codes = torch.empty((n, Lv), dtype=torch.int64, device=xs.device)
-            stats = (ctypes.c_int64 * 4)()
-            check(_cabi.lib().rqb200_get_indices(self._handle, int(self.encode_mode), ptr(x2), n, ptr(codes), 0, stats,
+            check(_cabi.lib().rqb200_get_indices(self._handle, int(self.encode_mode), ptr(x2), n, ptr(codes), 0, None,
                                                  stream_ptr(xs.device)))
-            check(_cabi.lib().rqb200_model_last_tier_rows(self._handle, tiers))
-            rescued = int(stats[0])
-        fast = self.encode_mode == _cabi.ENCODE_FAST
-        self.last_stats = {"rescued_rows": rescued if fast else 0, "three_pass_rows": int(tiers[0]) if fast else 0}
+        self._stats_fast = self.encode_mode == _cabi.ENCODE_FAST          # nothing waited: the tier counts are read on demand
         return codes.view(*xs.shape[:-1], Lv)
 
     def compute_loss(self, out, quant_loss, xs=None):

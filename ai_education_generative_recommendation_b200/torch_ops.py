@@ -26,12 +26,21 @@ def load() -> None:
     _loaded = True
 
 
+_unavailable = False
+
+
 def available() -> bool:
+    """True once the op library is registered; a failed load is remembered (the ctypes binding of the same C ABI is then
+    what the module mirror calls)."""
+    global _unavailable
     if _loaded:
         return True
+    if _unavailable:
+        return False
     try:
         load()
     except Exception:
+        _unavailable = True
         return False
     return True
 

@@ -139,10 +139,10 @@ int rqb200_quantize(rqb200_model *m, const float *z_dev, int64_t n, int64_t *cod
  *       RQB200_ENCODE_FAST  — tcgen05 split-fp16 tensor-core encoder + quantizer with a margin gate, rows
  *                             inside the gate re-run by the exact kernels (same codes).
  * z_out (may be NULL) receives the latent.  stats (host, may be NULL): [0]=rows rescued.
- * Synchronisation: EXACT enqueues and returns.  FAST waits ONCE on the stream, after its tensor-core tiers are
- * enqueued, for the number of rows the margin gate handed to the exact tier (that count sizes the exact kernels'
- * grids and workspaces); callers that pipeline host copies against this call enqueue the next copy first
- * (rqb200_generate_codes_host does).                                                                       */
+ * Synchronisation: both modes enqueue and return.  The number of rows the margin gate hands to the exact tier stays
+ * on the device (the exact kernels run persistent grids over "row tiles below the count"), so the fast route can be
+ * captured in a CUDA graph; only a non-NULL stats pointer makes the call wait for the stream, and
+ * rqb200_model_last_tier_rows fetches the counts of the last call on demand.                                */
 #define RQB200_ENCODE_EXACT 0
 #define RQB200_ENCODE_FAST  1
 int rqb200_get_indices(rqb200_model *m, int mode, const float *x_dev, int64_t n,

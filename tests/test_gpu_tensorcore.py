@@ -1,4 +1,6 @@
 """GPU: the tcgen05 encoder and the margin-gated fast route give the same codes as the exact route."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -101,3 +103,45 @@ def test_one_cta_and_two_cta_kernels_agree():
             assert r.returncode == 0, r.stderr[-2000:]
             outs.append(torch.load(path))
     assert torch.equal(outs[0], outs[1])          # same K order, same MMA sequence ⇒ identical bits
+
+
+@pytest.mark.parametrize("name", ["c2_slice", "c3_slice"])
+def test_fast_route_enqueues_without_waiting_and_replays_from_a_cuda_graph(name):
+    """rqb200_get_indices(FAST, stats = NULL) keeps the row counts of its re-run tiers on the device (the exact tier runs
+    persistent grids over device-counted rows), so the whole call can be captured once and replayed: same codes as the
+    exact route, also on new data written into the captured input buffer."""
+    g, cfg, cbs = load_golden(name)
+    m = build_model(cfg, cbs)
+    n = 200_000 + 13
+    lib = _cabi.lib()
+    x = gpu_synth(2024, 0, n, cfg["in_dim"], int(g["n_total"]))
+    m.encode_mode = _cabi.ENCODE_EXACT
+    want = m.get_indices(x)
+    m._sync()
+    codes = torch.empty((n, len(cbs)), dtype=torch.int64, device=DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):                             # warm-up: workspaces, function attributes, weight images
+            _cabi.check(lib.rqb200_get_indices(m._handle, _cabi.ENCODE_FAST, x.data_ptr(), n, codes.data_ptr(), 0, None,
+                                               _cabi.stream_ptr()))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert torch.equal(codes, want)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        _cabi.check(lib.rqb200_get_indices(m._handle, _cabi.ENCODE_FAST, x.data_ptr(), n, codes.data_ptr(), 0, None,
+                                           _cabi.stream_ptr()))
+    codes.fill_(-1)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(codes, want)
+    x.copy_(gpu_synth(7, 5, n, cfg["in_dim"], int(g["n_total"])))          # other rows, another number of gated rows
+    m.encode_mode = _cabi.ENCODE_EXACT
+    want2 = m.get_indices(x)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(codes, want2)
+    tiers = (ctypes.c_int64 * 2)()
+    _cabi.check(lib.rqb200_model_last_tier_rows(m._handle, tiers))
+    assert 0 <= tiers[1] <= n and 0 <= tiers[0] <= n
