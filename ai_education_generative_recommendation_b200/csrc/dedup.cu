@@ -31,6 +31,7 @@ constexpr int RADIX = 256;
 
 struct PackArgs {
     int shift[RQB200_MAX_LEVELS];
+    int bits[RQB200_MAX_LEVELS];     // width of the field of level l (the key is unpacked again by seg_rank_kernel)
     int L;
 };
 
@@ -74,21 +75,43 @@ __global__ void column_minmax_kernel(const int64_t *__restrict__ codes, int64_t 
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t k, int shift) { return (uint32_t)(k >> shift) & (RADIX - 1); }
 
-// per-CTA digit histogram of the current key order → hist[d * nblocks + block]
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist,
-                  int nblocks) {
-    __shared__ uint32_t s_hist[RADIX];
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+// One read of the input for ALL digit passes: pack the codes (PACK) or take the keys as they are, and add every
+// 8-bit digit of every key to the global histograms ghist[pass][digit] (shared-memory partials first).  The
+// histogram of a digit does not depend on the order of the keys, so the passes below never count again.
+constexpr int MAX_PASSES = 8;
+
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+pack_hist_kernel(const int64_t *__restrict__ codes, int64_t n, PackArgs pa, uint64_t *__restrict__ keys, int npasses,
+                 uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t s_h[MAX_PASSES][RADIX];
+    __shared__ int64_t s_codes[PACK ? 256 * RQB200_MAX_LEVELS : 1];      // 256 rows, read with coalesced loads
+    for (int p = 0; p < npasses; ++p) s_h[p][threadIdx.x] = 0;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
+        const int cnt = n - base < 256 ? (int)(n - base) : 256;
+        uint64_t k = 0;
+        if (PACK) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < cnt * pa.L; e += 256) s_codes[e] = codes[base * pa.L + e];
+            __syncthreads();
+            if ((int)threadIdx.x < cnt) {
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        int64_t idx = base + i * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&s_hist[digit_of(keys[idx], shift)], 1u);
+                for (int l = 0; l < RQB200_MAX_LEVELS; ++l)
+                    if (l < pa.L) k |= (uint64_t)s_codes[threadIdx.x * pa.L + l] << pa.shift[l];
+                keys[base + threadIdx.x] = k;
+            }
+        } else {
+            if (base == (int64_t)blockIdx.x * 256) __syncthreads();     // histograms cleared
+            if ((int)threadIdx.x < cnt) k = keys[base + threadIdx.x];
+        }
+        if ((int)threadIdx.x < cnt)
+            for (int p = 0; p < npasses; ++p) atomicAdd(&s_h[p][(uint32_t)(k >> (8 * p)) & (RADIX - 1)], 1u);
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
+    for (int p = 0; p < npasses; ++p) {
+        const uint32_t c = s_h[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * RADIX + threadIdx.x], c);
+    }
 }
 
 // per-digit exclusive scan over blocks (one CTA per digit) + digit totals; then a 256-wide scan of the totals
@@ -129,79 +152,211 @@ __global__ void __launch_bounds__(256) radix_scan_rows_kernel(uint32_t *__restri
     if (threadIdx.x == 0) digit_total[blockIdx.x] = s_carry;
 }
 
-__global__ void __launch_bounds__(256) radix_scan_digits_kernel(const uint32_t *__restrict__ digit_total,
-                                                                uint32_t *__restrict__ digit_base) {
-    __shared__ uint32_t s_warp[8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t v = digit_total[threadIdx.x];
-    uint32_t inc = v;
+// ---- one digit pass in ONE launch (decoupled look-back)
+//
+// A tile = OS_TILE consecutive keys of the current order; tiles are handed out by an atomic ticket, so a CTA
+// only ever waits for tiles whose CTAs already run (no dead-lock whatever the scheduling order).  Per digit d,
+// thread d publishes the tile's count ("aggregate"), walks back over the earlier tiles adding aggregates until it
+// meets a tile whose inclusive prefix is known, then publishes its own prefix.  One 64-bit word per (tile, digit):
+// tag << 32 | count, tag = 2·pass + 1 (aggregate) / 2·pass + 2 (prefix) — words left by an earlier pass carry a
+// smaller tag and read as "not there yet", so the table is cleared once per sort, not per pass.
+// Stability: warp w owns keys [w·OS_WARP_CHUNK, +OS_WARP_CHUNK) of the tile in rounds of 32 lanes, so the order
+// (tile, warp, round, lane) is the memory order; equal digits keep it.
+constexpr int OS_THREADS = 256;
+#ifndef RQB_OS_ITEMS
+#define RQB_OS_ITEMS 16
+#endif
+constexpr int OS_ITEMS = RQB_OS_ITEMS;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;          // 4096 keys per CTA
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_WARP_CHUNK = 32 * OS_ITEMS;
+constexpr int OS_LOOKBACK = 4;                          // earlier tiles polled per round trip
+constexpr unsigned long long OS_SPIN_TIMEOUT_NS = 4ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// lanes of this warp holding the same digit as the caller (d in [0, RADIX]; RADIX = "no element")
+// (measured the same with nine ballots, one per digit bit, in place of match.any, and with 8 keys per thread: a pass is
+// a chain of short phases — load 3 us, count 2-4, offsets 1.5, stage 2-5, look back 2-3, store 2 — not one bottleneck;
+// tools/time_dedup.py with a -DRQB_OS_TRACE build prints the phases per tile)
+__device__ __forceinline__ uint32_t os_peers(uint32_t d) { return __match_any_sync(0xffffffffu, d); }
+__device__ __forceinline__ unsigned long long os_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+#ifdef RQB_OS_TRACE
+__device__ unsigned long long g_os_trace[3][1024][8];
+#define OS_TRACE(slot) do { if (threadIdx.x == 0 && tile < 1024 && pass < 3) g_os_trace[pass][tile][slot] = os_globaltimer_ns(); } while (0)
+#else
+#define OS_TRACE(slot) do { } while (0)
+#endif
+
+// FIRST: the values are the positions themselves (no value buffer is read).
+// Order of work inside a tile: count → publish the aggregate → rank the tile locally and stage it SORTED in shared
+// memory → look back (by now the earlier tiles have published) → copy out: consecutive threads store consecutive
+// addresses of a digit's run, so a warp store touches two or three lines instead of 32.
+constexpr int OS_SMEM = OS_TILE * 12 + OS_WARPS * RADIX * 4 + RADIX * 4;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(OS_THREADS)
+onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int pass,
+                     const uint32_t *__restrict__ ghist, uint32_t *__restrict__ ticket,
+                     unsigned long long *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char os_smem[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(os_smem);
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(os_smem + OS_TILE * 8);
+    uint32_t(*s_cnt)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(os_smem + OS_TILE * 12);
+    uint32_t *s_goff = reinterpret_cast<uint32_t *>(os_smem + OS_TILE * 12 + OS_WARPS * RADIX * 4);
+    __shared__ uint32_t s_warp[OS_WARPS], s_warp2[OS_WARPS];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int shift = 8 * pass;
+    if (tid == 0) s_tile = atomicAdd(ticket + pass, 1u);
+    for (int i = tid; i < OS_WARPS * RADIX; i += OS_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    OS_TRACE(0);
+    const int64_t tbase = (int64_t)tile * OS_TILE;
+    const int64_t wbase = tbase + wid * OS_WARP_CHUNK;
+    uint64_t k[OS_ITEMS];
+    uint32_t v[OS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const int64_t idx = wbase + i * 32 + lane;
+        const bool ok = idx < n;
+        k[i] = ok ? keys_in[idx] : 0;
+        v[i] = FIRST ? (uint32_t)idx : (ok ? vals_in[idx] : 0u);
+    }
+    // phase A: per-warp digit counts
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const bool ok = wbase + i * 32 + lane < n;
+        const uint32_t d = ok ? digit_of(k[i], shift) : RADIX;     // RADIX = "no element"
+        const uint32_t peers = os_peers(d);
+        if (ok && lane == (__ffs(peers) - 1)) s_cnt[wid][d] += __popc(peers);
+        __syncwarp();
+    }
+    // start of digit `tid` in the output = exclusive scan of the global histogram
+    const uint32_t g = ghist[pass * RADIX + tid];
+    uint32_t inc = g;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < wid; ++w) woff += s_warp[w];
-    digit_base[threadIdx.x] = woff + inc - v;
-}
-
-// stable scatter: warp w owns keys [base + w*WARP_CHUNK, +WARP_CHUNK) in rounds of 32 lanes, so the
-// order (warp, round, lane) equals the memory order.
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                     uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n,
-                     int shift, const uint32_t *__restrict__ hist, const uint32_t *__restrict__ digit_base,
-                     int nblocks) {
-    __shared__ uint32_t s_cnt[SORT_WARPS][RADIX];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
-    __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + wid * WARP_CHUNK;
-    uint64_t k[SORT_ITEMS];
-    uint32_t v[SORT_ITEMS];
-    bool ok[SORT_ITEMS];
-    // phase A: per-warp digit counts
+    OS_TRACE(1);
+    uint32_t base = inc - g;
+    for (int w = 0; w < wid; ++w) base += s_warp[w];
+    // phase B (thread d): tile count of digit d, published at once
+    uint32_t total = 0;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        int64_t idx = wbase + i * 32 + lane;
-        ok[i] = idx < n;
-        k[i] = ok[i] ? keys_in[idx] : 0;
-        v[i] = ok[i] ? vals_in[idx] : 0;
-        uint32_t d = ok[i] ? digit_of(k[i], shift) : RADIX;      // RADIX = "no element"
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (ok[i] && lane == (__ffs(peers) - 1)) s_cnt[wid][d] += __popc(peers);
-        __syncwarp();
+    for (int w = 0; w < OS_WARPS; ++w) total += s_cnt[w][tid];
+    const unsigned long long tag_agg = (unsigned long long)(2 * pass + 1) << 32;
+    const unsigned long long tag_pre = (unsigned long long)(2 * pass + 2) << 32;
+    unsigned long long *mine = status + (size_t)tile * RADIX + tid;
+    st_relaxed_gpu(mine, (tile == 0 ? tag_pre : tag_agg) | total);
+    // start of digit d inside the sorted tile, then per warp
+    uint32_t linc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, linc, o);
+        if (lane >= o) linc += t;
     }
+    if (lane == 31) s_warp2[wid] = linc;
     __syncthreads();
-    // phase B: thread d turns counts into start offsets per warp
+    uint32_t lstart = linc - total;
+    for (int w = 0; w < wid; ++w) lstart += s_warp2[w];
     {
-        uint32_t run = digit_base[tid] + hist[(int64_t)tid * nblocks + blockIdx.x];
+        uint32_t run = lstart;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            uint32_t c = s_cnt[w][tid];
+        for (int w = 0; w < OS_WARPS; ++w) {
+            const uint32_t c = s_cnt[w][tid];
             s_cnt[w][tid] = run;
             run += c;
         }
     }
     __syncthreads();
-    // phase C: ranked scatter
+    OS_TRACE(2);
+    // phase C: rank inside the tile, stage sorted
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t d = ok[i] ? digit_of(k[i], shift) : RADIX;
-        uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t below = __popc(peers & ((1u << lane) - 1u));
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const bool ok = wbase + i * 32 + lane < n;
+        const uint32_t d = ok ? digit_of(k[i], shift) : RADIX;
+        const uint32_t peers = os_peers(d);
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
         uint32_t pos = 0;
-        if (ok[i]) pos = s_cnt[wid][d] + below;
+        if (ok) pos = s_cnt[wid][d] + below;
         __syncwarp();
-        if (ok[i] && lane == (__ffs(peers) - 1)) s_cnt[wid][d] += __popc(peers);
+        if (ok && lane == (__ffs(peers) - 1)) s_cnt[wid][d] += __popc(peers);
         __syncwarp();
-        if (ok[i]) {
-            keys_out[pos] = k[i];
-            vals_out[pos] = v[i];
+        if (ok) {
+            s_keys[pos] = k[i];
+            s_vals[pos] = v[i];
         }
     }
+    // phase D (thread d): look back over the earlier tiles
+    OS_TRACE(3);
+    {
+        uint32_t excl = 0;
+        if (tile != 0) {
+            long long t = (long long)tile - 1;
+            unsigned long long t0 = 0;
+            bool timing = false;
+            while (true) {
+                unsigned long long w[OS_LOOKBACK];
+#pragma unroll
+                for (int j = 0; j < OS_LOOKBACK; ++j)
+                    w[j] = (t - j >= 0) ? ld_relaxed_gpu(status + (size_t)(t - j) * RADIX + tid) : tag_pre;
+                int adv = 0;
+                bool fin = false;
+#pragma unroll
+                for (int j = 0; j < OS_LOOKBACK; ++j) {
+                    if (fin || adv != j) continue;                 // stop at the first word that is not there yet
+                    const unsigned long long tag = w[j] & 0xffffffff00000000ull;
+                    if (tag == tag_pre) { excl += (uint32_t)w[j]; fin = true; ++adv; }
+                    else if (tag == tag_agg) { excl += (uint32_t)w[j]; ++adv; }
+                }
+                if (fin) break;
+                t -= adv;
+                if (adv == 0) {
+                    if (!timing) { t0 = os_globaltimer_ns(); timing = true; }
+                    else if (os_globaltimer_ns() - t0 > OS_SPIN_TIMEOUT_NS) __trap();   // never hang the GPU
+                    __nanosleep(20);
+                } else {
+                    timing = false;
+                }
+            }
+            st_relaxed_gpu(mine, tag_pre | (unsigned long long)(excl + total));
+        }
+        s_goff[tid] = base + excl - lstart;       // sorted tile position p of digit d goes to s_goff[d] + p (mod 2^32)
+    }
+    __syncthreads();
+    OS_TRACE(4);
+    // phase E: copy out
+    const int64_t left = n - tbase;
+    const uint32_t cnt_tile = left < OS_TILE ? (uint32_t)left : (uint32_t)OS_TILE;
+#pragma unroll
+    for (int i = 0; i < OS_ITEMS; ++i) {
+        const uint32_t p = i * OS_THREADS + tid;
+        if (p < cnt_tile) {
+            const uint64_t key = s_keys[p];
+            const uint32_t gpos = s_goff[digit_of(key, shift)] + p;
+            keys_out[gpos] = key;
+            vals_out[gpos] = s_vals[p];
+        }
+    }
+    OS_TRACE(5);
 }
 
 // ---------------------------------------------------------------- segmented rank over sorted keys
@@ -210,73 +365,22 @@ constexpr int SEG_THREADS = 256;
 constexpr int SEG_ITEMS = 8;
 constexpr int SEG_TILE = SEG_THREADS * SEG_ITEMS;
 
-// tile summary: index of the last run head inside the tile (or -1)
-__global__ void __launch_bounds__(SEG_THREADS)
-seg_tile_last_head_kernel(const uint64_t *__restrict__ ks, int64_t n, long long *__restrict__ tile_last) {
-    __shared__ long long s_best;
-    if (threadIdx.x == 0) s_best = -1;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SEG_TILE;
-    long long best = -1;
-#pragma unroll
-    for (int i = 0; i < SEG_ITEMS; ++i) {
-        int64_t idx = base + i * SEG_THREADS + threadIdx.x;
-        if (idx < n) {
-            bool head = idx == 0 || ks[idx] != ks[idx - 1];
-            if (head) best = idx;
-        }
+// start of the run that contains position b - 1 (b > 0, ks[b - 1] == ks[b]): the keys are sorted, so positions
+// with ks[j] == key form the interval [start, b]; gallop backwards until the key changes, then bisect.
+__device__ __forceinline__ long long run_start_before(const uint64_t *__restrict__ ks, int64_t b) {
+    const uint64_t key = ks[b];
+    long long hi = b - 1, lo = -1;                    // ks[hi] == key; ks[lo] != key (or lo == -1)
+    for (long long step = 1;; step <<= 1) {
+        const long long j = b - 1 - step;
+        if (j < 0) break;
+        if (ks[j] != key) { lo = j; break; }
+        hi = j;
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        long long t = __shfl_xor_sync(0xffffffffu, best, o);
-        best = t > best ? t : best;
+    while (hi - lo > 1) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (ks[mid] == key) hi = mid; else lo = mid;
     }
-    if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(&s_best, best);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_last[blockIdx.x] = s_best;
-}
-
-// running max over tiles: carry[b] = last head strictly before tile b (single CTA, sequential chunks)
-__global__ void __launch_bounds__(1024) seg_carry_kernel(const long long *__restrict__ tile_last,
-                                                         long long *__restrict__ carry, int ntiles) {
-    __shared__ long long s_warp[32];
-    __shared__ long long s_run;
-    if (threadIdx.x == 0) s_run = -1;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = 0; base < ntiles; base += 1024) {
-        int i = base + threadIdx.x;
-        long long v = i < ntiles ? tile_last[i] : -1;
-        long long inc = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc = t > inc ? t : inc;
-        }
-        if (lane == 31) s_warp[wid] = inc;
-        __syncthreads();
-        if (wid == 0) {
-            long long w = s_warp[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                long long t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w = t > w ? t : w;
-            }
-            s_warp[lane] = w;   // inclusive max over warps 0..lane
-        }
-        __syncthreads();
-        long long prev_warps = wid > 0 ? s_warp[wid - 1] : -1;
-        long long run = s_run;
-        long long incl = inc;
-        incl = prev_warps > incl ? prev_warps : incl;
-        incl = run > incl ? run : incl;
-        // exclusive value = max of everything before i
-        long long up = __shfl_up_sync(0xffffffffu, inc, 1);
-        long long excl = lane > 0 ? up : -1;
-        excl = prev_warps > excl ? prev_warps : excl;
-        excl = run > excl ? run : excl;
-        if (i < ntiles) carry[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_run = incl;
-        __syncthreads();
-    }
+    return hi;
 }
 
 // rank[i] = i - (start of the run containing i), in sorted order.  Optionally also:
@@ -284,14 +388,19 @@ __global__ void __launch_bounds__(1024) seg_carry_kernel(const long long *__rest
 //   statistics: number of runs, longest run
 __global__ void __launch_bounds__(SEG_THREADS)
 seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ perm, int64_t n,
-                const long long *__restrict__ carry, int64_t *__restrict__ rank_out,
-                const int64_t *__restrict__ codes, int L, int64_t *__restrict__ out,
+                int64_t *__restrict__ rank_out, PackArgs pa, int64_t *__restrict__ out,
                 unsigned long long *__restrict__ stats /* [0]=runs [1]=max run */,
                 uint32_t *__restrict__ rank_by_item /* rank_by_item[perm[i]] = rank, may be NULL */) {
     __shared__ long long s_warp[SEG_THREADS / 32];
     __shared__ unsigned long long s_runs, s_maxrun;
+    __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_runs = 0; s_maxrun = 0; }
+    if (tid == 0) {
+        s_runs = 0; s_maxrun = 0;
+        // the run that reaches into this tile from the left starts where the tile's first key starts
+        const int64_t b = (int64_t)blockIdx.x * SEG_TILE;
+        s_carry = (b > 0 && b < n && ks[b - 1] == ks[b]) ? run_start_before(ks, b) : -1;
+    }
     // blocked arrangement: thread t owns items [base + t*SEG_ITEMS, +SEG_ITEMS)
     const int64_t base = (int64_t)blockIdx.x * SEG_TILE + (int64_t)tid * SEG_ITEMS;
     long long start[SEG_ITEMS];
@@ -313,7 +422,7 @@ seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ pe
     }
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    long long before = carry[blockIdx.x];
+    long long before = s_carry;
     for (int w = 0; w < wid; ++w) before = s_warp[w] > before ? s_warp[w] : before;
     long long up = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane > 0) before = up > before ? up : before;
@@ -327,9 +436,22 @@ seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ pe
         if (rank_out) rank_out[idx] = rk;
         if (rank_by_item) rank_by_item[perm[idx]] = (uint32_t)rk;
         if (out) {
-            int64_t item = perm[idx];
-            for (int l = 0; l < L; ++l) out[item * (L + 1) + l] = codes[item * L + l];
-            out[item * (L + 1) + L] = rk;
+            // the row is rebuilt from the key (the packing is lossless): no second, scattered read of the codes
+            const int64_t item = perm[idx];
+            const uint64_t key = ks[idx];
+            int64_t *row = out + item * (pa.L + 1);
+            if (pa.L == 3 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+                const longlong2 r01 = make_longlong2((long long)((key >> pa.shift[0]) & ((1ull << pa.bits[0]) - 1ull)),
+                                                     (long long)((key >> pa.shift[1]) & ((1ull << pa.bits[1]) - 1ull)));
+                const longlong2 r23 = make_longlong2((long long)((key >> pa.shift[2]) & ((1ull << pa.bits[2]) - 1ull)), rk);
+                *reinterpret_cast<longlong2 *>(row) = r01;          // rows of 32 bytes: 16-byte aligned
+                *reinterpret_cast<longlong2 *>(row + 2) = r23;
+            } else {
+#pragma unroll
+                for (int l = 0; l < RQB200_MAX_LEVELS; ++l)
+                    if (l < pa.L) row[l] = (int64_t)((key >> pa.shift[l]) & ((1ull << pa.bits[l]) - 1ull));
+                row[pa.L] = rk;
+            }
         }
         maxrun = (unsigned long long)(rk + 1) > maxrun ? (unsigned long long)(rk + 1) : maxrun;
     }
@@ -497,10 +619,6 @@ __global__ void write_total_offset_kernel(const uint64_t *__restrict__ total, in
     offsets[(uint32_t)(t >> 32)] = (int64_t)(t & 0xffffffffull);
 }
 
-__global__ void iota_u32_kernel(uint32_t *__restrict__ out, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)i;
-}
 __global__ void gather_i64_kernel(const int64_t *__restrict__ in, const uint32_t *__restrict__ perm, int64_t n,
                                   int64_t *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,17 +630,22 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct SortScratch {
     uint64_t *keys[2];
     uint32_t *vals[2];
-    uint32_t *hist;
-    long long *tile_last;   // also reused as u64 tile sums
-    long long *carry;
+    uint32_t *hist;         // owner histograms of the sharded partition (rows of nblocks)
+    long long *tile_last;   // u64 tile sums of the group compaction
     uint64_t *flags;
     unsigned long long *stats;   // [0]=runs [1]=max run [2..] column min/max
+    // one-sweep control block, cleared once per sort: digit histograms of all passes, tile tickets, look-back table
+    uint32_t *ghist;             // [MAX_PASSES][RADIX]
+    uint32_t *ticket;            // [MAX_PASSES]
+    unsigned long long *status;  // [tiles][RADIX]
+    size_t control_bytes;        // ghist .. end of status (for this n)
     int nblocks;
 };
 
 int carve(rqb200_model *m, int64_t n, SortScratch &sc) {
     const int nblocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
-    const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
+    const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    const size_t os_tiles = (size_t)((n + OS_TILE - 1) / OS_TILE);
     size_t need = 0;
     size_t o_k0 = need; need += align256(sizeof(uint64_t) * n);
     size_t o_k1 = need; need += align256(sizeof(uint64_t) * n);
@@ -530,37 +653,56 @@ int carve(rqb200_model *m, int64_t n, SortScratch &sc) {
     size_t o_v1 = need; need += align256(sizeof(uint32_t) * n);
     size_t o_h = need; need += align256(sizeof(uint32_t) * ((size_t)RADIX * nblocks + 2 * RADIX));
     size_t o_tl = need; need += align256(sizeof(long long) * (ntiles + 2));
-    size_t o_c = need; need += align256(sizeof(long long) * (ntiles + 2));
     size_t o_f = need; need += align256(sizeof(uint64_t) * n);
     size_t o_s = need; need += 256;
+    size_t o_g = need; need += align256(sizeof(uint32_t) * MAX_PASSES * RADIX);
+    size_t o_t = need; need += 256;
+    size_t o_st = need; need += align256(sizeof(unsigned long long) * os_tiles * RADIX);
     RQB_TRY(ws_reserve(m->sortws, need));
     char *p = (char *)m->sortws.ptr;
     sc.keys[0] = (uint64_t *)(p + o_k0); sc.keys[1] = (uint64_t *)(p + o_k1);
     sc.vals[0] = (uint32_t *)(p + o_v0); sc.vals[1] = (uint32_t *)(p + o_v1);
     sc.hist = (uint32_t *)(p + o_h);
     sc.tile_last = (long long *)(p + o_tl);
-    sc.carry = (long long *)(p + o_c);
     sc.flags = (uint64_t *)(p + o_f);
     sc.stats = (unsigned long long *)(p + o_s);
+    sc.ghist = (uint32_t *)(p + o_g);
+    sc.ticket = (uint32_t *)(p + o_t);
+    sc.status = (unsigned long long *)(p + o_st);
+    sc.control_bytes = need - o_g;
     sc.nblocks = nblocks;
     return 0;
 }
 
-// sorts sc.keys[0]/vals[0]; returns the buffer index holding the result
-int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *result_buf) {
+// Stable LSD radix sort of sc.keys[0] (values = positions) with 8-bit digits: one launch that counts every digit
+// of every key (`codes` given: it also packs the keys), then ONE launch per digit.  Returns the buffer index
+// holding the result.  `n` may be smaller than what carve() was sized for.
+int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *result_buf,
+               const int64_t *codes = nullptr, const PackArgs *pa = nullptr) {
+    const int npasses = (key_bits + 7) / 8;
+    RQB_CHECK(npasses >= 1 && npasses <= MAX_PASSES, "key_bits=%d out of range", key_bits);
+    const int os_tiles = (int)((n + OS_TILE - 1) / OS_TILE);
+    const size_t control = (size_t)((char *)sc.status - (char *)sc.ghist) + sizeof(unsigned long long) * (size_t)os_tiles * RADIX;
+    RQB_CUDA(cudaMemsetAsync(sc.ghist, 0, control < sc.control_bytes ? control : sc.control_bytes, s));
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    rqb::count_launch();
+    if (codes) pack_hist_kernel<true><<<blocks, 256, 0, s>>>(codes, n, *pa, sc.keys[0], npasses, sc.ghist);
+    else pack_hist_kernel<false><<<blocks, 256, 0, s>>>(nullptr, n, PackArgs(), sc.keys[0], npasses, sc.ghist);
+    static rqb::DeviceOnce attr_once;
+    if (attr_once.first()) {
+        RQB_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM));
+        RQB_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM));
+    }
     int cur = 0;
-    for (int shift = 0; shift < key_bits; shift += 8) {
+    for (int pass = 0; pass < npasses; ++pass) {
         rqb::count_launch();
-        radix_hist_kernel<<<sc.nblocks, SORT_THREADS, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sc.nblocks);
-        uint32_t *digit_total = sc.hist + (size_t)RADIX * sc.nblocks;
-        uint32_t *digit_base = digit_total + RADIX;
-        rqb::count_launch();
-        radix_scan_rows_kernel<<<RADIX, 256, 0, s>>>(sc.hist, sc.nblocks, digit_total);
-        rqb::count_launch();
-        radix_scan_digits_kernel<<<1, 256, 0, s>>>(digit_total, digit_base);
-        rqb::count_launch();
-        radix_scatter_kernel<<<sc.nblocks, SORT_THREADS, 0, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1],
-                                                               sc.vals[cur ^ 1], n, shift, sc.hist, digit_base, sc.nblocks);
+        if (pass == 0)
+            onesweep_pass_kernel<true><<<os_tiles, OS_THREADS, OS_SMEM, s>>>(sc.keys[cur], nullptr, sc.keys[cur ^ 1], sc.vals[cur ^ 1], n,
+                                                                       pass, sc.ghist, sc.ticket, sc.status);
+        else
+            onesweep_pass_kernel<false><<<os_tiles, OS_THREADS, OS_SMEM, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1],
+                                                                        sc.vals[cur ^ 1], n, pass, sc.ghist, sc.ticket, sc.status);
         cur ^= 1;
     }
     RQB_LAUNCH_CHECK();
@@ -603,7 +745,8 @@ int plan_pack(SortScratch &sc, const int64_t *codes, int64_t n, int L, const int
     // level 0 is the most significant field so that key order == lexicographic row order
     for (int l = L - 1; l >= 0; --l) {
         pa.shift[l] = total;
-        total += bits_for(mx[l]);
+        pa.bits[l] = bits_for(mx[l]);
+        total += pa.bits[l];
     }
     RQB_CHECK(total <= 64, "codes need %d key bits (> 64)", total);
     pa.L = L;
@@ -612,29 +755,24 @@ int plan_pack(SortScratch &sc, const int64_t *codes, int64_t n, int L, const int
 }
 
 int sort_codes(rqb200_model *m, const int64_t *codes, int64_t n, int L, const int *K_host,
-               SortScratch &sc, int *buf, cudaStream_t s) {
+               SortScratch &sc, int *buf, cudaStream_t s, PackArgs *pa_out = nullptr) {
     RQB_CHECK(n < ((int64_t)1 << 32), "n too large for 32-bit item indices");
     RQB_TRY(carve(m, n, sc));
     PackArgs pa;
     int key_bits = 0;
     RQB_TRY(plan_pack(sc, codes, n, L, K_host, pa, &key_bits, s));
-    rqb::count_launch();
-    pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(codes, n, pa, sc.keys[0], sc.vals[0]);
-    RQB_LAUNCH_CHECK();
-    return radix_sort(sc, n, key_bits, s, buf);
+    if (pa_out) *pa_out = pa;
+    return radix_sort(sc, n, key_bits, s, buf, codes, &pa);
 }
 
-int run_seg_rank(SortScratch &sc, int buf, int64_t n, int64_t *rank_out, const int64_t *codes, int L,
+// pa = nullptr: no output rows
+int run_seg_rank(SortScratch &sc, int buf, int64_t n, int64_t *rank_out, const PackArgs *pa,
                  int64_t *out, bool want_stats, cudaStream_t s, uint32_t *rank_by_item = nullptr) {
     const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
     if (want_stats) RQB_CUDA(cudaMemsetAsync(sc.stats, 0, 2 * sizeof(unsigned long long), s));
     rqb::count_launch();
-    seg_tile_last_head_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sc.keys[buf], n, sc.tile_last);
-    rqb::count_launch();
-    seg_carry_kernel<<<1, 1024, 0, s>>>(sc.tile_last, sc.carry, ntiles);
-    rqb::count_launch();
-    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sc.keys[buf], sc.vals[buf], n, sc.carry, rank_out, codes, L,
-                                                   out, want_stats ? sc.stats : nullptr, rank_by_item);
+    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sc.keys[buf], sc.vals[buf], n, rank_out, pa ? *pa : PackArgs(),
+                                                   pa ? out : nullptr, want_stats ? sc.stats : nullptr, rank_by_item);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -868,6 +1006,12 @@ __global__ void shard_finalize_kernel(const int64_t *__restrict__ codes, int64_t
 
 using namespace rqb;
 
+#ifdef RQB_OS_TRACE
+extern "C" __attribute__((visibility("default"))) int rqb200_debug_os_trace(unsigned long long *host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, rqb::g_os_trace, sizeof(rqb::g_os_trace));
+}
+#endif
+
 extern "C" int rqb200_suffix_dedup(rqb200_model *m, const int64_t *codes_dev, int64_t n, int L,
                                    const int *K_host, int64_t *out_dev, int64_t *n_distinct_host,
                                    int64_t *max_group_host, void *stream) {
@@ -883,8 +1027,9 @@ extern "C" int rqb200_suffix_dedup(rqb200_model *m, const int64_t *codes_dev, in
     int buf = 0;
     ProfScope ps(PROF_DEDUP, s);
     const bool stats = n_distinct_host || max_group_host;
-    RQB_TRY(sort_codes(m, codes_dev, n, L, K_host, sc, &buf, s));
-    RQB_TRY(run_seg_rank(sc, buf, n, nullptr, codes_dev, L, out_dev, stats, s));
+    PackArgs pa;
+    RQB_TRY(sort_codes(m, codes_dev, n, L, K_host, sc, &buf, s, &pa));
+    RQB_TRY(run_seg_rank(sc, buf, n, nullptr, &pa, out_dev, stats, s));
     if (stats) {
         unsigned long long h[2];
         RQB_CUDA(cudaMemcpyAsync(h, sc.stats, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -909,7 +1054,7 @@ static int collision_groups_impl(rqb200_model *m, const int64_t *codes_dev, int6
     SortScratch sc;
     int buf = 0;
     RQB_TRY(sort_codes(m, codes_dev, n, L, K_host, sc, &buf, s));
-    if (max_group_host) RQB_TRY(run_seg_rank(sc, buf, n, nullptr, nullptr, L, nullptr, true, s));
+    if (max_group_host) RQB_TRY(run_seg_rank(sc, buf, n, nullptr, nullptr, nullptr, true, s));
     const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
     uint64_t *tile_sums = (uint64_t *)sc.tile_last;
     rqb::count_launch();
@@ -972,7 +1117,8 @@ extern "C" int rqb200_pack_keys(const int64_t *codes_dev, int64_t n, int L, cons
     int total = 0;
     for (int l = L - 1; l >= 0; --l) {
         pa.shift[l] = total;
-        total += bits_for(K_host[l] > 1 ? K_host[l] - 1 : 1);
+        pa.bits[l] = bits_for(K_host[l] > 1 ? K_host[l] - 1 : 1);
+        total += pa.bits[l];
     }
     RQB_CHECK(total <= 64, "codes need %d key bits (> 64)", total);
     pa.L = L;
@@ -993,10 +1139,7 @@ extern "C" int rqb200_sort_pairs(rqb200_model *m, uint64_t *keys_dev, int64_t *v
     SortScratch sc;
     RQB_TRY(carve(m, n, sc));
     RQB_CUDA(cudaMemcpyAsync(sc.keys[0], keys_dev, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s));
-    // values travel as 32-bit positions; the caller's int64 payload is permuted at the end
-    rqb::count_launch();
-    iota_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc.vals[0], n);
-    RQB_LAUNCH_CHECK();
+    // values travel as 32-bit positions (the first digit pass makes them); the caller's int64 payload is permuted at the end
     int buf = 0;
     RQB_TRY(radix_sort(sc, n, key_bits, s, &buf));
     RQB_CUDA(cudaMemcpyAsync(keys_dev, sc.keys[buf], sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s));
@@ -1016,16 +1159,8 @@ extern "C" int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_
     if (n == 0) return 0;
     RQB_CUDA(cudaSetDevice(m->device));
     const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
-    RQB_TRY(ws_reserve(m->misc, sizeof(long long) * 2 * (size_t)(ntiles + 2) + 512));
-    long long *tile_last = (long long *)m->misc.ptr;
-    long long *carry = tile_last + ntiles + 2;
     rqb::count_launch();
-    seg_tile_last_head_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, n, tile_last);
-    rqb::count_launch();
-    seg_carry_kernel<<<1, 1024, 0, s>>>(tile_last, carry, ntiles);
-    rqb::count_launch();
-    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, nullptr, n, carry, rank_dev, nullptr, 0,
-                                                   nullptr, nullptr, nullptr);
+    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, nullptr, n, rank_dev, PackArgs(), nullptr, nullptr, nullptr);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -1166,12 +1301,9 @@ extern "C" int rqb200_shard_suffix_dedup(rqb200_shard *sh, const int64_t *codes_
     const int64_t R = hp.status == 0 ? (int64_t)hp.recv_total : 0;
     if (R > 0) {
         RQB_CUDA(cudaMemcpyAsync(sc.keys[0], sh->block + sh->recv_off, sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
-        rqb::count_launch();
-        iota_u32_kernel<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(sc.vals[0], R);
-        sc.nblocks = (int)((R + SORT_TILE - 1) / SORT_TILE);
         int buf = 0;
         RQB_TRY(radix_sort(sc, R, key_bits, s, &buf));
-        RQB_TRY(run_seg_rank(sc, buf, R, nullptr, nullptr, 0, nullptr, false, s, rank_slot));
+        RQB_TRY(run_seg_rank(sc, buf, R, nullptr, nullptr, nullptr, false, s, rank_slot));
         int blocks = (int)((R + 255) / 256);
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         rqb::count_launch();

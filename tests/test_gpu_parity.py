@@ -203,6 +203,39 @@ def test_suffix_dedup_bit_exact(oracle, n, L, K):
         assert np.array_equal(out2.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("case", ["one_run", "two_runs_and_tail", "wide_keys_8_passes", "eight_levels", "tile_edges"])
+def test_suffix_dedup_long_runs_and_wide_keys(oracle, case):
+    """The one-launch digit passes (look-back over many tiles) and the rank kernel's backward search for the start of a
+    run that reaches into a tile: runs spanning hundreds of tiles, keys of 60 / 64 bits (eight digit passes), runs that
+    begin and end exactly on tile boundaries."""
+    rng = np.random.default_rng(5)
+    n = 300_007
+    if case == "one_run":
+        codes, K = np.full((n, 3), 7, dtype=np.int64), [256] * 3
+    elif case == "two_runs_and_tail":
+        codes, K = rng.integers(0, 256, size=(n, 3)).astype(np.int64), [256] * 3
+        codes[rng.permutation(n)[:200_000]] = (3, 1, 4)
+        codes[rng.permutation(n)[:60_000]] = (3, 1, 5)
+    elif case == "wide_keys_8_passes":
+        codes, K = rng.integers(0, 4096, size=(n, 5)).astype(np.int64), [4096] * 5
+        codes[rng.integers(0, n, size=n // 2)] = codes[rng.integers(0, n, size=n // 2)]
+    elif case == "eight_levels":
+        codes, K = rng.integers(0, 256, size=(n, 8)).astype(np.int64), [256] * 8
+        codes[:, :6] = codes[:, :1] % 3                         # few distinct high digits, random low ones
+        codes[rng.integers(0, n, size=n // 2)] = codes[rng.integers(0, n, size=n // 2)]
+    else:
+        n = 4 * 4096 + 2048                                     # sorted positions: runs of exactly 2048 / 4096 keys
+        codes, K = (np.arange(n)[:, None] // np.array([[4096, 2048, 1 << 30]])).astype(np.int64), [8, 16, 2]
+        codes = codes[rng.permutation(n)]
+    ct = torch.from_numpy(codes).to(DEV)
+    ref = oracle.suffix_dedup(codes)
+    for Ks in (K, None):
+        out, stats = rq.suffix_dedup(None, ct, Ks)
+        assert np.array_equal(out.cpu().numpy(), ref)
+        assert stats["max_conflicts"] == int(ref[:, -1].max()) + 1
+        assert stats["distinct"] == len(np.unique(codes, axis=0))
+
+
 def test_peer_memory_dedup_single_rank_equals_plain_dedup(oracle):
     """rqb200_shard_* with world = 1 (no peers): the owner is the rank itself, same ids as rqb200_suffix_dedup."""
     from ai_education_generative_recommendation_b200 import sharding
