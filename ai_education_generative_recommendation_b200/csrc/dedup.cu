@@ -83,8 +83,9 @@ constexpr int MAX_PASSES = 8;
 template <bool PACK>
 __global__ void __launch_bounds__(256)
 pack_hist_kernel(const int64_t *__restrict__ codes, int64_t n, PackArgs pa, uint64_t *__restrict__ keys, int npasses,
-                 uint32_t *__restrict__ ghist) {
+                 uint32_t *__restrict__ ghist, const unsigned long long *__restrict__ n_dev) {
     __shared__ uint32_t s_h[MAX_PASSES][RADIX];
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     __shared__ int64_t s_codes[PACK ? 256 * RQB200_MAX_LEVELS : 1];      // 256 rows, read with coalesced loads
     for (int p = 0; p < npasses; ++p) s_h[p][threadIdx.x] = 0;
     for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
@@ -210,8 +211,10 @@ __global__ void __launch_bounds__(OS_THREADS)
 onesweep_pass_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int pass,
                      const uint32_t *__restrict__ ghist, uint32_t *__restrict__ ticket,
-                     unsigned long long *__restrict__ status) {
+                     unsigned long long *__restrict__ status, const unsigned long long *__restrict__ n_dev) {
     extern __shared__ __align__(16) unsigned char os_smem[];
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
+    if ((int64_t)blockIdx.x * OS_TILE >= n) return;          // grid sized for the capacity: as many CTAs as tiles take a ticket
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(os_smem);
     uint32_t *s_vals = reinterpret_cast<uint32_t *>(os_smem + OS_TILE * 8);
     uint32_t(*s_cnt)[RADIX] = reinterpret_cast<uint32_t(*)[RADIX]>(os_smem + OS_TILE * 12);
@@ -390,8 +393,11 @@ __global__ void __launch_bounds__(SEG_THREADS)
 seg_rank_kernel(const uint64_t *__restrict__ ks, const uint32_t *__restrict__ perm, int64_t n,
                 int64_t *__restrict__ rank_out, PackArgs pa, int64_t *__restrict__ out,
                 unsigned long long *__restrict__ stats /* [0]=runs [1]=max run */,
-                uint32_t *__restrict__ rank_by_item /* rank_by_item[perm[i]] = rank, may be NULL */) {
+                uint32_t *__restrict__ rank_by_item /* rank_by_item[perm[i]] = rank, may be NULL */,
+                const unsigned long long *__restrict__ n_dev) {
     __shared__ long long s_warp[SEG_THREADS / 32];
+    if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
+    if ((int64_t)blockIdx.x * SEG_TILE >= n) return;
     __shared__ unsigned long long s_runs, s_maxrun;
     __shared__ long long s_carry;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -677,8 +683,11 @@ int carve(rqb200_model *m, int64_t n, SortScratch &sc) {
 // Stable LSD radix sort of sc.keys[0] (values = positions) with 8-bit digits: one launch that counts every digit
 // of every key (`codes` given: it also packs the keys), then ONE launch per digit.  Returns the buffer index
 // holding the result.  `n` may be smaller than what carve() was sized for.
+// `keys_src`: the first pass reads the keys from there instead of sc.keys[0] (no copy); `n_dev`: the number of keys is on the
+// device (n = its upper bound: grids and the look-back table are sized for it, surplus CTAs leave at once).
 int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *result_buf,
-               const int64_t *codes = nullptr, const PackArgs *pa = nullptr) {
+               const int64_t *codes = nullptr, const PackArgs *pa = nullptr, uint64_t *keys_src = nullptr,
+               const unsigned long long *n_dev = nullptr) {
     const int npasses = (key_bits + 7) / 8;
     RQB_CHECK(npasses >= 1 && npasses <= MAX_PASSES, "key_bits=%d out of range", key_bits);
     const int os_tiles = (int)((n + OS_TILE - 1) / OS_TILE);
@@ -687,8 +696,9 @@ int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *re
     int blocks = (int)((n + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     rqb::count_launch();
-    if (codes) pack_hist_kernel<true><<<blocks, 256, 0, s>>>(codes, n, *pa, sc.keys[0], npasses, sc.ghist);
-    else pack_hist_kernel<false><<<blocks, 256, 0, s>>>(nullptr, n, PackArgs(), sc.keys[0], npasses, sc.ghist);
+    uint64_t *first_in = keys_src ? keys_src : sc.keys[0];
+    if (codes) pack_hist_kernel<true><<<blocks, 256, 0, s>>>(codes, n, *pa, first_in, npasses, sc.ghist, n_dev);
+    else pack_hist_kernel<false><<<blocks, 256, 0, s>>>(nullptr, n, PackArgs(), first_in, npasses, sc.ghist, n_dev);
     static rqb::DeviceOnce attr_once;
     if (attr_once.first()) {
         RQB_CUDA(cudaFuncSetAttribute(onesweep_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM));
@@ -698,11 +708,11 @@ int radix_sort(SortScratch &sc, int64_t n, int key_bits, cudaStream_t s, int *re
     for (int pass = 0; pass < npasses; ++pass) {
         rqb::count_launch();
         if (pass == 0)
-            onesweep_pass_kernel<true><<<os_tiles, OS_THREADS, OS_SMEM, s>>>(sc.keys[cur], nullptr, sc.keys[cur ^ 1], sc.vals[cur ^ 1], n,
-                                                                       pass, sc.ghist, sc.ticket, sc.status);
+            onesweep_pass_kernel<true><<<os_tiles, OS_THREADS, OS_SMEM, s>>>(first_in, nullptr, sc.keys[cur ^ 1], sc.vals[cur ^ 1], n,
+                                                                             pass, sc.ghist, sc.ticket, sc.status, n_dev);
         else
             onesweep_pass_kernel<false><<<os_tiles, OS_THREADS, OS_SMEM, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1],
-                                                                        sc.vals[cur ^ 1], n, pass, sc.ghist, sc.ticket, sc.status);
+                                                                        sc.vals[cur ^ 1], n, pass, sc.ghist, sc.ticket, sc.status, n_dev);
         cur ^= 1;
     }
     RQB_LAUNCH_CHECK();
@@ -767,12 +777,13 @@ int sort_codes(rqb200_model *m, const int64_t *codes, int64_t n, int L, const in
 
 // pa = nullptr: no output rows
 int run_seg_rank(SortScratch &sc, int buf, int64_t n, int64_t *rank_out, const PackArgs *pa,
-                 int64_t *out, bool want_stats, cudaStream_t s, uint32_t *rank_by_item = nullptr) {
+                 int64_t *out, bool want_stats, cudaStream_t s, uint32_t *rank_by_item = nullptr,
+                 const unsigned long long *n_dev = nullptr) {
     const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
     if (want_stats) RQB_CUDA(cudaMemsetAsync(sc.stats, 0, 2 * sizeof(unsigned long long), s));
     rqb::count_launch();
     seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sc.keys[buf], sc.vals[buf], n, rank_out, pa ? *pa : PackArgs(),
-                                                   pa ? out : nullptr, want_stats ? sc.stats : nullptr, rank_by_item);
+                                                   pa ? out : nullptr, want_stats ? sc.stats : nullptr, rank_by_item, n_dev);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -806,6 +817,7 @@ struct ShardPlan {                         // device-resident, written by shard_
     uint32_t src_off[SHARD_MAX_WORLD + 1]; // receive buffer: slots [src_off[r], src_off[r+1]) came from rank r
     uint32_t ret_off[SHARD_MAX_WORLD];     // where my block starts in source r's return buffer
     unsigned long long recv_total;
+    unsigned long long sort_n;             // keys the owner sorts: recv_total, or 0 when the exchange failed (shard_barrier_kernel)
     int status;                            // 0 ok, 1 receive capacity exceeded, 2 peer timeout
 };
 
@@ -975,6 +987,7 @@ __global__ void __launch_bounds__(32)
 shard_barrier_kernel(ShardPeers peers, size_t sig_off, int rank, int world, unsigned long long epoch,
                      ShardPlan *__restrict__ plan) {
     shard_signal_and_wait(peers, sig_off, rank, world, epoch, &plan->status);
+    if (threadIdx.x == 0) plan->sort_n = plan->status == 0 ? plan->recv_total : 0ull;
 }
 
 // the owner returns the ranks: slot s of source r → r's return buffer at ret_off[r] + (s - src_off[r])
@@ -1160,7 +1173,8 @@ extern "C" int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_
     RQB_CUDA(cudaSetDevice(m->device));
     const int ntiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
     rqb::count_launch();
-    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, nullptr, n, rank_dev, PackArgs(), nullptr, nullptr, nullptr);
+    seg_rank_kernel<<<ntiles, SEG_THREADS, 0, s>>>(sorted_keys_dev, nullptr, n, rank_dev, PackArgs(), nullptr, nullptr, nullptr,
+                                                   nullptr);
     RQB_LAUNCH_CHECK();
     return 0;
 }
@@ -1295,16 +1309,15 @@ extern "C" int rqb200_shard_suffix_dedup(rqb200_shard *sh, const int64_t *codes_
     rqb::count_launch();
     shard_barrier_kernel<<<1, 32, 0, s>>>(sh->peers, sh->sig_off, rank, world, ++sh->epoch, sh->plan);
     RQB_LAUNCH_CHECK();
-    rqb::ShardPlan hp;
-    RQB_CUDA(cudaMemcpyAsync(&hp, sh->plan, sizeof(hp), cudaMemcpyDeviceToHost, s));
-    RQB_CUDA(cudaStreamSynchronize(s));
-    const int64_t R = hp.status == 0 ? (int64_t)hp.recv_total : 0;
-    if (R > 0) {
-        RQB_CUDA(cudaMemcpyAsync(sc.keys[0], sh->block + sh->recv_off, sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, s));
+    // The owner's part runs on a count that stays on the device (plan->sort_n): grids and the look-back table are sized for the
+    // receive capacity, the keys are sorted straight out of the receive buffer, nothing waits for the host in mid-step.
+    {
+        const int64_t Rcap = sh->cap_recv;
+        const unsigned long long *n_dev = &sh->plan->sort_n;
         int buf = 0;
-        RQB_TRY(radix_sort(sc, R, key_bits, s, &buf));
-        RQB_TRY(run_seg_rank(sc, buf, R, nullptr, nullptr, nullptr, false, s, rank_slot));
-        int blocks = (int)((R + 255) / 256);
+        RQB_TRY(radix_sort(sc, Rcap, key_bits, s, &buf, nullptr, nullptr, reinterpret_cast<uint64_t *>(sh->block + sh->recv_off), n_dev));
+        RQB_TRY(run_seg_rank(sc, buf, Rcap, nullptr, nullptr, nullptr, false, s, rank_slot, n_dev));
+        int blocks = (int)((Rcap + 255) / 256);
         if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
         rqb::count_launch();
         shard_return_kernel<<<blocks, 256, 0, s>>>(rank_slot, world, sh->peers, sh->ret_off, sh->plan);
@@ -1320,7 +1333,6 @@ extern "C" int rqb200_shard_suffix_dedup(rqb200_shard *sh, const int64_t *codes_
     int status = 0;
     RQB_CUDA(cudaMemcpyAsync(&status, &sh->plan->status, sizeof(int), cudaMemcpyDeviceToHost, s));
     RQB_CUDA(cudaStreamSynchronize(s));
-    if (hp.status != 0) status = hp.status;
     if (status == 1) { set_error("sharded dedup: a key owner would receive more than max_recv_items=%lld keys", (long long)sh->cap_recv); return RQB200_ENOMEM; }
     if (status != 0) { set_error("sharded dedup: timed out waiting for a peer rank"); return RQB200_ESTATE; }
     return 0;
