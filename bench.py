@@ -614,7 +614,7 @@ def main():
                     stage["quantize_incl_rescue_quantizer"], 2.0 * sum(Ks) * e_dim * n, tc_peak, "TFLOP/s",
                     "2*sum(K)*e flop of ONE pass; the kernel issues 3 fp16 passes and is bound by its per-level latency chain"),
                 _st("suffix dedup (radix sort + segmented rank)", "hbm", stage["dedup"], (8.0 * n_levels + 8.0 * (n_levels + 1)) * n,
-                    hbm_peak, "GB/s", "reads codes, writes ids; launch-bound at 1M items"),
+                    hbm_peak, "GB/s", "reads codes, writes ids; 5 launches (digit histograms, three one-sweep digit passes, rank + output rows), working set in L2"),
             ]
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None,
                     "traffic": traffic, "kernel": kname, "kernel_ms": k_ms,

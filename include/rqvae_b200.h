@@ -255,7 +255,8 @@ int rqb200_segment_rank(rqb200_model *m, const uint64_t *sorted_keys_dev, int64_
  * itself straight into the owner's receive buffer (peer memory mapped with cudaIpc, NVLink underneath); the
  * owner ranks them with the same radix sort + segmented rank as rqb200_suffix_dedup and writes the ranks
  * back into the sources' return buffers.  Cross-GPU ordering uses system-scope release/acquire flags; there
- * is no NCCL call and one stream synchronisation (the owner needs its receive count to size the sort).
+ * is no NCCL call and no host wait in mid-step: the owner's receive count stays on the device (the sort's grids
+ * are sized for max_recv_items); the call synchronises the stream once, at its end, to return the status.
  * Result: out[n_local, L+1], bit-identical to rqb200_suffix_dedup on the concatenated catalogue.
  *
  * Setup: every rank calls rqb200_shard_create, exchanges the rqb200_shard_handle_bytes()-byte handle of
