@@ -53,7 +53,23 @@ struct QtcArgs {
     int K[RQB200_MAX_LEVELS];
     float inv_scale[RQB200_MAX_LEVELS];
     int L;
+    uint32_t keep_mask;                            // 0xFFFFFFF0 (see pack_col)
 };
+
+#ifdef RQB_QTC_TRACE
+// per-phase clock stamps of the SECOND batch of CTA 0 (tools/trace_qtc.py): [group 0..QG-1 | QG = MMA lane][event]
+__device__ long long g_qtc_trace[QG + 1][512];
+__device__ int g_qtc_trace_n[QG + 1];
+#define QTRACE(who, cond) do { if ((cond) && blockIdx.x == 0 && trace_on) { int i_ = g_qtc_trace_n[who]; if (i_ < 512) { g_qtc_trace[who][i_] = clock64(); g_qtc_trace_n[who] = i_ + 1; } } } while (0)
+#else
+#define QTRACE(who, cond) do { } while (0)
+#endif
+
+// (x & keep) | col: with the mask in a register (opaque to the compiler) the two operations fuse into ONE LOP3 with the column
+// as its immediate; with two literals they stay two instructions
+__device__ __forceinline__ float pack_col(float x, uint32_t keep, uint32_t col) {
+    return __uint_as_float((__float_as_uint(x) & keep) | col);
+}
 
 __device__ __forceinline__ int q_swz(int rloc, int c) {          // byte offset of 16-byte chunk c of row rloc (SW128 K-major tile)
     return (rloc >> 3) * 1024 + (rloc & 7) * 128 + ((c ^ (rloc & 7)) << 4);
@@ -70,7 +86,8 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                    int64_t *__restrict__ list, unsigned long long *__restrict__ list_count, float gate_gamma,
                    float gate_floor, const int64_t *__restrict__ rows, const unsigned long long *__restrict__ n_dev) {
     static_assert(E % 8 == 0 && E <= 64, "tensor-core quantizer supports e_dim <= 64");
-    constexpr bool AUG = E < 64;           // the 64-wide K slab has a free column: the MMA itself adds the code norm
+    constexpr bool AUG = E < 64;           // the 64-wide K slab has a free column: the MMA itself adds the code norm (adding it in
+                                           // the scan instead, three MMA k-steps -> two, measured slower at e = 32: 0.456 vs 0.411 ms)
     if (n_dev) { const int64_t nd = (int64_t)*n_dev; n = nd < n ? nd : n; }
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -131,6 +148,11 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
         for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
             const int64_t tile = batch * QG + g;
             if (tile >= ntiles) continue;         // idle group in the last batch (the MMA warp skips it too)
+#ifdef RQB_QTC_TRACE
+            const bool trace_on = batch == (int64_t)blockIdx.x + gridDim.x;
+            const bool tr = (warp & 3) == 0 && lane == 0;
+#endif
+            QTRACE(g, tr);
             const int64_t row = tile * QTM + rloc;
             const bool live = row < n;
             const int64_t item = live ? (rows ? __ldg(rows + row) : row) : 0;      // where the codes of this row go
@@ -156,6 +178,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 xx = s0 + s1;
             }
             float min_margin = __int_as_float(0x7f800000);
+            const uint32_t keep_mask = qa.keep_mask;      // 0xFFFFFFF0 from the host: a literal would be folded back into two instructions
             const float gate_eps = gate_gamma * (sqrtf(xx) + gate_floor);
             int cc_base = 0;                                                   // offset of this level's norms in cc_s
             for (int l = 0; l < qa.L; cc_base += (qa.K[l] + QCH - 1) / QCH * QCH, ++l) {
@@ -164,14 +187,20 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[g]);
+                QTRACE(g, tr);
                 const float inv_s = qa.inv_scale[l];
-                // Scan of the accumulator (= 2^s (|c_j|^2 - 2 r.c_j), the distance up to the row constant |r|^2): four
-                // independent (best, second) trackers (column mod 4) keep the compare chains short; inside a 32-column
-                // block the column index is an immediate (no per-element index arithmetic).
-                float bd[4], sd[4];
-                int bi[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { bd[u] = __int_as_float(0x7f800000); sd[u] = __int_as_float(0x7f800000); bi[u] = 0; }
+                // Scan of the accumulator (= 2^s (|c_j|^2 - 2 r.c_j), the distance up to the row constant |r|^2).  The scan is what
+                // bounds this kernel (profiles/r2_qtc_phase_trace.txt: with the ALU work compiled out a 128-column chunk takes 355
+                // clocks per group, with it 5.5 k), so it is written for the fewest issue slots per distance:
+                //   * the column number inside its 16-column block replaces the four low mantissa bits of the value (one LOP3;
+                //     relative change < 2^-19, covered by the gate's rounding term), so the arg-min needs no compare + select per
+                //     distance — only "which block held the best so far", once per block;
+                //   * two distances a time: lo = min(a, b), hi = max(a, b), second = min3(second, max(best, lo), hi),
+                //     best = min(best, lo) — 2.5 slots per distance (min3 is one FMNMX3);
+                //   * two independent (best, second) trackers (even / odd pairs) keep the dependent chains short.
+                float B[2], S[2];
+                int blk[2] = {0, 0};
+                B[0] = B[1] = S[0] = S[1] = __int_as_float(0x7f800000);
                 const int K = qa.K[l];
                 for (int c0 = 0; c0 < K; c0 += QCH) {
                     const int ncols = min(QCH, ((K - c0) + 31) & ~31);
@@ -180,48 +209,76 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     mbar_wait(&d_full[QB * g + buf], (round / QB) & 1);
                     ++round;
                     tc_fence_after();
+                    QTRACE(g, tr);
                     const float *ccs_l = cc_in_smem ? cc_s + cc_base + c0 : qa.ccs[l] + c0;      // scaled norms of this chunk
-                    int bil[4] = {0, 0, 0, 0}, bcc[4] = {-1, -1, -1, -1};
-#pragma unroll 1
-                    for (int cc0 = 0; cc0 < ncols; cc0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + (uint32_t)cc0, v);
-                        float before[4];
+                    // The accumulator comes out of tensor memory 16 columns at a time, software-pipelined: the read of the next
+                    // half block is in flight while this one is scanned.
+                    auto scan16 = [&](const uint32_t (&v)[16], const int cc0, const int half) {      // columns cc0 + half .. + 15 of the chunk (half: literal 0 / 16)
+#ifdef RQB_QTC_NO_ALU
+                        return;
+#endif
+                        const float b0 = B[0], b1 = B[1];
+                        float nn[16];
+                        if (!AUG) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) before[u] = bd[u];
-#pragma unroll
-                        for (int t4 = 0; t4 < 8; ++t4) {
-                            float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (!AUG) n4 = *reinterpret_cast<const float4 *>(ccs_l + cc0 + 4 * t4);   // same address in every lane
-                            const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float d = __uint_as_float(v[4 * t4 + u]);
-                                if (!AUG) d += nn[u];
-                                sd[u] = fminf(sd[u], fmaxf(d, bd[u]));
-                                if (d < bd[u]) { bd[u] = d; bil[u] = 4 * t4 + u; }
+                            for (int q = 0; q < 4; ++q) {       // same address in every lane
+                                const float4 n4 = *reinterpret_cast<const float4 *>(ccs_l + cc0 + half + 4 * q);
+                                nn[4 * q] = n4.x; nn[4 * q + 1] = n4.y; nn[4 * q + 2] = n4.z; nn[4 * q + 3] = n4.w;
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (bd[u] < before[u]) bcc[u] = cc0;
-                    }
+                        for (int p = 0; p < 8; ++p) {
+                            float x = __uint_as_float(v[2 * p]), y = __uint_as_float(v[2 * p + 1]);
+                            if (!AUG) {
+                                x += nn[2 * p];
+                                y += nn[2 * p + 1];
+                            }
+                            x = pack_col(x, keep_mask, (uint32_t)(2 * p));
+                            y = pack_col(y, keep_mask, (uint32_t)(2 * p + 1));
+                            const float lo = fminf(x, y), hi = fmaxf(x, y);
+                            const int t = p & 1;
+                            S[t] = fminf(S[t], fminf(fmaxf(B[t], lo), hi));
+                            B[t] = fminf(B[t], lo);
+                        }
+                        const int here = c0 + cc0 + half;
+                        if (B[0] < b0) blk[0] = here;
+                        if (B[1] < b1) blk[1] = here;
+                    };
+#ifdef RQB_QTC_NO_LD
+#define tmem_ld16_async(a, v) do { for (int q_ = 0; q_ < 16; ++q_) v[q_] = (uint32_t)(a) + q_ * 0x3f000u + (uint32_t)xx; } while (0)
+#define tmem_ld16_wait(v) do { } while (0)
+#endif
+                    if (ncols == QCH) {
+                        // straight-line, one register window per 16-column read: with a rolled loop (or a conditional read) the
+                        // register allocator copies the windows around — one move per distance
+                        uint32_t v[QCH / 16][16];
+                        tmem_ld16_async(t_addr, v[0]);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (bcc[u] >= 0) bi[u] = c0 + bcc[u] + bil[u];
+                        for (int j = 0; j < QCH / 16; ++j) {
+                            tmem_ld16_wait(v[j]);
+                            if (j + 1 < QCH / 16) tmem_ld16_async(t_addr + (uint32_t)(16 * (j + 1)), v[j + 1]);
+                            scan16(v[j], (j >> 1) * 32, (j & 1) * 16);
+                        }
+                    } else {                            // ragged last chunk of a codebook whose size is no multiple of 128
+                        uint32_t va[16];
+#pragma unroll 1
+                        for (int cc = 0; cc < ncols; cc += 16) {
+                            tmem_ld16_async(t_addr + (uint32_t)cc, va);
+                            tmem_ld16_wait(va);
+                            scan16(va, cc & ~31, cc & 16);
+                        }
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&d_empty[QB * g + buf]);
+                    QTRACE(g, tr);
                 }
-                // merge the trackers: global best, and second = min(other bests, all seconds)
-                float bestd = bd[0], second = sd[0];
-                int best = bi[0];
-#pragma unroll
-                for (int u = 1; u < 4; ++u) {
-                    second = fminf(second, sd[u]);
-                    if (bd[u] < bestd || (bd[u] == bestd && bi[u] < best)) { second = fminf(second, bestd); bestd = bd[u]; best = bi[u]; }
-                    else second = fminf(second, bd[u]);
-                }
+                // merge the trackers: global best (its low four bits = column inside the block), second = min(other best, both seconds);
+                // equal bests leave a zero gap, i.e. the row goes to the next tier
+                const bool odd = B[1] < B[0];
+                float bestd = odd ? B[1] : B[0];
+                float second = fminf(fminf(S[0], S[1]), odd ? B[0] : B[1]);
+                int best = (odd ? blk[1] : blk[0]) + (int)(__float_as_uint(bestd) & 15u);
                 // back to distance units: d = acc * 2^-s + |r|^2
                 const bool bad_index = best >= K;                 // a padded code won: only possible for wild inputs
                 if (bad_index) best = 0;
@@ -235,41 +292,57 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM,
                     // of the fp16-pair residual and of the reference's own fp32 evaluation of d.
                     const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
-                    const float tau = 4.0f * gate_eps * (rho + gate_eps) + 4.0e-6f * (xx + fabsf(ccb));
+                    const float tau = 4.0f * gate_eps * (rho + gate_eps) + 8.0e-6f * (xx + fabsf(ccb));    // 4e-6 rounding + 4e-6 for the index bits
                     const float mg = (second - bestd) - tau;
                     min_margin = (mg == mg && min_margin == min_margin && !bad_index) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
                 }
+                QTRACE(g, tr);
                 if (l + 1 < qa.L) {
                     // gather + straight-through residual update (vq.py:95 / rq.py:47) on the A tile, 8 dims at a time:
                     // r = hi + lo, xres = r + (q - r), r' = r - xres → split → back into the tile; |r'|^2 for the next level
                     const float4 *q4 = reinterpret_cast<const float4 *>(qa.cb[l] + (int64_t)best * E);
                     float s0 = 0.f, s1 = 0.f;
+                    // the chosen code's fp32 row comes from L2: all its loads are issued together, ahead of the first use (the warp
+                    // barrier keeps the register-bound schedule from sinking each load to its use, i.e. one L2 round trip per 8 dims)
+                    constexpr int HALF = E / 8;                     // 8-dim pieces per batch of loads: the whole row
 #pragma unroll
-                    for (int c = 0; c < E / 8; ++c) {
-                        const float4 qa4 = __ldg(q4 + 2 * c), qb4 = __ldg(q4 + 2 * c + 1);
-                        const uint4 hi = *reinterpret_cast<const uint4 *>(a_hi + q_swz(rloc, c));
-                        const uint4 lo = *reinterpret_cast<const uint4 *>(a_lo + q_swz(rloc, c));
-                        const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-                        const float qv[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
-                        float rn[8];
+                    for (int h0 = 0; h0 < E / 8; h0 += HALF) {
+                        float4 qv[2 * HALF];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&hw[t]));
-                            const float2 l2 = __half22float2(*reinterpret_cast<const __half2 *>(&lw[t]));
-                            const float r0 = h2.x + l2.x, r1 = h2.y + l2.y;
-                            const float x0 = __fadd_rn(r0, __fsub_rn(qv[2 * t], r0)), x1 = __fadd_rn(r1, __fsub_rn(qv[2 * t + 1], r1));
-                            rn[2 * t] = __fsub_rn(r0, x0);
-                            rn[2 * t + 1] = __fsub_rn(r1, x1);
-                            s0 = fmaf(rn[2 * t], rn[2 * t], s0);
-                            s1 = fmaf(rn[2 * t + 1], rn[2 * t + 1], s1);
+                        for (int c = 0; c < 2 * HALF; ++c)
+                            qv[c] = (h0 + c / 2 < E / 8) ? __ldg(q4 + 2 * h0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncwarp();
+                        QTRACE(g, tr);
+#pragma unroll
+                        for (int cc = 0; cc < HALF; ++cc) {
+                            const int c = h0 + cc;
+                            if (c >= E / 8) break;
+                            const float4 qa4 = qv[2 * cc], qb4 = qv[2 * cc + 1];
+                            const uint4 hi = *reinterpret_cast<const uint4 *>(a_hi + q_swz(rloc, c));
+                            const uint4 lo = *reinterpret_cast<const uint4 *>(a_lo + q_swz(rloc, c));
+                            const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+                            const float qv8[8] = {qa4.x, qa4.y, qa4.z, qa4.w, qb4.x, qb4.y, qb4.z, qb4.w};
+                            float rn[8];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 h2 = __half22float2(*reinterpret_cast<const __half2 *>(&hw[t]));
+                                const float2 l2 = __half22float2(*reinterpret_cast<const __half2 *>(&lw[t]));
+                                const float r0 = h2.x + l2.x, r1 = h2.y + l2.y;
+                                const float x0 = __fadd_rn(r0, __fsub_rn(qv8[2 * t], r0)), x1 = __fadd_rn(r1, __fsub_rn(qv8[2 * t + 1], r1));
+                                rn[2 * t] = __fsub_rn(r0, x0);
+                                rn[2 * t + 1] = __fsub_rn(r1, x1);
+                                s0 = fmaf(rn[2 * t], rn[2 * t], s0);
+                                s1 = fmaf(rn[2 * t + 1], rn[2 * t + 1], s1);
+                            }
+                            uint4 nh, nl;
+                            split2(rn[0], rn[1], nh.x, nl.x); split2(rn[2], rn[3], nh.y, nl.y);
+                            split2(rn[4], rn[5], nh.z, nl.z); split2(rn[6], rn[7], nh.w, nl.w);
+                            *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = nh;
+                            *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = nl;
                         }
-                        uint4 nh, nl;
-                        split2(rn[0], rn[1], nh.x, nl.x); split2(rn[2], rn[3], nh.y, nl.y);
-                        split2(rn[4], rn[5], nh.z, nl.z); split2(rn[6], rn[7], nh.w, nl.w);
-                        *reinterpret_cast<uint4 *>(a_hi + q_swz(rloc, c)) = nh;
-                        *reinterpret_cast<uint4 *>(a_lo + q_swz(rloc, c)) = nl;
                     }
                     xx = s0 + s1;
+                    QTRACE(g, tr);
                 }
             }
             // rows that cannot be certified → rescue list (warp-aggregated append)
@@ -295,12 +368,16 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
             }
             uint32_t cb_round = 0;
             for (int64_t batch = blockIdx.x; batch < nbatches; batch += gridDim.x) {
+#ifdef RQB_QTC_TRACE
+                const bool trace_on = batch == (int64_t)blockIdx.x + gridDim.x;
+#endif
                 for (int l = 0; l < qa.L; ++l) {
                     const int K = qa.K[l];
                     for (int c0 = 0; c0 < K; c0 += QCH, ++cb_round) {
                         const int ncols = min(QCH, ((K - c0) + 31) & ~31);
                         const int st = cb_round % Q_STAGES;
                         mbar_wait(&cb_full[st], (cb_round / Q_STAGES) & 1);
+                        QTRACE(QG, true);
                         const uint64_t dw_hi = umma_desc(smem_u32(cb_base + st * Q_STAGE_BYTES));
                         const uint64_t dw_lo = umma_desc(smem_u32(cb_base + st * Q_STAGE_BYTES + Q_CB_TILE));
                         const uint32_t idesc = umma_idesc(QTM, ncols);
@@ -312,6 +389,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                             mbar_wait(&d_empty[QB * g + buf], ((d_round[g] / QB) & 1) ^ 1);
                             ++d_round[g];
                             tc_fence_after();
+                            QTRACE(QG, true);
                             const uint32_t d_tmem = tmem_base + (uint32_t)((g * QB + buf) * QCH);
 #pragma unroll
                             for (int kk = 0; kk < (E + (AUG ? 1 : 0) + 15) / 16; ++kk) {      // E residual columns (+ the augmented norm column)
@@ -354,6 +432,15 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
     }
 }
 
+}  // namespace
+#ifdef RQB_QTC_TRACE
+extern "C" __attribute__((visibility("default"))) int rqb200_debug_qtc_trace(long long *host_out, int *n_out, int reset) {
+    if (reset) { int z[QG + 1] = {0}; return (int)cudaMemcpyToSymbol(g_qtc_trace_n, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(n_out, g_qtc_trace_n, sizeof(int) * (QG + 1));
+    return (int)cudaMemcpyFromSymbol(host_out, g_qtc_trace, sizeof(long long) * (QG + 1) * 512);
+}
+#endif
+namespace {
 // codebook [K,e] fp32 → per QCH-code chunk: hi tile | lo tile (SW128 K-major, 64-wide K slab).  Column k < e holds
 // -2 c_jk 2^s, column e holds |c_j|^2 2^(s-t) (the A operand carries 2^t there), padded codes get a huge norm.
 __global__ void pack_codebook_kernel(const float *__restrict__ cb, const float *__restrict__ cc, int K, int e, float scale,
@@ -450,6 +537,7 @@ static int launch_qtc(rqb200_model *m, const float *z, int64_t n, int64_t *codes
     }
     QtcArgs qa;
     qa.L = m->L;
+    qa.keep_mask = 0xFFFFFFF0u;
     for (int l = 0; l < RQB200_MAX_LEVELS; ++l) {
         const bool on = l < m->L;
         qa.cbp[l] = on ? (const unsigned char *)m->cb_tc[l] : nullptr;

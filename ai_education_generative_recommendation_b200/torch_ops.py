@@ -37,6 +37,9 @@ def available() -> bool:
         return True
     if _unavailable:
         return False
+    if os.environ.get("RQB200_LIB"):              # A/B build of the C-ABI library (tools/build_variant.sh): the op library is linked
+        _unavailable = True                       # against the regular one, so such runs go through the ctypes binding
+        return False
     try:
         load()
     except Exception:

@@ -22,3 +22,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_referen
 timeout 300 python tools/step_timeline.py c2_slice > gpurun_out/step_timeline_c2.txt 2>&1; tail -n 3 gpurun_out/step_timeline_c2.txt | cut -c1-140
 timeout 300 python tools/time_dedup.py c2_slice > gpurun_out/time_dedup_c2.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-full-driver > gpurun_out/ncu_bench.log 2>&1; tail -n 2 gpurun_out/ncu_bench.log | cut -c1-200
+# phase trace of the tensor-core quantizer (needs tools/build_variant.sh qt quantize_tc.cu -DRQB_QTC_TRACE beforehand)
+QT=$PWD/ai_education_generative_recommendation_b200/librqvae_b200_qt.so
+if [ -f "$QT" ]; then
+  (RQB200_LIB=$QT timeout 200 python tools/trace_qtc.py c2_slice; RQB200_LIB=$QT timeout 200 python tools/trace_qtc.py c5_slice 400000) > gpurun_out/qtc_phase_trace.txt 2>&1
+fi
