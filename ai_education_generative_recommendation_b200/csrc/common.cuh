@@ -140,9 +140,11 @@ int ws_reserve(Workspace &w, size_t bytes);
 // linear_exact.cu
 // batch_rows: how many rows the reference would have in the batch these n rows belong to (decides the summation order,
 // small_batch.cu); -1 = n.  Internal callers that recompute a SUBSET of a large batch (rescue tier) pass the batch size.
-// n_dev (may be NULL): the row count lives on the device (n = capacity; persistent grid) — the exact tier of the fast route.
+// n_dev (may be NULL): the row count lives on the device (n = capacity; persistent grid) — the exact tier of the fast route;
+// rows_hint: about how many rows that count will be (picks the tile shape only).
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s, int64_t batch_rows = -1, const unsigned long long *n_dev = nullptr);
+                 bool relu, cudaStream_t s, int64_t batch_rows = -1, const unsigned long long *n_dev = nullptr,
+                 int64_t rows_hint = -1);
 // small_batch.cu: the reference's order for batches of 2..15 rows (and per-row batch sizes for the group re-encode)
 int linear_small(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y, bool relu, cudaStream_t s);
 int quantize_small(const rqb200_model *m, const float *z, const int64_t *items, const int *msize, int m_uniform, int64_t n,

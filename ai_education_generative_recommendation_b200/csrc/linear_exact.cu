@@ -258,7 +258,7 @@ int launch(const Linear &lin, const float *x, const int64_t *rows, int64_t n, fl
 }  // namespace
 
 int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t n, float *y,
-                 bool relu, cudaStream_t s, int64_t batch_rows, const unsigned long long *n_dev) {
+                 bool relu, cudaStream_t s, int64_t batch_rows, const unsigned long long *n_dev, int64_t rows_hint) {
     if (n == 0) return 0;
     if (n_dev) {
         // device-counted rows (rescue tier): n is the capacity; always a subset of a large batch (catalogue order)
@@ -266,6 +266,11 @@ int linear_exact(const Linear &lin, const float *x, const int64_t *rows, int64_t
         RQB_CHECK(lin.in % 4 == 0, "in_features must be a multiple of 4 (got %d)", lin.in);
         RQB_CHECK(lin.nblk >= 1 && lin.nblk <= 8, "at most 8 K-blocks supported (got %d)", lin.nblk);
         RQB_CHECK(!small_batch_lane16(batch_rows, lin.in), "device-counted rows must belong to a batch of 16 or more rows");
+        // wide layers: 64 x 64 tiles (4 x 4 per thread) keep every SM busy when only a few thousand rows come through (7 k rows
+        // x 256 features = 440 CTAs), but they are bound by shared-memory wavefronts (3-4 per 16 FMAs); from about 12 k rows
+        // on 128 x 64 tiles (8 x 4 per thread, half the wavefronts per FMA) fill the GPU as well: measured 133 vs 85 us at
+        // 7 k rows, 352 vs 436 us at 21 k rows x 1024 inputs.  Same chains, same bits.
+        if (lin.out > 64 && rows_hint >= 12288) return launch<128, 64, 8, 4>(lin, x, rows, n, y, relu, s, n_dev);
         if (lin.out > 64) return launch<64, 64, 4, 4>(lin, x, rows, n, y, relu, s, n_dev);
         if (lin.out > 32) return launch<128, 64, 8, 4>(lin, x, rows, n, y, relu, s, n_dev);
         return launch<128, 32, 4, 4>(lin, x, rows, n, y, relu, s, n_dev);

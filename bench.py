@@ -347,6 +347,9 @@ def run_sharded_checks(rank, world, dev, group):
     model = build_model(cfg, cbs, device=dev)
     x = torch.empty((hi - lo, cfg["in_dim"]), dtype=torch.float32, device=dev)
     _cabi.check(lib.rqb200_synth_items(SEED, lo, hi - lo, cfg["in_dim"], 1_000_000, x.data_ptr(), _cabi.stream_ptr()))
+    # warm-up on a small slice: NCCL opens its point-to-point connections on the first all-to-all between each pair of ranks
+    # (seconds at N = 8), which is set-up, not the driver
+    sharding.generate_codes_sharded(build_model(cfg, cbs, device=dev), x[:min(2048, hi - lo)].contiguous(), group)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     mine, stats = sharding.generate_codes_sharded(model, x, group)
