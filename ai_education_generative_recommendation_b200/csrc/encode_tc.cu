@@ -850,10 +850,11 @@ int get_indices_fast(rqb200_model *m, const float *x, int64_t n, int64_t *codes,
     {
         ProfScope ps(PROF_RESCUE, s);
         const unsigned long long *nr_dev = counts + 1;
-        const int64_t hint = m->last_tier_rows[1] > 0 ? m->last_tier_rows[1] : n / 64 + 1;      // picks the quantizer mapping only
-        // tile shape of the exact Linears: the last count that was fetched, else the typical share of the route (0.7 % of
-        // the rows behind the screening tier, 1.6-2.1 % without it)
-        const int64_t lin_hint = m->last_tier_rows[1] > 0 ? m->last_tier_rows[1] : (screen ? n / 128 : n / 48) + 1;
+        // about how many rows will come through (picks the quantizer mapping and the tile shape of the exact Linears, nothing
+        // else): the last count that was fetched, else the typical share of the route — 0.7 % of the rows behind the screening
+        // tier, 1.6-2.1 % without it
+        const int64_t hint = m->last_tier_rows[1] > 0 ? m->last_tier_rows[1] : (screen ? n / 128 : n / 48) + 1;
+        const int64_t lin_hint = hint;
         float *zr = z2;                                                    // [n, e]: tier 2 has consumed it
         const float *cur = x;
         for (int i = 0; i < m->n_layers; ++i) {

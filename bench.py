@@ -579,7 +579,8 @@ def main():
         k_ms = prof_ms[slot] / max(prof_cnt[slot], 1)
         alg_bytes = 4.0 * in_dim * n
         alg_flops = 2.0 * in_dim * first_out * n
-        screen_active = fast_ok and model.last_stats.get("three_pass_rows", 0) > 0     # the TF32 screening tier ran
+        tiers = model.last_stats if fast_ok else {}
+        screen_active = fast_ok and tiers.get("three_pass_rows", 0) > 0     # the TF32 screening tier ran
         l1_kernel = "linear_tf32_kernel" if screen_active else "linear_tc2_kernel"
         l1_desc = ("encoder layer 1 over every row: ONE tcgen05 kind::tf32 pass, cta_group::2, operands delivered by TMA "
                    "(cp.async.bulk.tensor) straight from the fp32 rows" if screen_active
@@ -628,7 +629,13 @@ def main():
                                              if screen_active else "algorithmic flops of ONE pass; the kernel issues 3 fp16 passes for fp32-class accuracy")},
                     "step_share": (prof_ms[slot] / args.steps) / ms_step if ms_step else None,
                     "whole_step_hbm_frac": (value / world) * (4 * in_dim + 8 * n_levels) / (hbm_peak * 1e9),
-                    "stage_ms_per_step": stage, "stages": stages}
+                    "stage_ms_per_step": stage, "stages": stages,
+                    "tier_rows_last_step": ({"rows": n, "three_pass_rerun_rows": tiers.get("three_pass_rows", 0),
+                                             "exact_rescue_rows": tiers.get("rescued_rows", 0),
+                                             "exact_rescue_fraction": tiers.get("rescued_rows", 0) / n if n else 0.0,
+                                             "note": "rows this rank re-ran on the three-pass tier (behind the TF32 screen) and on the "
+                                                     "exact SIMT tier in the last step; every other row was certified by a margin gate"}
+                                            if fast_ok else None)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
