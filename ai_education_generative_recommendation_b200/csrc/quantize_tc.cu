@@ -193,7 +193,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 // bounds this kernel (profiles/r2_qtc_phase_trace.txt: with the ALU work compiled out a 128-column chunk takes 355
                 // clocks per group, with it 5.5 k), so it is written for the fewest issue slots per distance:
                 //   * the column number inside its 16-column block replaces the four low mantissa bits of the value (one LOP3;
-                //     relative change < 2^-19, covered by the gate's rounding term), so the arg-min needs no compare + select per
+                //     relative change < 2^-20 once cleared again, covered by the gate's rounding term), so the arg-min needs no compare + select per
                 //     distance — only "which block held the best so far", once per block;
                 //   * two distances a time: lo = min(a, b), hi = max(a, b), second = min3(second, max(best, lo), hi),
                 //     best = min(best, lo) — 2.5 slots per distance (min3 is one FMNMX3);
@@ -282,8 +282,10 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                 // back to distance units: d = acc * 2^-s + |r|^2
                 const bool bad_index = best >= K;                 // a padded code won: only possible for wild inputs
                 if (bad_index) best = 0;
-                second = fmaf(second, inv_s, xx);
-                bestd = fmaf(bestd, inv_s, xx);
+                // the index bits are cleared again before the gap is formed: both values are then truncated the same way (towards
+                // zero by less than 2^-20 of their magnitude), so the gap moves by less than 2^-20 (|r|^2 + 2 |c|^2)
+                second = fmaf(__uint_as_float(__float_as_uint(second) & 0xFFFFFFF0u), inv_s, xx);
+                bestd = fmaf(__uint_as_float(__float_as_uint(bestd) & 0xFFFFFFF0u), inv_s, xx);
                 const float ccb = cc_in_smem ? cc_s[cc_base + best] * inv_s : __ldg(qa.cc[l] + best);
                 if (live) codes[item * qa.L + l] = best;
                 {
@@ -292,7 +294,7 @@ quantize_tc_kernel(const float *__restrict__ z, int64_t n, QtcArgs qa, int64_t *
                     // 2 eps (2 rho + 2 eps); the remaining term covers the rounding of the split-fp16 distance GEMM,
                     // of the fp16-pair residual and of the reference's own fp32 evaluation of d.
                     const float rho = sqrtf(fmaxf(bestd, 0.0f)) + gate_eps;
-                    const float tau = 4.0f * gate_eps * (rho + gate_eps) + 8.0e-6f * (xx + fabsf(ccb));    // 4e-6 rounding + 4e-6 for the index bits
+                    const float tau = 4.0f * gate_eps * (rho + gate_eps) + 6.0e-6f * (xx + fabsf(ccb));    // 4e-6 rounding + 2e-6 for the index bits
                     const float mg = (second - bestd) - tau;
                     min_margin = (mg == mg && min_margin == min_margin && !bad_index) ? fminf(min_margin, mg) : __int_as_float(0x7fc00000);
                 }

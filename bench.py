@@ -524,6 +524,7 @@ def main():
     lib.rqb200_profile_read(prof_ms, prof_cnt, 12)
     lib.rqb200_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
+    tiers = model.last_stats if fast_ok else {}          # tier row counts of the LAST TIMED step (the e2e leg below runs in chunks)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total.item()) / args.steps
@@ -579,7 +580,6 @@ def main():
         k_ms = prof_ms[slot] / max(prof_cnt[slot], 1)
         alg_bytes = 4.0 * in_dim * n
         alg_flops = 2.0 * in_dim * first_out * n
-        tiers = model.last_stats if fast_ok else {}
         screen_active = fast_ok and tiers.get("three_pass_rows", 0) > 0     # the TF32 screening tier ran
         l1_kernel = "linear_tf32_kernel" if screen_active else "linear_tc2_kernel"
         l1_desc = ("encoder layer 1 over every row: ONE tcgen05 kind::tf32 pass, cta_group::2, operands delivered by TMA "
