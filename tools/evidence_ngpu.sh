@@ -14,4 +14,4 @@ print("N=$N value", round(d["value"] / 1e6, 1), "M/s  ms", round(d["ms_per_step"
 for k, v in (d["config"].get("extra") or {}).items():
     print("  extra", k, {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if not isinstance(vv, (dict, list, str))})
 PY
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 tools/check_shard_p2p.py 2>&1 | grep -E "^case|peer_memory|nccl_all" > gpurun_out/shard_peer_dedup_n$N.txt; cat gpurun_out/shard_peer_dedup_n$N.txt
+[ -n "$SKIP_P2P" ] || timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 tools/check_shard_p2p.py 2>&1 | grep -E "^case|peer_memory|nccl_all" > gpurun_out/shard_peer_dedup_n$N.txt; cat gpurun_out/shard_peer_dedup_n$N.txt
