@@ -11,11 +11,15 @@
 // the kernel also decides which rows can be trusted: a row is appended to the rescue list when, at any
 // level, the gap between its two smallest distances is within the error bound of the approximate
 // arithmetic (see the derivation at `tau` below).  Rows on the list are recomputed by the exact
-// kernels; all other rows provably have the reference's codes.
+// kernels; all other rows carry the reference's codes (the bound is calibrated and checked at scale, not proven: DESIGN.md §4).
 //
 // CTA = 576 threads: four independent "row groups" of four warps each (one 128-row tile per group, thread
 // = row), warp 16 issues the MMAs for all groups, warp 17 streams codebook chunks.  While one group is
 // in its top-2 epilogue the tensor core works for the others.
+//
+// Diagnostic builds (tools/build_variant.sh … quantize_tc.cu -D…): RQB_QTC_TRACE records clock stamps of one steady-state
+// batch (tools/trace_qtc.py); RQB_QTC_NO_ALU / RQB_QTC_NO_LD compile the scan's arithmetic / its tensor-memory reads out
+// (timing only, wrong codes) — the measurements behind "what bounds this kernel" in DESIGN.md §4.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
