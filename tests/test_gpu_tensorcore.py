@@ -52,6 +52,33 @@ def test_fast_route_codes_equal_exact_route(name):
         assert rescued <= 0.05 * n, rescued
 
 
+@pytest.mark.parametrize("e_dim", [32, 64])
+def test_fast_route_with_ragged_codebooks(e_dim):
+    """Codebook sizes that are no multiple of the 128-code chunk of the tensor-core quantizer (its last chunk then scans
+    32 / 64 / 96 columns through the rolled path), five levels, both e_dim the tensor-core encoder ends in: fast route ==
+    exact route."""
+    Ks = [100, 7, 300, 5, 200]
+    cfg = {"in_dim": 768, "layers": [256, 128], "e_dim": e_dim, "num_emb_list": Ks, "sk_epsilons": [0.0] * len(Ks), "sk_iters": 50}
+    rng = np.random.default_rng(e_dim)
+    probe = build_model(cfg, [np.zeros((k, e_dim), np.float32) for k in Ks])
+    n = 60_000 + 19
+    x = gpu_synth(2024, 0, n, cfg["in_dim"], 1_000_000)
+    z = probe.encoder(x[:4096]).cpu().numpy()
+    scale = float(z.std())
+    cbs = [z[rng.permutation(4096)[:Ks[0]]].copy()]                       # level 0: latents themselves (rows ON codes)
+    for l in range(1, len(Ks)):
+        cbs.append((rng.standard_normal((Ks[l], e_dim)) * scale * 0.6 ** l).astype(np.float32))
+    m = build_model(cfg, cbs)
+    m.encode_mode = _cabi.ENCODE_FAST
+    fast = m.get_indices(x)
+    stats = m.last_stats
+    m.encode_mode = _cabi.ENCODE_EXACT
+    exact = m.get_indices(x)
+    assert torch.equal(fast, exact)
+    assert int(fast.max()) < max(Ks) and all(int(fast[:, l].max()) < Ks[l] for l in range(len(Ks)))
+    assert stats["rescued_rows"] < n                                      # the gate certified rows: the fast kernels did run
+
+
 @pytest.mark.parametrize("name", ["c2_slice", "c3_slice", "c5_slice"])
 def test_screening_tier_keeps_codes_bit_exact(name):
     """Opt-in tier 1 (one fp16 pass, looser gate) → three-pass re-run of the gated rows → exact rescue: same codes."""
