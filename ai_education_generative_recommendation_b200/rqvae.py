@@ -338,7 +338,7 @@ class RQVAE(nn.Module):
         """Shapes the tensor-core route is built for (everything else runs the exact SIMT route)."""
         dims = list(self.encode_layer_dims)
         return (not self.bn and dims[0] % 8 == 0 and all(d in (32, 64, 128, 256) for d in dims[1:])
-                and self.e_dim in (16, 32, 48, 64))
+                and self.e_dim in (32, 64))
 
     def set_screen(self, enabled, gamma1: float = 0.0):
         """Screening tier of the fast route (rqb200_model_set_screen): 0 / False off, 2 / "tf32" the TMA-fed TF32 first
