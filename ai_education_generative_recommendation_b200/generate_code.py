@@ -76,8 +76,12 @@ def collision_groups(model: RQVAE, codes: torch.Tensor):
 
 
 @torch.no_grad()
-def suffix_dedup(model: Optional[RQVAE], codes: torch.Tensor, num_emb_list=None) -> Tuple[torch.Tensor, dict]:
-    """Suffix column (infer.py:152-163) → ([N, L+1] int64, stats)."""
+def suffix_dedup(model: Optional[RQVAE], codes: torch.Tensor, num_emb_list=None, want_stats: bool = True
+                 ) -> Tuple[torch.Tensor, Optional[dict]]:
+    """Suffix column (infer.py:152-163) → ([N, L+1] int64, stats).
+
+    want_stats=False (and the code ranges known, i.e. a model or num_emb_list given): the call only enqueues — the collision
+    statistics are the one thing it would otherwise wait for the device to read back — and returns (ids, None)."""
     if not codes.is_cuda:
         raise RuntimeError("suffix_dedup: CUDA tensor required (no CPU fallback)")
     codes = codes.contiguous()
@@ -87,7 +91,10 @@ def suffix_dedup(model: Optional[RQVAE], codes: torch.Tensor, num_emb_list=None)
     Ks = num_emb_list if num_emb_list is not None else (model.num_emb_list if model is not None else None)
     handle = model._handle if model is not None else _scratch_handle(codes.device)
     check(_cabi.lib().rqb200_suffix_dedup(handle, ptr(codes), n, Lv, _cabi.int_array(Ks) if Ks else None, ptr(out),
-                                          ctypes.byref(nd), ctypes.byref(mg), stream_ptr(codes.device)))
+                                          ctypes.byref(nd) if want_stats else None, ctypes.byref(mg) if want_stats else None,
+                                          stream_ptr(codes.device)))
+    if not want_stats:
+        return out, None
     return out, {"distinct": int(nd.value), "max_conflicts": int(mg.value),
                  "collision_rate": (n - int(nd.value)) / n if n else 0.0}
 

