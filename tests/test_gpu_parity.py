@@ -201,6 +201,8 @@ def test_suffix_dedup_bit_exact(oracle, n, L, K):
         assert stats["max_conflicts"] == int(ref[:, -1].max()) + 1
         out2, _ = rq.suffix_dedup(None, ct, None)               # column ranges scanned on the device
         assert np.array_equal(out2.cpu().numpy(), ref)
+        out3, none = rq.suffix_dedup(None, ct, [K] * L, want_stats=False)      # enqueue-only form: no statistics, same ids
+        assert none is None and np.array_equal(out3.cpu().numpy(), ref)
 
 
 @pytest.mark.parametrize("case", ["one_run", "two_runs_and_tail", "wide_keys_8_passes", "eight_levels", "tile_edges"])
